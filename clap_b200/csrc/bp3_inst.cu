@@ -1,0 +1,81 @@
+/*
+ * bp3_inst.cu -- instantiates ca3d_sweep_kernel for ONE rule (-DBP3_RULE=0..9)
+ * and all (P, WPL) variants, and provides its cooperative launcher.
+ */
+#include "bp3_launch.h"
+
+#ifndef BP3_RULE
+#error "compile with -DBP3_RULE=<0..9>"
+#endif
+
+namespace clapca {
+
+#define B(n) (1u << (n))
+#define RANGE(s, e) (((1u << ((e) - (s))) - 1u) << (s))     /* core/ca3d.h:34 */
+
+/* cas[]: core/ca3d.c:110-122 -- <surv, born, nr_states> */
+#if BP3_RULE == 0
+typedef Rule3Const<B(4), B(4), 5> TheRule;                                          /* ca_445m */
+#elif BP3_RULE == 1
+typedef Rule3Const<B(6) | B(7) | B(8), B(6) | B(7) | B(8), 3> TheRule;              /* ca_678_678_3m */
+#elif BP3_RULE == 2
+typedef Rule3Const<B(4) | B(5) | B(6) | B(7), B(6) | B(7) | B(8), 10> TheRule;      /* ca_pyroclastic */
+#elif BP3_RULE == 3
+typedef Rule3Const<RANGE(9, 26), B(5) | B(6) | B(7) | B(12) | B(13) | B(15), 5> TheRule;   /* ca_amoeba */
+#elif BP3_RULE == 4
+typedef Rule3Const<B(2) | B(6) | B(9), B(4) | B(6) | B(8) | B(9), 10> TheRule;      /* ca_builder */
+#elif BP3_RULE == 5
+typedef Rule3Const<B(1) | B(4) | B(8) | B(11) | RANGE(13, 26), RANGE(13, 26), 5> TheRule;  /* ca_slow_decay */
+#elif BP3_RULE == 6
+typedef Rule3Const<RANGE(0, 3) | RANGE(7, 9) | RANGE(11, 13) | B(18) | B(21) | B(22) | B(24) | B(26),
+                   B(4) | B(13) | B(17) | RANGE(20, 24) | B(26), 4> TheRule;        /* ca_spiky_growth */
+#elif BP3_RULE == 7
+typedef Rule3Const<RANGE(5, 8), RANGE(6, 7) | B(9) | B(12), 4> TheRule;             /* ca_coral */
+#elif BP3_RULE == 8
+typedef Rule3Const<RANGE(0, 6), B(1) | B(3), 2> TheRule;                            /* ca_crystal_1 */
+#else
+typedef Rule3Dyn TheRule;                                                           /* run-time masks */
+#endif
+
+template <int P, int WPL>
+static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, Bp3LaunchInfo *info)
+{
+    auto kern = ca3d_sweep_kernel<P, WPL, TheRule>;
+    const int threads = 256;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int blocks = per_sm * sms;
+    const int need = (p.nsweeps + threads / 32 - 1) / (threads / 32);
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    if (info) {
+        info->blocks = blocks;
+        info->threads = threads;
+        info->workers = blocks * (threads / 32);
+        info->regs = fa.numRegs;
+    }
+    Bp3Params pp = p;
+    void *args[] = { &pp };
+    /* cooperative launch: fails instead of silently running a non-co-resident grid */
+    return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(threads), args, 0, stream);
+}
+
+#define BP3_CONCAT2(a, b) a##b
+#define BP3_CONCAT(a, b) BP3_CONCAT2(a, b)
+
+cudaError_t BP3_CONCAT(bp3_launch_rule, BP3_RULE)(int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream,
+                                                  Bp3LaunchInfo *info)
+{
+#define BP3_CASE(PP, WW) if (P == PP && WPL == WW) return launch_one<PP, WW>(p, sms, stream, info);
+    BP3_CASE(3, 1) BP3_CASE(3, 2) BP3_CASE(3, 4)
+    BP3_CASE(4, 1) BP3_CASE(4, 2) BP3_CASE(4, 4)
+    BP3_CASE(8, 1) BP3_CASE(8, 2) BP3_CASE(8, 4)
+    return cudaErrorInvalidValue;
+}
+
+} // namespace clapca

@@ -1,0 +1,424 @@
+/*
+ * ca3d_bitplane.cuh -- bit-plane engine for ca3d_run() (core/ca3d.c:124-142).
+ *
+ * The reference updates the volume IN PLACE in z/y/x order, so a cell sees
+ * the new generation of the 13 neighbours that precede it in the sweep and the
+ * old generation of the other 13.  This engine reproduces that order exactly,
+ * for all generations at once:
+ *
+ * Layout.  The uint8 volume is re-laid as bit planes.  For every grid row
+ * (y,z) there is one "row record" of NP = 2 + P plane-rows, each RWP 32-bit
+ * words (bit i of word w = cell x = 32 w + i):
+ *     [ H0 | H1 | S0 ... S(P-1) ]
+ * S_p is bit p of the cell state (P = bits needed for the largest value that
+ * can ever occur), H1:H0 is the horizontal alive 3-sum a(x-1)+a(x)+a(x+1) of
+ * the row, published so consumers never recompute it.  Padding bits of S are
+ * always 0.
+ *
+ * Row step.  For row (y,z) of generation g every input except the new alive
+ * bit of cell x-1 is known before the row starts:
+ *     K = V(z-1,new)[y] + V(z+1,old)[y] + H(y-1,new) + H(y+1,old) + a_old(x+1)
+ * with V = H(y-1)+H(y)+H(y+1) of one plane.  f0/f1 = new alive bit for
+ * n = K / K+1 come from the rule tables, and the in-row chain is resolved by
+ * the GF(2) affine scan of bitslice.cuh.  One warp updates a whole row.
+ *
+ * Sweeps and dataflow.  A "sweep" (z,g) = rows y = 0..H-1 of plane z at
+ * generation g, run by one persistent warp.  Row y of sweep (z,g) needs rows
+ * <= y+1 of (z-1,g) [new plane below], of (z+1,g-1) [old plane above] and of
+ * (z,g-1) [own old state]; each sweep publishes a progress counter
+ * prog[g][z] = rows completed (store after __threadfence), consumers poll it.
+ * Sweeps are claimed from a ticket counter in an order that extends the
+ * dependency order (key 2z+4g), so with all warps co-resident (cooperative
+ * launch) the earliest unfinished sweep can always advance: no deadlock.  All
+ * generations of a plane follow each other a few rows apart, so the working
+ * set lives in L2 and HBM sees one read and one write of the volume for the
+ * whole run (temporal blocking over ALL generations).  The same in-place
+ * argument as the reference's makes single buffering safe: a row is only
+ * overwritten after every reader of its previous version has passed it.
+ */
+#ifndef CLAPCA_CA3D_BITPLANE_CUH
+#define CLAPCA_CA3D_BITPLANE_CUH
+
+#include "bitslice.cuh"
+
+namespace clapca {
+
+struct Bp3Params {
+    uint32_t *rows;         /* row records, [(z*H + y) * NP + plane] * RWP */
+    int W, H, Z, G;         /* cells per row, rows per plane, planes, generations */
+    int RWP;                /* words per plane-row = 32 * WPL */
+    int *prog;              /* [G][Z] rows completed by sweep (z,g) */
+    const int2 *order;      /* sweep claim order: (z, g) */
+    int nsweeps;
+    unsigned *ticket;       /* next sweep to claim */
+    int *err;               /* != 0: watchdog fired, everybody bails out */
+    uint32_t surv, born;    /* rule masks (run-time rule only) */
+    uint32_t bornval;       /* (nr_states - 1) & 0xff */
+    long long spin_limit;   /* watchdog budget in clock ticks per wait */
+};
+
+/* ---- rules ---------------------------------------------------------------- */
+
+/* compile-time rule: the nine entries of cas[] (core/ca3d.c:110-122) */
+template <uint32_t SURV, uint32_t BORN, uint32_t NR>
+struct Rule3Const {
+    static constexpr uint32_t kBornVal = (NR - 1u) & 0xffu;
+    CA_MDEV uint32_t bornval(const Bp3Params &) { return kBornVal; }
+    /* tables at n = K and n = K + 1 */
+    CA_MDEV void eval(const Bp3Params &, const uint32_t k[5],
+                            uint32_t &s0, uint32_t &s1, uint32_t &b0, uint32_t &b1)
+    {
+        s0 = bs_tab5<SURV>(k);
+        s1 = bs_tab5<(SURV >> 1)>(k);
+        if (kBornVal) {
+            b0 = bs_tab5<BORN>(k);
+            b1 = bs_tab5<(BORN >> 1)>(k);
+        } else {
+            b0 = b1 = 0u;
+        }
+    }
+};
+
+/* run-time rule (arbitrary masks through the C ABI) */
+struct Rule3Dyn {
+    CA_MDEV uint32_t bornval(const Bp3Params &p) { return p.bornval; }
+    CA_MDEV void eval(const Bp3Params &p, const uint32_t k[5],
+                            uint32_t &s0, uint32_t &s1, uint32_t &b0, uint32_t &b1)
+    {
+        s0 = bs_tab_dyn(p.surv, k, 5);
+        s1 = bs_tab_dyn(p.surv >> 1, k, 5);
+        if (p.bornval) {
+            b0 = bs_tab_dyn(p.born, k, 5);
+            b1 = bs_tab_dyn(p.born >> 1, k, 5);
+        } else {
+            b0 = b1 = 0u;
+        }
+    }
+};
+
+/* ---- vector access to a lane's WPL consecutive words ------------------------ */
+
+template <int WPL> struct LaneVec;
+template <> struct LaneVec<1> {
+    CA_MDEV void ld(const uint32_t *p, uint32_t v[1]) { v[0] = dp_ld_cg(p); }
+    CA_MDEV void st(uint32_t *p, const uint32_t v[1]) { dp_st_cg(p, v[0]); }
+};
+template <> struct LaneVec<2> {
+    CA_MDEV void ld(const uint32_t *p, uint32_t v[2])
+    {
+        uint2 t = dp_ld_cg(reinterpret_cast<const uint2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    CA_MDEV void st(uint32_t *p, const uint32_t v[2])
+    {
+        dp_st_cg(reinterpret_cast<uint2 *>(p), make_uint2(v[0], v[1]));
+    }
+};
+template <> struct LaneVec<4> {
+    CA_MDEV void ld(const uint32_t *p, uint32_t v[4])
+    {
+        uint4 t = dp_ld_cg(reinterpret_cast<const uint4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    CA_MDEV void st(uint32_t *p, const uint32_t v[4])
+    {
+        dp_st_cg(reinterpret_cast<uint4 *>(p), make_uint4(v[0], v[1], v[2], v[3]));
+    }
+};
+
+/* horizontal 3-sum a(x-1)+a(x)+a(x+1) of a lane-distributed row -> 2 bit planes */
+template <int WPL>
+CA_DEV void bp_hsum(const uint32_t a[WPL], uint32_t h0[WPL], uint32_t h1[WPL])
+{
+    const int lane = dp_lane();
+    uint32_t prev = dp_shfl_up(a[WPL - 1], 1);      /* last word of the lane on the left  */
+    uint32_t next = dp_shfl_down(a[0], 1);          /* first word of the lane on the right */
+    if (lane == 0)  prev = 0u;
+    if (lane == 31) next = 0u;
+#pragma unroll
+    for (int j = 0; j < WPL; j++) {
+        uint32_t left  = j ? a[j - 1] : prev;
+        uint32_t right = (j + 1 < WPL) ? a[j + 1] : next;
+        uint32_t l = dp_funnel_l(left, a[j], 1);    /* bit i = a(x-1) */
+        uint32_t r = dp_funnel_r(a[j], right, 1);   /* bit i = a(x+1) */
+        h0[j] = bs_xor3(l, a[j], r);
+        h1[j] = bs_maj3(l, a[j], r);
+    }
+}
+
+/* valid-cell mask of word w of a row of W cells */
+CA_DEV uint32_t bp_valid_mask(int w, int W)
+{
+    int rem = W - 32 * w;
+    return rem >= 32 ? ~0u : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+/* ---- the persistent sweep kernel -------------------------------------------- */
+
+template <int P, int WPL, class Rule>
+struct Sweep3 {
+    static constexpr int NP = P + 2;
+
+    struct Flags {          /* cached progress of the three producers of a sweep */
+        const int *dn, *up, *own;
+        int vdn, vup, vown;
+    };
+
+    /* wait until all three producers have completed `need` rows; false = watchdog/abort */
+    CA_MDEV bool wait_rows(const Bp3Params &p, Flags &f, int need)
+    {
+        if (f.vdn >= need && f.vup >= need && f.vown >= need)
+            return true;
+        long long t0 = dp_clock();
+        unsigned spins = 0;
+        for (;;) {
+            /* lanes 0..2 poll one producer each; the values are made warp-uniform by shuffle */
+            const int lane = dp_lane();
+            const int *src = lane == 0 ? f.dn : (lane == 1 ? f.up : (lane == 2 ? f.own : nullptr));
+            uint32_t v = src ? (uint32_t)dp_ld_flag(src) : 0x7fffffffu;
+            f.vdn  = (int)dp_shfl(v, 0);
+            f.vup  = (int)dp_shfl(v, 1);
+            f.vown = (int)dp_shfl(v, 2);
+            if (f.vdn >= need && f.vup >= need && f.vown >= need)
+                break;
+            dp_nanosleep(40);
+            if ((++spins & 63u) == 0u) {
+                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
+                if (!dp_all(!bad)) {
+                    if (dp_lane() == 0)
+                        dp_atomic_max(p.err, 1);
+                    return false;
+                }
+            }
+        }
+        /* acquire: the polling lanes fence after their relaxed load, the warp barrier extends it to all lanes */
+        dp_fence_acquire();
+        dp_syncwarp();
+        return true;
+    }
+
+    struct RowIn {          /* what one row step pulls from memory for row r */
+        uint32_t hd[2][WPL], hu[2][WPL], ho[2][WPL];
+    };
+
+    CA_MDEV void load_h(const uint32_t *rec, int RWP, int lane, uint32_t h[2][WPL])
+    {
+        LaneVec<WPL>::ld(rec + 0 * RWP + lane * WPL, h[0]);
+        LaneVec<WPL>::ld(rec + 1 * RWP + lane * WPL, h[1]);
+    }
+    CA_MDEV void zero_h(uint32_t h[2][WPL])
+    {
+#pragma unroll
+        for (int j = 0; j < WPL; j++) h[0][j] = h[1][j] = 0u;
+    }
+    CA_MDEV void load_s(const uint32_t *rec, int RWP, int lane, uint32_t s[P][WPL])
+    {
+#pragma unroll
+        for (int q = 0; q < P; q++)
+            LaneVec<WPL>::ld(rec + (2 + q) * RWP + lane * WPL, s[q]);
+    }
+
+    /* rows r of the three sources of sweep (z,g): H of dn/up/own-old and S of own-old */
+    CA_MDEV void load_row(const Bp3Params &p, int z, int r, int lane, bool have_dn, bool have_up,
+                                RowIn &in, uint32_t so[P][WPL])
+    {
+        const size_t recw = (size_t)NP * p.RWP;
+        if (r < p.H) {
+            const uint32_t *own = p.rows + ((size_t)z * p.H + r) * recw;
+            if (have_dn) load_h(own - (size_t)p.H * recw, p.RWP, lane, in.hd); else zero_h(in.hd);
+            if (have_up) load_h(own + (size_t)p.H * recw, p.RWP, lane, in.hu); else zero_h(in.hu);
+            load_h(own, p.RWP, lane, in.ho);
+            load_s(own, p.RWP, lane, so);
+        } else {
+            zero_h(in.hd); zero_h(in.hu); zero_h(in.ho);
+#pragma unroll
+            for (int q = 0; q < P; q++)
+#pragma unroll
+                for (int j = 0; j < WPL; j++) so[q][j] = 0u;
+        }
+    }
+
+    /* one sweep: all rows of plane z at generation g.  false = aborted */
+    CA_MDEV bool run_sweep(const Bp3Params &p, int z, int g)
+    {
+        const int lane = dp_lane();
+        const int H = p.H, Z = p.Z;
+        const bool have_dn = z > 0, have_up = z + 1 < Z;
+        const uint32_t bornval = Rule::bornval(p);
+        const size_t recw = (size_t)NP * p.RWP;
+        int *myprog = p.prog + (size_t)g * Z + z;
+
+        Flags f;
+        f.dn  = have_dn ? p.prog + (size_t)g * Z + (z - 1) : nullptr;
+        f.up  = (g > 0 && have_up) ? p.prog + (size_t)(g - 1) * Z + (z + 1) : nullptr;
+        f.own = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
+        f.vdn  = f.dn  ? 0 : 0x7fffffff;
+        f.vup  = f.up  ? 0 : 0x7fffffff;
+        f.vown = f.own ? 0 : 0x7fffffff;
+
+        uint32_t vmask[WPL];
+#pragma unroll
+        for (int j = 0; j < WPL; j++) vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
+
+        /* sliding windows (see file header) */
+        uint32_t hdA[2][WPL], hdB[2][WPL], huA[2][WPL], huB[2][WPL], hn[2][WPL];
+        uint32_t so[P][WPL], so1[P][WPL], so2[P][WPL];
+        RowIn in;
+
+        zero_h(hdA); zero_h(huA); zero_h(hn);
+        if (!wait_rows(p, f, H < 2 ? H : 2))
+            return false;
+        {
+            RowIn r0;
+            load_row(p, z, 0, lane, have_dn, have_up, r0, so);
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int j = 0; j < WPL; j++) { hdB[b][j] = r0.hd[b][j]; huB[b][j] = r0.hu[b][j]; }
+            load_row(p, z, 1, lane, have_dn, have_up, in, so1);
+        }
+
+        for (int y = 0; y < H; y++) {
+            uint32_t k[WPL][5], ao[WPL], ge2[WPL];
+
+            /* ---- neighbour count K (everything but the in-row predecessor) ---- */
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                uint32_t a = so[0][j], hi = 0u;
+#pragma unroll
+                for (int q = 1; q < P; q++) hi |= so[q][j];
+                ao[j] = a | hi;
+                ge2[j] = hi;
+            }
+            uint32_t nxt = dp_shfl_down(ao[0], 1);
+            if (lane == 31) nxt = 0u;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                uint32_t a_[2] = { hdA[0][j], hdA[1][j] }, b_[2] = { hdB[0][j], hdB[1][j] };
+                uint32_t c_[2] = { in.hd[0][j], in.hd[1][j] };
+                uint32_t vd[4], vu[4];
+                bs_add3x2(a_, b_, c_, vd);
+                uint32_t e_[2] = { huA[0][j], huA[1][j] }, f_[2] = { huB[0][j], huB[1][j] };
+                uint32_t g_[2] = { in.hu[0][j], in.hu[1][j] };
+                bs_add3x2(e_, f_, g_, vu);
+                uint32_t n_[2] = { hn[0][j], hn[1][j] }, o_[2] = { in.ho[0][j], in.ho[1][j] };
+                uint32_t right = (j + 1 < WPL) ? ao[j + 1] : nxt;
+                uint32_t r = dp_funnel_r(ao[j], right, 1);      /* old alive bit of x+1 */
+                bs_count3d(vd, vu, n_, o_, r, k[j]);
+            }
+            /* rotate the H windows: `in` is free from here on */
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int j = 0; j < WPL; j++) {
+                    hdA[b][j] = hdB[b][j]; hdB[b][j] = in.hd[b][j];
+                    huA[b][j] = huB[b][j]; huB[b][j] = in.hu[b][j];
+                }
+
+            /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
+            {
+                int need = y + 3 < H ? y + 3 : H;
+                if (!wait_rows(p, f, need))
+                    return false;
+                load_row(p, z, y + 2, lane, have_dn, have_up, in, so2);
+            }
+
+            /* ---- rule tables, in-row scan ---- */
+            uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], D[WPL], C[WPL];
+            uint32_t dl = 1u, cl = 0u;          /* lane map: identity so far */
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                Rule::eval(p, k[j], s0[j], s1[j], b0[j], b1[j]);
+                /* new alive bit if the predecessor's new alive bit is 0 / 1 */
+                uint32_t f0 = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & vmask[j];
+                uint32_t f1 = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & vmask[j];
+                D[j] = f0 ^ f1;
+                C[j] = f0;
+                bs_scan_word(D[j], C[j]);
+                /* compose into the lane map: carry-out = c ^ (d & carry-in) */
+                uint32_t d = D[j] >> 31, c = C[j] >> 31;
+                cl = c ^ (d & cl);
+                dl = d & dl;
+            }
+            uint32_t cin = bs_scan_warp(dl, cl, 0u);
+
+            /* ---- apply: new alive bits, state planes ---- */
+            uint32_t an[WPL];
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                uint32_t cm = 0u - cin;
+                an[j] = C[j] ^ (D[j] & cm);
+                uint32_t pred = (an[j] << 1) | cin;              /* new alive bit of x-1 */
+                cin = an[j] >> 31;
+                uint32_t sv = bs_mux(pred, s1[j], s0[j]);
+                uint32_t bn = bs_mux(pred, b1[j], b0[j]);
+                uint32_t dec = ao[j] & ~sv;                      /* alive, not surviving: state - 1 */
+                uint32_t brn = ~ao[j] & bn & vmask[j];           /* dead, born: state = nr_states - 1 */
+                uint32_t borrow = dec;
+#pragma unroll
+                for (int q = 0; q < P; q++) {
+                    uint32_t t = so[q][j];
+                    so[q][j] = t ^ borrow;
+                    borrow &= ~t;
+                    if ((bornval >> q) & 1u) so[q][j] |= brn;
+                }
+            }
+            bp_hsum<WPL>(an, hn[0], hn[1]);
+
+            /* ---- publish row y ---- */
+            {
+                uint32_t *rec = p.rows + ((size_t)z * H + y) * recw;
+                LaneVec<WPL>::st(rec + 0 * p.RWP + lane * WPL, hn[0]);
+                LaneVec<WPL>::st(rec + 1 * p.RWP + lane * WPL, hn[1]);
+#pragma unroll
+                for (int q = 0; q < P; q++)
+                    LaneVec<WPL>::st(rec + (2 + q) * p.RWP + lane * WPL, so[q]);
+                /*
+                 * release: warp barrier (orders every lane's row stores before lane 0),
+                 * then ONE cumulative gpu-scope fence and the relaxed counter store --
+                 * the same shape as cooperative-groups' grid barrier arrive.
+                 */
+                dp_syncwarp();
+                if (lane == 0) {
+                    dp_fence_release();
+                    dp_st_flag(myprog, y + 1);
+                }
+            }
+
+            /* ---- rotate the state pipeline ---- */
+#pragma unroll
+            for (int q = 0; q < P; q++)
+#pragma unroll
+                for (int j = 0; j < WPL; j++) { so[q][j] = so1[q][j]; so1[q][j] = so2[q][j]; }
+        }
+        return true;
+    }
+
+    CA_MDEV void kernel_body(const Bp3Params &p)
+    {
+        const int lane = dp_lane();
+        for (;;) {
+            unsigned t = 0;
+            if (lane == 0) {
+                t = dp_atomic_inc(p.ticket);
+                if (dp_ld_flag(p.err) != 0)
+                    t = 0xffffffffu;
+            }
+            t = dp_shfl(t, 0);
+            if (t >= (unsigned)p.nsweeps)
+                break;
+            int2 zg = p.order[t];
+            if (!run_sweep(p, zg.x, zg.y))
+                break;
+        }
+    }
+};
+
+template <int P, int WPL, class Rule>
+CA_GLOBAL void __launch_bounds__(256) ca3d_sweep_kernel(Bp3Params p)
+{
+    Sweep3<P, WPL, Rule>::kernel_body(p);
+}
+
+} // namespace clapca
+#endif

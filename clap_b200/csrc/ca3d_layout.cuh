@@ -1,0 +1,90 @@
+/*
+ * ca3d_layout.cuh -- conversion between the reference layout (uint8 cells,
+ * z*d0*d1 + y*d0 + x, core/xyarray.c:43) and the row records of the bit-plane
+ * engine (see ca3d_bitplane.cuh), plus the population count of the result
+ * (xyzarray_count(), core/xyarray.c:68-78) fused into the way back.
+ */
+#ifndef CLAPCA_CA3D_LAYOUT_CUH
+#define CLAPCA_CA3D_LAYOUT_CUH
+
+#include "devport.h"
+
+namespace clapca {
+
+/* ---- layout conversion ------------------------------------------------------- */
+
+struct Bp3Layout {
+    uint8_t *cells;         /* reference layout, z*W*H + y*W + x */
+    uint32_t *rows;         /* row records */
+    int W, H, Z, P, RWP;
+    unsigned long long *population;     /* unpack: number of non-zero cells */
+};
+
+/* uint8 volume -> row records (one thread per word of a plane-row) */
+CA_GLOBAL void ca3d_pack_kernel(Bp3Layout L)
+{
+    const int NP = L.P + 2;
+    const size_t nwords = (size_t)L.Z * L.H * L.RWP;
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < nwords; i += stride) {
+        const int w = (int)(i % L.RWP);
+        const size_t row = i / L.RWP;
+        uint32_t *rec = L.rows + row * NP * L.RWP + w;
+        const uint8_t *src = L.cells + row * L.W;
+        const int x0 = 32 * w;
+        uint32_t s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        uint32_t alive = 0u;
+        int n = L.W - x0;
+        n = n > 32 ? 32 : n;
+        for (int i2 = 0; i2 < n; i2++) {
+            uint32_t v = src[x0 + i2];
+#pragma unroll
+            for (int q = 0; q < 8; q++) s[q] |= ((v >> q) & 1u) << i2;
+            alive |= (uint32_t)(v != 0) << i2;
+        }
+        uint32_t left  = (n > 0 && x0 > 0) ? (uint32_t)(src[x0 - 1] != 0) : 0u;
+        uint32_t right = (n > 0 && x0 + 32 < L.W) ? (uint32_t)(src[x0 + 32] != 0) : 0u;
+        uint32_t l = (alive << 1) | left, r = (alive >> 1) | (right << 31);
+        rec[0] = l ^ alive ^ r;
+        rec[(size_t)L.RWP] = (l & alive) | (l & r) | (alive & r);
+        for (int q = 0; q < L.P; q++)
+            rec[(size_t)(2 + q) * L.RWP] = s[q];
+    }
+}
+
+/* row records -> uint8 volume, and the population count of the result */
+CA_GLOBAL void ca3d_unpack_kernel(Bp3Layout L)
+{
+    const int NP = L.P + 2;
+    const int RW = (L.W + 31) / 32;
+    const size_t nwords = (size_t)L.Z * L.H * RW;
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    unsigned long long pop = 0;
+    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < nwords; i += stride) {
+        const int w = (int)(i % RW);
+        const size_t row = i / RW;
+        const uint32_t *rec = L.rows + row * NP * L.RWP + w;
+        uint8_t *dst = L.cells + row * L.W;
+        const int x0 = 32 * w;
+        uint32_t s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        uint32_t alive = 0u;
+        for (int q = 0; q < L.P; q++) {
+            s[q] = rec[(size_t)(2 + q) * L.RWP];
+            alive |= s[q];
+        }
+        pop += (unsigned)dp_popc(alive);
+        int n = L.W - x0;
+        n = n > 32 ? 32 : n;
+        for (int i2 = 0; i2 < n; i2++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v |= ((s[q] >> i2) & 1u) << q;
+            dst[x0 + i2] = (uint8_t)v;
+        }
+    }
+    if (pop)
+        dp_atomic_add64(L.population, pop);
+}
+
+} // namespace clapca
+#endif

@@ -1,0 +1,709 @@
+/*
+ * clapca_api.cu -- the C ABI of libclapca_cuda (include/clapca.h): device
+ * context, device-resident grids, engine selection and kernel launches.
+ * Everything here runs on the GPU or fails; there is no host fallback.
+ */
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/clapca.h"
+#include "bp3_launch.h"
+#include "ca3d_layout.cuh"
+#include "ca_wavefront.cuh"
+#include "field_kernels.cuh"
+#include "bp_plan.h"
+
+using namespace clapca;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA, \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Ctx {
+    int device = -1;
+    int sms = 0;
+    size_t mem = 0;
+    int coop = 0;
+    cudaStream_t stream = nullptr;
+    /* small device scalars shared by the helpers below */
+    unsigned long long *d_count = nullptr;
+    unsigned *d_max = nullptr;
+} g_ctx;
+
+int need_init()
+{
+    if (g_ctx.device < 0)
+        return fail(CLAPCA_ERR_STATE, "clapca_init() has not been called");
+    return CLAPCA_OK;
+}
+
+int grid_blocks_for(size_t work_items, int threads, int per_sm_cap = 8)
+{
+    size_t b = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)g_ctx.sms * per_sm_cap;        /* grid-stride: a multiple of the SM count */
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+/* the nine cas[] entries: core/ca3d.c:110-122 (surv, born, nr_states) */
+#define B(n) (1u << (n))
+#define RANGE(s, e) (((1u << ((e) - (s))) - 1u) << (s))
+const uint32_t kCas[9][3] = {
+    { B(4), B(4), 5 },
+    { B(6) | B(7) | B(8), B(6) | B(7) | B(8), 3 },
+    { B(4) | B(5) | B(6) | B(7), B(6) | B(7) | B(8), 10 },
+    { RANGE(9, 26), B(5) | B(6) | B(7) | B(12) | B(13) | B(15), 5 },
+    { B(2) | B(6) | B(9), B(4) | B(6) | B(8) | B(9), 10 },
+    { B(1) | B(4) | B(8) | B(11) | RANGE(13, 26), RANGE(13, 26), 5 },
+    { RANGE(0, 3) | RANGE(7, 9) | RANGE(11, 13) | B(18) | B(21) | B(22) | B(24) | B(26),
+      B(4) | B(13) | B(17) | RANGE(20, 24) | B(26), 4 },
+    { RANGE(5, 8), RANGE(6, 7) | B(9) | B(12), 4 },
+    { RANGE(0, 6), B(1) | B(3), 2 },
+};
+
+} // namespace
+
+namespace clapca {
+cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream,
+                       Bp3LaunchInfo *info)
+{
+    typedef cudaError_t (*fn_t)(int, int, const Bp3Params &, int, cudaStream_t, Bp3LaunchInfo *);
+    static const fn_t tab[BP3_NRULES] = {
+        bp3_launch_rule0, bp3_launch_rule1, bp3_launch_rule2, bp3_launch_rule3, bp3_launch_rule4,
+        bp3_launch_rule5, bp3_launch_rule6, bp3_launch_rule7, bp3_launch_rule8, bp3_launch_rule9,
+    };
+    if (rule < 0 || rule >= BP3_NRULES)
+        return cudaErrorInvalidValue;
+    return tab[rule](P, WPL, p, sms, stream, info);
+}
+} // namespace clapca
+
+struct clapca_grid {
+    int64_t d0, d1, d2;
+    size_t n;
+    uint8_t *cells = nullptr;
+    /* bit-plane engine scratch, grown on demand */
+    uint32_t *rows = nullptr;
+    size_t rows_bytes = 0;
+    int *prog = nullptr;
+    size_t prog_count = 0;
+    int2 *order = nullptr;
+    size_t order_count = 0;
+    int order_Z = -1, order_G = -1;
+    unsigned *ticket = nullptr;     /* [0] ticket, [1] err (as int) */
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    clapca_run_stats stats;
+};
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int clapca_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *clapca_last_error(void) { return g_err.c_str(); }
+
+int clapca_init(int device)
+{
+    if (g_ctx.device == device)
+        return CLAPCA_OK;
+    if (g_ctx.device >= 0)
+        clapca_shutdown();
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n)
+        return fail(CLAPCA_ERR_ARG, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(CLAPCA_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only",
+                    device, prop.major, prop.minor);
+    g_ctx.sms = prop.multiProcessorCount;
+    g_ctx.mem = prop.totalGlobalMem;
+    CU(cudaDeviceGetAttribute(&g_ctx.coop, cudaDevAttrCooperativeLaunch, device));
+    if (!g_ctx.coop)
+        return fail(CLAPCA_ERR_CUDA, "device %d does not support cooperative launch", device);
+    CU(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&g_ctx.d_count, sizeof(unsigned long long)));
+    CU(cudaMalloc(&g_ctx.d_max, sizeof(unsigned)));
+    g_ctx.device = device;
+    return CLAPCA_OK;
+}
+
+void clapca_shutdown(void)
+{
+    if (g_ctx.device < 0)
+        return;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    if (g_ctx.d_count) cudaFree(g_ctx.d_count);
+    if (g_ctx.d_max) cudaFree(g_ctx.d_max);
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Ctx();
+}
+
+int clapca_sm_count(void) { return g_ctx.sms; }
+size_t clapca_device_mem_bytes(void) { return g_ctx.mem; }
+
+int clapca_ca3d_rule(int nca, uint32_t *surv, uint32_t *born, uint32_t *nr_states)
+{
+    int i = nca % 9;            /* core/ca3d.c:126 */
+    if (i < 0)
+        return fail(CLAPCA_ERR_ARG, "negative rule index %d", nca);
+    if (surv) *surv = kCas[i][0];
+    if (born) *born = kCas[i][1];
+    if (nr_states) *nr_states = kCas[i][2];
+    return CLAPCA_OK;
+}
+
+/* ---- grids ---------------------------------------------------------------- */
+
+int clapca_grid_create(clapca_grid **out, int64_t d0, int64_t d1, int64_t d2)
+{
+    if (int rc = need_init()) return rc;
+    if (!out || d0 < 1 || d1 < 1 || d2 < 1)
+        return fail(CLAPCA_ERR_ARG, "grid_create: bad dims %lld x %lld x %lld", (long long)d0, (long long)d1,
+                    (long long)d2);
+    clapca_grid *g = new (std::nothrow) clapca_grid();
+    if (!g)
+        return fail(CLAPCA_ERR_NOMEM, "grid_create: host allocation failed");
+    g->d0 = d0; g->d1 = d1; g->d2 = d2;
+    g->n = (size_t)d0 * (size_t)d1 * (size_t)d2;
+    memset(&g->stats, 0, sizeof(g->stats));
+    g->stream = g_ctx.stream;
+    cudaError_t e = cudaMalloc(&g->cells, g->n);
+    if (e == cudaSuccess) e = cudaMalloc(&g->ticket, 2 * sizeof(unsigned));
+    for (int i = 0; i < 4 && e == cudaSuccess; i++)
+        e = cudaEventCreate(&g->ev[i]);
+    if (e != cudaSuccess) {
+        clapca_grid_destroy(g);
+        return fail(e == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA,
+                    "grid_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return CLAPCA_OK;
+}
+
+int clapca_grid_destroy(clapca_grid *g)
+{
+    if (!g)
+        return CLAPCA_OK;
+    if (g->cells) cudaFree(g->cells);
+    if (g->rows) cudaFree(g->rows);
+    if (g->prog) cudaFree(g->prog);
+    if (g->order) cudaFree(g->order);
+    if (g->ticket) cudaFree(g->ticket);
+    for (int i = 0; i < 4; i++)
+        if (g->ev[i]) cudaEventDestroy(g->ev[i]);
+    delete g;
+    return CLAPCA_OK;
+}
+
+int clapca_grid_upload(clapca_grid *g, const uint8_t *host)
+{
+    if (!g || !host) return fail(CLAPCA_ERR_ARG, "grid_upload: NULL argument");
+    CU(cudaMemcpyAsync(g->cells, host, g->n, cudaMemcpyHostToDevice, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return CLAPCA_OK;
+}
+
+int clapca_grid_download(clapca_grid *g, uint8_t *host)
+{
+    if (!g || !host) return fail(CLAPCA_ERR_ARG, "grid_download: NULL argument");
+    CU(cudaMemcpyAsync(host, g->cells, g->n, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return CLAPCA_OK;
+}
+
+void *clapca_grid_device_ptr(clapca_grid *g) { return g ? g->cells : nullptr; }
+void *clapca_grid_stream(clapca_grid *g) { return g ? (void *)g->stream : nullptr; }
+
+int clapca_grid_last_stats(clapca_grid *g, clapca_run_stats *st)
+{
+    if (!g || !st) return fail(CLAPCA_ERR_ARG, "grid_last_stats: NULL argument");
+    *st = g->stats;
+    return CLAPCA_OK;
+}
+
+static int count_on_stream(const uint8_t *cells, size_t n, cudaStream_t s, int64_t *population)
+{
+    CU(cudaMemsetAsync(g_ctx.d_count, 0, sizeof(unsigned long long), s));
+    count_nonzero_kernel<<<grid_blocks_for((n + 15) / 16, 256), 256, 0, s>>>(cells, n, g_ctx.d_count);
+    CU(cudaGetLastError());
+    unsigned long long c = 0;
+    CU(cudaMemcpyAsync(&c, g_ctx.d_count, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *population = (int64_t)c;
+    return CLAPCA_OK;
+}
+
+int clapca_grid_count(clapca_grid *g, int64_t *population)
+{
+    if (!g || !population) return fail(CLAPCA_ERR_ARG, "grid_count: NULL argument");
+    return count_on_stream(g->cells, g->n, g->stream, population);
+}
+
+/* ---- ca3d ------------------------------------------------------------------- */
+
+static int run3d_wavefront(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps)
+{
+    Wf3Params p;
+    p.a = g->cells;
+    p.d0 = g->d0; p.d1 = g->d1; p.d2 = g->d2;
+    p.surv = surv; p.born = born; p.bornval = (nr_states - 1u) & 0xffu;
+    p.G = steps;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ca3d_wavefront_kernel, 256, 0));
+    if (per_sm < 1) return fail(CLAPCA_ERR_CUDA, "ca3d_wavefront_kernel does not fit on an SM");
+    size_t pairs = (size_t)g->d1 * g->d2;
+    int blocks = (int)std::min<size_t>((pairs + 255) / 256, (size_t)per_sm * g_ctx.sms);
+    if (blocks < 1) blocks = 1;
+    void *args[] = { &p };
+    CU(cudaEventRecord(g->ev[1], g->stream));
+    CU(cudaLaunchCooperativeKernel((void *)ca3d_wavefront_kernel, dim3(blocks), dim3(256), args, 0, g->stream));
+    CU(cudaEventRecord(g->ev[2], g->stream));
+    g->stats.launches = 1;
+    g->stats.engine = CLAPCA_ENGINE_WAVEFRONT;
+    g->stats.planes = 0;
+    g->stats.workers = blocks * 256;
+    return CLAPCA_OK;
+}
+
+static int ensure_bytes(void **ptr, size_t *have, size_t want)
+{
+    if (*have >= want)
+        return CLAPCA_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    CU(cudaMalloc(ptr, want));
+    *have = want;
+    return CLAPCA_OK;
+}
+
+/* generations fused per launch: bounds the progress-counter table, not the result */
+static const int kMaxFusedGenerations = 4096;
+
+static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps,
+                          int64_t *population)
+{
+    const int W = (int)g->d0, H = (int)g->d1, Z = (int)g->d2;
+    const int WPL = bp_wpl_for(W);
+    const uint32_t bornval = (nr_states - 1u) & 0xffu;
+
+    /* largest value that can ever occur decides the number of state planes */
+    unsigned maxv = 0;
+    CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+    max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&maxv, g_ctx.d_max, sizeof(maxv), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (born && bornval > maxv) maxv = bornval;
+    const int P = bp_planes_for(maxv);
+    const int NP = P + 2, RWP = 32 * WPL;
+
+    int rule = BP3_RULE_DYN;
+    for (int i = 0; i < 9; i++)
+        if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { rule = i; break; }
+
+    size_t rows_bytes = (size_t)Z * H * NP * RWP * sizeof(uint32_t);
+    {
+        void *p = g->rows;
+        if (int rc = ensure_bytes(&p, &g->rows_bytes, rows_bytes)) { g->rows = nullptr; return rc; }
+        g->rows = (uint32_t *)p;
+    }
+
+    unsigned long long *d_pop = g_ctx.d_count;
+    Bp3Layout L = { g->cells, g->rows, W, H, Z, P, RWP, d_pop };
+    const size_t nwords = (size_t)Z * H * RWP;
+
+    CU(cudaEventRecord(g->ev[0], g->stream));
+    ca3d_pack_kernel<<<grid_blocks_for(nwords, 256, 16), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[1], g->stream));
+
+    int launches = 0, workers = 0;
+    for (int done = 0; done < steps;) {
+        const int G = std::min(steps - done, kMaxFusedGenerations);
+        if (g->order_Z != Z || g->order_G != G) {
+            std::vector<SweepId> order;
+            bp3_make_order(Z, G, order);
+            size_t have = g->order_count * sizeof(int2);
+            void *p = g->order;
+            if (int rc = ensure_bytes(&p, &have, order.size() * sizeof(int2))) { g->order = nullptr; return rc; }
+            g->order = (int2 *)p;
+            g->order_count = have / sizeof(int2);
+            static_assert(sizeof(SweepId) == sizeof(int2), "SweepId must alias int2");
+            CU(cudaMemcpyAsync(g->order, order.data(), order.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                               g->stream));
+            CU(cudaStreamSynchronize(g->stream));       /* `order` is a stack vector */
+            g->order_Z = Z; g->order_G = G;
+        }
+        {
+            size_t have = g->prog_count * sizeof(int);
+            void *p = g->prog;
+            if (int rc = ensure_bytes(&p, &have, (size_t)G * Z * sizeof(int))) { g->prog = nullptr; return rc; }
+            g->prog = (int *)p;
+            g->prog_count = have / sizeof(int);
+        }
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * Z * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
+
+        Bp3Params p;
+        memset(&p, 0, sizeof(p));
+        p.rows = g->rows;
+        p.W = W; p.H = H; p.Z = Z; p.G = G; p.RWP = RWP;
+        p.prog = g->prog;
+        p.order = g->order;
+        p.nsweeps = Z * G;
+        p.ticket = g->ticket;
+        p.err = (int *)(g->ticket + 1);
+        p.surv = surv; p.born = born; p.bornval = bornval;
+        p.spin_limit = 4000000000LL;        /* ~2 s of SM clock in a single wait */
+        Bp3LaunchInfo info;
+        CU(bp3_launch(rule, P, WPL, p, g_ctx.sms, g->stream, &info));
+        launches++;
+        workers = info.workers;
+        done += G;
+    }
+    CU(cudaEventRecord(g->ev[2], g->stream));
+
+    CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
+    ca3d_unpack_kernel<<<grid_blocks_for((size_t)Z * H * ((W + 31) / 32), 256, 16), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[3], g->stream));
+
+    unsigned long long pop = 0;
+    int err = 0;
+    CU(cudaMemcpyAsync(&pop, d_pop, sizeof(pop), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(&err, g->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (err)
+        return fail(CLAPCA_ERR_TIMEOUT, "ca3d bit-plane engine: dataflow watchdog fired (err=%d)", err);
+    if (population) *population = (int64_t)pop;
+    g->stats.launches = launches + 2;
+    g->stats.engine = CLAPCA_ENGINE_BITPLANE;
+    g->stats.planes = P;
+    g->stats.workers = workers;
+    return CLAPCA_OK;
+}
+
+int clapca_grid_run3d(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps, int engine,
+                      int64_t *population)
+{
+    if (int rc = need_init()) return rc;
+    if (!g) return fail(CLAPCA_ERR_ARG, "grid_run3d: NULL grid");
+    if (steps < 0) return fail(CLAPCA_ERR_ARG, "grid_run3d: negative step count");
+    memset(&g->stats, 0, sizeof(g->stats));
+    if (steps == 0) {
+        int64_t pop = 0;
+        if (int rc = count_on_stream(g->cells, g->n, g->stream, &pop)) return rc;
+        if (population) *population = pop;
+        return CLAPCA_OK;
+    }
+    const bool bp_ok = g->d0 <= 4096 && g->d1 < (1 << 30) && g->d2 < (1 << 30) &&
+                       (double)g->d2 * (double)std::min(steps, kMaxFusedGenerations) < 2.0e9;
+    if (engine == CLAPCA_ENGINE_AUTO)
+        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
+    if (engine == CLAPCA_ENGINE_BITPLANE) {
+        if (!bp_ok)
+            return fail(CLAPCA_ERR_UNSUPPORTED, "bit-plane engine handles rows of at most 4096 cells (d0 = %lld)",
+                        (long long)g->d0);
+        if (int rc = run3d_bitplane(g, surv, born, nr_states, steps, population)) return rc;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, g->ev[0], g->ev[3]));
+        g->stats.total_ms = ms;
+        CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+        g->stats.kernel_ms = ms;
+        return CLAPCA_OK;
+    }
+    if (engine != CLAPCA_ENGINE_WAVEFRONT)
+        return fail(CLAPCA_ERR_ARG, "grid_run3d: unknown engine %d", engine);
+    if (int rc = run3d_wavefront(g, surv, born, nr_states, steps)) return rc;
+    int64_t pop = 0;
+    if (int rc = count_on_stream(g->cells, g->n, g->stream, &pop)) return rc;
+    if (population) *population = pop;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+    g->stats.kernel_ms = g->stats.total_ms = ms;
+    return CLAPCA_OK;
+}
+
+int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3], uint32_t surv, uint32_t born, uint32_t nr_states,
+                    int steps, int engine, int64_t *population)
+{
+    if (int rc = need_init()) return rc;
+    if (!arr || !dim) return fail(CLAPCA_ERR_ARG, "ca3d_run: NULL argument");
+    clapca_grid *g = nullptr;
+    int rc = clapca_grid_create(&g, dim[0], dim[1], dim[2]);
+    if (rc) return rc;
+    rc = clapca_grid_upload(g, arr);
+    if (!rc) rc = clapca_grid_run3d(g, surv, born, nr_states, steps, engine, population);
+    if (!rc && steps > 0) rc = clapca_grid_download(g, arr);
+    clapca_grid_destroy(g);
+    return rc;
+}
+
+/* ---- ca2d ------------------------------------------------------------------- */
+
+int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv, uint32_t nr_states, int decay,
+                      int neigh, int steps, int engine)
+{
+    if (int rc = need_init()) return rc;
+    if (!g) return fail(CLAPCA_ERR_ARG, "grid_run2d: NULL grid");
+    if (g->d2 != 1) return fail(CLAPCA_ERR_ARG, "grid_run2d: grid is not 2D (d2 = %lld)", (long long)g->d2);
+    if (neigh < CLAPCA_NEIGH_VN1 || neigh > CLAPCA_NEIGH_MV)
+        return fail(CLAPCA_ERR_ARG, "grid_run2d: unknown neighbourhood %d", neigh);
+    if (steps < 0) return fail(CLAPCA_ERR_ARG, "grid_run2d: negative step count");
+    memset(&g->stats, 0, sizeof(g->stats));
+    if (steps == 0 || side <= 0)
+        return CLAPCA_OK;
+    if (engine == CLAPCA_ENGINE_BITPLANE)
+        return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine is not available in this build");
+    if (engine != CLAPCA_ENGINE_AUTO && engine != CLAPCA_ENGINE_WAVEFRONT)
+        return fail(CLAPCA_ERR_ARG, "grid_run2d: unknown engine %d", engine);
+
+    Wf2Params p;
+    p.a = g->cells;
+    p.w = g->d0; p.h = g->d1;
+    p.sx = std::min<long long>(side, g->d0);
+    p.sy = std::min<long long>(side, g->d1);
+    p.born = born; p.surv = surv; p.nrval = nr_states & 0xffu;
+    p.decay = decay ? 1 : 0; p.neigh = neigh; p.G = steps;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ca2d_wavefront_kernel, 256, 0));
+    if (per_sm < 1) return fail(CLAPCA_ERR_CUDA, "ca2d_wavefront_kernel does not fit on an SM");
+    int blocks = (int)std::min<size_t>(((size_t)p.sx + 255) / 256, (size_t)per_sm * g_ctx.sms);
+    if (blocks < 1) blocks = 1;
+    void *args[] = { &p };
+    CU(cudaEventRecord(g->ev[1], g->stream));
+    CU(cudaLaunchCooperativeKernel((void *)ca2d_wavefront_kernel, dim3(blocks), dim3(256), args, 0, g->stream));
+    CU(cudaEventRecord(g->ev[2], g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+    g->stats.kernel_ms = g->stats.total_ms = ms;
+    g->stats.launches = 1;
+    g->stats.engine = CLAPCA_ENGINE_WAVEFRONT;
+    g->stats.workers = blocks * 256;
+    return CLAPCA_OK;
+}
+
+int clapca_ca2d_run(uint8_t *arr, int64_t w, int64_t h, int64_t side, uint32_t born, uint32_t surv,
+                    uint32_t nr_states, int decay, int neigh, int steps, int engine)
+{
+    if (int rc = need_init()) return rc;
+    if (!arr) return fail(CLAPCA_ERR_ARG, "ca2d_run: NULL array");
+    clapca_grid *g = nullptr;
+    int rc = clapca_grid_create(&g, w, h, 1);
+    if (rc) return rc;
+    rc = clapca_grid_upload(g, arr);
+    if (!rc) rc = clapca_grid_run2d(g, side, born, surv, nr_states, decay, neigh, steps, engine);
+    if (!rc && steps > 0) rc = clapca_grid_download(g, arr);
+    clapca_grid_destroy(g);
+    return rc;
+}
+
+/* ---- fields ------------------------------------------------------------------- */
+
+void *clapca_device_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (g_ctx.device < 0 || cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+int clapca_device_free(void *p)
+{
+    if (p) CU(cudaFree(p));
+    return CLAPCA_OK;
+}
+
+int clapca_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    if (int rc = need_init()) return rc;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    CU(cudaStreamSynchronize(g_ctx.stream));
+    return CLAPCA_OK;
+}
+
+int clapca_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+    if (int rc = need_init()) return rc;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CU(cudaStreamSynchronize(g_ctx.stream));
+    return CLAPCA_OK;
+}
+
+static int timed_sync(cudaEvent_t a, cudaEvent_t b, float *ms)
+{
+    CU(cudaStreamSynchronize(g_ctx.stream));
+    if (ms) CU(cudaEventElapsedTime(ms, a, b));
+    return CLAPCA_OK;
+}
+
+int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
+                             float period_units, uint32_t seed, float *kernel_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_out || size < 1 || size > 4096 || octaves < 0 || (int)period_units < 1)
+        return fail(CLAPCA_ERR_ARG, "noise bake: bad arguments (size %zu, octaves %d, period %g)", size, octaves,
+                    (double)period_units);
+    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed };
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    size_t voxels = size * size * size;
+    CU(cudaEventRecord(a, g_ctx.stream));
+    noise_bake_kernel<<<grid_blocks_for(voxels, 256, 8), 256, 0, g_ctx.stream>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b, g_ctx.stream));
+    int rc = timed_sync(a, b, kernel_ms);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return rc;
+}
+
+int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float lacunarity, float gain,
+                                   float period_units, uint32_t seed)
+{
+    if (int rc = need_init()) return rc;
+    if (!out) return fail(CLAPCA_ERR_ARG, "noise bake: NULL output");
+    size_t bytes = size * size * size * 4;
+    void *d = nullptr;
+    CU(cudaMalloc(&d, bytes ? bytes : 4));
+    int rc = clapca_noise_bake_device(d, size, octaves, lacunarity, gain, period_units, seed, nullptr);
+    if (!rc) rc = clapca_memcpy_d2h(out, d, bytes);
+    cudaFree(d);
+    return rc;
+}
+
+int clapca_noise_fbm3(float *out, const float *xyz, size_t n, int octaves, float lacunarity, float gain,
+                      int period, uint32_t seed)
+{
+    if (int rc = need_init()) return rc;
+    if (!out || !xyz || period < 1) return fail(CLAPCA_ERR_ARG, "noise_fbm3: bad arguments");
+    if (!n) return CLAPCA_OK;
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, n * 3 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, n * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(CLAPCA_ERR_NOMEM, "noise_fbm3: %s", cudaGetErrorString(e)); }
+    int rc = clapca_memcpy_h2d(d_in, xyz, n * 3 * sizeof(float));
+    if (!rc) {
+        noise_fbm3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_ctx.stream>>>(d_out, d_in, n, octaves, lacunarity,
+                                                                                 gain, period, seed);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(CLAPCA_ERR_CUDA, "noise_fbm3 launch failed");
+    }
+    if (!rc) rc = clapca_memcpy_d2h(out, d_out, n * sizeof(float));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsigned nr_v, float ty,
+                                    const void *d_maze, unsigned mside, float amp, int oct,
+                                    float *map0_ms, float *map_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_map0 || nr_v < 1 || nr_v > 46340)
+        return fail(CLAPCA_ERR_ARG, "terrain: bad arguments (nr_v %u)", nr_v);
+    if (d_maze && mside < 1) return fail(CLAPCA_ERR_ARG, "terrain: maze without a side length");
+    cudaEvent_t e0, e1, e2;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventCreate(&e2));
+    size_t n = (size_t)nr_v * nr_v;
+    CU(cudaEventRecord(e0, g_ctx.stream));
+    terrain_map0_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>((float *)d_map0, (long long)seed, nr_v);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e1, g_ctx.stream));
+    if (d_map) {
+        TerrainParams p = { (float *)d_map, (const float *)d_map0, (const uint8_t *)d_maze, nr_v, mside, ty, amp, oct };
+        terrain_heightmap_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e2, g_ctx.stream));
+    int rc = timed_sync(e0, e1, map0_ms);
+    if (!rc && map_ms) {
+        cudaError_t e = cudaEventElapsedTime(map_ms, e1, e2);
+        if (e != cudaSuccess) rc = fail(CLAPCA_ERR_CUDA, "terrain: %s", cudaGetErrorString(e));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    return rc;
+}
+
+int clapca_terrain_map0(float *map0, long seed, unsigned nr_v)
+{
+    if (int rc = need_init()) return rc;
+    if (!map0) return fail(CLAPCA_ERR_ARG, "terrain_map0: NULL output");
+    size_t bytes = (size_t)nr_v * nr_v * sizeof(float);
+    void *d = nullptr;
+    CU(cudaMalloc(&d, bytes ? bytes : 4));
+    int rc = clapca_terrain_heightmap_device(nullptr, d, seed, nr_v, 0.f, nullptr, 0, 0.f, 0, nullptr, nullptr);
+    if (!rc) rc = clapca_memcpy_d2h(map0, d, bytes);
+    cudaFree(d);
+    return rc;
+}
+
+int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty, const uint8_t *maze, unsigned mside,
+                             float amp, int oct)
+{
+    if (int rc = need_init()) return rc;
+    if (!map) return fail(CLAPCA_ERR_ARG, "terrain_heightmap: NULL output");
+    size_t bytes = (size_t)nr_v * nr_v * sizeof(float);
+    void *d_map = nullptr, *d_map0 = nullptr, *d_maze = nullptr;
+    CU(cudaMalloc(&d_map, bytes ? bytes : 4));
+    cudaError_t e = cudaMalloc(&d_map0, bytes ? bytes : 4);
+    if (e == cudaSuccess && maze) e = cudaMalloc(&d_maze, (size_t)mside * mside);
+    int rc = e == cudaSuccess ? CLAPCA_OK : fail(CLAPCA_ERR_NOMEM, "terrain_heightmap: %s", cudaGetErrorString(e));
+    if (!rc && maze) rc = clapca_memcpy_h2d(d_maze, maze, (size_t)mside * mside);
+    if (!rc) rc = clapca_terrain_heightmap_device(d_map, d_map0, seed, nr_v, ty, d_maze, mside, amp, oct, nullptr, nullptr);
+    if (!rc) rc = clapca_memcpy_d2h(map, d_map, bytes);
+    cudaFree(d_map);
+    cudaFree(d_map0);
+    cudaFree(d_maze);
+    return rc;
+}
+
+#pragma GCC visibility pop
+} /* extern "C" */

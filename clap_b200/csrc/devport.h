@@ -1,0 +1,187 @@
+/*
+ * devport.h -- the handful of CUDA device primitives the CA kernels use, with a
+ * second implementation for the host-side *kernel emulator* (tests/emu/).
+ *
+ * Product builds (nvcc, sm_100a) see only the CUDA branch.  The emulator branch
+ * (-DCLAPCA_EMU, g++) runs the very same kernel source on the CPU: every warp
+ * is a ring of 32 ucontext fibers, warp collectives are rendez-vous points
+ * between the fibers, and persistent warps run on separate OS threads so the
+ * flag-based dataflow protocol is exercised with real concurrency.  It is test
+ * infrastructure for the `-m "not gpu"` suite; it is never linked into
+ * libclapca_cuda and there is no CPU fallback in the product.
+ */
+#ifndef CLAPCA_DEVPORT_H
+#define CLAPCA_DEVPORT_H
+
+#include <stdint.h>
+
+#ifndef CLAPCA_EMU
+/* ------------------------------------------------------------------ CUDA -- */
+#include <cuda_runtime.h>
+
+#define CA_DEV      __device__ __forceinline__
+#define CA_MDEV     __device__ __forceinline__ static      /* static member function */
+#define CA_HOSTDEV  __host__ __device__ __forceinline__
+#define CA_GLOBAL   __global__
+#define CA_FULL     0xffffffffu
+
+namespace clapca {
+
+CA_DEV int  dp_lane()            { return (int)(threadIdx.x & 31); }
+CA_DEV int  dp_warp_in_block()   { return (int)(threadIdx.x >> 5); }
+CA_DEV int  dp_block()           { return (int)blockIdx.x; }
+CA_DEV int  dp_grid_blocks()     { return (int)gridDim.x; }
+CA_DEV int  dp_block_threads()   { return (int)blockDim.x; }
+CA_DEV int  dp_thread()          { return (int)threadIdx.x; }
+
+CA_DEV uint32_t dp_shfl(uint32_t v, int src)      { return __shfl_sync(CA_FULL, v, src); }
+CA_DEV uint32_t dp_shfl_up(uint32_t v, int d)     { return __shfl_up_sync(CA_FULL, v, d); }
+CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { return __shfl_down_sync(CA_FULL, v, d); }
+CA_DEV uint32_t dp_ballot(bool p)                 { return __ballot_sync(CA_FULL, p); }
+CA_DEV bool     dp_all(bool p)                    { return __all_sync(CA_FULL, p); }
+CA_DEV void     dp_syncwarp()                     { __syncwarp(); }
+
+/* data written by other SMs inside the same launch: bypass the (incoherent) L1 */
+CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return __ldcg(p); }
+CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return __ldcg(p); }
+CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return __ldcg(p); }
+CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return __ldcg(p); }
+CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { __stcg(p, v); }
+CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { __stcg(p, v); }
+
+/* progress flags: relaxed polling load, release store (gpu scope) */
+CA_DEV int dp_ld_flag(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+CA_DEV void dp_st_flag(int *p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+/* fence.acq_rel.gpu (MEMBAR.ALL.GPU); __threadfence() would be the heavier fence.sc */
+CA_DEV void dp_fence_release()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+CA_DEV void dp_nanosleep(unsigned ns)             { __nanosleep(ns); }
+CA_DEV long long dp_clock()                       { return clock64(); }
+CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return atomicAdd(p, 1u); }
+CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+CA_DEV void dp_atomic_max(int *p, int v)          { atomicMax(p, v); }
+CA_DEV int  dp_popc(uint32_t v)                   { return __popc(v); }
+CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s) { return __funnelshift_l(lo, hi, s); }
+CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, s); }
+
+/* one LOP3 with a compile-time truth table: bit (a<<2|b<<1|c) of LUT */
+template <unsigned LUT>
+CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+
+} // namespace clapca
+
+#else
+/* -------------------------------------------------------------- emulator -- */
+#include <string.h>
+
+#define CA_DEV      static inline
+#define CA_MDEV     static inline
+#define CA_HOSTDEV  static inline
+#define CA_GLOBAL   static
+#define CA_FULL     0xffffffffu
+#define __restrict__
+#define __launch_bounds__(...)
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct int2  { int x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = { x, y }; return r; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = { x, y, z, w }; return r; }
+static inline int2  make_int2(int x, int y) { int2 r = { x, y }; return r; }
+
+namespace clapca {
+
+/* provided by tests/emu/emu_runtime.cpp */
+int      emu_lane();
+int      emu_warp_in_block();
+int      emu_block();
+int      emu_grid_blocks();
+int      emu_block_threads();
+uint32_t emu_exchange(uint32_t v, int src_lane);     /* returns v deposited by src_lane (or own if out of range) */
+uint32_t emu_ballot(bool p);
+void     emu_yield();
+long long emu_clock();
+
+CA_DEV int  dp_lane()            { return emu_lane(); }
+CA_DEV int  dp_warp_in_block()   { return emu_warp_in_block(); }
+CA_DEV int  dp_block()           { return emu_block(); }
+CA_DEV int  dp_grid_blocks()     { return emu_grid_blocks(); }
+CA_DEV int  dp_block_threads()   { return emu_block_threads(); }
+CA_DEV int  dp_thread()          { return emu_warp_in_block() * 32 + emu_lane(); }
+
+CA_DEV uint32_t dp_shfl(uint32_t v, int src)      { return emu_exchange(v, src); }
+CA_DEV uint32_t dp_shfl_up(uint32_t v, int d)     { int l = emu_lane(); return emu_exchange(v, l - d >= 0 ? l - d : l); }
+CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { int l = emu_lane(); return emu_exchange(v, l + d < 32 ? l + d : l); }
+CA_DEV uint32_t dp_ballot(bool p)                 { return emu_ballot(p); }
+CA_DEV bool     dp_all(bool p)                    { return emu_ballot(p) == CA_FULL; }
+CA_DEV void     dp_syncwarp()                     { (void)emu_ballot(true); }
+
+template <typename T> CA_DEV T dp_ld_cg_any(const T *p)
+{
+    T v;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    memcpy(&v, (const void *)p, sizeof(T));
+    return v;
+}
+CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return dp_ld_cg_any(p); }
+CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return dp_ld_cg_any(p); }
+CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return dp_ld_cg_any(p); }
+CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return dp_ld_cg_any(p); }
+CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { *p = v; }
+CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { *p = v; }
+CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { *p = v; }
+
+CA_DEV int  dp_ld_flag(const int *p)              { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV void dp_st_flag(int *p, int v)             { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV void dp_fence_acquire()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV void dp_nanosleep(unsigned)                { emu_yield(); }
+CA_DEV long long dp_clock()                       { return emu_clock(); }
+CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
+CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+CA_DEV void dp_atomic_max(int *p, int v)
+{
+    int o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED))
+        ;
+}
+CA_DEV int  dp_popc(uint32_t v)                   { return __builtin_popcount(v); }
+CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s)
+{
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s)
+{
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+
+template <unsigned LUT>
+CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 8; i++)
+        if (LUT & (1u << i)) {
+            uint32_t ta = (i & 4) ? a : ~a, tb = (i & 2) ? b : ~b, tc = (i & 1) ? c : ~c;
+            r |= ta & tb & tc;
+        }
+    return r;
+}
+
+} // namespace clapca
+#endif /* CLAPCA_EMU */
+
+#endif /* CLAPCA_DEVPORT_H */

@@ -1,0 +1,272 @@
+/*
+ * field_kernels.cuh -- per-lattice-point field evaluation:
+ *   N1: noise.c fBm-gradient bake   (core/noise.h:9-17, core/noise.c:171-270)
+ *   N2: terrain.c heightmap chain   (core/terrain.c:15-91, :447-467)
+ *
+ * Numerics.  The reference's interp.h helpers mix float arguments with double
+ * literals, so parts of every lerp / smoothstep are evaluated in double and
+ * rounded back to float.  The device functions below keep the
+ * same expression trees, and this translation unit is compiled with
+ * -fmad=false so nothing is contracted into an FMA: hash31, the value noise,
+ * the fBm sum, the gradient and the RGBA8 packing are then bit-identical to
+ * the x86-64 build of the reference (floorf, lrintf, sqrtf and IEEE division
+ * are exactly rounded on both sides).  The heightmap differs only through
+ * cosf()/powf(), whose CUDA implementations are within 2 ulp of glibc's.
+ *
+ * Both kernels are embarrassingly parallel and ALU-bound: one thread per
+ * output element, consecutive threads on consecutive addresses so stores
+ * coalesce into full 128-byte lines.
+ */
+#ifndef CLAPCA_FIELD_KERNELS_CUH
+#define CLAPCA_FIELD_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace clapca {
+
+#define CLAPCA_PI 3.14159265358979323846   /* M_PI */
+
+/* smoothf(): core/interp.h:11-14 */
+__device__ __forceinline__ float fk_smoothf(float x)
+{
+    float xx = x * x;
+    return (float)((double)xx * (3.0 - 2.0 * (double)x));
+}
+
+/* linf_interp(): core/interp.h:25-29 */
+__device__ __forceinline__ float fk_linf(float a, float b, float blend)
+{
+    float bb = b * blend;
+    return (float)((double)a * (1.0 - (double)blend) + (double)bb);
+}
+
+/* cosf_interp(): core/interp.h:35-42 */
+__device__ __forceinline__ float fk_cosf_interp(float a, float b, float blend)
+{
+    float theta = (float)((double)blend * CLAPCA_PI);
+    float f = (float)((1.0 - (double)cosf(theta)) / 2.0);
+    float bf = b * f;
+    return (float)((double)a * (1.0 - (double)f) + (double)bf);
+}
+
+/* hash31(): core/noise.h:9-17 */
+__device__ __forceinline__ float fk_hash31(int x, int y, int z, uint32_t seed)
+{
+    uint32_t h = (uint32_t)x * 374761393u + (uint32_t)y * 668265263u +
+                 (uint32_t)z * 362437u + seed * 2246822519u;
+    h = (h ^ (h >> 13)) * 1274126177u;
+    return (float)(h ^ (h >> 16)) * (1.0f / 4294967296.0f);
+}
+
+__device__ __forceinline__ int fk_wrap(int v, int period)
+{
+    return (v % period + period) % period;
+}
+
+/* value_noise3d_periodic(): core/noise.c:171-202 */
+__device__ __forceinline__ float fk_value_noise3d(float x, float y, float z, int period, uint32_t seed)
+{
+    int x0 = (int)floorf(x), y0 = (int)floorf(y), z0 = (int)floorf(z);
+    float xf = x - (float)x0, yf = y - (float)y0, zf = z - (float)z0;
+    int x1 = fk_wrap(x0 + 1, period), y1 = fk_wrap(y0 + 1, period), z1 = fk_wrap(z0 + 1, period);
+    x0 = fk_wrap(x0, period);
+    y0 = fk_wrap(y0, period);
+    z0 = fk_wrap(z0, period);
+
+    float ux = fk_smoothf(xf), uy = fk_smoothf(yf), uz = fk_smoothf(zf);
+    float lo0 = fk_linf(fk_hash31(x0, y0, z0, seed), fk_hash31(x1, y0, z0, seed), ux);
+    float lo1 = fk_linf(fk_hash31(x0, y1, z0, seed), fk_hash31(x1, y1, z0, seed), ux);
+    float hi0 = fk_linf(fk_hash31(x0, y0, z1, seed), fk_hash31(x1, y0, z1, seed), ux);
+    float hi1 = fk_linf(fk_hash31(x0, y1, z1, seed), fk_hash31(x1, y1, z1, seed), ux);
+    return fk_linf(fk_linf(lo0, lo1, uy), fk_linf(hi0, hi1, uy), uz);
+}
+
+/* fbm3_periodic(): core/noise.c:204-220 */
+__device__ __forceinline__ float fk_fbm3(float x, float y, float z, int octaves, float lacunarity, float gain,
+                                         int period, uint32_t seed)
+{
+    float amp = 0.5f, sum = 0.0f;
+    for (int i = 0; i < octaves; i++) {
+        sum += fk_value_noise3d(x, y, z, period, seed + (uint32_t)i) * amp;
+        x *= lacunarity;
+        y *= lacunarity;
+        z *= lacunarity;
+        period = (int)lrintf((float)period * lacunarity);
+        amp *= gain;
+    }
+    return sum;
+}
+
+__device__ __forceinline__ uint32_t fk_unorm8(float g)
+{
+    return (uint32_t)(uint8_t)lrintf((g * 0.5f + 0.5f) * 255.0f);
+}
+
+struct NoiseBakeParams {
+    uint32_t *out;          /* RGBA8 texels, x fastest */
+    unsigned size;
+    int octaves;
+    float lacunarity, gain, period_units;
+    uint32_t seed;
+};
+
+/* noise_grad3d_bake_rgba8(): core/noise.c:222-270, one thread per voxel */
+__global__ void __launch_bounds__(256) noise_bake_kernel(NoiseBakeParams p)
+{
+    const size_t voxels = (size_t)p.size * p.size * p.size;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float step = p.period_units / (float)p.size;
+    const float eps = step;
+    const int period = (int)p.period_units;
+    const float scale = 0.5f / eps;
+
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += stride) {
+        const unsigned x = (unsigned)(i % p.size), y = (unsigned)((i / p.size) % p.size);
+        const unsigned z = (unsigned)(i / ((size_t)p.size * p.size));
+        const float px = (float)x * step, py = (float)y * step, pz = (float)z * step;
+
+        float gx = (fk_fbm3(px + eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                    fk_fbm3(px - eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+        float gy = (fk_fbm3(px, py + eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                    fk_fbm3(px, py - eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+        float gz = (fk_fbm3(px, py, pz + eps, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                    fk_fbm3(px, py, pz - eps, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+        float len2 = gx * gx + gy * gy + gz * gz;
+        float inv = 1.0f / sqrtf(len2 > FLT_MIN ? len2 : FLT_MIN);
+
+        p.out[i] = fk_unorm8(gx * inv) | (fk_unorm8(gy * inv) << 8) | (fk_unorm8(gz * inv) << 16);
+    }
+}
+
+/* fbm3_periodic() at arbitrary points (parity tests of the float field) */
+__global__ void noise_fbm3_kernel(float *out, const float *xyz, size_t n, int octaves, float lacunarity,
+                                  float gain, int period, uint32_t seed)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = fk_fbm3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], octaves, lacunarity, gain, period, seed);
+}
+
+/* ---- terrain ------------------------------------------------------------------ */
+
+/*
+ * get_rand_height(): core/terrain.c:15-19 = glibc srand48(seed ^ (x + z*43210))
+ * followed by drand48(): X0 = low32(s) << 16 | 0x330E, X1 = (a X0 + c) mod 2^48,
+ * value = X1 / 2^48 (exact in double), then *2 - 1 and a float rounding.
+ */
+__device__ __forceinline__ float fk_rand_height(long long seed, int x, int z)
+{
+    long long s = seed ^ (long long)(x + z * 43210);
+    unsigned long long X = (((unsigned long long)s & 0xffffffffULL) << 16) | 0x330EULL;
+    X = (X * 0x5DEECE66DULL + 0xBULL) & 0xFFFFFFFFFFFFULL;
+    double d = (double)X * (1.0 / 281474976710656.0);       /* 2^-48, exact */
+    return (float)(d * 2 - 1);
+}
+
+/* lattice fill: core/terrain.c:447-450, map0[x*nr_v + z] */
+__global__ void __launch_bounds__(256) terrain_map0_kernel(float *map0, long long seed, unsigned nr_v)
+{
+    const size_t n = (size_t)nr_v * nr_v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        map0[i] = fk_rand_height(seed, (int)(i / nr_v), (int)(i % nr_v));
+}
+
+struct TerrainParams {
+    float *map;
+    const float *map0;
+    const uint8_t *maze;        /* mside x mside, index y*mside + x; NULL = plain octave field */
+    unsigned nr_v, mside;
+    float ty, amp;
+    int oct;
+};
+
+/* get_mapped_rand_height(): core/terrain.c:21-33 */
+__device__ __forceinline__ float fk_lattice(const TerrainParams &p, int x, int z)
+{
+    const int nr = (int)p.nr_v;
+    if (x < 0) x = nr - 1; else if (x >= nr) x = 0;
+    if (z < 0) z = nr - 1; else if (z >= nr) z = 0;
+    return __ldg(p.map0 + (size_t)x * nr + z);
+}
+
+/* get_avg_height(): core/terrain.c:35-54 */
+__device__ __forceinline__ float fk_smooth3x3(const TerrainParams &p, int x, int z)
+{
+    float corners, sides, self;
+    corners  = fk_lattice(p, x - 1, z - 1);
+    corners += fk_lattice(p, x + 1, z - 1);
+    corners += fk_lattice(p, x - 1, z + 1);
+    corners += fk_lattice(p, x + 1, z + 1);
+    corners /= 16.f;
+    sides  = fk_lattice(p, x - 1, z);
+    sides += fk_lattice(p, x + 1, z);
+    sides += fk_lattice(p, x, z - 1);
+    sides += fk_lattice(p, x, z + 1);
+    sides /= 8.f;
+    self = fk_lattice(p, x, z) / 4.f;
+    return corners + sides + self;
+}
+
+/* get_interp_height(): core/terrain.c:56-71 */
+__device__ __forceinline__ float fk_interp_height(const TerrainParams &p, float x, float z)
+{
+    int ix = (int)floor((double)x), iz = (int)floor((double)z);
+    float fx = x - (float)ix, fz = z - (float)iz;
+    float v1 = fk_smooth3x3(p, ix, iz), v2 = fk_smooth3x3(p, ix + 1, iz);
+    float v3 = fk_smooth3x3(p, ix, iz + 1), v4 = fk_smooth3x3(p, ix + 1, iz + 1);
+    return fk_cosf_interp(fk_cosf_interp(v1, v2, fx), fk_cosf_interp(v3, v4, fx), fz);
+}
+
+/* get_height(): core/terrain.c:77-91; pow(2,i), pow(0.5f,i) are exact powers of two */
+__device__ __forceinline__ float fk_octave_height(const TerrainParams &p, int x, int z, float amp0, int oct)
+{
+    float total = 0;
+    float d = (float)ldexp(1.0, oct - 1);
+    for (int i = 0; i < oct; i++) {
+        float freq = (float)(ldexp(1.0, i) / (double)d);
+        float amp = (float)(ldexp(1.0, -i) * (double)amp0);
+        total += fk_interp_height(p, (float)x * freq, (float)z * freq) * amp;
+    }
+    return p.ty + total;
+}
+
+__device__ __forceinline__ int fk_maze(const TerrainParams &p, int x, int y)
+{
+    if (x < 0 || y < 0 || x >= (int)p.mside || y >= (int)p.mside)
+        return 0;                                       /* xyarray_get(): OOB reads 0 */
+    return p.maze[(size_t)y * p.mside + x];
+}
+
+/*
+ * Map fill: core/terrain.c:451-467 (MAZE_FAC 8, OCTAVES 4).  Thread per vertex,
+ * j (the contiguous index of map[i*nr_v + j]) fastest across the warp.
+ */
+__global__ void __launch_bounds__(256) terrain_heightmap_kernel(TerrainParams p)
+{
+    const size_t n = (size_t)p.nr_v * p.nr_v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx / p.nr_v), j = (int)(idx % p.nr_v);
+        float h;
+        if (p.maze) {
+            float fi = fmodf((float)i, 8.f) / 8, fj = fmodf((float)j, 8.f) / 8;
+            int mi = i / 8, mj = j / 8;
+            int cn = fk_maze(p, mi, mj);
+            int xn = fk_maze(p, (double)fi >= 0.5 ? mi + 1 : mi - 1, mj);
+            int yn = fk_maze(p, mi, (double)fj >= 0.5 ? mj + 1 : mj - 1);
+            float xa = cn > xn ? (float)cn : fk_cosf_interp((float)cn, (float)xn, 2 * fi - 1);
+            float ya = cn > yn ? (float)cn : fk_cosf_interp((float)cn, (float)yn, 2 * fj - 1);
+            float avg = fk_cosf_interp(xa, ya, fabsf(fi - fj));
+            h = fk_octave_height(p, i, j, powf(1.5f, avg), 4) + avg;
+        } else {
+            h = fk_octave_height(p, i, j, p.amp, p.oct);
+        }
+        p.map[idx] = h;
+    }
+}
+
+} // namespace clapca
+#endif

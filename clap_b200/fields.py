@@ -1,0 +1,52 @@
+"""Field evaluation: the noise.c fBm-gradient bake and the terrain.c heightmap chain."""
+from ctypes import c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def noise_grad3d_bake_rgba8(size, octaves=4, lacunarity=2.0, gain=0.5, period_units=64.0, seed=0xC14D):
+    """noise_grad3d_bake_rgba8(): core/noise.c:222-270 (defaults of noise3d_make, :309-317).
+    Returns uint8[size, size, size, 4] indexed [z, y, x, rgba]."""
+    lib = _lib.lib()
+    out = np.empty((size, size, size, 4), dtype=np.uint8)
+    check(lib, lib.clapca_noise_grad3d_bake_rgba8(out.ctypes.data_as(c_void_p), size, octaves, lacunarity, gain,
+                                                  period_units, seed))
+    return out
+
+
+def noise_fbm3(xyz, octaves, lacunarity, gain, period, seed):
+    """fbm3_periodic(): core/noise.c:204-220 at the points xyz[n, 3] (float32)."""
+    lib = _lib.lib()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    out = np.empty(xyz.shape[0], dtype=np.float32)
+    check(lib, lib.clapca_noise_fbm3(out.ctypes.data_as(c_void_p), xyz.ctypes.data_as(c_void_p), xyz.shape[0],
+                                     octaves, lacunarity, gain, period, seed))
+    return out
+
+
+def terrain_map0(seed, nr_v):
+    """Lattice t->map0 of terrain_init_square_landscape(): core/terrain.c:447-450 (float32[nr_v, nr_v],
+    indexed [x, z])."""
+    lib = _lib.lib()
+    out = np.empty((nr_v, nr_v), dtype=np.float32)
+    check(lib, lib.clapca_terrain_map0(out.ctypes.data_as(c_void_p), seed, nr_v))
+    return out
+
+
+def terrain_heightmap(seed, nr_v, y=0.0, maze=None, amp=1.0, octaves=4):
+    """Heightmap t->map: core/terrain.c:451-467.  With ``maze`` (uint8[mside, mside], the ca2d cave grid,
+    mside = nr_v // 8) the maze-modulated map; without it the plain field get_height(i, j, amp, octaves)."""
+    lib = _lib.lib()
+    out = np.empty((nr_v, nr_v), dtype=np.float32)
+    if maze is not None:
+        maze = np.ascontiguousarray(maze, dtype=np.uint8)
+        if maze.ndim != 2 or maze.shape[0] != maze.shape[1]:
+            raise ValueError("maze must be a square 2-D uint8 array")
+        mptr, mside = maze.ctypes.data_as(c_void_p), maze.shape[0]
+    else:
+        mptr, mside = None, 0
+    check(lib, lib.clapca_terrain_heightmap(out.ctypes.data_as(c_void_p), seed, nr_v, y, mptr, mside, amp, octaves))
+    return out

@@ -1,0 +1,19 @@
+/*
+ * noise_bake.h -- host entry point for the fBm-gradient RGBA8 bake that
+ * core/noise.c:222-270 (noise_grad3d_bake_rgba8) performs on one CPU core.
+ * The reference wraps its result in the engine's cresp(void) error union
+ * (core/error.h); outside the engine tree the same contract is a malloc()ed
+ * buffer or NULL.  INTEGRATION.md shows the three-line body that turns this
+ * into the reference's own signature.
+ */
+#ifndef CLAPCA_COMPAT_NOISE_BAKE_H
+#define CLAPCA_COMPAT_NOISE_BAKE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+/* size^3 * 4 bytes (x fastest; R,G,B = packed unit gradient, A = 0); caller frees with free() */
+unsigned char *clap_noise_grad3d_bake_rgba8(size_t size, int octaves, float lacunarity, float gain,
+                                            float period_units, uint32_t seed);
+
+#endif

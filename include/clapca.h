@@ -1,0 +1,183 @@
+/*
+ * clapca.h -- C ABI of libclapca_cuda, the B200 (sm_100a) implementation of the
+ * virtuoso/clap procedural-generation hot path.
+ *
+ * Every entry point is extern "C", takes plain pointers / sizes / scalars and
+ * returns an int status (CLAPCA_OK == 0).  The library owns all device
+ * buffers, streams and events; callers hand in host memory laid out exactly
+ * like the reference's containers (struct xyzarray payload: uint8,
+ * index = z*d0*d1 + y*d0 + x, core/xyarray.c:43) and get results back in the
+ * same layout.  There is no CPU fallback anywhere behind this interface: if
+ * no CUDA device is usable the calls fail with CLAPCA_ERR_CUDA.
+ *
+ * Each function cites the reference interface (file:line under
+ * /root/reference) whose work it takes over.  The source-compatible C headers
+ * a reference caller would keep including (ca-common.h, ca2d.h, ca3d.h,
+ * xyarray.h, noise_bake.h, terrain_field.h) live in include/clap/ and are
+ * implemented by the host shim clap_b200/host/ on top of this ABI
+ * (see INTEGRATION.md).
+ */
+#ifndef CLAPCA_H
+#define CLAPCA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    CLAPCA_OK              = 0,
+    CLAPCA_ERR_CUDA        = 1,   /* a CUDA runtime/driver call failed (no device, launch error, ...) */
+    CLAPCA_ERR_ARG         = 2,   /* bad argument (NULL, non-positive size, unknown enum) */
+    CLAPCA_ERR_NOMEM       = 3,   /* device or pinned-host allocation failed */
+    CLAPCA_ERR_TIMEOUT     = 4,   /* in-kernel dataflow watchdog fired (would have dead-locked) */
+    CLAPCA_ERR_UNSUPPORTED = 5,   /* shape/rule outside what the requested engine handles */
+    CLAPCA_ERR_STATE       = 6,   /* library not initialised / handle in the wrong state */
+};
+
+/* 2D neighbourhood selectors: the four functions of core/ca2d.c:11-59 */
+enum {
+    CLAPCA_NEIGH_VN1 = 0,         /* ca2d_neigh_vn1: alive count, 4 neighbours */
+    CLAPCA_NEIGH_M1  = 1,         /* ca2d_neigh_m1 : alive count, 8 neighbours */
+    CLAPCA_NEIGH_VNV = 2,         /* ca2d_neigh_vnv: neighbours with value > own, 4 */
+    CLAPCA_NEIGH_MV  = 3,         /* ca2d_neigh_mv : neighbours with value > own, 8 */
+};
+
+/* kernel family used by the *_run calls */
+enum {
+    CLAPCA_ENGINE_AUTO      = 0,  /* fastest engine that supports the shape/rule */
+    CLAPCA_ENGINE_WAVEFRONT = 1,  /* uint8 cells, skewed cell wavefront + grid barrier (any rule/shape) */
+    CLAPCA_ENGINE_BITPLANE  = 2,  /* bit-sliced planes, row scan, flag dataflow, all generations fused */
+};
+
+/* ---- library lifetime --------------------------------------------------- */
+
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int clapca_device_count(void);
+
+/*
+ * Bind this process to `device` (one process per GPU), create the streams and
+ * scratch the engines need.  Idempotent for the same device.
+ */
+int clapca_init(int device);
+void clapca_shutdown(void);
+
+/* Human-readable description of the last non-OK status on this thread. */
+const char *clapca_last_error(void);
+
+/* SM count and HBM bytes of the bound device (0 before clapca_init). */
+int    clapca_sm_count(void);
+size_t clapca_device_mem_bytes(void);
+
+/* ---- one-shot calls on host buffers (what the C shim binds) ------------- */
+
+/*
+ * ca3d_run(): core/ca3d.c:124-142.  `steps` in-place generations of the 3D
+ * rule (surv_mask, born_mask, nr_states) in z/y/x sweep order with the 26-cell
+ * Moore neighbourhood, on the uint8 volume `arr` (dim = {d0,d1,d2}, d0
+ * fastest).  *population (optional) receives xyzarray_count() of the result
+ * (core/xyarray.c:68-78).  Host -> device -> host copies are inside the call.
+ */
+int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3],
+                    uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states,
+                    int steps, int engine, int64_t *population);
+
+/* Rule table cas[] of core/ca3d.c:110-122, indexed like ca3d_run (nca % 9). */
+int clapca_ca3d_rule(int nca, uint32_t *surv_mask, uint32_t *born_mask, uint32_t *nr_states);
+
+/*
+ * ca2d_step() x steps: core/ca2d.c:61-77.  `arr` is a w*h uint8 grid
+ * (index y*w + x); cells x,y < side are swept x-outer / y-inner in place.
+ * The reference passes w == h == side.
+ */
+int clapca_ca2d_run(uint8_t *arr, int64_t w, int64_t h, int64_t side,
+                    uint32_t born_mask, uint32_t surv_mask, uint32_t nr_states,
+                    int decay, int neigh, int steps, int engine);
+
+/*
+ * noise_grad3d_bake_rgba8(): core/noise.c:222-270.  Fills out[size^3 * 4]
+ * (x fastest, RGBA8, A = 0) with the normalised central-difference gradient
+ * of the periodic fBm field (hash31 / value_noise3d_periodic / fbm3_periodic,
+ * core/noise.h:9-17, core/noise.c:171-220).
+ */
+int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float lacunarity,
+                                   float gain, float period_units, uint32_t seed);
+
+/* fbm3_periodic() at n sample points (xyz interleaved), for parity tests of the float field. */
+int clapca_noise_fbm3(float *out, const float *xyz, size_t n, int octaves, float lacunarity,
+                      float gain, int period, uint32_t seed);
+
+/*
+ * Lattice of terrain_init_square_landscape(): core/terrain.c:447-450 with
+ * get_rand_height() (:15-19): map0[x*nr_v + z] = drand48-after-srand48(seed ^ (x + z*43210))*2-1.
+ */
+int clapca_terrain_map0(float *map0, long seed, unsigned nr_v);
+
+/*
+ * Heightmap fill: core/terrain.c:451-467 on top of get_height() (:21-91).
+ * map[i*nr_v + j] = get_height(i, j, powf(1.5, avg), 4) + avg, where avg is the
+ * cosine blend of the `maze` cell (mside x mside xyarray payload, mside =
+ * nr_v/8) and its neighbours.  The lattice is generated on the device from
+ * `seed`.  With maze == NULL the plain octave field get_height(i, j, amp, oct)
+ * is written instead (amp/oct are ignored when a maze is given: the reference
+ * fixes OCTAVES = 4 there).
+ */
+int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty,
+                             const uint8_t *maze, unsigned mside, float amp, int oct);
+
+/* ---- device-resident grids (benchmarks, pipelines, multi-GPU slabs) ------ */
+
+typedef struct clapca_grid clapca_grid;
+
+/* A d0 x d1 x d2 uint8 grid in device memory (2D grids: d2 == 1). */
+int clapca_grid_create(clapca_grid **out, int64_t d0, int64_t d1, int64_t d2);
+int clapca_grid_destroy(clapca_grid *g);
+/* host <-> device in the reference layout (async on the grid's stream + sync) */
+int clapca_grid_upload(clapca_grid *g, const uint8_t *host);
+int clapca_grid_download(clapca_grid *g, uint8_t *host);
+/* raw device pointer of the uint8 cells (for zero-copy interop with torch tensors) */
+void *clapca_grid_device_ptr(clapca_grid *g);
+/* the CUDA stream (cudaStream_t) the grid's kernels are launched on */
+void *clapca_grid_stream(clapca_grid *g);
+
+int clapca_grid_run3d(clapca_grid *g, uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states,
+                      int steps, int engine, int64_t *population);
+int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born_mask, uint32_t surv_mask,
+                      uint32_t nr_states, int decay, int neigh, int steps, int engine);
+/* xyzarray_count(): core/xyarray.c:68-78 */
+int clapca_grid_count(clapca_grid *g, int64_t *population);
+
+/*
+ * Timing of the last *_run on this grid, measured with CUDA events on the
+ * grid's stream: total device milliseconds, the share spent in the
+ * generation kernel(s) alone (excludes layout pack/unpack and the count), the
+ * number of kernel launches, and the engine that actually ran.
+ */
+typedef struct clapca_run_stats {
+    float   total_ms;
+    float   kernel_ms;
+    int     launches;
+    int     engine;
+    int     planes;          /* bit planes used by the bit-plane engine (0 otherwise) */
+    int     workers;         /* persistent warps (bit-plane) / threads per wavefront step */
+} clapca_run_stats;
+int clapca_grid_last_stats(clapca_grid *g, clapca_run_stats *st);
+
+/* device-resident field evaluation for benchmarks: results stay in device memory */
+int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
+                             float period_units, uint32_t seed, float *kernel_ms);
+int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsigned nr_v, float ty,
+                                    const void *d_maze, unsigned mside, float amp, int oct,
+                                    float *map0_ms, float *map_ms);
+void *clapca_device_alloc(size_t bytes);
+int   clapca_device_free(void *p);
+int   clapca_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int   clapca_memcpy_d2h(void *dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAPCA_H */

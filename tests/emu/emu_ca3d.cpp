@@ -1,0 +1,186 @@
+/*
+ * emu_ca3d.cpp -- runs the bit-plane ca3d kernels (the real kernel source,
+ * compiled with -DCLAPCA_EMU) on the host warp emulator and compares the final
+ * volume and the population with the oracle restatement of ca3d_run().
+ * TEST ONLY: built and executed by tests/test_emu_kernels.py.
+ *
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps]
+ *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
+ *            10   = run-time rule with random masks
+ *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "emu_runtime.h"
+#include "../../clap_b200/csrc/ca3d_bitplane.cuh"
+#include "../../clap_b200/csrc/ca3d_layout.cuh"
+#include "../../clap_b200/csrc/bp_plan.h"
+extern "C" {
+#include "../../oracle/port/oracle_port.h"
+}
+
+using namespace clapca;
+
+#define B(n) (1u << (n))
+#define RANGE(s, e) (((1u << ((e) - (s))) - 1u) << (s))
+
+typedef Rule3Const<B(4), B(4), 5> R0;
+typedef Rule3Const<B(6) | B(7) | B(8), B(6) | B(7) | B(8), 3> R1;
+typedef Rule3Const<B(4) | B(5) | B(6) | B(7), B(6) | B(7) | B(8), 10> R2;
+typedef Rule3Const<RANGE(9, 26), B(5) | B(6) | B(7) | B(12) | B(13) | B(15), 5> R3;
+typedef Rule3Const<B(2) | B(6) | B(9), B(4) | B(6) | B(8) | B(9), 10> R4;
+typedef Rule3Const<B(1) | B(4) | B(8) | B(11) | RANGE(13, 26), RANGE(13, 26), 5> R5;
+typedef Rule3Const<RANGE(0, 3) | RANGE(7, 9) | RANGE(11, 13) | B(18) | B(21) | B(22) | B(24) | B(26),
+                   B(4) | B(13) | B(17) | RANGE(20, 24) | B(26), 4> R6;
+typedef Rule3Const<RANGE(5, 8), RANGE(6, 7) | B(9) | B(12), 4> R7;
+typedef Rule3Const<RANGE(0, 6), B(1) | B(3), 2> R8;
+
+template <int P, int WPL, class Rule>
+static void launch_sweep(const Bp3Params &p, int warps)
+{
+    emu_launch(1, warps * 32, [&]() { Sweep3<P, WPL, Rule>::kernel_body(p); });
+}
+
+template <int P, int WPL>
+static void dispatch_rule(int nca, const Bp3Params &p, int warps)
+{
+    switch (nca) {
+    case 0: launch_sweep<P, WPL, R0>(p, warps); break;
+    case 1: launch_sweep<P, WPL, R1>(p, warps); break;
+    case 2: launch_sweep<P, WPL, R2>(p, warps); break;
+    case 3: launch_sweep<P, WPL, R3>(p, warps); break;
+    case 4: launch_sweep<P, WPL, R4>(p, warps); break;
+    case 5: launch_sweep<P, WPL, R5>(p, warps); break;
+    case 6: launch_sweep<P, WPL, R6>(p, warps); break;
+    case 7: launch_sweep<P, WPL, R7>(p, warps); break;
+    case 8: launch_sweep<P, WPL, R8>(p, warps); break;
+    default: launch_sweep<P, WPL, Rule3Dyn>(p, warps); break;
+    }
+}
+
+template <int P>
+static void dispatch_wpl(int WPL, int nca, const Bp3Params &p, int warps)
+{
+    switch (WPL) {
+    case 1: dispatch_rule<P, 1>(nca, p, warps); break;
+    case 2: dispatch_rule<P, 2>(nca, p, warps); break;
+    case 4: dispatch_rule<P, 4>(nca, p, warps); break;
+    default: fprintf(stderr, "bad WPL\n"); exit(2);
+    }
+}
+
+static uint64_t rng_state = 88172645463325252ULL;
+static uint32_t rnd()
+{
+    rng_state ^= rng_state << 13;
+    rng_state ^= rng_state >> 7;
+    rng_state ^= rng_state << 17;
+    return (uint32_t)(rng_state >> 11);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 10) {
+        fprintf(stderr, "usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps]\n");
+        return 2;
+    }
+    int W = atoi(argv[1]), H = atoi(argv[2]), Z = atoi(argv[3]), G = atoi(argv[4]);
+    int nca = atoi(argv[5]), P = atoi(argv[6]), WPL = atoi(argv[7]), seedkind = atoi(argv[8]);
+    rng_state ^= (uint64_t)atoll(argv[9]) * 0x9E3779B97F4A7C15ULL;
+    int warps = argc > 10 ? atoi(argv[10]) : 6;
+
+    unsigned surv, born, nr;
+    if (nca <= 9) {
+        ora_ca3d_rule(nca == 9 ? 7 : nca, &surv, &born, &nr);
+    } else {
+        surv = rnd() & 0x7ffffff;
+        born = rnd() & rnd() & 0x7ffffff;
+        nr = 1 + rnd() % ((1u << (P > 7 ? 8 : P)) - 1);
+    }
+    unsigned bornval = (nr - 1) & 0xff;
+    if (bornval >> P) {
+        fprintf(stderr, "rule needs more than %d planes\n", P);
+        return 2;
+    }
+
+    size_t n = (size_t)W * H * Z;
+    std::vector<uint8_t> cells(n), want(n);
+    unsigned vmax = P >= 8 ? 255u : (1u << P) - 1u;
+    if (seedkind == 2) {
+        uint64_t st;
+        ora_srand48(&st, (long)atoll(argv[9]));
+        ora_ca3d_make(cells.data(), W, H, Z, &st);
+        if (P < 8)
+            for (auto &c : cells) if (c > vmax) c = (uint8_t)vmax;
+    } else {
+        for (auto &c : cells) {
+            if (seedkind == 0)
+                c = (rnd() % 4 == 0) ? (uint8_t)(1 + rnd() % (vmax < 5 ? vmax : 5)) : 0;
+            else
+                c = (rnd() % 5 < 2) ? 0 : (uint8_t)(rnd() % (vmax + 1));
+        }
+    }
+    want = cells;
+    int64_t want_pop = ora_ca3d_run(want.data(), W, H, Z, surv, born, nr, G);
+
+    /* device-side flow: pack -> sweep -> unpack */
+    int RWP = 32 * WPL;
+    if (W > 32 * RWP) {
+        fprintf(stderr, "row too wide for WPL\n");
+        return 2;
+    }
+    int NP = P + 2;
+    std::vector<uint32_t> rows((size_t)Z * H * NP * RWP, 0xdeadbeefu);
+    unsigned long long pop = 0;
+    Bp3Layout L = { cells.data(), rows.data(), W, H, Z, P, RWP, &pop };
+    emu_launch(2, 64, [&]() { ca3d_pack_kernel(L); });
+
+    std::vector<SweepId> order;
+    bp3_make_order(Z, G, order);
+    std::vector<int2> order2(order.size());
+    for (size_t i = 0; i < order.size(); i++) order2[i] = make_int2(order[i].z, order[i].g);
+    std::vector<int> prog((size_t)G * Z, 0);
+    unsigned ticket = 0;
+    int err = 0;
+    Bp3Params p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows.data();
+    p.W = W; p.H = H; p.Z = Z; p.G = G; p.RWP = RWP;
+    p.prog = prog.data();
+    p.order = order2.data();
+    p.nsweeps = (int)order2.size();
+    p.ticket = &ticket;
+    p.err = &err;
+    p.surv = surv; p.born = born; p.bornval = bornval;
+    p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
+
+    if (G > 0) {
+        switch (P) {
+        case 3: dispatch_wpl<3>(WPL, nca, p, warps); break;
+        case 4: dispatch_wpl<4>(WPL, nca, p, warps); break;
+        case 8: dispatch_wpl<8>(WPL, nca, p, warps); break;
+        default: fprintf(stderr, "bad P\n"); return 2;
+        }
+    }
+    if (err) {
+        printf("FAIL watchdog err=%d\n", err);
+        return 1;
+    }
+    std::vector<uint8_t> got(n, 0xEE);
+    L.cells = got.data();
+    emu_launch(2, 64, [&]() { ca3d_unpack_kernel(L); });
+
+    size_t diff = 0, first = n;
+    for (size_t i = 0; i < n; i++)
+        if (got[i] != want[i]) { if (!diff) first = i; diff++; }
+    if (diff || (int64_t)pop != want_pop) {
+        printf("FAIL diff=%zu first=%zu (x=%zu y=%zu z=%zu got=%d want=%d) pop=%llu want_pop=%lld\n", diff, first,
+               first % W, (first / W) % H, first / ((size_t)W * H), first < n ? got[first] : -1,
+               first < n ? want[first] : -1, pop, (long long)want_pop);
+        return 1;
+    }
+    printf("OK W=%d H=%d Z=%d G=%d nca=%d P=%d WPL=%d pop=%llu\n", W, H, Z, G, nca, P, WPL, pop);
+    return 0;
+}

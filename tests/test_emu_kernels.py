@@ -1,0 +1,55 @@
+"""CPU: the real bit-plane kernel source, compiled with -DCLAPCA_EMU and run on the host warp emulator
+(tests/emu/), must reproduce the oracle bit for bit -- this covers the row-scan algebra, the rule tables,
+the sliding windows, the pack/unpack layout and the flag-based dataflow between concurrent sweeps."""
+import os
+import subprocess
+
+import pytest
+
+EMU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+
+
+@pytest.fixture(scope="module")
+def emu_bin():
+    subprocess.run(["make", "-C", EMU, "-j4"], check=True, capture_output=True)
+    return os.path.join(EMU, "build")
+
+
+def _run(exe, *args):
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, f"{args}: {r.stdout} {r.stderr}"
+    assert r.stdout.startswith("OK")
+
+
+@pytest.mark.parametrize("nca", range(11))
+def test_ca3d_every_rule(emu_bin, nca):
+    exe = os.path.join(emu_bin, "emu_ca3d")
+    planes = 4 if nca in (2, 4) else 3
+    #        W   H  Z  G  rule P       WPL seedkind seed warps
+    _run(exe, 45, 7, 6, 3, nca, planes, 1, 0, nca, 5)
+    _run(exe, 33, 5, 4, 4, nca, 8, 1, 2, nca, 3)          # ca3d_make seed: contains 255s
+    _run(exe, 64, 4, 3, 2, nca, 4, 2, 1, nca, 7)
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 1, 1, 3), (5, 1, 1, 3), (1, 5, 1, 3), (1, 1, 5, 3), (32, 3, 3, 2), (31, 3, 3, 2), (33, 2, 2, 5),
+    (40, 6, 5, 0), (16, 8, 4, 4),
+])
+def test_ca3d_edge_shapes(emu_bin, shape):
+    w, h, z, g = shape
+    _run(os.path.join(emu_bin, "emu_ca3d"), w, h, z, g, 7, 3, 1, 1, 5, 2)
+
+
+def test_ca3d_wide_rows_and_words_per_lane(emu_bin):
+    exe = os.path.join(emu_bin, "emu_ca3d")
+    _run(exe, 97, 4, 5, 5, 7, 3, 4, 1, 7, 4)
+    _run(exe, 1024, 3, 3, 2, 0, 3, 1, 1, 8, 3)
+    _run(exe, 1030, 2, 3, 2, 0, 3, 2, 1, 8, 3)
+    _run(exe, 2048, 2, 2, 2, 7, 3, 2, 0, 9, 4)
+
+
+def test_ca3d_many_generations_few_and_many_workers(emu_bin):
+    exe = os.path.join(emu_bin, "emu_ca3d")
+    _run(exe, 24, 12, 10, 12, 10, 8, 1, 1, 3, 12)
+    _run(exe, 24, 12, 10, 9, 10, 3, 1, 1, 5, 1)          # a single worker: pure claim order
+    _run(exe, 24, 12, 10, 9, 7, 3, 1, 0, 5, 2)
