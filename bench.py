@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the clap procedural-generation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): CA cell-updates per second (GCUPS) for ca3d_run() -- core/ca3d.c:124-142 -- on a
+synthetic 2048^3 uint8 volume, 50 generations of ca_coral (BASELINE config 4; fits one GPU, so it is also the
+N = 1 workload).  One "step" = one full run of all generations over the volume.
+
+  value      cells * generations / device time of the step (CUDA events on the library's stream, max over
+             ranks), input already resident in HBM in the reference's uint8 layout; the layout pack/unpack
+             kernels and the population count are INSIDE the timed region.
+  e2e        same metric through the C-ABI grid calls with pinned HOST buffers: H2D of the seed volume and
+             D2H of the result (+ population) inside the timed region, wall clock.
+  roofline   the dominant kernel (the fused sweep kernel): algorithmic bytes = 2 B per cell update
+              over its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference: the reference's own C (oracle/_ref/libclapref.so, built from the unmodified
+             sources; oracle/port when that is absent) on one host core -- the path is single-threaded and
+             sequentially dependent -- on a bounded sample of the same workload.
+
+Rank 0 prints exactly one JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (d0, d1, d2, generations, rule index)
+    "ca3d_2048": (2048, 2048, 2048, 50, 7),
+    "ca3d_1024": (1024, 1024, 1024, 50, 7),
+    "ca3d_512": (512, 512, 512, 50, 7),
+    "ca3d_128": (128, 128, 128, 10, 7),
+}
+SEED = 0xC1A9
+CHUNK_PLANES = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ca3d_2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "wavefront", "bitplane"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic seed volume: P(alive) = 1/4, values uniform 1..5, zero boundary outside (SURVEY.md 8d cfg 4).
+# Generated per 64-plane chunk from a (seed, chunk) keyed generator so any slab owner produces the same
+# cells as a single GPU would.
+# ------------------------------------------------------------------------------------------------
+def synth_planes(torch, d0, d1, z0, z1, device):
+    out = torch.empty((z1 - z0, d1, d0), dtype=torch.uint8, device=device)
+    z = z0
+    while z < z1:
+        c = z // CHUNK_PLANES
+        cz0, cz1 = c * CHUNK_PLANES, (c + 1) * CHUNK_PLANES
+        gen = torch.Generator(device=device)
+        gen.manual_seed(SEED * 1000003 + c)
+        r = torch.randint(0, 20, (CHUNK_PLANES, d1, d0), dtype=torch.uint8, device=device, generator=gen)
+        r = torch.where(r < 5, r + 1, torch.zeros_like(r))
+        lo, hi = max(z, cz0), min(z1, cz1)
+        out[lo - z0:hi - z0] = r[lo - cz0:hi - cz0]
+        z = hi
+    return out
+
+
+def synth_numpy(np, shape, seed):
+    rng = np.random.default_rng(seed)
+    r = rng.integers(0, 20, shape, dtype=np.uint8)
+    return np.where(r < 5, r + 1, 0).astype(np.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference C on one host core, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(np, rule_index, gens_full, budget_s):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    ref = oracle_lib.ref()
+    side = 256
+    vol = synth_numpy(np, (side, side, side), SEED)
+    # ~50 MCUPS on one core -> one generation of 256^3 is ~0.35 s; size the sample to the budget
+    gens = int(max(1, min(gens_full, budget_s / 0.40)))
+    if ref is not None:
+        kind = "reference"
+        t0 = time.perf_counter()
+        ref.ca3d_run(vol, rule_index, gens)
+        dt = time.perf_counter() - t0
+    else:
+        kind = "port"
+        port = oracle_lib.port()
+        s, b, n = port.ca3d_rule(rule_index)
+        t0 = time.perf_counter()
+        port.ca3d_run(vol, s, b, n, gens)
+        dt = time.perf_counter() - t0
+    gcups = side ** 3 * gens / dt / 1e9
+    return {"value": gcups, "unit": "GCUPS", "cores": 1, "kind": kind,
+            "sample": f"ca3d_run ca_coral on a {side}^3 corner-sized synthetic volume (same P(alive)=1/4, values "
+                      f"1..5), {gens} generations, {dt:.1f} s on one core of {os.cpu_count()} (reference path is "
+                      f"single-threaded and sequentially dependent)"}
+
+
+def run_reference_arm(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d0, d1, d2, gens, rule = WORKLOADS[args.workload]
+    total = args.steps + args.warmup
+    budget = max(2.0, min(20.0, 150.0 / max(1, total)))
+    vals = []
+    base = None
+    for i in range(total):
+        base = cpu_reference_sample(np, rule, gens, budget)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": "ca3d cell-updates/s", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: ca3d_run {d0}x{d1}x{d2}, {gens} generations, rule ca_coral"},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import clap_b200
+    from clap_b200 import _lib
+    from clap_b200.rules import ca3d_rule
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    clap_b200.init(local)
+
+    d0, d1, d2, gens, rule_index = WORKLOADS[args.workload]
+    rule = ca3d_rule(rule_index)
+    engine = {"auto": 0, "wavefront": 1, "bitplane": 2}[args.engine]
+
+    if world > 1:
+        from clap_b200.slab import run_sharded_bench
+        return run_sharded_bench(args, WORKLOADS[args.workload], synth_planes)
+
+    cells = d0 * d1 * d2
+    updates = cells * gens
+    seed_dev = synth_planes(torch, d0, d1, 0, d2, dev)
+    torch.cuda.synchronize()
+    grid = clap_b200.Grid(d0, d1, d2)
+
+    def step():
+        grid.upload(seed_dev.data_ptr())            # device-to-device reset of the state (not timed)
+        pop = grid.run3d(rule, gens, engine=engine)
+        return pop, grid.stats()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    tot_ms, ker_ms, launches, pop, st = 0.0, 0.0, 0, 0, None
+    for _ in range(args.steps):
+        pop, st = step()
+        tot_ms += st["total_ms"]
+        ker_ms += st["kernel_ms"]
+        launches += st["launches"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    ms_per_step = tot_ms / args.steps
+    value = updates / (ms_per_step * 1e-3) / 1e9
+    kernel_ms = ker_ms / args.steps
+    peak, peak_src = measured_peak()
+    achieved = updates * 2.0 / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "ca3d_sweep_kernel (all generations fused)",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_update": 2.0, "peak_source": peak_src}
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(cells, dtype=torch.uint8, pin_memory=True)
+        host_out = torch.empty(cells, dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(seed_dev.reshape(-1))
+        torch.cuda.synchronize()
+        n_e2e = max(1, min(args.steps, 3))
+        for i in range(1 + n_e2e):
+            if i == 1:
+                t0 = time.perf_counter()
+            grid.upload(host_in.data_ptr())
+            pop_e = grid.run3d(rule, gens, engine=engine)
+            grid.download(host_out.data_ptr())
+        dt = (time.perf_counter() - t0) / n_e2e
+        assert pop_e == pop, "end-to-end population differs from the device-resident run"
+        e2e = {"value": updates / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": cells,
+               "d2h_bytes_per_step": cells + 8, "ms_per_step": dt * 1e3, "steps": n_e2e}
+        del host_in, host_out
+
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_reference_sample(np, rule_index, gens, args.cpu_seconds)
+
+    line = {
+        "metric": "ca3d cell-updates/s", "value": value, "unit": "GCUPS", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: ca3d_run {d0}x{d1}x{d2} uint8, {gens} generations, rule {rule.name}, "
+                               f"seed P(alive)=1/4 values 1..5",
+                   "engine": st["engine"], "planes": st["planes"], "workers": st["workers"],
+                   "l2": "input volume (%.1f GiB) is larger than L2; state is reset from a pristine device copy "
+                         "before every step" % (cells / 2 ** 30),
+                   "population": pop, "wall_s_timed_region": wall},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -237,7 +237,7 @@ int clapca_grid_destroy(clapca_grid *g)
 int clapca_grid_upload(clapca_grid *g, const uint8_t *host)
 {
     if (!g || !host) return fail(CLAPCA_ERR_ARG, "grid_upload: NULL argument");
-    CU(cudaMemcpyAsync(g->cells, host, g->n, cudaMemcpyHostToDevice, g->stream));
+    CU(cudaMemcpyAsync(g->cells, host, g->n, cudaMemcpyDefault, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return CLAPCA_OK;
 }
@@ -245,7 +245,7 @@ int clapca_grid_upload(clapca_grid *g, const uint8_t *host)
 int clapca_grid_download(clapca_grid *g, uint8_t *host)
 {
     if (!g || !host) return fail(CLAPCA_ERR_ARG, "grid_download: NULL argument");
-    CU(cudaMemcpyAsync(host, g->cells, g->n, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(host, g->cells, g->n, cudaMemcpyDefault, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return CLAPCA_OK;
 }

@@ -1,0 +1,286 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs, against
+the committed golden vectors, and -- at sizes the oracle cannot reach in seconds -- through engine cross-checks
+and size-independent properties.  CA results must be bit-exact; float fields carry their tolerance here."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WAVEFRONT, BITPLANE = 1, 2
+ENGINES = [pytest.param(WAVEFRONT, id="wavefront"), pytest.param(BITPLANE, id="bitplane")]
+
+
+def synth(rng, shape, p_alive=0.25, vmax=5, with255=False):
+    vol = (rng.integers(1, vmax + 1, shape) * (rng.random(shape) < p_alive)).astype(np.uint8)
+    if with255:
+        vol[rng.random(shape) < 0.003] = 255
+    return vol
+
+
+# ---- ca3d -----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_ca3d_golden_all_rules(gpu, engine):
+    g = np.load(os.path.join(G, "ca3d.npz"))
+    pops = g["pops_37_23_32"].tolist()
+    k = 0
+    for nca in range(9):
+        for tag in "AB":
+            vol = g[f"seed{tag}_37_23_32"].copy()
+            pop = gpu.ca3d_run(vol, nca, 5, engine=engine)
+            assert pop == pops[k], (nca, tag)
+            assert np.array_equal(vol, g[f"rule{nca}_seed{tag}_5gen"]), (nca, tag)
+            k += 1
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_ca3d_test0_shape(gpu, engine):
+    """The reference's own test shape: ca3d_make(16, 8, 4) then 4 steps of ca_coral (core/test.c:628-633)."""
+    g = np.load(os.path.join(G, "ca3d.npz"))
+    vol = g["make_16_8_4"].copy()
+    pop = gpu.ca3d_run(vol, 7, 4, engine=engine)
+    assert pop == int(g["make_16_8_4_coral4_pop"]) and pop != 0
+    assert np.array_equal(vol, g["make_16_8_4_coral4"])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_ca3d_cfg2_128cube_10gen(gpu, oracle, engine):
+    """BASELINE config 2: 128^3, 10 generations, coral, on the srand48(42) ca3d_make seed."""
+    g = np.load(os.path.join(G, "ca3d.npz"))
+    oracle.ca3d_make(16, 8, 4, 42)
+    vol = oracle.ca3d_make(128, 128, 128, 42)
+    assert oracle.fnv(vol) == int(g["cfg2_seed_hash"])
+    pop = gpu.ca3d_run(vol, 7, 10, engine=engine)
+    assert pop == int(g["cfg2_pop"]) == 272840
+    assert oracle.fnv(vol) == int(g["cfg2_final_hash"])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 7, 3), (5, 1, 9), (9, 5, 1), (31, 6, 5), (32, 6, 5), (33, 6, 5),
+                                   (100, 17, 11), (130, 9, 40)])
+def test_ca3d_ragged_shapes_vs_oracle(gpu, oracle, engine, shape):
+    d0, d1, d2 = shape
+    rng = np.random.default_rng(d0 * 1000 + d1 * 10 + d2)
+    for nca in (0, 3, 6, 7, 8):
+        vol = synth(rng, (d2, d1, d0), 0.4, 6, with255=True)
+        want = vol.copy()
+        s, b, n = oracle.ca3d_rule(nca)
+        wpop = oracle.ca3d_run(want, s, b, n, 6)
+        pop = gpu.ca3d_run(vol, nca, 6, engine=engine)
+        assert pop == wpop and np.array_equal(vol, want), (shape, nca)
+
+
+def test_ca3d_custom_masks_run_time_rule(gpu, oracle):
+    """Masks outside cas[] go through the run-time-table kernel."""
+    rng = np.random.default_rng(11)
+    for _ in range(4):
+        rule = gpu.CellAutomaton("custom", born_mask=int(rng.integers(0, 1 << 27)) & int(rng.integers(0, 1 << 27)),
+                                 surv_mask=int(rng.integers(0, 1 << 27)), nr_states=int(rng.integers(1, 200)))
+        vol = synth(rng, (9, 14, 50), 0.5, 9)
+        want = vol.copy()
+        wpop = oracle.ca3d_run(want, rule.surv_mask, rule.born_mask, rule.nr_states, 5)
+        assert gpu.ca3d_run(vol, rule, 5, engine=BITPLANE) == wpop
+        assert np.array_equal(vol, want)
+
+
+def test_ca3d_wide_rows_thin_slab_vs_oracle(gpu, oracle):
+    """Rows of the BASELINE config-4 width (2048 cells = 2 words per lane) on a thin slab the oracle finishes."""
+    rng = np.random.default_rng(12)
+    for d0 in (1024, 1500, 2048, 4096):
+        vol = synth(rng, (6, 40, d0))
+        want = vol.copy()
+        s, b, n = oracle.ca3d_rule(7)
+        wpop = oracle.ca3d_run(want, s, b, n, 4)
+        assert gpu.ca3d_run(vol, 7, 4, engine=BITPLANE) == wpop
+        assert np.array_equal(vol, want), d0
+
+
+def test_ca3d_zero_steps_and_population(gpu):
+    rng = np.random.default_rng(13)
+    vol = synth(rng, (8, 9, 10))
+    keep = vol.copy()
+    assert gpu.ca3d_run(vol, 7, 0) == int(np.count_nonzero(keep))
+    assert np.array_equal(vol, keep)
+
+
+def test_ca3d_engines_agree_256cube(gpu):
+    """No CPU in the loop: the two independent GPU engines must agree bit for bit at 256^3 x 6."""
+    rng = np.random.default_rng(14)
+    vol = synth(rng, (256, 256, 256))
+    a, b = vol.copy(), vol.copy()
+    pa = gpu.ca3d_run(a, 7, 6, engine=WAVEFRONT)
+    pb = gpu.ca3d_run(b, 7, 6, engine=BITPLANE)
+    assert pa == pb == int(np.count_nonzero(a))
+    assert np.array_equal(a, b)
+
+
+def test_ca3d_generations_compose_large(gpu):
+    """Size-independent property at 1024 x 1024 x 96: G1 then G2 generations == G1 + G2 in one fused run."""
+    rng = np.random.default_rng(15)
+    vol = synth(rng, (96, 1024, 1024))
+    grid = gpu.Grid(1024, 1024, 96)
+    out1 = np.empty_like(vol)
+    out2 = np.empty_like(vol)
+    grid.upload(vol)
+    p1 = grid.run3d(7, 9, engine=BITPLANE)
+    grid.download(out1)
+    grid.upload(vol)
+    grid.run3d(7, 4, engine=BITPLANE)
+    p2 = grid.run3d(7, 5, engine=BITPLANE)
+    grid.download(out2)
+    grid.close()
+    assert p1 == p2 == int(np.count_nonzero(out1))
+    assert np.array_equal(out1, out2)
+
+
+def test_ca3d_device_resident_grid_stats(gpu, oracle):
+    rng = np.random.default_rng(16)
+    vol = synth(rng, (20, 30, 70))
+    want = vol.copy()
+    s, b, n = oracle.ca3d_rule(0)
+    wpop = oracle.ca3d_run(want, s, b, n, 3)
+    grid = gpu.Grid(70, 30, 20)
+    grid.upload(vol)
+    assert grid.run3d(0, 3) == wpop == grid.count()
+    st = grid.stats()
+    assert st["engine"] == "bitplane" and st["planes"] == 3 and st["kernel_ms"] > 0 and st["launches"] >= 3
+    got = np.empty_like(vol)
+    grid.download(got)
+    grid.close()
+    assert np.array_equal(got, want)
+
+
+# ---- ca2d -----------------------------------------------------------------------------------------
+
+def test_ca2d_golden_cases(gpu):
+    g = np.load(os.path.join(G, "ca2d.npz"))
+    for i, (neigh, born, surv, nr, decay, side) in enumerate(g["cases"].tolist()):
+        ca = gpu.CellAutomaton("case", born, surv, nr, bool(decay), neigh)
+        arr = g[f"case{i}_start"].copy()
+        gpu.ca2d_step(ca, arr, steps=6)
+        assert np.array_equal(arr, g[f"case{i}_final6"]), (i, neigh)
+        arr = g[f"case{i}_start"].copy()
+        gpu.ca2d_step(ca, arr, side=side - 7, steps=3)
+        assert np.array_equal(arr, g[f"case{i}_partial3"]), (i, neigh)
+
+
+def test_ca2d_cfg1_cave_generation(gpu):
+    """BASELINE config 1: ca2d_generate(&ca_test, 256, 5) after srand48(1234)."""
+    from clap_b200.ca import Rand48
+    g = np.load(os.path.join(G, "ca2d.npz"))
+    arr = gpu.ca2d_generate(gpu.CA_TEST, 256, 5, Rand48(1234))
+    assert np.array_equal(arr, g["cfg1_final"])
+
+
+def test_ca2d_instantiator_rules_and_steps_compose(gpu, oracle):
+    rng = np.random.default_rng(21)
+    maze = oracle.ca2d_run(oracle.ca2d_seed(128, 4, 7), 3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_M1, 4)
+    want = maze.copy()
+    for ca in gpu.CA_INSTORS:           # core/terrain.c:473-477: one step of each instantiator rule
+        gpu.ca2d_step(ca, maze)
+        oracle.ca2d_run(want, ca.born_mask, ca.surv_mask, ca.nr_states, ca.decay, ca.neigh, 1)
+    assert np.array_equal(maze, want)
+    arr = synth(rng, (300, 300), 0.6, 4)
+    a, b = arr.copy(), arr.copy()
+    gpu.ca2d_step(gpu.CA_TEST, a, steps=7)
+    gpu.ca2d_step(gpu.CA_TEST, b, steps=3)
+    gpu.ca2d_step(gpu.CA_TEST, b, steps=4)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, oracle.ca2d_run(arr.copy(), 3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_M1, 7))
+
+
+def test_ca2d_rectangular_and_empty(gpu, oracle):
+    rng = np.random.default_rng(22)
+    arr = synth(rng, (37, 91), 0.5, 4)           # h = 37, w = 91; side sweeps min(side, extent)
+    want = oracle.ca2d_run(arr.copy(), 3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_MV, 3, side=60)
+    ca = gpu.CellAutomaton("r", 3 << 2, 3 << 7, 4, True, oracle_lib.NEIGH_MV)
+    gpu.ca2d_step(ca, arr, side=60, steps=3)
+    assert np.array_equal(arr, want)
+    z = np.zeros((16, 16), np.uint8)
+    gpu.ca2d_step(gpu.CA_TEST, z, steps=5)
+    assert not z.any()
+
+
+# ---- noise ----------------------------------------------------------------------------------------
+
+def test_noise_bake_golden_exact(gpu, oracle):
+    g = np.load(os.path.join(G, "noise.npz"))
+    a = gpu.noise_grad3d_bake_rgba8(16, 4, 2.0, 0.5, 5.0, 0xC14D)
+    assert np.array_equal(a, g["bake_16_p5"])
+    a = gpu.noise_grad3d_bake_rgba8(24, 3, 2.3, 0.45, 37.0, 99)
+    assert np.array_equal(a, g["bake_24_p37_o3"])
+    d = gpu.noise_grad3d_bake_rgba8(64)          # engine defaults (noise.c:309-317)
+    assert oracle.fnv(d) == int(g["bake_64_default_hash"])
+    assert d.reshape(-1)[:4].tolist() == [122, 5, 93, 0]
+
+
+def test_noise_fbm_float_field(gpu):
+    """north_star tolerance: 1e-5 relative; the kernel mirrors the reference's double promotions and is
+    expected (and checked) to be exact to the last bit."""
+    g = np.load(os.path.join(G, "noise.npz"))
+    got = gpu.noise_fbm3(g["fbm_points"], 4, 2.0, 0.5, 37, 0xC14D)
+    want = g["fbm_values"]
+    assert np.allclose(got, want, rtol=1e-5, atol=0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_noise_bake_256_against_oracle_slices(gpu, oracle):
+    """SURVEY 8(d) N1 case (size 256, period 37): exact-match on the z slices the oracle computes in seconds."""
+    got = gpu.noise_grad3d_bake_rgba8(256, 4, 2.0, 0.5, 37.0, 0xC14D)
+    for z in (0, 101, 255):
+        want = oracle.noise_bake(256, 4, 2.0, 0.5, 37.0, 0xC14D, z0=z, z1=z + 1)
+        assert np.array_equal(got[z], want[z]), z
+    assert not got[..., 3].any()
+
+
+# ---- terrain --------------------------------------------------------------------------------------
+
+def _field_close(got, want):
+    """|delta| <= 1e-5 * max(|ref|, field RMS) (cosf/powf differ from glibc by <= 2 ulp)."""
+    rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+    tol = 1e-5 * np.maximum(np.abs(want), rms)
+    bad = np.abs(got.astype(np.float64) - want) > tol
+    assert not bad.any(), (int(bad.sum()), float(np.abs(got - want).max()))
+
+
+def test_terrain_map0_exact(gpu):
+    g = np.load(os.path.join(G, "terrain.npz"))
+    for seed in (12345, -99, (1 << 40) + 17):
+        m = gpu.terrain_map0(seed, 64)
+        assert np.array_equal(m.view(np.uint32), g[f"map0_64_seed{seed}"].view(np.uint32))
+
+
+def test_terrain_heightmap_golden(gpu):
+    g = np.load(os.path.join(G, "terrain.npz"))
+    _field_close(gpu.terrain_heightmap(12345, 128, 0.0, None, 1.0, 4), g["field_128"])
+    _field_close(gpu.terrain_heightmap(12345, 128, 3.0, None, 2.5, 3), g["field_128_y3_amp2_o3"])
+    _field_close(gpu.terrain_heightmap(12345, 128, 0.0, g["maze_16"]), g["heightmap_128"])
+
+
+def test_terrain_survey_spot_values_1024(gpu):
+    g = np.load(os.path.join(G, "terrain.npz"))
+    m = gpu.terrain_map0(12345, 1024)
+    assert m.reshape(-1)[7] == g["survey_map0_7"]
+    f = gpu.terrain_heightmap(12345, 1024, 0.0, None, 1.0, 4)
+    assert abs(float(f.reshape(-1)[12345]) - float(g["survey_map_12345"])) < 1e-5
+    assert abs(float(f.astype(np.float64).sum()) - float(g["survey_map_sum"])) < 0.05
+
+
+def test_terrain_cfg5_rows_vs_oracle(gpu, oracle):
+    """BASELINE config 5 shape (8192^2 with the 1024^2 ca_test maze): full GPU map, oracle on sampled rows."""
+    from clap_b200.ca import Rand48
+    nr_v = 8192
+    maze = gpu.ca2d_generate(gpu.CA_TEST, nr_v // 8, 4, Rand48(7))
+    want_maze = oracle.ca2d_run(oracle.ca2d_seed(nr_v // 8, 4, 7), 3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_M1, 4)
+    assert np.array_equal(maze, want_maze)
+    got = gpu.terrain_heightmap(12345, nr_v, 0.0, maze)
+    map0 = oracle.terrain_map0(12345, nr_v)
+    assert np.array_equal(gpu.terrain_map0(12345, nr_v).view(np.uint32), map0.view(np.uint32))
+    for i0 in (0, 4093, 8188):
+        want = oracle.terrain_heightmap(map0, 0.0, maze, i0=i0, i1=i0 + 4)
+        _field_close(got[i0:i0 + 4], want[i0:i0 + 4])
