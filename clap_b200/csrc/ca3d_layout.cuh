@@ -20,6 +20,45 @@ struct Bp3Layout {
     unsigned long long *population;     /* unpack: number of non-zero cells */
 };
 
+
+/* gather bit q of each of 4 packed cells (bytes) into a nibble: cell k -> bit k */
+CA_DEV uint32_t lay_gather4(uint32_t bytes_lsb)
+{
+    /* bytes_lsb has the wanted bit at bit 0 of every byte; 0x01020408 moves byte k's bit to bit 24+k */
+    return ((bytes_lsb & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+/* spread a nibble to the lsb of 4 bytes: bit k -> byte k */
+CA_DEV uint32_t lay_spread4(uint32_t nibble)
+{
+    return ((nibble & 0xfu) * 0x00204081u) & 0x01010101u;
+}
+
+/* 0x01 in every byte of v that is non-zero */
+CA_DEV uint32_t lay_nonzero4(uint32_t v)
+{
+    v |= v >> 4;
+    v |= v >> 2;
+    v |= v >> 1;
+    return v & 0x01010101u;
+}
+
+/* 32 cells held in r[8] (4 per register, x ascending) -> P state words + alive word */
+CA_DEV void lay_pack32(const uint32_t r[8], int P, uint32_t s[8], uint32_t &alive)
+{
+    alive = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s[q] = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        alive |= lay_gather4(lay_nonzero4(r[j])) << (4 * j);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (q < P)
+                s[q] |= lay_gather4(r[j] >> q) << (4 * j);
+    }
+}
+
 /* uint8 volume -> row records (one thread per word of a plane-row) */
 CA_GLOBAL void ca3d_pack_kernel(Bp3Layout L)
 {
@@ -36,11 +75,19 @@ CA_GLOBAL void ca3d_pack_kernel(Bp3Layout L)
         uint32_t alive = 0u;
         int n = L.W - x0;
         n = n > 32 ? 32 : n;
-        for (int i2 = 0; i2 < n; i2++) {
-            uint32_t v = src[x0 + i2];
+        if (n == 32 && (L.W & 15) == 0) {
+            /* whole word, 16-byte aligned rows: two 128-bit loads, multiply-gather per plane */
+            const uint4 lo = *reinterpret_cast<const uint4 *>(src + x0);
+            const uint4 hi = *reinterpret_cast<const uint4 *>(src + x0 + 16);
+            const uint32_t r[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+            lay_pack32(r, L.P, s, alive);
+        } else {
+            for (int i2 = 0; i2 < n; i2++) {
+                uint32_t v = src[x0 + i2];
 #pragma unroll
-            for (int q = 0; q < 8; q++) s[q] |= ((v >> q) & 1u) << i2;
-            alive |= (uint32_t)(v != 0) << i2;
+                for (int q = 0; q < 8; q++) s[q] |= ((v >> q) & 1u) << i2;
+                alive |= (uint32_t)(v != 0) << i2;
+            }
         }
         uint32_t left  = (n > 0 && x0 > 0) ? (uint32_t)(src[x0 - 1] != 0) : 0u;
         uint32_t right = (n > 0 && x0 + 32 < L.W) ? (uint32_t)(src[x0 + 32] != 0) : 0u;
@@ -75,11 +122,26 @@ CA_GLOBAL void ca3d_unpack_kernel(Bp3Layout L)
         pop += (unsigned)dp_popc(alive);
         int n = L.W - x0;
         n = n > 32 ? 32 : n;
-        for (int i2 = 0; i2 < n; i2++) {
-            uint32_t v = 0;
+        if (n == 32 && (L.W & 15) == 0) {
+            uint32_t r[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v |= ((s[q] >> i2) & 1u) << q;
-            dst[x0 + i2] = (uint8_t)v;
+            for (int j = 0; j < 8; j++) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (q < L.P)
+                        v |= lay_spread4(s[q] >> (4 * j)) << q;
+                r[j] = v;
+            }
+            *reinterpret_cast<uint4 *>(dst + x0) = make_uint4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<uint4 *>(dst + x0 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+        } else {
+            for (int i2 = 0; i2 < n; i2++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) v |= ((s[q] >> i2) & 1u) << q;
+                dst[x0 + i2] = (uint8_t)v;
+            }
         }
     }
     if (pop)
