@@ -47,8 +47,10 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int blocks = per_sm * sms;
-    const int need = (p.nsweeps + threads / 32 - 1) / (threads / 32);
-    if (blocks > need) blocks = need;
+    if (p.nsweeps >= 0) {
+        const int need = (p.nsweeps + threads / 32 - 1) / (threads / 32);
+        if (blocks > need) blocks = need;
+    }
     if (blocks < 1) blocks = 1;
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, kern);
@@ -59,6 +61,8 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
         info->workers = blocks * (threads / 32);
         info->regs = fa.numRegs;
     }
+    if (p.nsweeps < 0)
+        return cudaSuccess;             /* occupancy query (bp3_max_workers) */
     Bp3Params pp = p;
     void *args[] = { &pp };
     /* cooperative launch: fails instead of silently running a non-co-resident grid */

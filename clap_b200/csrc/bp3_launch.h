@@ -21,6 +21,9 @@ struct Bp3LaunchInfo {
 cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream,
                        Bp3LaunchInfo *info);
 
+/* number of persistent warps a cooperative launch of this variant can keep resident */
+int bp3_max_workers(int rule, int P, int WPL, int sms);
+
 #define BP3_DECLARE_RULE(n) \
     cudaError_t bp3_launch_rule##n(int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream, \
                                    Bp3LaunchInfo *info);

@@ -1,38 +1,18 @@
 /*
  * bp_plan.h -- host-side planning shared by the C-ABI library and the kernel
- * emulator tests: sweep claim order and bit-plane count for the bit-plane
- * engines.  Plain C++ (no CUDA).
+ * emulator tests: bit-plane count, sweep claim order, and the z-block slab
+ * decomposition (who owns which planes, where ghost planes live, whom an
+ * edge plane feeds).  Plain C++ (no CUDA).
  */
 #ifndef CLAPCA_BP_PLAN_H
 #define CLAPCA_BP_PLAN_H
 #include <stdint.h>
+#include <stddef.h>
 #include <vector>
 #include <algorithm>
+#include "bp3_types.h"
 
 namespace clapca {
-
-struct SweepId { int z, g; };
-
-/*
- * Claim order of the (z,g) sweeps.  Sweep (z,g) consumes (z-1,g), (z+1,g-1)
- * and (z,g-1); any order that is monotone in key = 2z + 4g extends that
- * partial order (the three producers have keys key-2, key-2, key-4), and it
- * keeps all generations of a plane a few rows apart (L2-resident window).
- */
-inline void bp3_make_order(int Z, int G, std::vector<SweepId> &order)
-{
-    order.clear();
-    order.reserve((size_t)Z * G);
-    const long long kmax = 2LL * (Z - 1) + 4LL * (G - 1);
-    for (long long key = 0; key <= kmax; key += 2)
-        for (int g = 0; g < G; g++) {
-            long long z2 = key - 4LL * g;
-            if (z2 < 0)
-                break;
-            if (z2 / 2 < Z)
-                order.push_back(SweepId{ (int)(z2 / 2), g });
-        }
-}
 
 /* bit planes needed so that every value that can ever occur fits: {3,4,8} are instantiated */
 inline int bp_planes_for(unsigned maxval)
@@ -49,6 +29,187 @@ inline int bp_wpl_for(int W)
     if (W <= 2048) return 2;
     if (W <= 4096) return 4;
     return 0;
+}
+
+/*
+ * Slab decomposition of the z axis (the outermost sweep axis, core/ca3d.c:130)
+ * over R ranks: the Zg planes are cut into blocks of B planes, block j belongs
+ * to rank j % R (block-cyclic).  Each rank stores its blocks back to back.
+ * Contiguous slabs are the special case B = ceil(Zg / R).  Small blocks keep
+ * the pipeline fill short: rank r can start 3*r*B row steps after rank 0
+ * instead of 3*r*Zg/R.
+ */
+struct SlabGeom {
+    int Zg, R, rank, B;
+    int nblocks() const { return (Zg + B - 1) / B; }
+    int blocks_per_rank_max() const { return (nblocks() + R - 1) / R; }
+    int local_blocks() const { int n = nblocks(); return n > rank ? (n - rank + R - 1) / R : 0; }
+    int block_z0(int j) const { return j * B; }
+    int block_len(int j) const { return std::min(B, Zg - j * B); }
+    int global_block(int lb) const { return lb * R + rank; }
+    int local_planes() const
+    {
+        int n = 0;
+        for (int lb = 0; lb < local_blocks(); lb++) n += block_len(global_block(lb));
+        return n;
+    }
+    /* local index of the first plane of local block lb */
+    int local_z0(int lb) const
+    {
+        int n = 0;
+        for (int i = 0; i < lb; i++) n += block_len(global_block(i));
+        return n;
+    }
+};
+
+/* size (in 32-bit words) of one ghost plane: H rows of [H0 | H1] */
+inline size_t slab_ghost_plane_words(int H, int RWP) { return (size_t)H * 2 * RWP; }
+
+/*
+ * Layout of a rank's halo region (one device allocation, exported to the two
+ * neighbouring ranks): ghost planes below / above each local block, then the
+ * progress counters the neighbours store into.  Offsets in 32-bit words.
+ */
+struct HaloLayout {
+    size_t ghost_dn, ghost_up, flag_dn, flag_up, total_words;
+    int nlb_max;
+};
+
+inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP, int Gcap)
+{
+    HaloLayout h;
+    h.nlb_max = geo.blocks_per_rank_max();
+    size_t gp = slab_ghost_plane_words(H, RWP);
+    h.ghost_dn = 0;
+    h.ghost_up = h.ghost_dn + gp * h.nlb_max;
+    h.flag_dn = h.ghost_up + gp * h.nlb_max;
+    h.flag_up = h.flag_dn + (size_t)Gcap * h.nlb_max;
+    h.total_words = h.flag_up + (size_t)Gcap * h.nlb_max;
+    return h;
+}
+
+/* base pointers of one rank as seen from its own process */
+struct SlabPtrs {
+    uint32_t *rows;         /* local row records */
+    int *prog;              /* local progress counters [G][Zl] */
+    uint32_t *halo;         /* own halo region */
+    uint32_t *halo_next;    /* halo region of rank (rank + 1) % R, peer-mapped */
+    uint32_t *halo_prev;    /* halo region of rank (rank - 1 + R) % R, peer-mapped */
+};
+
+/* plane descriptors for every local plane of `geo.rank` */
+inline void bp3_build_planes(const SlabGeom &geo, const SlabPtrs &ptr, const HaloLayout &hl, int H, int RWP, int NP,
+                             std::vector<Bp3Plane> &out)
+{
+    const size_t recw = (size_t)NP * RWP;
+    const size_t planew = (size_t)H * recw;
+    const size_t gp = slab_ghost_plane_words(H, RWP);
+    const int Zl = geo.local_planes();
+    const int nb = geo.nblocks();
+    out.assign(Zl, Bp3Plane());
+    for (int lb = 0; lb < geo.local_blocks(); lb++) {
+        const int j = geo.global_block(lb);
+        const int l0 = geo.local_z0(lb), len = geo.block_len(j);
+        for (int i = 0; i < len; i++) {
+            const int l = l0 + i;
+            Bp3Plane &p = out[l];
+            p = Bp3Plane();
+            p.zglobal = geo.block_z0(j) + i;
+            if (i > 0) {
+                p.dn_rows = ptr.rows + (size_t)(l - 1) * planew;
+                p.dn_stride = (uint32_t)recw;
+                p.dn_flag = ptr.prog + (l - 1);
+                p.dn_gstride = (uint32_t)Zl;
+            } else if (j > 0) {
+                p.dn_rows = ptr.halo + hl.ghost_dn + gp * lb;
+                p.dn_stride = 2u * RWP;
+                p.dn_flag = (const int *)(ptr.halo + hl.flag_dn) + lb;
+                p.dn_gstride = (uint32_t)hl.nlb_max;
+                p.remote_mask |= 1u;
+                /* ... and this plane feeds the ghost plane ABOVE the previous block */
+                const int lbp = (j - 1) / geo.R;
+                p.push_dn_rows = ptr.halo_prev + hl.ghost_up + gp * lbp;
+                p.push_dn_stride = 2u * RWP;
+                p.push_dn_flag = (int *)(ptr.halo_prev + hl.flag_up) + lbp;
+                p.push_dn_gstride = (uint32_t)hl.nlb_max;
+            }
+            if (i + 1 < len) {
+                p.up_rows = ptr.rows + (size_t)(l + 1) * planew;
+                p.up_stride = (uint32_t)recw;
+                p.up_flag = ptr.prog + (l + 1);
+                p.up_gstride = (uint32_t)Zl;
+            } else if (j + 1 < nb) {
+                p.up_rows = ptr.halo + hl.ghost_up + gp * lb;
+                p.up_stride = 2u * RWP;
+                p.up_flag = (const int *)(ptr.halo + hl.flag_up) + lb;
+                p.up_gstride = (uint32_t)hl.nlb_max;
+                p.remote_mask |= 2u;
+                /* ... and this plane feeds the ghost plane BELOW the next block */
+                const int lbn = (j + 1) / geo.R;
+                p.push_up_rows = ptr.halo_next + hl.ghost_dn + gp * lbn;
+                p.push_up_stride = 2u * RWP;
+                p.push_up_flag = (int *)(ptr.halo_next + hl.flag_dn) + lbn;
+                p.push_up_gstride = (uint32_t)hl.nlb_max;
+            }
+        }
+    }
+}
+
+struct WorkItem { int z, g, y0, y1; };      /* local plane, generation, rows [y0, y1) */
+
+/*
+ * Work items and their claim order.
+ *
+ * Dependencies (global z): rows <= y+2 of (z-1,g) [new plane below], of (z+1,g-1) [old plane
+ * above] and of (z,g-1) [own old state] must be complete before row y of (z,g).  Cutting every
+ * sweep into segments of L rows whose boundaries are skewed by 3 rows per plane and 6 rows per
+ * generation,
+ *         segment s of (z,g) = rows [s L - 3 z - 6 g, (s+1) L - 3 z - 6 g)  clipped to [0,H),
+ * makes segment s of (z,g) depend only on segment s (and earlier) of its three producers and on
+ * its own segment s-1.  Items are claimed band by band (s), inside a band along anti-diagonals
+ * z + g (then g): this extends the dependency order -- (z-1,g,s), (z,g-1,s) lie on the previous
+ * anti-diagonal, (z+1,g-1,s) earlier on the same one -- and it makes consecutive generations of a
+ * plane follow each other a handful of rows apart, so a band's working set stays in L2 and HBM
+ * sees roughly one read and one write of the volume for ALL generations.  Every rank enumerates
+ * the same global order and keeps its own planes, so the globally first unfinished item is always
+ * running or next in line on its rank: no deadlock.
+ */
+inline void bp3_make_items(const std::vector<Bp3Plane> &planes, int Zg, int H, int G, int L,
+                           std::vector<WorkItem> &items)
+{
+    items.clear();
+    if (G <= 0 || planes.empty())
+        return;
+    std::vector<int> local_of(Zg, -1);
+    for (size_t l = 0; l < planes.size(); l++)
+        local_of[planes[l].zglobal] = (int)l;
+    const long long span = (long long)H + 3LL * (Zg - 1) + 6LL * (G - 1);
+    const int nbands = (int)((span + L - 1) / L);
+    for (int s = 0; s < nbands; s++)
+        for (int d = 0; d <= (Zg - 1) + (G - 1); d++)
+            for (int g = std::max(0, d - (Zg - 1)); g <= std::min(G - 1, d); g++) {
+                const int z = d - g;
+                const int l = local_of[z];
+                if (l < 0)
+                    continue;
+                long long y0 = (long long)s * L - 3LL * z - 6LL * g;
+                long long y1 = y0 + L;
+                if (y0 < 0) y0 = 0;
+                if (y1 > H) y1 = H;
+                if (y0 < y1)
+                    items.push_back(WorkItem{ l, g, (int)y0, (int)y1 });
+            }
+}
+
+/* segment length: long enough that a band offers ~2x more independent items than there are workers */
+inline int bp3_segment_rows(int Zg, int H, int G, int workers)
+{
+    const double chain = 3.0 * Zg + 6.0 * G;            /* dependency chain through one band, in rows */
+    int L = 32;
+    while (L < 256 && (double)Zg * G * L / (chain + L) < 2.0 * workers)
+        L *= 2;
+    if (L > H) L = std::max(H, 1);
+    return L;
 }
 
 } // namespace clapca

@@ -40,16 +40,19 @@
 #define CLAPCA_CA3D_BITPLANE_CUH
 
 #include "bitslice.cuh"
+#include "bp3_types.h"
 
 namespace clapca {
 
 struct Bp3Params {
-    uint32_t *rows;         /* row records, [(z*H + y) * NP + plane] * RWP */
-    int W, H, Z, G;         /* cells per row, rows per plane, planes, generations */
+    uint32_t *rows;         /* local row records, [(z*H + y) * NP + plane] * RWP */
+    const Bp3Plane *planes; /* [Z] */
+    int W, H, Z, G;         /* cells per row, rows per plane, LOCAL planes, generations */
     int RWP;                /* words per plane-row = 32 * WPL */
-    int *prog;              /* [G][Z] rows completed by sweep (z,g) */
-    const int2 *order;      /* sweep claim order: (z, g) */
-    int nsweeps;
+    int *prog;              /* [G][Z] rows completed by local sweep (z,g) */
+    const int4 *order;      /* work items in claim order: (local z, g, first row, end row) */
+    int nsweeps;            /* number of work items */
+    int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
     unsigned *ticket;       /* next sweep to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
     uint32_t surv, born;    /* rule masks (run-time rule only) */
@@ -160,26 +163,33 @@ struct Sweep3 {
     static constexpr int NP = P + 2;
 
     struct Flags {          /* cached progress of the three producers of a sweep */
-        const int *dn, *up, *own;
-        int vdn, vup, vown;
+        const int *dn, *up, *own, *self;
+        int vdn, vup, vown, vself;
+        uint32_t remote;    /* bit 0 / 1: dn / up counter is stored by a peer GPU (system scope) */
     };
 
-    /* wait until all three producers have completed `need` rows; false = watchdog/abort */
-    CA_MDEV bool wait_rows(const Bp3Params &p, Flags &f, int need)
+    /*
+     * Wait until the three producers have completed `need` rows and this sweep's own
+     * earlier segments `need_self` rows; false = watchdog fired / abort requested.
+     */
+    CA_MDEV bool wait_rows(const Bp3Params &p, Flags &f, int need, int need_self)
     {
-        if (f.vdn >= need && f.vup >= need && f.vown >= need)
+        if (f.vdn >= need && f.vup >= need && f.vown >= need && f.vself >= need_self)
             return true;
         long long t0 = dp_clock();
         unsigned spins = 0;
         for (;;) {
-            /* lanes 0..2 poll one producer each; the values are made warp-uniform by shuffle */
+            /* lanes 0..3 poll one counter each; the values are made warp-uniform by shuffle */
             const int lane = dp_lane();
-            const int *src = lane == 0 ? f.dn : (lane == 1 ? f.up : (lane == 2 ? f.own : nullptr));
-            uint32_t v = src ? (uint32_t)dp_ld_flag(src) : 0x7fffffffu;
-            f.vdn  = (int)dp_shfl(v, 0);
-            f.vup  = (int)dp_shfl(v, 1);
-            f.vown = (int)dp_shfl(v, 2);
-            if (f.vdn >= need && f.vup >= need && f.vown >= need)
+            const int *src = lane == 0 ? f.dn : (lane == 1 ? f.up : (lane == 2 ? f.own : (lane == 3 ? f.self : nullptr)));
+            uint32_t v = 0x7fffffffu;
+            if (src)
+                v = (uint32_t)(((f.remote >> lane) & 1u) ? dp_ld_flag_sys(src) : dp_ld_flag(src));
+            f.vdn   = (int)dp_shfl(v, 0);
+            f.vup   = (int)dp_shfl(v, 1);
+            f.vown  = (int)dp_shfl(v, 2);
+            f.vself = (int)dp_shfl(v, 3);
+            if (f.vdn >= need && f.vup >= need && f.vown >= need && f.vself >= need_self)
                 break;
             dp_nanosleep(40);
             if ((++spins & 63u) == 0u) {
@@ -192,7 +202,7 @@ struct Sweep3 {
             }
         }
         /* acquire: the polling lanes fence after their relaxed load, the warp barrier extends it to all lanes */
-        dp_fence_acquire();
+        if (f.remote) dp_fence_sys(); else dp_fence_acquire();
         dp_syncwarp();
         return true;
     }
@@ -218,15 +228,15 @@ struct Sweep3 {
             LaneVec<WPL>::ld(rec + (2 + q) * RWP + lane * WPL, s[q]);
     }
 
-    /* rows r of the three sources of sweep (z,g): H of dn/up/own-old and S of own-old */
-    CA_MDEV void load_row(const Bp3Params &p, int z, int r, int lane, bool have_dn, bool have_up,
-                                RowIn &in, uint32_t so[P][WPL])
+    /* rows r of the three sources of a sweep: H of dn/up/own-old and S of own-old */
+    CA_MDEV void load_row(const Bp3Params &p, const Bp3Plane &pl, int z, int r, int lane, RowIn &in,
+                          uint32_t so[P][WPL])
     {
         const size_t recw = (size_t)NP * p.RWP;
         if (r < p.H) {
             const uint32_t *own = p.rows + ((size_t)z * p.H + r) * recw;
-            if (have_dn) load_h(own - (size_t)p.H * recw, p.RWP, lane, in.hd); else zero_h(in.hd);
-            if (have_up) load_h(own + (size_t)p.H * recw, p.RWP, lane, in.hu); else zero_h(in.hu);
+            if (pl.dn_rows) load_h(pl.dn_rows + (size_t)r * pl.dn_stride, p.RWP, lane, in.hd); else zero_h(in.hd);
+            if (pl.up_rows) load_h(pl.up_rows + (size_t)r * pl.up_stride, p.RWP, lane, in.hu); else zero_h(in.hu);
             load_h(own, p.RWP, lane, in.ho);
             load_s(own, p.RWP, lane, so);
         } else {
@@ -238,23 +248,26 @@ struct Sweep3 {
         }
     }
 
-    /* one sweep: all rows of plane z at generation g.  false = aborted */
-    CA_MDEV bool run_sweep(const Bp3Params &p, int z, int g)
+    /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
+    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
-        const bool have_dn = z > 0, have_up = z + 1 < Z;
+        const Bp3Plane pl = p.planes[z];
         const uint32_t bornval = Rule::bornval(p);
         const size_t recw = (size_t)NP * p.RWP;
         int *myprog = p.prog + (size_t)g * Z + z;
 
         Flags f;
-        f.dn  = have_dn ? p.prog + (size_t)g * Z + (z - 1) : nullptr;
-        f.up  = (g > 0 && have_up) ? p.prog + (size_t)(g - 1) * Z + (z + 1) : nullptr;
+        f.dn  = pl.dn_rows ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
+        f.up  = (g > 0 && pl.up_rows) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
         f.own = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
         f.vdn  = f.dn  ? 0 : 0x7fffffff;
         f.vup  = f.up  ? 0 : 0x7fffffff;
         f.vown = f.own ? 0 : 0x7fffffff;
+        f.self = y0 > 0 ? myprog : nullptr;         /* rows < y0 belong to earlier segments of this sweep */
+        f.vself = f.self ? 0 : 0x7fffffff;
+        f.remote = pl.remote_mask;
 
         uint32_t vmask[WPL];
 #pragma unroll
@@ -265,20 +278,32 @@ struct Sweep3 {
         uint32_t so[P][WPL], so1[P][WPL], so2[P][WPL];
         RowIn in;
 
-        zero_h(hdA); zero_h(huA); zero_h(hn);
-        if (!wait_rows(p, f, H < 2 ? H : 2))
+        if (!wait_rows(p, f, y0 + 2 < H ? y0 + 2 : H, y0))
             return false;
         {
+            /* (re)build the sliding windows: rows y0-1, y0 and y0+1 of the sources */
             RowIn r0;
-            load_row(p, z, 0, lane, have_dn, have_up, r0, so);
+            if (y0 > 0) {
+                load_row(p, pl, z, y0 - 1, lane, r0, so);
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int j = 0; j < WPL; j++) {
+                        hdA[b][j] = r0.hd[b][j]; huA[b][j] = r0.hu[b][j];
+                        hn[b][j] = r0.ho[b][j];     /* row y0-1 of this plane is already generation g */
+                    }
+            } else {
+                zero_h(hdA); zero_h(huA); zero_h(hn);
+            }
+            load_row(p, pl, z, y0, lane, r0, so);
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
                 for (int j = 0; j < WPL; j++) { hdB[b][j] = r0.hd[b][j]; huB[b][j] = r0.hu[b][j]; }
-            load_row(p, z, 1, lane, have_dn, have_up, in, so1);
+            load_row(p, pl, z, y0 + 1, lane, in, so1);
         }
 
-        for (int y = 0; y < H; y++) {
+        for (int y = y0; y < y1; y++) {
             uint32_t k[WPL][5], ao[WPL], ge2[WPL];
 
             /* ---- neighbour count K (everything but the in-row predecessor) ---- */
@@ -316,11 +341,11 @@ struct Sweep3 {
                 }
 
             /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
-            {
+            if (y + 2 <= y1) {          /* row y1 is still needed (as "row y+1" of the last step), y1+1 is not */
                 int need = y + 3 < H ? y + 3 : H;
-                if (!wait_rows(p, f, need))
+                if (!wait_rows(p, f, need, 0))
                     return false;
-                load_row(p, z, y + 2, lane, have_dn, have_up, in, so2);
+                load_row(p, pl, z, y + 2, lane, in, so2);
             }
 
             /* ---- rule tables, in-row scan ---- */
@@ -373,15 +398,32 @@ struct Sweep3 {
 #pragma unroll
                 for (int q = 0; q < P; q++)
                     LaneVec<WPL>::st(rec + (2 + q) * p.RWP + lane * WPL, so[q]);
+                /* a z-block's edge plane also feeds the neighbouring GPU's ghost plane (peer stores over NVLink) */
+                const bool push = pl.push_dn_rows || pl.push_up_rows;
+                if (pl.push_dn_rows) {
+                    uint32_t *dst = pl.push_dn_rows + (size_t)y * pl.push_dn_stride;
+                    LaneVec<WPL>::st(dst + 0 * p.RWP + lane * WPL, hn[0]);
+                    LaneVec<WPL>::st(dst + 1 * p.RWP + lane * WPL, hn[1]);
+                }
+                if (pl.push_up_rows) {
+                    uint32_t *dst = pl.push_up_rows + (size_t)y * pl.push_up_stride;
+                    LaneVec<WPL>::st(dst + 0 * p.RWP + lane * WPL, hn[0]);
+                    LaneVec<WPL>::st(dst + 1 * p.RWP + lane * WPL, hn[1]);
+                }
                 /*
                  * release: warp barrier (orders every lane's row stores before lane 0),
-                 * then ONE cumulative gpu-scope fence and the relaxed counter store --
-                 * the same shape as cooperative-groups' grid barrier arrive.
+                 * then ONE cumulative fence and the relaxed counter store(s) -- the same
+                 * shape as cooperative-groups' grid barrier arrive.  System scope when a
+                 * peer GPU is among the consumers.
                  */
-                dp_syncwarp();
-                if (lane == 0) {
-                    dp_fence_release();
+                const bool raise = (y + 1 == y1) || ((y + 1) % p.flag_rows) == 0;
+                if (raise)
+                    dp_syncwarp();
+                if (raise && lane == 0) {
+                    if (push) dp_fence_sys(); else dp_fence_release();
                     dp_st_flag(myprog, y + 1);
+                    if (pl.push_dn_flag) dp_st_flag_sys(pl.push_dn_flag + (size_t)g * pl.push_dn_gstride, y + 1);
+                    if (pl.push_up_flag) dp_st_flag_sys(pl.push_up_flag + (size_t)g * pl.push_up_gstride, y + 1);
                 }
             }
 
@@ -407,8 +449,8 @@ struct Sweep3 {
             t = dp_shfl(t, 0);
             if (t >= (unsigned)p.nsweeps)
                 break;
-            int2 zg = p.order[t];
-            if (!run_sweep(p, zg.x, zg.y))
+            int4 it = p.order[t];
+            if (!run_segment(p, it.x, it.y, it.z, it.w))
                 break;
         }
     }

@@ -102,6 +102,16 @@ cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cu
         return cudaErrorInvalidValue;
     return tab[rule](P, WPL, p, sms, stream, info);
 }
+int bp3_max_workers(int rule, int P, int WPL, int sms)
+{
+    Bp3Params p;
+    memset(&p, 0, sizeof(p));
+    p.nsweeps = -1;                     /* query only: the launcher returns before launching */
+    Bp3LaunchInfo info = { 0, 0, 0, 0 };
+    if (bp3_launch(rule, P, WPL, p, sms, nullptr, &info) != cudaSuccess)
+        return sms * 8;
+    return info.workers;
+}
 } // namespace clapca
 
 struct clapca_grid {
@@ -113,9 +123,15 @@ struct clapca_grid {
     size_t rows_bytes = 0;
     int *prog = nullptr;
     size_t prog_count = 0;
-    int2 *order = nullptr;
-    size_t order_count = 0;
-    int order_Z = -1, order_G = -1;
+    int4 *order = nullptr;          /* work items in claim order */
+    size_t order_bytes = 0;
+    int n_items = 0;
+    int order_Z = -1, order_H = -1, order_G = -1, order_L = -1;
+    Bp3Plane *planes = nullptr;     /* per-plane source descriptors */
+    size_t planes_bytes = 0;
+    const void *planes_rows = nullptr;
+    const void *planes_prog = nullptr;
+    int planes_NP = -1, planes_RWP = -1;
     unsigned *ticket = nullptr;     /* [0] ticket, [1] err (as int) */
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -227,6 +243,7 @@ int clapca_grid_destroy(clapca_grid *g)
     if (g->rows) cudaFree(g->rows);
     if (g->prog) cudaFree(g->prog);
     if (g->order) cudaFree(g->order);
+    if (g->planes) cudaFree(g->planes);
     if (g->ticket) cudaFree(g->ticket);
     for (int i = 0; i < 4; i++)
         if (g->ev[i]) cudaEventDestroy(g->ev[i]);
@@ -316,6 +333,9 @@ static int ensure_bytes(void **ptr, size_t *have, size_t want)
     return CLAPCA_OK;
 }
 
+/* progress counters are raised every kFlagRows rows: one fence per kFlagRows row steps */
+static const int kFlagRows = 2;
+
 /* generations fused per launch: bounds the progress-counter table, not the result */
 static const int kMaxFusedGenerations = 4096;
 
@@ -360,20 +380,6 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     int launches = 0, workers = 0;
     for (int done = 0; done < steps;) {
         const int G = std::min(steps - done, kMaxFusedGenerations);
-        if (g->order_Z != Z || g->order_G != G) {
-            std::vector<SweepId> order;
-            bp3_make_order(Z, G, order);
-            size_t have = g->order_count * sizeof(int2);
-            void *p = g->order;
-            if (int rc = ensure_bytes(&p, &have, order.size() * sizeof(int2))) { g->order = nullptr; return rc; }
-            g->order = (int2 *)p;
-            g->order_count = have / sizeof(int2);
-            static_assert(sizeof(SweepId) == sizeof(int2), "SweepId must alias int2");
-            CU(cudaMemcpyAsync(g->order, order.data(), order.size() * sizeof(int2), cudaMemcpyHostToDevice,
-                               g->stream));
-            CU(cudaStreamSynchronize(g->stream));       /* `order` is a stack vector */
-            g->order_Z = Z; g->order_G = G;
-        }
         {
             size_t have = g->prog_count * sizeof(int);
             void *p = g->prog;
@@ -381,16 +387,54 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
             g->prog = (int *)p;
             g->prog_count = have / sizeof(int);
         }
+        /* per-plane source descriptors: on one GPU every neighbour plane is local (one z-block, no ghosts) */
+        std::vector<Bp3Plane> planes;
+        {
+            SlabGeom geo = { Z, 1, 0, Z };
+            SlabPtrs ptr = { g->rows, g->prog, nullptr, nullptr, nullptr };
+            HaloLayout hl = slab_halo_layout(geo, H, RWP, 1);
+            bp3_build_planes(geo, ptr, hl, H, RWP, NP, planes);
+        }
+        if (g->planes_rows != g->rows || g->planes_prog != g->prog || g->planes_NP != NP || g->planes_RWP != RWP ||
+            g->planes_bytes < planes.size() * sizeof(Bp3Plane)) {
+            void *p = g->planes;
+            if (int rc = ensure_bytes(&p, &g->planes_bytes, planes.size() * sizeof(Bp3Plane))) {
+                g->planes = nullptr;
+                return rc;
+            }
+            g->planes = (Bp3Plane *)p;
+            CU(cudaMemcpyAsync(g->planes, planes.data(), planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice,
+                               g->stream));
+            CU(cudaStreamSynchronize(g->stream));
+            g->planes_rows = g->rows; g->planes_prog = g->prog; g->planes_NP = NP; g->planes_RWP = RWP;
+        }
+        const int max_workers = bp3_max_workers(rule, P, WPL, g_ctx.sms);
+        const int L = bp3_segment_rows(Z, H, G, max_workers);
+        if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != L) {
+            std::vector<WorkItem> items;
+            bp3_make_items(planes, Z, H, G, L, items);
+            static_assert(sizeof(WorkItem) == sizeof(int4), "WorkItem must alias int4");
+            void *p = g->order;
+            if (int rc = ensure_bytes(&p, &g->order_bytes, items.size() * sizeof(int4))) { g->order = nullptr; return rc; }
+            g->order = (int4 *)p;
+            CU(cudaMemcpyAsync(g->order, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice,
+                               g->stream));
+            CU(cudaStreamSynchronize(g->stream));       /* `items` is a stack vector */
+            g->n_items = (int)items.size();
+            g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = L;
+        }
         CU(cudaMemsetAsync(g->prog, 0, (size_t)G * Z * sizeof(int), g->stream));
         CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
 
         Bp3Params p;
         memset(&p, 0, sizeof(p));
         p.rows = g->rows;
+        p.planes = g->planes;
         p.W = W; p.H = H; p.Z = Z; p.G = G; p.RWP = RWP;
         p.prog = g->prog;
         p.order = g->order;
-        p.nsweeps = Z * G;
+        p.nsweeps = g->n_items;
+        p.flag_rows = kFlagRows;
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.surv = surv; p.born = born; p.bornval = bornval;

@@ -61,6 +61,17 @@ CA_DEV void dp_st_flag(int *p, int v)
 {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+CA_DEV int dp_ld_flag_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+CA_DEV void dp_st_flag_sys(int *p, int v)
+{
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+CA_DEV void dp_fence_sys()                        { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 /* fence.acq_rel.gpu (MEMBAR.ALL.GPU); __threadfence() would be the heavier fence.sc */
 CA_DEV void dp_fence_release()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
@@ -99,9 +110,11 @@ CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 struct int2  { int x, y; };
+struct int4  { int x, y, z, w; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = { x, y }; return r; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = { x, y, z, w }; return r; }
 static inline int2  make_int2(int x, int y) { int2 r = { x, y }; return r; }
+static inline int4  make_int4(int x, int y, int z, int w) { int4 r = { x, y, z, w }; return r; }
 
 namespace clapca {
 
@@ -148,6 +161,9 @@ CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { *p = v; }
 CA_DEV int  dp_ld_flag(const int *p)              { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV void dp_st_flag(int *p, int v)             { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV void dp_fence_sys()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV void dp_st_flag_sys(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 CA_DEV void dp_fence_acquire()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV void dp_nanosleep(unsigned)                { emu_yield(); }
 CA_DEV long long dp_clock()                       { return emu_clock(); }

@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows]]]]]
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
  *            10   = run-time rule with random masks
  *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <thread>
 #include "emu_runtime.h"
 #include "../../clap_b200/csrc/ca3d_bitplane.cuh"
 #include "../../clap_b200/csrc/ca3d_layout.cuh"
@@ -83,13 +84,17 @@ static uint32_t rnd()
 int main(int argc, char **argv)
 {
     if (argc < 10) {
-        fprintf(stderr, "usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps]\n");
+        fprintf(stderr, "usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows]]]]]\n");
         return 2;
     }
     int W = atoi(argv[1]), H = atoi(argv[2]), Z = atoi(argv[3]), G = atoi(argv[4]);
     int nca = atoi(argv[5]), P = atoi(argv[6]), WPL = atoi(argv[7]), seedkind = atoi(argv[8]);
     rng_state ^= (uint64_t)atoll(argv[9]) * 0x9E3779B97F4A7C15ULL;
     int warps = argc > 10 ? atoi(argv[10]) : 6;
+    int ranks = argc > 11 ? atoi(argv[11]) : 1;      /* emulated GPUs (z-block slab decomposition) */
+    int blockB = argc > 12 ? atoi(argv[12]) : 0;     /* planes per z-block, 0 = contiguous slabs */
+    int segL = argc > 13 ? atoi(argv[13]) : 0;       /* rows per work item, 0 = planner default */
+    int flagRows = argc > 14 ? atoi(argv[14]) : 2;   /* rows per progress-counter update */
 
     unsigned surv, born, nr;
     if (nca <= 9) {
@@ -125,52 +130,115 @@ int main(int argc, char **argv)
     want = cells;
     int64_t want_pop = ora_ca3d_run(want.data(), W, H, Z, surv, born, nr, G);
 
-    /* device-side flow: pack -> sweep -> unpack */
+    /* device-side flow per rank: pack -> (halo init) -> sweep -> unpack; ranks run concurrently */
     int RWP = 32 * WPL;
     if (W > 32 * RWP) {
         fprintf(stderr, "row too wide for WPL\n");
         return 2;
     }
-    int NP = P + 2;
-    std::vector<uint32_t> rows((size_t)Z * H * NP * RWP, 0xdeadbeefu);
-    unsigned long long pop = 0;
-    Bp3Layout L = { cells.data(), rows.data(), W, H, Z, P, RWP, &pop };
-    emu_launch(2, 64, [&]() { ca3d_pack_kernel(L); });
-
-    std::vector<SweepId> order;
-    bp3_make_order(Z, G, order);
-    std::vector<int2> order2(order.size());
-    for (size_t i = 0; i < order.size(); i++) order2[i] = make_int2(order[i].z, order[i].g);
-    std::vector<int> prog((size_t)G * Z, 0);
-    unsigned ticket = 0;
+    const int NP = P + 2;
+    const int Gcap = G > 0 ? G : 1;
+    struct Rank {
+        SlabGeom geo;
+        HaloLayout hl;
+        std::vector<uint8_t> cells;         /* local planes, reference layout */
+        std::vector<uint32_t> rows, halo;
+        std::vector<int> prog;
+        std::vector<Bp3Plane> planes;
+        std::vector<int4> order;
+        unsigned ticket = 0;
+        unsigned long long pop = 0;
+        Bp3Params p;
+    };
+    std::vector<Rank> rk(ranks);
     int err = 0;
-    Bp3Params p;
-    memset(&p, 0, sizeof(p));
-    p.rows = rows.data();
-    p.W = W; p.H = H; p.Z = Z; p.G = G; p.RWP = RWP;
-    p.prog = prog.data();
-    p.order = order2.data();
-    p.nsweeps = (int)order2.size();
-    p.ticket = &ticket;
-    p.err = &err;
-    p.surv = surv; p.born = born; p.bornval = bornval;
-    p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
-
-    if (G > 0) {
-        switch (P) {
-        case 3: dispatch_wpl<3>(WPL, nca, p, warps); break;
-        case 4: dispatch_wpl<4>(WPL, nca, p, warps); break;
-        case 8: dispatch_wpl<8>(WPL, nca, p, warps); break;
-        default: fprintf(stderr, "bad P\n"); return 2;
+    for (int r = 0; r < ranks; r++) {
+        Rank &k = rk[r];
+        k.geo = SlabGeom{ Z, ranks, r, blockB > 0 ? blockB : (Z + ranks - 1) / ranks };
+        k.hl = slab_halo_layout(k.geo, H, RWP, Gcap);
+        const int Zl = k.geo.local_planes();
+        k.cells.resize((size_t)W * H * (Zl ? Zl : 1));
+        for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
+            int jb = k.geo.global_block(lb);
+            memcpy(k.cells.data() + (size_t)k.geo.local_z0(lb) * W * H,
+                   cells.data() + (size_t)k.geo.block_z0(jb) * W * H, (size_t)k.geo.block_len(jb) * W * H);
         }
+        k.rows.assign((size_t)(Zl ? Zl : 1) * H * NP * RWP, 0xdeadbeefu);
+        k.halo.assign(k.hl.total_words, 0u);
+        k.prog.assign((size_t)Gcap * (Zl ? Zl : 1), 0);
+    }
+    for (int r = 0; r < ranks; r++) {
+        Rank &k = rk[r];
+        const int Zl = k.geo.local_planes();
+        SlabPtrs ptr = { k.rows.data(), k.prog.data(), k.halo.data(), rk[(r + 1) % ranks].halo.data(),
+                         rk[(r + ranks - 1) % ranks].halo.data() };
+        bp3_build_planes(k.geo, ptr, k.hl, H, RWP, NP, k.planes);
+        std::vector<WorkItem> items;
+        bp3_make_items(k.planes, Z, H, G, segL > 0 ? segL : bp3_segment_rows(Z, H, G, warps), items);
+        k.order.resize(items.size());
+        for (size_t i = 0; i < items.size(); i++) k.order[i] = make_int4(items[i].z, items[i].g, items[i].y0, items[i].y1);
+        if (Zl) {
+            Bp3Layout L = { k.cells.data(), k.rows.data(), W, H, Zl, P, RWP, &k.pop };
+            emu_launch(2, 64, [&]() { ca3d_pack_kernel(L); });
+        }
+        memset(&k.p, 0, sizeof(k.p));
+        k.p.rows = k.rows.data();
+        k.p.planes = k.planes.data();
+        k.p.W = W; k.p.H = H; k.p.Z = Zl; k.p.G = G; k.p.RWP = RWP;
+        k.p.prog = k.prog.data();
+        k.p.order = k.order.data();
+        k.p.nsweeps = (int)k.order.size();
+        k.p.flag_rows = flagRows;
+        k.p.ticket = &k.ticket;
+        k.p.err = &err;
+        k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;
+        k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
+    }
+    /* halo init: the first plane of every block but the first seeds the ghost plane above the previous block */
+    for (int r = 0; r < ranks; r++)
+        for (size_t l = 0; l < rk[r].planes.size(); l++) {
+            const Bp3Plane &pl = rk[r].planes[l];
+            if (!pl.push_dn_rows) continue;
+            for (int y = 0; y < H; y++)
+                memcpy(pl.push_dn_rows + (size_t)y * pl.push_dn_stride,
+                       rk[r].rows.data() + ((size_t)l * H + y) * NP * RWP, sizeof(uint32_t) * 2 * RWP);
+        }
+    if (G > 0) {
+        std::vector<std::thread> ths;
+        for (int r = 0; r < ranks; r++)
+            ths.emplace_back([&, r]() {
+                const Bp3Params &p = rk[r].p;
+                if (!p.nsweeps) return;
+                switch (P) {
+                case 3: dispatch_wpl<3>(WPL, nca, p, warps); break;
+                case 4: dispatch_wpl<4>(WPL, nca, p, warps); break;
+                case 8: dispatch_wpl<8>(WPL, nca, p, warps); break;
+                default: fprintf(stderr, "bad P\n"); exit(2);
+                }
+            });
+        for (auto &t : ths) t.join();
     }
     if (err) {
         printf("FAIL watchdog err=%d\n", err);
         return 1;
     }
     std::vector<uint8_t> got(n, 0xEE);
-    L.cells = got.data();
-    emu_launch(2, 64, [&]() { ca3d_unpack_kernel(L); });
+    unsigned long long pop = 0;
+    for (int r = 0; r < ranks; r++) {
+        Rank &k = rk[r];
+        const int Zl = k.geo.local_planes();
+        if (!Zl) continue;
+        std::vector<uint8_t> out(k.cells.size(), 0xEE);
+        k.pop = 0;
+        Bp3Layout L = { out.data(), k.rows.data(), W, H, Zl, P, RWP, &k.pop };
+        emu_launch(2, 64, [&]() { ca3d_unpack_kernel(L); });
+        pop += k.pop;
+        for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
+            int jb = k.geo.global_block(lb);
+            memcpy(got.data() + (size_t)k.geo.block_z0(jb) * W * H, out.data() + (size_t)k.geo.local_z0(lb) * W * H,
+                   (size_t)k.geo.block_len(jb) * W * H);
+        }
+    }
 
     size_t diff = 0, first = n;
     for (size_t i = 0; i < n; i++)
@@ -181,6 +249,6 @@ int main(int argc, char **argv)
                first < n ? want[first] : -1, pop, (long long)want_pop);
         return 1;
     }
-    printf("OK W=%d H=%d Z=%d G=%d nca=%d P=%d WPL=%d pop=%llu\n", W, H, Z, G, nca, P, WPL, pop);
+    printf("OK W=%d H=%d Z=%d G=%d nca=%d P=%d WPL=%d ranks=%d B=%d pop=%llu\n", W, H, Z, G, nca, P, WPL, ranks, blockB, pop);
     return 0;
 }

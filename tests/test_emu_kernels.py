@@ -53,3 +53,28 @@ def test_ca3d_many_generations_few_and_many_workers(emu_bin):
     _run(exe, 24, 12, 10, 12, 10, 8, 1, 1, 3, 12)
     _run(exe, 24, 12, 10, 9, 10, 3, 1, 1, 5, 1)          # a single worker: pure claim order
     _run(exe, 24, 12, 10, 9, 7, 3, 1, 0, 5, 2)
+
+
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows
+    (45, 40, 12, 4, 7, 3, 1, 1, 3, 3, 1, 0, 8, 1),       # skewed row segments, counter raised every row
+    (45, 40, 12, 4, 7, 3, 1, 1, 3, 3, 1, 0, 8, 3),
+    (64, 33, 6, 9, 10, 4, 2, 1, 9, 7, 1, 0, 4, 5),
+    (31, 20, 5, 3, 8, 3, 1, 2, 3, 3, 1, 0, 3, 1),
+])
+def test_ca3d_row_segments(emu_bin, args):
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
+@pytest.mark.parametrize("args", [
+    (45, 7, 12, 4, 7, 3, 1, 1, 3, 3, 2, 0, 0, 2),        # 2 emulated GPUs, contiguous slabs
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 5, 2, 2, 5, 2),       # 2 GPUs, z-blocks of 2 planes, segments of 5 rows
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 3, 3, 2, 16, 4),      # 3 GPUs, ragged last block
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 2, 4, 1, 7, 2),      # 4 GPUs, single-plane blocks (every plane is an edge)
+    (33, 64, 9, 6, 0, 3, 1, 0, 4, 2, 4, 5, 32, 2),       # more ranks than blocks need
+    (20, 5, 3, 4, 7, 3, 1, 1, 4, 2, 4, 1, 1, 1),         # ranks without any plane
+])
+def test_ca3d_slab_decomposition_peer_ghost_planes(emu_bin, args):
+    """The multi-GPU path: ranks run concurrently, edge planes push their H rows into the neighbour's ghost
+    planes and raise its counters, exactly as the peer stores over NVLink do on the real machine."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
