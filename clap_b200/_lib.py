@@ -58,6 +58,18 @@ SIGNATURES = {
     "clapca_grid_run2d": (c_int, [c_void_p, c_int64, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, c_int]),
     "clapca_grid_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "clapca_grid_last_stats": (c_int, [c_void_p, POINTER(RunStats)]),
+    "clapca_slab_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_uint]),
+    "clapca_slab_destroy": (c_int, [c_void_p]),
+    "clapca_slab_local_planes": (c_int, [c_void_p, POINTER(c_int)]),
+    "clapca_slab_plane_map": (c_int, [c_void_p, POINTER(c_int64)]),
+    "clapca_slab_device_ptr": (c_void_p, [c_void_p]),
+    "clapca_slab_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "clapca_slab_connect": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "clapca_slab_upload": (c_int, [c_void_p, c_void_p]),
+    "clapca_slab_download": (c_int, [c_void_p, c_void_p]),
+    "clapca_slab_prepare": (c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_int]),
+    "clapca_slab_run": (c_int, [c_void_p, POINTER(c_int64)]),
+    "clapca_slab_last_stats": (c_int, [c_void_p, POINTER(RunStats)]),
     "clapca_noise_bake_device": (c_int, [c_void_p, c_size_t, c_int, c_float, c_float, c_float, c_uint32,
                                          POINTER(c_float)]),
     "clapca_terrain_heightmap_device": (c_int, [c_void_p, c_void_p, c_long, c_uint, c_float, c_void_p, c_uint,

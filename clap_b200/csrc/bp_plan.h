@@ -201,6 +201,27 @@ inline void bp3_make_items(const std::vector<Bp3Plane> &planes, int Zg, int H, i
             }
 }
 
+/*
+ * Alternative claim order: whole-plane sweeps (one item per (z,g)) sorted by the time key 2 z + 4 g.
+ * Items with equal key are mutually independent and their producers sit 50..100 tickets earlier,
+ * so claimed items rarely stall on each other; the price is that consecutive generations of a plane
+ * run far apart and the volume streams through HBM once per generation.
+ */
+inline void bp3_make_items_timekey(const std::vector<Bp3Plane> &planes, int H, int G, std::vector<WorkItem> &items)
+{
+    std::vector<std::pair<long long, WorkItem>> tmp;
+    tmp.reserve(planes.size() * (size_t)G);
+    for (int g = 0; g < G; g++)
+        for (size_t l = 0; l < planes.size(); l++)
+            tmp.push_back({ (2LL * planes[l].zglobal + 4LL * g) * 65536 + g, WorkItem{ (int)l, g, 0, H } });
+    std::sort(tmp.begin(), tmp.end(),
+              [](const std::pair<long long, WorkItem> &a, const std::pair<long long, WorkItem> &b) {
+                  return a.first < b.first;
+              });
+    items.clear();
+    for (auto &t : tmp) items.push_back(t.second);
+}
+
 /* segment length: long enough that a band offers ~2x more independent items than there are workers */
 inline int bp3_segment_rows(int Zg, int H, int G, int workers)
 {

@@ -52,6 +52,7 @@ struct Bp3Params {
     int *prog;              /* [G][Z] rows completed by local sweep (z,g) */
     const int4 *order;      /* work items in claim order: (local z, g, first row, end row) */
     int nsweeps;            /* number of work items */
+    int no_fence;           /* experiments only: skip the release fence (NOT a valid configuration) */
     int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
     unsigned *ticket;       /* next sweep to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
@@ -420,7 +421,7 @@ struct Sweep3 {
                 if (raise)
                     dp_syncwarp();
                 if (raise && lane == 0) {
-                    if (push) dp_fence_sys(); else dp_fence_release();
+                    if (push) dp_fence_sys(); else if (!p.no_fence) dp_fence_release();
                     dp_st_flag(myprog, y + 1);
                     if (pl.push_dn_flag) dp_st_flag_sys(pl.push_dn_flag + (size_t)g * pl.push_dn_gstride, y + 1);
                     if (pl.push_up_flag) dp_st_flag_sys(pl.push_up_flag + (size_t)g * pl.push_up_gstride, y + 1);

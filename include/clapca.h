@@ -166,6 +166,41 @@ typedef struct clapca_run_stats {
 } clapca_run_stats;
 int clapca_grid_last_stats(clapca_grid *g, clapca_run_stats *st);
 
+/* ---- multi-GPU: z-block slabs of one ca3d volume, one process per GPU ------------------ */
+
+/*
+ * The d2_global planes of the volume are cut into blocks of `block_planes` planes, block j lives on
+ * rank j % nranks (contiguous slabs: block_planes = ceil(d2_global / nranks)).  The in-place sweep
+ * order of ca3d_run() (core/ca3d.c:129-140) makes plane z of generation g depend on plane z-1 of
+ * generation g and plane z+1 of generation g-1, so neighbouring ranks exchange one H-row per plane
+ * row and generation.  That exchange is fused into the sweep kernel: edge planes store their rows
+ * straight into the neighbour GPU's ghost plane over NVLink (CUDA IPC peer mapping) and raise its
+ * progress counter; there is no separate halo kernel and no host round trip per generation.
+ *
+ * Call order on every rank: create -> ipc_handle -> (exchange handles) -> connect -> upload ->
+ * prepare -> (barrier across ranks) -> run -> download.  `max_value` must be the largest cell value
+ * over ALL ranks (it fixes the number of state planes), `max_generations` bounds `steps`.
+ */
+typedef struct clapca_slab clapca_slab;
+
+int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_global, int rank, int nranks,
+                       int block_planes, int max_generations, unsigned max_value);
+int clapca_slab_destroy(clapca_slab *s);
+/* number of planes this rank owns, and the global z of each of them (local storage order) */
+int clapca_slab_local_planes(clapca_slab *s, int *n);
+int clapca_slab_plane_map(clapca_slab *s, int64_t *zglobal);
+/* device pointer of the local planes (uint8, d0*d1 bytes per plane, local order) */
+void *clapca_slab_device_ptr(clapca_slab *s);
+/* 64-byte CUDA IPC handle of this rank's halo region; connect() maps the two neighbours' regions */
+int clapca_slab_ipc_handle(clapca_slab *s, void *handle64);
+int clapca_slab_connect(clapca_slab *s, const void *handle_next_rank, const void *handle_prev_rank);
+/* local planes from/to host or device memory, local order */
+int clapca_slab_upload(clapca_slab *s, const uint8_t *src);
+int clapca_slab_download(clapca_slab *s, uint8_t *dst);
+int clapca_slab_prepare(clapca_slab *s, uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states, int steps);
+int clapca_slab_run(clapca_slab *s, int64_t *local_population);
+int clapca_slab_last_stats(clapca_slab *s, clapca_run_stats *st);
+
 /* device-resident field evaluation for benchmarks: results stay in device memory */
 int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
                              float period_units, uint32_t seed, float *kernel_ms);
