@@ -10,24 +10,31 @@ namespace clapca {
 
 /*
  * Where one plane of this device's slab gets its neighbours from and whom it
- * feeds.  Built on the host (bp_plan.h).  On a single GPU every source is the
- * adjacent local plane; in a multi-GPU slab decomposition the plane below the
- * first / above the last plane of a z-block is a "ghost" plane that the
- * neighbouring GPU fills over NVLink (peer stores), and the block's edge
- * planes push their freshly computed H rows into the neighbour's ghost plane.
+ * feeds.  Built on the host (bp_plan.h).
  *
- * Row r of a source lives at rows + r * stride (words): H0 at +0, H1 at +RWP.
- * The progress counter of a source for generation g lives at flag[g * gstride].
+ * Local sources.  Row r of a neighbouring local plane lives at rows + r * stride
+ * (words): H0 at +0, H1 at +RWP; its progress counter for generation g at
+ * flag[g * gstride].
+ *
+ * Ghost sources (multi-GPU).  The plane below the first / above the last plane
+ * of a z-block belongs to the neighbouring GPU, which stores the H rows of its
+ * edge plane straight into a "ghost plane" in this GPU's memory (peer stores
+ * over NVLink).  Ghost rows carry no counters and need no fences: every 32-bit
+ * data word travels in one aligned 8-byte store together with a tag
+ *         tag = epoch << 16 | (generation + 1)        (0 = the seed state)
+ * so a consumer that reads {word, tag} atomically knows which version it got
+ * and simply re-reads until the expected tag shows up (the LL protocol of
+ * collective libraries).  A lane's 2*WPL words of a ghost row are the pairs
+ * {H0[0..WPL), H1[0..WPL)} at ghost + r * stride + lane * 4 * WPL.
  */
 struct Bp3Plane {
     const uint32_t *dn_rows, *up_rows;      /* NULL: outside the volume (reads 0) */
-    const int *dn_flag, *up_flag;           /* NULL with rows != NULL never happens */
+    const int *dn_flag, *up_flag;           /* NULL for ghost (tagged) sources */
     uint32_t *push_dn_rows, *push_up_rows;  /* peer ghost planes fed by this plane (NULL: none) */
-    int *push_dn_flag, *push_up_flag;
     uint32_t dn_stride, up_stride, dn_gstride, up_gstride;
-    uint32_t push_dn_stride, push_up_stride, push_dn_gstride, push_up_gstride;
-    uint32_t remote_mask;                   /* bit 0: dn_flag is written by a peer GPU, bit 1: up_flag */
-    int zglobal;                            /* global z of this plane (diagnostics) */
+    uint32_t push_dn_stride, push_up_stride;
+    uint32_t ghost_mask;                    /* bit 0: dn is a ghost plane, bit 1: up is a ghost plane */
+    int zglobal;                            /* global z of this plane */
 };
 
 } // namespace clapca

@@ -62,29 +62,28 @@ struct SlabGeom {
     }
 };
 
-/* size (in 32-bit words) of one ghost plane: H rows of [H0 | H1] */
-inline size_t slab_ghost_plane_words(int H, int RWP) { return (size_t)H * 2 * RWP; }
+/* size (in 32-bit words) of one ghost plane: H rows of {word, tag} pairs for [H0 | H1] */
+inline size_t slab_ghost_plane_words(int H, int RWP) { return (size_t)H * 4 * RWP; }
 
 /*
  * Layout of a rank's halo region (one device allocation, exported to the two
- * neighbouring ranks): ghost planes below / above each local block, then the
- * progress counters the neighbours store into.  Offsets in 32-bit words.
+ * neighbouring ranks): the ghost planes below / above each local block.
+ * Offsets in 32-bit words.
  */
 struct HaloLayout {
-    size_t ghost_dn, ghost_up, flag_dn, flag_up, total_words;
+    size_t ghost_dn, ghost_up, total_words;
     int nlb_max;
 };
 
-inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP, int Gcap)
+inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP)
 {
     HaloLayout h;
     h.nlb_max = geo.blocks_per_rank_max();
     size_t gp = slab_ghost_plane_words(H, RWP);
     h.ghost_dn = 0;
     h.ghost_up = h.ghost_dn + gp * h.nlb_max;
-    h.flag_dn = h.ghost_up + gp * h.nlb_max;
-    h.flag_up = h.flag_dn + (size_t)Gcap * h.nlb_max;
-    h.total_words = h.flag_up + (size_t)Gcap * h.nlb_max;
+    h.total_words = h.ghost_up + gp * h.nlb_max;
+    if (h.total_words == 0) h.total_words = 4;
     return h;
 }
 
@@ -122,16 +121,12 @@ inline void bp3_build_planes(const SlabGeom &geo, const SlabPtrs &ptr, const Hal
                 p.dn_gstride = (uint32_t)Zl;
             } else if (j > 0) {
                 p.dn_rows = ptr.halo + hl.ghost_dn + gp * lb;
-                p.dn_stride = 2u * RWP;
-                p.dn_flag = (const int *)(ptr.halo + hl.flag_dn) + lb;
-                p.dn_gstride = (uint32_t)hl.nlb_max;
-                p.remote_mask |= 1u;
+                p.dn_stride = 4u * RWP;
+                p.ghost_mask |= 1u;
                 /* ... and this plane feeds the ghost plane ABOVE the previous block */
                 const int lbp = (j - 1) / geo.R;
                 p.push_dn_rows = ptr.halo_prev + hl.ghost_up + gp * lbp;
-                p.push_dn_stride = 2u * RWP;
-                p.push_dn_flag = (int *)(ptr.halo_prev + hl.flag_up) + lbp;
-                p.push_dn_gstride = (uint32_t)hl.nlb_max;
+                p.push_dn_stride = 4u * RWP;
             }
             if (i + 1 < len) {
                 p.up_rows = ptr.rows + (size_t)(l + 1) * planew;
@@ -140,16 +135,12 @@ inline void bp3_build_planes(const SlabGeom &geo, const SlabPtrs &ptr, const Hal
                 p.up_gstride = (uint32_t)Zl;
             } else if (j + 1 < nb) {
                 p.up_rows = ptr.halo + hl.ghost_up + gp * lb;
-                p.up_stride = 2u * RWP;
-                p.up_flag = (const int *)(ptr.halo + hl.flag_up) + lb;
-                p.up_gstride = (uint32_t)hl.nlb_max;
-                p.remote_mask |= 2u;
+                p.up_stride = 4u * RWP;
+                p.ghost_mask |= 2u;
                 /* ... and this plane feeds the ghost plane BELOW the next block */
                 const int lbn = (j + 1) / geo.R;
                 p.push_up_rows = ptr.halo_next + hl.ghost_dn + gp * lbn;
-                p.push_up_stride = 2u * RWP;
-                p.push_up_flag = (int *)(ptr.halo_next + hl.flag_dn) + lbn;
-                p.push_up_gstride = (uint32_t)hl.nlb_max;
+                p.push_up_stride = 4u * RWP;
             }
         }
     }

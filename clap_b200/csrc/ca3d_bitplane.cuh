@@ -52,6 +52,7 @@ struct Bp3Params {
     int *prog;              /* [G][Z] rows completed by local sweep (z,g) */
     const int4 *order;      /* work items in claim order: (local z, g, first row, end row) */
     int nsweeps;            /* number of work items */
+    uint32_t epoch;         /* run number, upper half of the ghost-row tags */
     int no_fence;           /* experiments only: skip the release fence (NOT a valid configuration) */
     int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
     unsigned *ticket;       /* next sweep to claim */
@@ -166,7 +167,6 @@ struct Sweep3 {
     struct Flags {          /* cached progress of the three producers of a sweep */
         const int *dn, *up, *own, *self;
         int vdn, vup, vown, vself;
-        uint32_t remote;    /* bit 0 / 1: dn / up counter is stored by a peer GPU (system scope) */
     };
 
     /*
@@ -183,9 +183,7 @@ struct Sweep3 {
             /* lanes 0..3 poll one counter each; the values are made warp-uniform by shuffle */
             const int lane = dp_lane();
             const int *src = lane == 0 ? f.dn : (lane == 1 ? f.up : (lane == 2 ? f.own : (lane == 3 ? f.self : nullptr)));
-            uint32_t v = 0x7fffffffu;
-            if (src)
-                v = (uint32_t)(((f.remote >> lane) & 1u) ? dp_ld_flag_sys(src) : dp_ld_flag(src));
+            uint32_t v = src ? (uint32_t)dp_ld_flag(src) : 0x7fffffffu;
             f.vdn   = (int)dp_shfl(v, 0);
             f.vup   = (int)dp_shfl(v, 1);
             f.vown  = (int)dp_shfl(v, 2);
@@ -203,7 +201,7 @@ struct Sweep3 {
             }
         }
         /* acquire: the polling lanes fence after their relaxed load, the warp barrier extends it to all lanes */
-        if (f.remote) dp_fence_sys(); else dp_fence_acquire();
+        dp_fence_acquire();
         dp_syncwarp();
         return true;
     }
@@ -229,17 +227,68 @@ struct Sweep3 {
             LaneVec<WPL>::ld(rec + (2 + q) * RWP + lane * WPL, s[q]);
     }
 
-    /* rows r of the three sources of a sweep: H of dn/up/own-old and S of own-old */
-    CA_MDEV void load_row(const Bp3Params &p, const Bp3Plane &pl, int z, int r, int lane, RowIn &in,
+    /*
+     * Ghost rows (see bp3_types.h): {word, tag} pairs written by the neighbouring GPU.  Re-read until every
+     * pair of this lane -- and of the whole warp -- carries the expected tag.  false = watchdog / abort.
+     */
+    CA_MDEV bool load_h_tagged(const Bp3Params &p, const uint32_t *row, int lane, uint32_t expect, uint32_t h[2][WPL])
+    {
+        const uint32_t *src = row + (size_t)lane * 4 * WPL;
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) {             /* pairs 2i, 2i+1 of this lane */
+                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + i);
+                const int q0 = 2 * i, q1 = 2 * i + 1;   /* pair index -> (plane, word) = (q / WPL, q % WPL) */
+                h[q0 / WPL][q0 % WPL] = v.x;
+                h[q1 / WPL][q1 % WPL] = v.z;
+                ok = ok && v.y == expect && v.w == expect;
+            }
+            if (dp_all(ok))
+                return true;
+            if (spins == 0) t0 = dp_clock();
+            dp_nanosleep(100);
+            if ((spins & 63u) == 63u) {
+                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
+                if (!dp_all(!bad)) {
+                    if (dp_lane() == 0)
+                        dp_atomic_max(p.err, 2);
+                    return false;
+                }
+            }
+        }
+    }
+
+    CA_MDEV void store_h_tagged(uint32_t *row, int lane, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
+    {
+        uint32_t *dst = row + (size_t)lane * 4 * WPL;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            const int q0 = 2 * i, q1 = 2 * i + 1;
+            const uint32_t a = (q0 / WPL) ? h1[q0 % WPL] : h0[q0 % WPL];
+            const uint32_t b = (q1 / WPL) ? h1[q1 % WPL] : h0[q1 % WPL];
+            dp_st_cg(reinterpret_cast<uint4 *>(dst) + i, make_uint4(a, tag, b, tag));
+        }
+    }
+
+    /* rows r of the three sources of a sweep: H of dn/up/own-old and S of own-old.  false = aborted */
+    CA_MDEV bool load_row(const Bp3Params &p, const Bp3Plane &pl, int z, int g, int r, int lane, RowIn &in,
                           uint32_t so[P][WPL])
     {
         const size_t recw = (size_t)NP * p.RWP;
         if (r < p.H) {
             const uint32_t *own = p.rows + ((size_t)z * p.H + r) * recw;
-            if (pl.dn_rows) load_h(pl.dn_rows + (size_t)r * pl.dn_stride, p.RWP, lane, in.hd); else zero_h(in.hd);
-            if (pl.up_rows) load_h(pl.up_rows + (size_t)r * pl.up_stride, p.RWP, lane, in.hu); else zero_h(in.hu);
             load_h(own, p.RWP, lane, in.ho);
             load_s(own, p.RWP, lane, so);
+            if (!pl.dn_rows) zero_h(in.hd);
+            else if (!(pl.ghost_mask & 1u)) load_h(pl.dn_rows + (size_t)r * pl.dn_stride, p.RWP, lane, in.hd);
+            else if (!load_h_tagged(p, pl.dn_rows + (size_t)r * pl.dn_stride, lane,
+                                    (p.epoch << 16) | (uint32_t)(g + 1), in.hd)) return false;
+            if (!pl.up_rows) zero_h(in.hu);
+            else if (!(pl.ghost_mask & 2u)) load_h(pl.up_rows + (size_t)r * pl.up_stride, p.RWP, lane, in.hu);
+            else if (!load_h_tagged(p, pl.up_rows + (size_t)r * pl.up_stride, lane,
+                                    (p.epoch << 16) | (uint32_t)g, in.hu)) return false;
         } else {
             zero_h(in.hd); zero_h(in.hu); zero_h(in.ho);
 #pragma unroll
@@ -247,6 +296,7 @@ struct Sweep3 {
 #pragma unroll
                 for (int j = 0; j < WPL; j++) so[q][j] = 0u;
         }
+        return true;
     }
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
@@ -260,15 +310,15 @@ struct Sweep3 {
         int *myprog = p.prog + (size_t)g * Z + z;
 
         Flags f;
-        f.dn  = pl.dn_rows ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
-        f.up  = (g > 0 && pl.up_rows) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
+        /* ghost sources are synchronised by their row tags, not by counters */
+        f.dn  = (pl.dn_rows && !(pl.ghost_mask & 1u)) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
+        f.up  = (g > 0 && pl.up_rows && !(pl.ghost_mask & 2u)) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
         f.own = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
         f.vdn  = f.dn  ? 0 : 0x7fffffff;
         f.vup  = f.up  ? 0 : 0x7fffffff;
         f.vown = f.own ? 0 : 0x7fffffff;
         f.self = y0 > 0 ? myprog : nullptr;         /* rows < y0 belong to earlier segments of this sweep */
         f.vself = f.self ? 0 : 0x7fffffff;
-        f.remote = pl.remote_mask;
 
         uint32_t vmask[WPL];
 #pragma unroll
@@ -285,7 +335,7 @@ struct Sweep3 {
             /* (re)build the sliding windows: rows y0-1, y0 and y0+1 of the sources */
             RowIn r0;
             if (y0 > 0) {
-                load_row(p, pl, z, y0 - 1, lane, r0, so);
+                if (!load_row(p, pl, z, g, y0 - 1, lane, r0, so)) return false;
 #pragma unroll
                 for (int b = 0; b < 2; b++)
 #pragma unroll
@@ -296,12 +346,12 @@ struct Sweep3 {
             } else {
                 zero_h(hdA); zero_h(huA); zero_h(hn);
             }
-            load_row(p, pl, z, y0, lane, r0, so);
+            if (!load_row(p, pl, z, g, y0, lane, r0, so)) return false;
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
                 for (int j = 0; j < WPL; j++) { hdB[b][j] = r0.hd[b][j]; huB[b][j] = r0.hu[b][j]; }
-            load_row(p, pl, z, y0 + 1, lane, in, so1);
+            if (!load_row(p, pl, z, g, y0 + 1, lane, in, so1)) return false;
         }
 
         for (int y = y0; y < y1; y++) {
@@ -346,7 +396,7 @@ struct Sweep3 {
                 int need = y + 3 < H ? y + 3 : H;
                 if (!wait_rows(p, f, need, 0))
                     return false;
-                load_row(p, pl, z, y + 2, lane, in, so2);
+                if (!load_row(p, pl, z, g, y + 2, lane, in, so2)) return false;
             }
 
             /* ---- rule tables, in-row scan ---- */
@@ -399,32 +449,26 @@ struct Sweep3 {
 #pragma unroll
                 for (int q = 0; q < P; q++)
                     LaneVec<WPL>::st(rec + (2 + q) * p.RWP + lane * WPL, so[q]);
-                /* a z-block's edge plane also feeds the neighbouring GPU's ghost plane (peer stores over NVLink) */
-                const bool push = pl.push_dn_rows || pl.push_up_rows;
-                if (pl.push_dn_rows) {
-                    uint32_t *dst = pl.push_dn_rows + (size_t)y * pl.push_dn_stride;
-                    LaneVec<WPL>::st(dst + 0 * p.RWP + lane * WPL, hn[0]);
-                    LaneVec<WPL>::st(dst + 1 * p.RWP + lane * WPL, hn[1]);
-                }
-                if (pl.push_up_rows) {
-                    uint32_t *dst = pl.push_up_rows + (size_t)y * pl.push_up_stride;
-                    LaneVec<WPL>::st(dst + 0 * p.RWP + lane * WPL, hn[0]);
-                    LaneVec<WPL>::st(dst + 1 * p.RWP + lane * WPL, hn[1]);
-                }
                 /*
-                 * release: warp barrier (orders every lane's row stores before lane 0),
-                 * then ONE cumulative fence and the relaxed counter store(s) -- the same
-                 * shape as cooperative-groups' grid barrier arrive.  System scope when a
-                 * peer GPU is among the consumers.
+                 * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
+                 * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).
+                 */
+                const uint32_t tag = (p.epoch << 16) | (uint32_t)(g + 1);
+                if (pl.push_dn_rows)
+                    store_h_tagged(pl.push_dn_rows + (size_t)y * pl.push_dn_stride, lane, tag, hn[0], hn[1]);
+                if (pl.push_up_rows)
+                    store_h_tagged(pl.push_up_rows + (size_t)y * pl.push_up_stride, lane, tag, hn[0], hn[1]);
+                /*
+                 * Local consumers: warp barrier (orders every lane's row stores before lane 0), then ONE
+                 * cumulative gpu-scope fence and the relaxed counter store -- the same shape as
+                 * cooperative-groups' grid barrier arrive.  Counters are raised every flag_rows rows.
                  */
                 const bool raise = (y + 1 == y1) || ((y + 1) % p.flag_rows) == 0;
                 if (raise)
                     dp_syncwarp();
                 if (raise && lane == 0) {
-                    if (push) dp_fence_sys(); else if (!p.no_fence) dp_fence_release();
+                    if (!p.no_fence) dp_fence_release();
                     dp_st_flag(myprog, y + 1);
-                    if (pl.push_dn_flag) dp_st_flag_sys(pl.push_dn_flag + (size_t)g * pl.push_dn_gstride, y + 1);
-                    if (pl.push_up_flag) dp_st_flag_sys(pl.push_up_flag + (size_t)g * pl.push_up_gstride, y + 1);
                 }
             }
 

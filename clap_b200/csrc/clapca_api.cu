@@ -336,8 +336,6 @@ static int ensure_bytes(void **ptr, size_t *have, size_t want)
 
 /* progress counters are raised every kFlagRows rows: one fence per kFlagRows row steps */
 static const int kFlagRows = 8;
-/* sharded runs keep cross-GPU lag short: the neighbour waits on these counters over NVLink */
-static const int kFlagRowsSharded = 2;
 
 /* generations fused per launch: bounds the progress-counter table, not the result */
 static const int kMaxFusedGenerations = 4096;
@@ -395,7 +393,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         {
             SlabGeom geo = { Z, 1, 0, Z };
             SlabPtrs ptr = { g->rows, g->prog, nullptr, nullptr, nullptr };
-            HaloLayout hl = slab_halo_layout(geo, H, RWP, 1);
+            HaloLayout hl = slab_halo_layout(geo, H, RWP);
             bp3_build_planes(geo, ptr, hl, H, RWP, NP, planes);
         }
         if (g->planes_rows != g->rows || g->planes_prog != g->prog || g->planes_NP != NP || g->planes_RWP != RWP ||
@@ -627,6 +625,7 @@ struct clapca_slab {
     uint32_t surv = 0, born = 0, nr_states = 0;
     int G = 0, rule = BP3_RULE_DYN;
     bool prepared = false;
+    uint32_t epoch = 0;             /* run number: upper half of the ghost-row tags */
     clapca_run_stats stats;
 };
 
@@ -649,7 +648,7 @@ int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_glo
     s->WPL = WPL; s->RWP = 32 * WPL; s->NP = s->P + 2;
     s->Gcap = max_generations;
     s->Zl = s->geo.local_planes();
-    s->hl = slab_halo_layout(s->geo, s->H, s->RWP, s->Gcap);
+    s->hl = slab_halo_layout(s->geo, s->H, s->RWP);
     s->stream = g_ctx.stream;
     memset(&s->stats, 0, sizeof(s->stats));
     const size_t zl = s->Zl ? s->Zl : 1;
@@ -782,6 +781,8 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     if (born && (bornval >> s->P))
         return fail(CLAPCA_ERR_ARG, "slab_prepare: rule needs more than the %d state planes of this slab", s->P);
     s->surv = surv; s->born = born; s->nr_states = nr_states; s->G = steps;
+    s->epoch = (s->epoch + 1) & 0xffffu;        /* every rank prepares the same number of times */
+    if (!s->epoch) s->epoch = 1;
     s->rule = BP3_RULE_DYN;
     for (int i = 0; i < 9; i++)
         if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { s->rule = i; break; }
@@ -805,18 +806,17 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
         Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };
         ca3d_pack_kernel<<<grid_blocks_for((size_t)s->Zl * s->H * s->RWP, 256, 16), 256, 0, s->stream>>>(L);
         CU(cudaGetLastError());
-        /* halo seed: H rows (the first two plane-rows of every row record) of each block's first plane */
+        /* halo seed: H rows of each block's first plane -> ghost plane above the previous block, tag = seed state */
         for (size_t l = 0; l < s->h_planes.size(); l++) {
             const Bp3Plane &pl = s->h_planes[l];
             if (!pl.push_dn_rows) continue;
-            CU(cudaMemcpy2DAsync(pl.push_dn_rows, (size_t)pl.push_dn_stride * 4,
-                                 s->rows + l * (size_t)s->H * s->NP * s->RWP, (size_t)s->NP * s->RWP * 4,
-                                 (size_t)2 * s->RWP * 4, s->H, cudaMemcpyDefault, s->stream));
+            halo_seed_kernel<<<grid_blocks_for((size_t)s->H * 2 * s->RWP, 256, 4), 256, 0, s->stream>>>(
+                pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->WPL,
+                s->epoch << 16);
+            CU(cudaGetLastError());
         }
     }
-    /* counters: local table and the two tables the neighbours store into */
     CU(cudaMemsetAsync(s->prog, 0, (size_t)s->Gcap * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
-    CU(cudaMemsetAsync(s->halo + s->hl.flag_dn, 0, (s->hl.total_words - s->hl.flag_dn) * sizeof(uint32_t), s->stream));
     CU(cudaMemsetAsync(s->ticket, 0, 2 * sizeof(unsigned), s->stream));
     CU(cudaEventRecord(s->ev[1], s->stream));
     CU(cudaStreamSynchronize(s->stream));
@@ -845,7 +845,8 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.prog = s->prog;
         p.order = s->order;
         p.nsweeps = s->n_items;
-        p.flag_rows = s->geo.R > 1 ? kFlagRowsSharded : kFlagRows;
+        p.flag_rows = kFlagRows;
+        p.epoch = s->epoch;
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
         p.ticket = s->ticket;
         p.err = (int *)(s->ticket + 1);

@@ -155,7 +155,7 @@ int main(int argc, char **argv)
     for (int r = 0; r < ranks; r++) {
         Rank &k = rk[r];
         k.geo = SlabGeom{ Z, ranks, r, blockB > 0 ? blockB : (Z + ranks - 1) / ranks };
-        k.hl = slab_halo_layout(k.geo, H, RWP, Gcap);
+        k.hl = slab_halo_layout(k.geo, H, RWP);
         const int Zl = k.geo.local_planes();
         k.cells.resize((size_t)W * H * (Zl ? Zl : 1));
         for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
@@ -195,14 +195,17 @@ int main(int argc, char **argv)
         k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
     }
     /* halo init: the first plane of every block but the first seeds the ghost plane above the previous block */
-    for (int r = 0; r < ranks; r++)
+    const uint32_t epoch = 7;
+    for (int r = 0; r < ranks; r++) {
+        rk[r].p.epoch = epoch;
         for (size_t l = 0; l < rk[r].planes.size(); l++) {
             const Bp3Plane &pl = rk[r].planes[l];
             if (!pl.push_dn_rows) continue;
-            for (int y = 0; y < H; y++)
-                memcpy(pl.push_dn_rows + (size_t)y * pl.push_dn_stride,
-                       rk[r].rows.data() + ((size_t)l * H + y) * NP * RWP, sizeof(uint32_t) * 2 * RWP);
+            const uint32_t *src = rk[r].rows.data() + (size_t)l * H * NP * RWP;
+            uint32_t *dst = pl.push_dn_rows;
+            emu_launch(1, 64, [&]() { halo_seed_kernel(dst, src, H, RWP, NP, WPL, epoch << 16); });
         }
+    }
     if (G > 0) {
         std::vector<std::thread> ths;
         for (int r = 0; r < ranks; r++)
