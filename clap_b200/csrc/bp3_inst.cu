@@ -2,6 +2,7 @@
  * bp3_inst.cu -- instantiates ca3d_sweep_kernel for ONE rule (-DBP3_RULE=0..9)
  * and all (P, WPL) variants, and provides its cooperative launcher.
  */
+#include <stdlib.h>
 #include "bp3_launch.h"
 
 #ifndef BP3_RULE
@@ -41,7 +42,9 @@ template <int P, int WPL>
 static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, Bp3LaunchInfo *info)
 {
     auto kern = ca3d_sweep_kernel<P, WPL, TheRule>;
-    const int threads = 256;
+    /* small CTAs: co-residency is bounded by registers, 128-thread granularity wastes the least of the file */
+    int threads = 128;
+    if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) threads = v; }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
     if (e != cudaSuccess) return e;

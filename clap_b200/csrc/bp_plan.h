@@ -213,6 +213,41 @@ inline void bp3_make_items_timekey(const std::vector<Bp3Plane> &planes, int H, i
     for (auto &t : tmp) items.push_back(t.second);
 }
 
+/*
+ * Generation-batched diagonal order (whole-plane sweeps): the G generations are cut into batches of Gb;
+ * inside a batch items are claimed along anti-diagonals d = z + (g - g0), generation ascending.  This
+ * extends the dependency order -- (z-1,g) lies on the previous diagonal, (z+1,g-1) just before (z,g) on the
+ * same one, earlier batches come first -- and it puts (z,g+1) only Gb tickets after (z,g): consecutive
+ * generations of a plane chase each other a few rows apart, so a row written by generation g is still in
+ * L2 when generation g+1 reads and overwrites it.  HBM then sees one read and one write of the volume per
+ * BATCH instead of per generation.  (In time-key order every key holds one item per generation, G tickets
+ * separate (z,g) from (z,g+1), and with ~2400 resident warps that is ~40 rows x 2400 rows of other traffic:
+ * far more than L2.)  Small Gb = short reuse distance but fewer independent chains per diagonal.
+ */
+inline void bp3_make_items_batched(const std::vector<Bp3Plane> &planes, int Zg, int H, int G, int Gb,
+                                   std::vector<WorkItem> &items)
+{
+    items.clear();
+    if (G <= 0 || planes.empty())
+        return;
+    if (Gb < 1) Gb = 1;
+    std::vector<int> local_of(Zg, -1);
+    for (size_t l = 0; l < planes.size(); l++)
+        local_of[planes[l].zglobal] = (int)l;
+    /* equal-sized batches: ceil(G / Gb) of them */
+    const int nb = (G + Gb - 1) / Gb;
+    for (int b = 0; b < nb; b++) {
+        const int g0 = (int)((long long)G * b / nb), g1 = (int)((long long)G * (b + 1) / nb);
+        const int n = g1 - g0;
+        for (int d = 0; d <= (Zg - 1) + (n - 1); d++)
+            for (int k = std::max(0, d - (Zg - 1)); k <= std::min(n - 1, d); k++) {
+                const int l = local_of[d - k];
+                if (l >= 0)
+                    items.push_back(WorkItem{ l, g0 + k, 0, H });
+            }
+    }
+}
+
 /* segment length: long enough that a band offers ~2x more independent items than there are workers */
 inline int bp3_segment_rows(int Zg, int H, int G, int workers)
 {

@@ -53,7 +53,6 @@ struct Bp3Params {
     const int4 *order;      /* work items in claim order: (local z, g, first row, end row) */
     int nsweeps;            /* number of work items */
     uint32_t epoch;         /* run number, upper half of the ghost-row tags */
-    int no_fence;           /* experiments only: skip the release fence (NOT a valid configuration) */
     int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
     unsigned *ticket;       /* next sweep to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
@@ -160,38 +159,57 @@ CA_DEV uint32_t bp_valid_mask(int w, int W)
 
 /* ---- the persistent sweep kernel -------------------------------------------- */
 
+/*
+ * Register budget and instruction count decide the speed of this kernel (ncu, round 1: it is issue-bound,
+ * not HBM-bound), so the row loop is written for a short instruction stream:
+ *   - all sliding windows live in register arrays whose slot is (row - y0) % 3 and the loop body is
+ *     instantiated three times (step<0>, step<1>, step<2>): no register rotation moves;
+ *   - every source is walked with a running, lane-adjusted pointer (one 64-bit add per row, plane offsets
+ *     are compile-time immediates because the record stride NP * 32 * WPL is a template constant);
+ *   - the producers' counters are cached as ONE number (`have` = min over the producers); the fast path of
+ *     a dependency check is one compare, the slow path polls with ld.acquire in lanes 0..2 and reduces
+ *     with redux.min;
+ *   - counters are published with st.release every flag_rows rows.
+ */
 template <int P, int WPL, class Rule>
 struct Sweep3 {
     static constexpr int NP = P + 2;
+    static constexpr int RWP = 32 * WPL;            /* words per plane-row */
+    static constexpr int RECW = NP * RWP;           /* words per row record */
+    static constexpr int GHW = 4 * RWP;             /* words per ghost row ({word, tag} pairs of H0|H1) */
+    enum { SRC_NONE = 0, SRC_LOCAL = 1, SRC_GHOST = 2 };
 
-    struct Flags {          /* cached progress of the three producers of a sweep */
-        const int *dn, *up, *own, *self;
-        int vdn, vup, vown, vself;
+    struct St {
+        /* slot of row r = (r - y0 + 3) % 3 */
+        uint32_t hd[3][2][WPL], hu[3][2][WPL];      /* H rows of the plane below (new) / above (old) */
+        uint32_t so[3][P][WPL];                     /* own state rows y, y+1, y+2 */
+        uint32_t ho[2][WPL];                        /* H of own old row y+1 */
+        uint32_t hn[2][WPL];                        /* H of own new row y-1 */
+        uint32_t vmask[WPL];
+        const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load */
+        uint32_t *rec;                              /* lane-adjusted own record of the current row */
+        uint32_t *push_dn, *push_up;                /* lane-adjusted peer ghost rows of the current row */
+        const int *flagp;                           /* the producer counter this lane polls (lanes 0..2) */
+        int have;                                   /* min over the producers' published row counts */
+        int next_raise;                             /* next row count at which the own counter is raised */
+        int dn_mode, up_mode;
+        uint32_t tag_dn, tag_up, tag_out;
     };
 
-    /*
-     * Wait until the three producers have completed `need` rows and this sweep's own
-     * earlier segments `need_self` rows; false = watchdog fired / abort requested.
-     */
-    CA_MDEV bool wait_rows(const Bp3Params &p, Flags &f, int need, int need_self)
+    /* false = watchdog fired / abort requested */
+    CA_MDEV bool wait_rows(const Bp3Params &p, St &st, int need)
     {
-        if (f.vdn >= need && f.vup >= need && f.vown >= need && f.vself >= need_self)
+        if (st.have >= need)
             return true;
-        long long t0 = dp_clock();
-        unsigned spins = 0;
-        for (;;) {
-            /* lanes 0..3 poll one counter each; the values are made warp-uniform by shuffle */
-            const int lane = dp_lane();
-            const int *src = lane == 0 ? f.dn : (lane == 1 ? f.up : (lane == 2 ? f.own : (lane == 3 ? f.self : nullptr)));
-            uint32_t v = src ? (uint32_t)dp_ld_flag(src) : 0x7fffffffu;
-            f.vdn   = (int)dp_shfl(v, 0);
-            f.vup   = (int)dp_shfl(v, 1);
-            f.vown  = (int)dp_shfl(v, 2);
-            f.vself = (int)dp_shfl(v, 3);
-            if (f.vdn >= need && f.vup >= need && f.vown >= need && f.vself >= need_self)
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            int v = st.flagp ? dp_ld_acquire(st.flagp) : 0x7fffffff;
+            st.have = dp_reduce_min(v);
+            if (st.have >= need)
                 break;
-            dp_nanosleep(40);
-            if ((++spins & 63u) == 0u) {
+            if (spins == 0) t0 = dp_clock();
+            dp_nanosleep(32);
+            if ((spins & 127u) == 127u) {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
@@ -200,40 +218,22 @@ struct Sweep3 {
                 }
             }
         }
-        /* acquire: the polling lanes fence after their relaxed load, the warp barrier extends it to all lanes */
-        dp_fence_acquire();
-        dp_syncwarp();
+        dp_syncwarp();          /* the polling lanes acquired; the warp barrier extends it to every lane */
         return true;
     }
 
-    struct RowIn {          /* what one row step pulls from memory for row r */
-        uint32_t hd[2][WPL], hu[2][WPL], ho[2][WPL];
-    };
-
-    CA_MDEV void load_h(const uint32_t *rec, int RWP, int lane, uint32_t h[2][WPL])
-    {
-        LaneVec<WPL>::ld(rec + 0 * RWP + lane * WPL, h[0]);
-        LaneVec<WPL>::ld(rec + 1 * RWP + lane * WPL, h[1]);
-    }
-    CA_MDEV void zero_h(uint32_t h[2][WPL])
+    CA_MDEV void zero2(uint32_t h[2][WPL])
     {
 #pragma unroll
         for (int j = 0; j < WPL; j++) h[0][j] = h[1][j] = 0u;
-    }
-    CA_MDEV void load_s(const uint32_t *rec, int RWP, int lane, uint32_t s[P][WPL])
-    {
-#pragma unroll
-        for (int q = 0; q < P; q++)
-            LaneVec<WPL>::ld(rec + (2 + q) * RWP + lane * WPL, s[q]);
     }
 
     /*
      * Ghost rows (see bp3_types.h): {word, tag} pairs written by the neighbouring GPU.  Re-read until every
      * pair of this lane -- and of the whole warp -- carries the expected tag.  false = watchdog / abort.
      */
-    CA_MDEV bool load_h_tagged(const Bp3Params &p, const uint32_t *row, int lane, uint32_t expect, uint32_t h[2][WPL])
+    CA_MDEV bool load_h_tagged(const Bp3Params &p, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL])
     {
-        const uint32_t *src = row + (size_t)lane * 4 * WPL;
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
             bool ok = true;
@@ -260,9 +260,8 @@ struct Sweep3 {
         }
     }
 
-    CA_MDEV void store_h_tagged(uint32_t *row, int lane, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
+    CA_MDEV void store_h_tagged(uint32_t *dst, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
     {
-        uint32_t *dst = row + (size_t)lane * 4 * WPL;
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
             const int q0 = 2 * i, q1 = 2 * i + 1;
@@ -272,29 +271,171 @@ struct Sweep3 {
         }
     }
 
-    /* rows r of the three sources of a sweep: H of dn/up/own-old and S of own-old.  false = aborted */
-    CA_MDEV bool load_row(const Bp3Params &p, const Bp3Plane &pl, int z, int g, int r, int lane, RowIn &in,
-                          uint32_t so[P][WPL])
+    /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
+    CA_MDEV bool load_side(const Bp3Params &p, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
     {
-        const size_t recw = (size_t)NP * p.RWP;
-        if (r < p.H) {
-            const uint32_t *own = p.rows + ((size_t)z * p.H + r) * recw;
-            load_h(own, p.RWP, lane, in.ho);
-            load_s(own, p.RWP, lane, so);
-            if (!pl.dn_rows) zero_h(in.hd);
-            else if (!(pl.ghost_mask & 1u)) load_h(pl.dn_rows + (size_t)r * pl.dn_stride, p.RWP, lane, in.hd);
-            else if (!load_h_tagged(p, pl.dn_rows + (size_t)r * pl.dn_stride, lane,
-                                    (p.epoch << 16) | (uint32_t)(g + 1), in.hd)) return false;
-            if (!pl.up_rows) zero_h(in.hu);
-            else if (!(pl.ghost_mask & 2u)) load_h(pl.up_rows + (size_t)r * pl.up_stride, p.RWP, lane, in.hu);
-            else if (!load_h_tagged(p, pl.up_rows + (size_t)r * pl.up_stride, lane,
-                                    (p.epoch << 16) | (uint32_t)g, in.hu)) return false;
+        if (mode == SRC_LOCAL) {
+            LaneVec<WPL>::ld(src, h[0]);
+            LaneVec<WPL>::ld(src + RWP, h[1]);
+            src += RECW;
+        } else if (mode == SRC_NONE) {
+            zero2(h);
         } else {
-            zero_h(in.hd); zero_h(in.hu); zero_h(in.ho);
+            if (!load_h_tagged(p, src, tag, h)) return false;
+            src += GHW;
+        }
+        return true;
+    }
+
+    /* own record at st.rec + D rows: state planes, and optionally the H planes */
+    template <int D>
+    CA_MDEV void load_own_s(const St &st, uint32_t s[P][WPL])
+    {
 #pragma unroll
-            for (int q = 0; q < P; q++)
+        for (int q = 0; q < P; q++)
+            LaneVec<WPL>::ld(st.rec + D * RECW + (2 + q) * RWP, s[q]);
+    }
+    template <int D>
+    CA_MDEV void load_own_h(const St &st, uint32_t h[2][WPL])
+    {
+        LaneVec<WPL>::ld(st.rec + D * RECW, h[0]);
+        LaneVec<WPL>::ld(st.rec + D * RECW + RWP, h[1]);
+    }
+    CA_MDEV void zero_s(uint32_t s[P][WPL])
+    {
 #pragma unroll
-                for (int j = 0; j < WPL; j++) so[q][j] = 0u;
+        for (int q = 0; q < P; q++)
+#pragma unroll
+            for (int j = 0; j < WPL; j++) s[q][j] = 0u;
+    }
+
+    /*
+     * One row step.  M = (y - y0) % 3 selects the register slots: rows y-1 / y / y+1 of the side planes
+     * sit in slots (M+2)%3 / M / (M+1)%3, own state rows y / y+1 in slots M / (M+1)%3; row y+2 is
+     * prefetched into slot (M+2)%3 once row y-1 has been consumed.
+     */
+    template <int M>
+    CA_MDEV bool step(const Bp3Params &p, St &st, int y, int y1, int *myprog)
+    {
+        constexpr int A = (M + 2) % 3, B = M, C = (M + 1) % 3;
+        const int lane = dp_lane();
+        const int H = p.H;
+        const uint32_t bornval = Rule::bornval(p);
+        uint32_t k[WPL][5], ao[WPL], ge2[WPL];
+
+        /* ---- neighbour count K (everything but the in-row predecessor) ---- */
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            uint32_t a = st.so[B][0][j], hi = 0u;
+#pragma unroll
+            for (int q = 1; q < P; q++) hi |= st.so[B][q][j];
+            ao[j] = a | hi;
+            ge2[j] = hi;
+        }
+        uint32_t nxt = dp_shfl_down(ao[0], 1);
+        if (lane == 31) nxt = 0u;
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            uint32_t a_[2] = { st.hd[A][0][j], st.hd[A][1][j] }, b_[2] = { st.hd[B][0][j], st.hd[B][1][j] };
+            uint32_t c_[2] = { st.hd[C][0][j], st.hd[C][1][j] };
+            uint32_t vd[4], vu[4];
+            bs_add3x2(a_, b_, c_, vd);
+            uint32_t e_[2] = { st.hu[A][0][j], st.hu[A][1][j] }, f_[2] = { st.hu[B][0][j], st.hu[B][1][j] };
+            uint32_t g_[2] = { st.hu[C][0][j], st.hu[C][1][j] };
+            bs_add3x2(e_, f_, g_, vu);
+            uint32_t n_[2] = { st.hn[0][j], st.hn[1][j] }, o_[2] = { st.ho[0][j], st.ho[1][j] };
+            uint32_t right = (j + 1 < WPL) ? ao[j + 1] : nxt;
+            uint32_t r = dp_funnel_r(ao[j], right, 1);      /* old alive bit of x+1 */
+            bs_count3d(vd, vu, n_, o_, r, k[j]);
+        }
+
+        /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
+        if (y + 2 <= y1) {          /* row y1 is still needed (as "row y+1" of the last step), y1+1 is not */
+            if (y + 2 < H) {
+                if (!wait_rows(p, st, y + 3 < H ? y + 3 : H))
+                    return false;
+                load_own_h<2>(st, st.ho);
+                load_own_s<2>(st, st.so[A]);
+                if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
+                if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
+            } else {
+                zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
+                zero_s(st.so[A]);
+            }
+        }
+
+        /* ---- rule tables, in-row scan ---- */
+        uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], D[WPL], Cc[WPL];
+        uint32_t dl = 1u, cl = 0u;          /* lane map: identity so far */
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            Rule::eval(p, k[j], s0[j], s1[j], b0[j], b1[j]);
+            /* new alive bit if the predecessor's new alive bit is 0 / 1 */
+            uint32_t f0 = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & st.vmask[j];
+            uint32_t f1 = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & st.vmask[j];
+            D[j] = f0 ^ f1;
+            Cc[j] = f0;
+            bs_scan_word(D[j], Cc[j]);
+            /* compose into the lane map: carry-out = c ^ (d & carry-in) */
+            uint32_t d = D[j] >> 31, c = Cc[j] >> 31;
+            cl = c ^ (d & cl);
+            dl = d & dl;
+        }
+        uint32_t cin = bs_scan_warp(dl, cl, 0u);
+
+        /* ---- apply: new alive bits, state planes ---- */
+        uint32_t an[WPL];
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            uint32_t cm = 0u - cin;
+            an[j] = Cc[j] ^ (D[j] & cm);
+            uint32_t pred = (an[j] << 1) | cin;              /* new alive bit of x-1 */
+            cin = an[j] >> 31;
+            uint32_t sv = bs_mux(pred, s1[j], s0[j]);
+            uint32_t bn = bs_mux(pred, b1[j], b0[j]);
+            uint32_t dec = ao[j] & ~sv;                      /* alive, not surviving: state - 1 */
+            uint32_t brn = ~ao[j] & bn & st.vmask[j];        /* dead, born: state = nr_states - 1 */
+            uint32_t borrow = dec;
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                uint32_t t = st.so[B][q][j];
+                st.so[B][q][j] = t ^ borrow;
+                borrow &= ~t;
+                if ((bornval >> q) & 1u) st.so[B][q][j] |= brn;
+            }
+        }
+        bp_hsum<WPL>(an, st.hn[0], st.hn[1]);
+
+        /* ---- publish row y ---- */
+        LaneVec<WPL>::st(st.rec, st.hn[0]);
+        LaneVec<WPL>::st(st.rec + RWP, st.hn[1]);
+#pragma unroll
+        for (int q = 0; q < P; q++)
+            LaneVec<WPL>::st(st.rec + (2 + q) * RWP, st.so[B][q]);
+        st.rec += RECW;
+        /*
+         * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
+         * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).
+         */
+        if (st.push_dn) {
+            store_h_tagged(st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
+            st.push_dn += GHW;
+        }
+        if (st.push_up) {
+            store_h_tagged(st.push_up, st.tag_out, st.hn[0], st.hn[1]);
+            st.push_up += GHW;
+        }
+        /*
+         * Local consumers: warp barrier (orders every lane's row stores before lane 0), then ONE
+         * release store of the counter (MEMBAR.GPU + store).  Raised every flag_rows rows.
+         */
+        const bool at_mark = (y + 1 == st.next_raise);
+        if (at_mark)
+            st.next_raise += p.flag_rows;
+        if (at_mark || y + 1 == y1) {
+            dp_syncwarp();
+            if (lane == 0)
+                dp_st_release(myprog, y + 1);
         }
         return true;
     }
@@ -305,178 +446,92 @@ struct Sweep3 {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
         const Bp3Plane pl = p.planes[z];
-        const uint32_t bornval = Rule::bornval(p);
-        const size_t recw = (size_t)NP * p.RWP;
         int *myprog = p.prog + (size_t)g * Z + z;
+        St st;
 
-        Flags f;
-        /* ghost sources are synchronised by their row tags, not by counters */
-        f.dn  = (pl.dn_rows && !(pl.ghost_mask & 1u)) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
-        f.up  = (g > 0 && pl.up_rows && !(pl.ghost_mask & 2u)) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
-        f.own = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
-        f.vdn  = f.dn  ? 0 : 0x7fffffff;
-        f.vup  = f.up  ? 0 : 0x7fffffff;
-        f.vown = f.own ? 0 : 0x7fffffff;
-        f.self = y0 > 0 ? myprog : nullptr;         /* rows < y0 belong to earlier segments of this sweep */
-        f.vself = f.self ? 0 : 0x7fffffff;
+        /* ---- sources ---- */
+        const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
+        st.dn_mode = !pl.dn_rows ? SRC_NONE : ((pl.ghost_mask & 1u) ? SRC_GHOST : SRC_LOCAL);
+        st.up_mode = !pl.up_rows ? SRC_NONE : ((pl.ghost_mask & 2u) ? SRC_GHOST : SRC_LOCAL);
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 * WPL : WPL)
+                           : nullptr;
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 * WPL : WPL)
+                           : nullptr;
+        st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
+        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
+        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
+        st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
+        st.tag_up = (p.epoch << 16) | (uint32_t)g;          /* plane above: still generation g-1 */
+        st.tag_out = (p.epoch << 16) | (uint32_t)(g + 1);
 
-        uint32_t vmask[WPL];
-#pragma unroll
-        for (int j = 0; j < WPL; j++) vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
-
-        /* sliding windows (see file header) */
-        uint32_t hdA[2][WPL], hdB[2][WPL], huA[2][WPL], huB[2][WPL], hn[2][WPL];
-        uint32_t so[P][WPL], so1[P][WPL], so2[P][WPL];
-        RowIn in;
-
-        if (!wait_rows(p, f, y0 + 2 < H ? y0 + 2 : H, y0))
-            return false;
+        /* ---- producers (ghost sources are synchronised by their row tags, not by counters) ---- */
         {
-            /* (re)build the sliding windows: rows y0-1, y0 and y0+1 of the sources */
-            RowIn r0;
-            if (y0 > 0) {
-                if (!load_row(p, pl, z, g, y0 - 1, lane, r0, so)) return false;
-#pragma unroll
-                for (int b = 0; b < 2; b++)
-#pragma unroll
-                    for (int j = 0; j < WPL; j++) {
-                        hdA[b][j] = r0.hd[b][j]; huA[b][j] = r0.hu[b][j];
-                        hn[b][j] = r0.ho[b][j];     /* row y0-1 of this plane is already generation g */
-                    }
-            } else {
-                zero_h(hdA); zero_h(huA); zero_h(hn);
-            }
-            if (!load_row(p, pl, z, g, y0, lane, r0, so)) return false;
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int j = 0; j < WPL; j++) { hdB[b][j] = r0.hd[b][j]; huB[b][j] = r0.hu[b][j]; }
-            if (!load_row(p, pl, z, g, y0 + 1, lane, in, so1)) return false;
+            const int *fdn = st.dn_mode == SRC_LOCAL ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
+            const int *fup = (g > 0 && st.up_mode == SRC_LOCAL) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
+            const int *fown = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
+            st.flagp = lane == 0 ? fdn : (lane == 1 ? fup : (lane == 2 ? fown : nullptr));
+            st.have = (fdn || fup || fown) ? 0 : 0x7fffffff;
         }
+        st.next_raise = (y0 / p.flag_rows + 1) * p.flag_rows;
+#pragma unroll
+        for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
 
-        for (int y = y0; y < y1; y++) {
-            uint32_t k[WPL][5], ao[WPL], ge2[WPL];
-
-            /* ---- neighbour count K (everything but the in-row predecessor) ---- */
-#pragma unroll
-            for (int j = 0; j < WPL; j++) {
-                uint32_t a = so[0][j], hi = 0u;
-#pragma unroll
-                for (int q = 1; q < P; q++) hi |= so[q][j];
-                ao[j] = a | hi;
-                ge2[j] = hi;
-            }
-            uint32_t nxt = dp_shfl_down(ao[0], 1);
-            if (lane == 31) nxt = 0u;
-#pragma unroll
-            for (int j = 0; j < WPL; j++) {
-                uint32_t a_[2] = { hdA[0][j], hdA[1][j] }, b_[2] = { hdB[0][j], hdB[1][j] };
-                uint32_t c_[2] = { in.hd[0][j], in.hd[1][j] };
-                uint32_t vd[4], vu[4];
-                bs_add3x2(a_, b_, c_, vd);
-                uint32_t e_[2] = { huA[0][j], huA[1][j] }, f_[2] = { huB[0][j], huB[1][j] };
-                uint32_t g_[2] = { in.hu[0][j], in.hu[1][j] };
-                bs_add3x2(e_, f_, g_, vu);
-                uint32_t n_[2] = { hn[0][j], hn[1][j] }, o_[2] = { in.ho[0][j], in.ho[1][j] };
-                uint32_t right = (j + 1 < WPL) ? ao[j + 1] : nxt;
-                uint32_t r = dp_funnel_r(ao[j], right, 1);      /* old alive bit of x+1 */
-                bs_count3d(vd, vu, n_, o_, r, k[j]);
-            }
-            /* rotate the H windows: `in` is free from here on */
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    hdA[b][j] = hdB[b][j]; hdB[b][j] = in.hd[b][j];
-                    huA[b][j] = huB[b][j]; huB[b][j] = in.hu[b][j];
-                }
-
-            /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
-            if (y + 2 <= y1) {          /* row y1 is still needed (as "row y+1" of the last step), y1+1 is not */
-                int need = y + 3 < H ? y + 3 : H;
-                if (!wait_rows(p, f, need, 0))
-                    return false;
-                if (!load_row(p, pl, z, g, y + 2, lane, in, so2)) return false;
-            }
-
-            /* ---- rule tables, in-row scan ---- */
-            uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], D[WPL], C[WPL];
-            uint32_t dl = 1u, cl = 0u;          /* lane map: identity so far */
-#pragma unroll
-            for (int j = 0; j < WPL; j++) {
-                Rule::eval(p, k[j], s0[j], s1[j], b0[j], b1[j]);
-                /* new alive bit if the predecessor's new alive bit is 0 / 1 */
-                uint32_t f0 = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & vmask[j];
-                uint32_t f1 = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & vmask[j];
-                D[j] = f0 ^ f1;
-                C[j] = f0;
-                bs_scan_word(D[j], C[j]);
-                /* compose into the lane map: carry-out = c ^ (d & carry-in) */
-                uint32_t d = D[j] >> 31, c = C[j] >> 31;
-                cl = c ^ (d & cl);
-                dl = d & dl;
-            }
-            uint32_t cin = bs_scan_warp(dl, cl, 0u);
-
-            /* ---- apply: new alive bits, state planes ---- */
-            uint32_t an[WPL];
-#pragma unroll
-            for (int j = 0; j < WPL; j++) {
-                uint32_t cm = 0u - cin;
-                an[j] = C[j] ^ (D[j] & cm);
-                uint32_t pred = (an[j] << 1) | cin;              /* new alive bit of x-1 */
-                cin = an[j] >> 31;
-                uint32_t sv = bs_mux(pred, s1[j], s0[j]);
-                uint32_t bn = bs_mux(pred, b1[j], b0[j]);
-                uint32_t dec = ao[j] & ~sv;                      /* alive, not surviving: state - 1 */
-                uint32_t brn = ~ao[j] & bn & vmask[j];           /* dead, born: state = nr_states - 1 */
-                uint32_t borrow = dec;
-#pragma unroll
-                for (int q = 0; q < P; q++) {
-                    uint32_t t = so[q][j];
-                    so[q][j] = t ^ borrow;
-                    borrow &= ~t;
-                    if ((bornval >> q) & 1u) so[q][j] |= brn;
+        /* rows < y0 of this sweep belong to earlier segments (skewed-segment order only) */
+        if (y0 > 0) {
+            long long t0 = dp_clock();
+            for (unsigned spins = 1;; spins++) {
+                int v = dp_reduce_min(lane == 0 ? dp_ld_acquire(myprog) : 0x7fffffff);
+                if (v >= y0)
+                    break;
+                dp_nanosleep(32);
+                if ((spins & 127u) == 0u) {
+                    bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
+                    if (!dp_all(!bad)) {
+                        if (lane == 0)
+                            dp_atomic_max(p.err, 1);
+                        return false;
+                    }
                 }
             }
-            bp_hsum<WPL>(an, hn[0], hn[1]);
+            dp_syncwarp();
+        }
+        if (!wait_rows(p, st, y0 + 2 < H ? y0 + 2 : H))
+            return false;
 
-            /* ---- publish row y ---- */
-            {
-                uint32_t *rec = p.rows + ((size_t)z * H + y) * recw;
-                LaneVec<WPL>::st(rec + 0 * p.RWP + lane * WPL, hn[0]);
-                LaneVec<WPL>::st(rec + 1 * p.RWP + lane * WPL, hn[1]);
-#pragma unroll
-                for (int q = 0; q < P; q++)
-                    LaneVec<WPL>::st(rec + (2 + q) * p.RWP + lane * WPL, so[q]);
-                /*
-                 * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
-                 * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).
-                 */
-                const uint32_t tag = (p.epoch << 16) | (uint32_t)(g + 1);
-                if (pl.push_dn_rows)
-                    store_h_tagged(pl.push_dn_rows + (size_t)y * pl.push_dn_stride, lane, tag, hn[0], hn[1]);
-                if (pl.push_up_rows)
-                    store_h_tagged(pl.push_up_rows + (size_t)y * pl.push_up_stride, lane, tag, hn[0], hn[1]);
-                /*
-                 * Local consumers: warp barrier (orders every lane's row stores before lane 0), then ONE
-                 * cumulative gpu-scope fence and the relaxed counter store -- the same shape as
-                 * cooperative-groups' grid barrier arrive.  Counters are raised every flag_rows rows.
-                 */
-                const bool raise = (y + 1 == y1) || ((y + 1) % p.flag_rows) == 0;
-                if (raise)
-                    dp_syncwarp();
-                if (raise && lane == 0) {
-                    if (!p.no_fence) dp_fence_release();
-                    dp_st_flag(myprog, y + 1);
-                }
-            }
+        /* ---- fill the windows: rows y0-1 (slot 2), y0 (slot 0), y0+1 (slot 1) ---- */
+        if (y0 > 0) {
+            if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
+            if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
+            load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
+        } else {
+            zero2(st.hd[2]); zero2(st.hu[2]); zero2(st.hn);
+        }
+        if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
+        if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
+        load_own_s<0>(st, st.so[0]);
+        if (y0 + 1 < H) {
+            if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
+            if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
+            load_own_h<1>(st, st.ho);
+            load_own_s<1>(st, st.so[1]);
+        } else {
+            zero2(st.hd[1]); zero2(st.hu[1]); zero2(st.ho);
+            zero_s(st.so[1]);
+        }
+        zero_s(st.so[2]);
 
-            /* ---- rotate the state pipeline ---- */
-#pragma unroll
-            for (int q = 0; q < P; q++)
-#pragma unroll
-                for (int j = 0; j < WPL; j++) { so[q][j] = so1[q][j]; so1[q][j] = so2[q][j]; }
+        int y = y0;
+        for (; y + 3 <= y1; y += 3) {
+            if (!step<0>(p, st, y, y1, myprog)) return false;
+            if (!step<1>(p, st, y + 1, y1, myprog)) return false;
+            if (!step<2>(p, st, y + 2, y1, myprog)) return false;
+        }
+        if (y < y1) {
+            if (!step<0>(p, st, y, y1, myprog)) return false;
+            y++;
+        }
+        if (y < y1) {
+            if (!step<1>(p, st, y, y1, myprog)) return false;
         }
         return true;
     }

@@ -340,6 +340,38 @@ static const int kFlagRows = 8;
 /* generations fused per launch: bounds the progress-counter table, not the result */
 static const int kMaxFusedGenerations = 4096;
 
+/* work-item claim order of the bit-plane sweep (see bp_plan.h) */
+struct OrderCfg {
+    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals */
+    int seg_rows;       /* mode 1 */
+    int gen_batch;      /* mode 2 */
+    int key() const { return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : 0)); }
+};
+
+static const int kGenBatch = 16;
+
+static OrderCfg order_config(int Z, int H, int G, int max_workers)
+{
+    OrderCfg oc = { 0, 0, kGenBatch };
+    if (const char *e = getenv("CLAPCA_ORDER")) { int v = atoi(e); if (v >= 0 && v <= 2) oc.mode = v; }
+    if (oc.mode == 1) {
+        oc.seg_rows = bp3_segment_rows(Z, H, G, max_workers);
+        if (const char *e = getenv("CLAPCA_SEG_ROWS")) { int v = atoi(e); if (v > 0) oc.seg_rows = std::min(v, H); }
+    }
+    if (oc.mode == 2) {
+        if (const char *e = getenv("CLAPCA_GEN_BATCH")) { int v = atoi(e); if (v > 0) oc.gen_batch = v; }
+    }
+    return oc;
+}
+
+static void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
+                       std::vector<WorkItem> &items)
+{
+    if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
+    else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
+    else bp3_make_items_timekey(planes, H, G, items);
+}
+
 static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps,
                           int64_t *population)
 {
@@ -409,25 +441,17 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
             CU(cudaStreamSynchronize(g->stream));
             g->planes_rows = g->rows; g->planes_prog = g->prog; g->planes_NP = NP; g->planes_RWP = RWP;
         }
-        const int max_workers = bp3_max_workers(rule, P, WPL, g_ctx.sms);
-        int L = bp3_segment_rows(Z, H, G, max_workers);
-        if (const char *e = getenv("CLAPCA_SEG_ROWS")) { int v = atoi(e); if (v > 0) L = std::min(v, H); }
-        {
-            const char *om = getenv("CLAPCA_ORDER");
-            if (!(om && atoi(om) == 1)) L = 0;
-        }
-        if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != L) {
+        /*
+         * Claim order (bp_plan.h).  Default: time-key order.  Measured on B200 at 2048^3 x 50
+         * (profiles/r01_knobs_order_ca3d_2048.txt): the generation-batched diagonals (CLAPCA_ORDER=2) cut DRAM
+         * traffic from 493 GB to 127-221 GB per run but not the run time (122 ms either way at batch 16, slower
+         * for smaller batches and for smaller volumes) -- the kernel is bound by the ALU pipe (LOP3), not by HBM.
+         * CLAPCA_ORDER=1 selects the skewed row segments; CLAPCA_GEN_BATCH / CLAPCA_SEG_ROWS tune them.
+         */
+        const OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms));
+        if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != oc.key()) {
             std::vector<WorkItem> items;
-            /*
-             * Measured on B200 (profiles/r01_knobs_ca3d_2048.txt): whole-plane sweeps in time-key order run
-             * 2048^3 x 50 in 143 ms, the L2-resident skewed-segment order in 173 ms -- the looser coupling
-             * between claimed items beats the HBM traffic it costs.  CLAPCA_ORDER=1 selects the segments.
-             */
-            const char *om = getenv("CLAPCA_ORDER");
-            if (om && atoi(om) == 1)
-                bp3_make_items(planes, Z, H, G, L, items);
-            else
-                bp3_make_items_timekey(planes, H, G, items);
+            make_items(oc, planes, Z, H, G, items);
             static_assert(sizeof(WorkItem) == sizeof(int4), "WorkItem must alias int4");
             void *p = g->order;
             if (int rc = ensure_bytes(&p, &g->order_bytes, items.size() * sizeof(int4))) { g->order = nullptr; return rc; }
@@ -436,7 +460,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
                                g->stream));
             CU(cudaStreamSynchronize(g->stream));       /* `items` is a stack vector */
             g->n_items = (int)items.size();
-            g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = L;
+            g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = oc.key();
         }
         CU(cudaMemsetAsync(g->prog, 0, (size_t)G * Z * sizeof(int), g->stream));
         CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
@@ -451,7 +475,6 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.nsweeps = g->n_items;
         p.flag_rows = kFlagRows;
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
-        if (const char *e = getenv("CLAPCA_NOFENCE")) p.no_fence = atoi(e);      /* tuning experiments only */
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.surv = surv; p.born = born; p.bornval = bornval;
@@ -789,7 +812,8 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
 
     if (s->order_G != steps) {
         std::vector<WorkItem> items;
-        bp3_make_items_timekey(s->h_planes, s->H, steps, items);
+        const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms));
+        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items);
         void *p = s->order;
         if (int rc = ensure_bytes(&p, &s->order_bytes, (items.size() ? items.size() : 1) * sizeof(int4))) {
             s->order = nullptr;

@@ -61,6 +61,18 @@ CA_DEV void dp_st_flag(int *p, int v)
 {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+/* acquire load / release store (gpu scope): LDG.STRONG + CCTL, MEMBAR.GPU + STG -- no separate fence */
+CA_DEV int dp_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+CA_DEV void dp_st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+CA_DEV int dp_reduce_min(int v)                   { return __reduce_min_sync(CA_FULL, v); }
 CA_DEV int dp_ld_flag_sys(const int *p)
 {
     int v;
@@ -160,6 +172,16 @@ CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { *p = v; }
 
 CA_DEV int  dp_ld_flag(const int *p)              { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV void dp_st_flag(int *p, int v)             { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV int  dp_ld_acquire(const int *p)           { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV void dp_st_release(int *p, int v)          { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV int  dp_reduce_min(int v)
+{
+    for (int o = 16; o; o >>= 1) {
+        int w = (int)emu_exchange((uint32_t)v, emu_lane() ^ o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
 CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV void dp_fence_sys()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }

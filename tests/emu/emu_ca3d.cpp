@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch]]]]]]
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
  *            10   = run-time rule with random masks
  *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
@@ -95,6 +95,7 @@ int main(int argc, char **argv)
     int blockB = argc > 12 ? atoi(argv[12]) : 0;     /* planes per z-block, 0 = contiguous slabs */
     int segL = argc > 13 ? atoi(argv[13]) : 0;       /* rows per work item, 0 = planner default */
     int flagRows = argc > 14 ? atoi(argv[14]) : 2;   /* rows per progress-counter update */
+    int genBatch = argc > 15 ? atoi(argv[15]) : 0;   /* > 0: generation-batched diagonal order, -1: time-key order */
 
     unsigned surv, born, nr;
     if (nca <= 9) {
@@ -174,7 +175,12 @@ int main(int argc, char **argv)
                          rk[(r + ranks - 1) % ranks].halo.data() };
         bp3_build_planes(k.geo, ptr, k.hl, H, RWP, NP, k.planes);
         std::vector<WorkItem> items;
-        bp3_make_items(k.planes, Z, H, G, segL > 0 ? segL : bp3_segment_rows(Z, H, G, warps), items);
+        if (genBatch > 0)
+            bp3_make_items_batched(k.planes, Z, H, G, genBatch, items);
+        else if (genBatch < 0)
+            bp3_make_items_timekey(k.planes, H, G, items);
+        else
+            bp3_make_items(k.planes, Z, H, G, segL > 0 ? segL : bp3_segment_rows(Z, H, G, warps), items);
         k.order.resize(items.size());
         for (size_t i = 0; i < items.size(); i++) k.order[i] = make_int4(items[i].z, items[i].g, items[i].y0, items[i].y1);
         if (Zl) {

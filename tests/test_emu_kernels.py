@@ -78,3 +78,16 @@ def test_ca3d_slab_decomposition_peer_ghost_planes(emu_bin, args):
     """The multi-GPU path: ranks run concurrently, edge planes push their H rows into the neighbour's ghost
     planes and raise its counters, exactly as the peer stores over NVLink do on the real machine."""
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch
+    (45, 20, 12, 7, 7, 3, 1, 1, 3, 5, 1, 0, 0, 2, 3),        # batches of 3,2,2 generations, diagonal order
+    (45, 20, 12, 7, 7, 3, 1, 1, 3, 1, 1, 0, 0, 4, 2),        # a single worker: the order alone must be executable
+    (64, 16, 9, 10, 10, 4, 2, 1, 9, 9, 1, 0, 0, 3, 4),
+    (33, 24, 10, 9, 0, 3, 1, 0, 4, 4, 3, 2, 0, 2, 4),        # 3 ranks, z-blocks of 2 planes
+    (33, 24, 10, 6, 8, 3, 1, 2, 4, 3, 2, 0, 0, 2, 50),       # batch larger than G == plain diagonal order
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1),       # time-key order
+])
+def test_ca3d_generation_batched_diagonal_order(emu_bin, args):
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
