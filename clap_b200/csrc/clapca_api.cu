@@ -15,6 +15,8 @@
 
 #include "../../include/clapca.h"
 #include "bp3_launch.h"
+#include "bp2_launch.h"
+#include "ca2d_layout.cuh"
 #include "ca3d_layout.cuh"
 #include "ca_wavefront.cuh"
 #include "field_kernels.cuh"
@@ -565,6 +567,113 @@ int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3], uint32_t surv, uint32_t 
 
 /* ---- ca2d ------------------------------------------------------------------- */
 
+/* rows are cut into at most 16 warps x 32 lanes x 4 words: 65536 cells (32768 with 8 state planes) */
+static bool bp2_supported(const clapca_grid *g, int64_t side, int decay, int neigh)
+{
+    if (side < g->d0 || side < g->d1)
+        return false;                       /* partial sweeps: cell-wavefront engine */
+    if ((neigh == CLAPCA_NEIGH_VNV || neigh == CLAPCA_NEIGH_MV) && decay)
+        return false;                       /* value-comparing counts that matter: cell-wavefront engine */
+    int wpl, warps;
+    return g->d0 < (1 << 30) && bp2_shape_for(g->d1, 3, &wpl, &warps);
+}
+
+static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh,
+                          int steps)
+{
+    const int W = (int)g->d0, H = (int)g->d1;       /* x extent = engine rows, y extent = cells per row */
+    const uint32_t nrval = nr_states & 0xffu;
+    const bool moore = (neigh == CLAPCA_NEIGH_M1 || neigh == CLAPCA_NEIGH_MV);
+
+    unsigned maxv = 0;
+    CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+    max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&maxv, g_ctx.d_max, sizeof(maxv), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (born && nrval > maxv) maxv = nrval;
+    const int P = bp2_planes_for(maxv);
+    int WPL = 0, warps = 0;
+    if (!bp2_shape_for(H, P, &WPL, &warps))
+        return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: rows of %d cells with %d state planes are too wide", H, P);
+    if (const char *e = getenv("CLAPCA_2D_WPL")) {          /* tuning: words per lane (more = fewer warps per row) */
+        int v = atoi(e);
+        const long long rw = (H + 31) / 32, nw = (rw + 32 * v - 1) / (32 * v);
+        if ((v == 1 || v == 2 || v == 4) && nw <= 16 && !(P >= 8 && v == 4)) { WPL = v; warps = (int)(nw < 1 ? 1 : nw); }
+    }
+    const int RWS = warps * 32 * WPL;
+
+    const size_t rows_bytes = (size_t)W * P * RWS * sizeof(uint32_t);
+    {
+        void *p = g->rows;
+        if (int rc = ensure_bytes(&p, &g->rows_bytes, rows_bytes)) { g->rows = nullptr; return rc; }
+        g->rows = (uint32_t *)p;
+    }
+    unsigned long long *d_pop = g_ctx.d_count;
+    Bp2Layout L = { g->cells, g->rows, W, H, P, RWS, d_pop };
+    const size_t tiles = (size_t)((W + 127) / 128) * ((H + 31) / 32);
+
+    CU(cudaEventRecord(g->ev[0], g->stream));
+    CU(cudaMemsetAsync(g->rows, 0, rows_bytes, g->stream));         /* padding words stay zero */
+    ca2d_pack_kernel<<<grid_blocks_for(tiles * 32, 256, 8), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[1], g->stream));
+
+    int launches = 0, ctas = 0;
+    for (int done = 0; done < steps;) {
+        const int G = std::min(steps - done, 1 << 20);
+        {
+            size_t have = g->prog_count * sizeof(int);
+            void *p = g->prog;
+            if (int rc = ensure_bytes(&p, &have, (size_t)G * sizeof(int))) { g->prog = nullptr; return rc; }
+            g->prog = (int *)p;
+            g->prog_count = have / sizeof(int);
+            g->planes_prog = nullptr;       /* the 3D plane descriptors cached on this grid are stale now */
+        }
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
+        Bp2Params p;
+        memset(&p, 0, sizeof(p));
+        p.rows = g->rows;
+        p.N = H; p.M = W; p.G = G; p.RWS = RWS;
+        p.prog = g->prog;
+        p.ticket = g->ticket;
+        p.err = (int *)(g->ticket + 1);
+        p.born = born & 0x1ffu;
+        /* a cell that neither survives nor decays keeps its value: same as surviving (core/ca2d.c:72-75) */
+        p.surv = decay ? (surv & 0x1ffu) : 0x1ffu;
+        p.nrval = nrval;
+        p.flag_rows = 8;
+        if (const char *e = getenv("CLAPCA_2D_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
+        p.spin_limit = 4000000000LL;
+        Bp2LaunchInfo info;
+        CU(bp2_launch(P, WPL, moore, warps, p, g_ctx.sms, g->stream, &info));
+        launches++;
+        ctas = info.blocks;
+        done += G;
+    }
+    CU(cudaEventRecord(g->ev[2], g->stream));
+    CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
+    ca2d_unpack_kernel<<<grid_blocks_for(tiles * 32, 256, 8), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[3], g->stream));
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, g->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (err)
+        return fail(CLAPCA_ERR_TIMEOUT, "ca2d bit-plane engine: dataflow watchdog fired (err=%d)", err);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g->ev[0], g->ev[3]));
+    g->stats.total_ms = ms;
+    CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+    g->stats.kernel_ms = ms;
+    g->stats.launches = launches + 2;
+    g->stats.engine = CLAPCA_ENGINE_BITPLANE;
+    g->stats.planes = P;
+    g->stats.workers = ctas * warps;
+    return CLAPCA_OK;
+}
+
 int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv, uint32_t nr_states, int decay,
                       int neigh, int steps, int engine)
 {
@@ -577,9 +686,16 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv
     memset(&g->stats, 0, sizeof(g->stats));
     if (steps == 0 || side <= 0)
         return CLAPCA_OK;
-    if (engine == CLAPCA_ENGINE_BITPLANE)
-        return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine is not available in this build");
-    if (engine != CLAPCA_ENGINE_AUTO && engine != CLAPCA_ENGINE_WAVEFRONT)
+    const bool bp_ok = bp2_supported(g, side, decay, neigh);
+    if (engine == CLAPCA_ENGINE_AUTO)
+        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
+    if (engine == CLAPCA_ENGINE_BITPLANE) {
+        if (!bp_ok)
+            return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: needs a full sweep (side >= extent), rows of at "
+                        "most 65536 cells and an alive-bit neighbourhood (vnv/mv only without decay)");
+        return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps);
+    }
+    if (engine != CLAPCA_ENGINE_WAVEFRONT)
         return fail(CLAPCA_ERR_ARG, "grid_run2d: unknown engine %d", engine);
 
     Wf2Params p;

@@ -24,6 +24,7 @@
 #define CA_HOSTDEV  __host__ __device__ __forceinline__
 #define CA_GLOBAL   __global__
 #define CA_FULL     0xffffffffu
+#define CA_SHARED(type, name, n) __shared__ type name[n]
 
 namespace clapca {
 
@@ -40,6 +41,7 @@ CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { return __shfl_down_sync(CA_F
 CA_DEV uint32_t dp_ballot(bool p)                 { return __ballot_sync(CA_FULL, p); }
 CA_DEV bool     dp_all(bool p)                    { return __all_sync(CA_FULL, p); }
 CA_DEV void     dp_syncwarp()                     { __syncwarp(); }
+CA_DEV void     dp_syncblock()                    { __syncthreads(); }
 
 /* data written by other SMs inside the same launch: bypass the (incoherent) L1 */
 CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return __ldcg(p); }
@@ -110,12 +112,14 @@ CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
 #else
 /* -------------------------------------------------------------- emulator -- */
 #include <string.h>
+#include <stddef.h>
 
 #define CA_DEV      static inline
 #define CA_MDEV     static inline
 #define CA_HOSTDEV  static inline
 #define CA_GLOBAL   static
 #define CA_FULL     0xffffffffu
+#define CA_SHARED(type, name, n) type *name = (type *)clapca::emu_block_shared((n) * sizeof(type))
 #define __restrict__
 #define __launch_bounds__(...)
 
@@ -140,6 +144,8 @@ uint32_t emu_exchange(uint32_t v, int src_lane);     /* returns v deposited by s
 uint32_t emu_ballot(bool p);
 void     emu_yield();
 long long emu_clock();
+void     emu_syncblock();                            /* all warps of the block */
+void    *emu_block_shared(size_t bytes);             /* the block's shared memory (same buffer for every thread) */
 
 CA_DEV int  dp_lane()            { return emu_lane(); }
 CA_DEV int  dp_warp_in_block()   { return emu_warp_in_block(); }
@@ -154,6 +160,7 @@ CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { int l = emu_lane(); return e
 CA_DEV uint32_t dp_ballot(bool p)                 { return emu_ballot(p); }
 CA_DEV bool     dp_all(bool p)                    { return emu_ballot(p) == CA_FULL; }
 CA_DEV void     dp_syncwarp()                     { (void)emu_ballot(true); }
+CA_DEV void     dp_syncblock()                    { emu_syncblock(); }
 
 template <typename T> CA_DEV T dp_ld_cg_any(const T *p)
 {

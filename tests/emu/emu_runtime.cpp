@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <atomic>
 #include <thread>
 #include <vector>
 #include "emu_runtime.h"
@@ -16,7 +17,15 @@ namespace {
 constexpr int kLanes = 32;
 constexpr size_t kStack = 256 * 1024;
 
+struct Block {
+    std::atomic<int> arrived{0};
+    std::atomic<unsigned> generation{0};
+    int warps = 0;
+    std::vector<char> smem;
+};
+
 struct Warp {
+    Block *blk;
     ucontext_t main_ctx;
     ucontext_t ctx[kLanes];
     std::vector<char> stacks;
@@ -149,6 +158,34 @@ void emu_yield()
     sched_yield();
 }
 
+void emu_syncblock()
+{
+    Warp *w = tw;
+    (void)emu_ballot(true);                 /* the whole warp has arrived */
+    if (w->cur == 0) {
+        Block *b = w->blk;
+        unsigned g = b->generation.load(std::memory_order_acquire);
+        if (b->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == b->warps) {
+            b->arrived.store(0, std::memory_order_relaxed);
+            b->generation.fetch_add(1, std::memory_order_acq_rel);
+        } else {
+            while (b->generation.load(std::memory_order_acquire) == g)
+                sched_yield();
+        }
+    }
+    (void)emu_ballot(true);                 /* lane 0 is through: release the other lanes */
+}
+
+void *emu_block_shared(size_t bytes)
+{
+    Block *b = tw->blk;
+    if (b->smem.size() < bytes) {
+        fprintf(stderr, "emu: block shared memory request %zu exceeds the launch's %zu bytes\n", bytes, b->smem.size());
+        abort();
+    }
+    return b->smem.data();
+}
+
 long long emu_clock()
 {
     using namespace std::chrono;
@@ -163,9 +200,15 @@ void emu_launch(int blocks, int threads, const std::function<void()> &body)
     }
     int wpb = threads / kLanes;
     std::vector<Warp *> warps;
+    std::vector<Block> blks(blocks);
+    for (int b = 0; b < blocks; b++) {
+        blks[b].warps = wpb;
+        blks[b].smem.assign(64 * 1024, 0);
+    }
     for (int b = 0; b < blocks; b++)
         for (int wi = 0; wi < wpb; wi++) {
             Warp *w = new Warp();
+            w->blk = &blks[b];
             w->block = b;
             w->warp_in_block = wi;
             w->grid_blocks = blocks;

@@ -91,3 +91,35 @@ def test_ca3d_slab_decomposition_peer_ghost_planes(emu_bin, args):
 ])
 def test_ca3d_generation_batched_diagonal_order(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
+# ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
+
+@pytest.mark.parametrize("args", [
+    #  W    H   G  born   surv  nr decay moore P WPL warps kind seed ctas flagrows
+    (40, 40, 3, 0xc, 0x180, 4, 1, 1, 3, 1, 1, 0, 1, 2, 2),            # ca_test (core/terrain.c:391-398)
+    (40, 70, 5, 0x1e0, 0x1f0, 1, 1, 1, 1, 1, 1, 0, 2, 3, 2),          # binary cave rule, 1 bit per cell
+    (33, 100, 4, 0xc, 0x180, 4, 1, 1, 3, 1, 2, 1, 3, 2, 1),
+    (20, 130, 6, 0x6, 0x1c, 2, 1, 0, 3, 2, 1, 1, 4, 3, 2),            # von Neumann
+    (17, 300, 3, 0x1e, 0xff, 20, 0, 1, 8, 2, 3, 0, 5, 2, 3),          # ca_instors[0] without decay, 8 planes
+    (50, 64, 7, 0x1e0, 0x1f0, 1, 1, 1, 1, 4, 1, 0, 6, 4, 4),
+    (1, 1, 3, 0x1, 0x0, 1, 1, 1, 1, 1, 1, 0, 7, 2, 2),
+    (5, 1, 3, 0x3, 0x0, 1, 1, 1, 1, 1, 1, 0, 7, 2, 2),
+    (1, 37, 3, 0x3, 0x2, 1, 1, 0, 1, 1, 1, 0, 7, 2, 2),
+    (64, 257, 9, 0xc, 0x180, 4, 1, 1, 4, 1, 9, 1, 8, 5, 2),
+    (12, 40, 4, 0xc, 0x180, 0, 1, 1, 3, 1, 1, 1, 8, 2, 2),            # nr_states == 0: births are no-ops
+    (12, 40, 4, 0xc, 0x180, 256 + 3, 1, 1, 3, 1, 1, 1, 8, 2, 2),      # nr_states wraps through uint8
+])
+def test_ca2d_bitplane_rules_and_shapes(emu_bin, args):
+    _run(os.path.join(emu_bin, "emu_ca2d"), *args)
+
+
+@pytest.mark.parametrize("args", [
+    (5, 2100, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 2, 0, 2, 3, 1),         # rows span two warps, 2 words per lane
+    (4, 3000, 3, 0x6, 0x1c, 2, 1, 0, 3, 1, 3, 1, 3, 2, 2),            # three warps, von Neumann
+    (7, 2050, 3, 0xc, 0x180, 4, 1, 1, 3, 1, 3, 0, 4, 1, 3),           # a single CTA runs every generation in turn
+    (5, 4200, 2, 0x1e0, 0x1f0, 1, 1, 1, 1, 4, 2, 0, 5, 2, 2),
+    (9, 1025, 5, 0x1fe, 0x0, 3, 1, 1, 3, 1, 2, 1, 9, 3, 2),           # one cell beyond a warp's span
+])
+def test_ca2d_bitplane_rows_across_warps(emu_bin, args):
+    _run(os.path.join(emu_bin, "emu_ca2d"), *args)

@@ -206,6 +206,97 @@ def test_ca2d_rectangular_and_empty(gpu, oracle):
     assert not z.any()
 
 
+# ---- ca2d bit-plane engine (transposed bit planes, one CTA per generation) ---------------------------------
+
+CAVE_BIN = dict(born=0x1E0, surv=0x1F0, nr=1, decay=True)          # SURVEY 8(d) cfg 3: binary cave smoothing
+
+
+def _ca(gpu, born, surv, nr, decay, neigh):
+    return gpu.CellAutomaton("t", born, surv, nr, bool(decay), neigh)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (31, 33), (64, 64), (100, 37), (257, 130), (1025, 40),
+                                   (2100, 24), (4097, 9)])
+def test_ca2d_bitplane_vs_oracle_shapes(gpu, oracle, shape):
+    """Every alive-bit rule family on ragged shapes (h = cells per engine row, crossing lane and warp spans)."""
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    rules = [
+        (3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_M1, 4),                     # ca_test, 3 planes
+        (0x1E0, 0x1F0, 1, 1, oracle_lib.NEIGH_M1, 1),                       # binary, 1 plane
+        (0x6, 0x1C, 2, 1, oracle_lib.NEIGH_VN1, 3),                         # von Neumann
+        (0x1E, 0xFF, 20, 0, oracle_lib.NEIGH_MV, 20),                       # ca_instors[0]: mv without decay
+        (0xFFFFFF, 0xFFFFFF, 21, 0, oracle_lib.NEIGH_VNV, 9),               # vnv without decay
+        (0x0C, 0x03, 300, 1, oracle_lib.NEIGH_M1, 255),                     # nr_states wraps to 44; 255-valued cells
+    ]
+    for born, surv, nr, decay, neigh, vmax in rules:
+        arr = synth(rng, shape, 0.45, vmax)
+        want = oracle.ca2d_run(arr.copy(), born, surv, nr, decay, neigh, 5, side=max(shape))
+        gpu.ca2d_step(_ca(gpu, born, surv, nr, decay, neigh), arr, side=max(shape), steps=5, engine=BITPLANE)
+        assert np.array_equal(arr, want), (shape, born, surv, nr, neigh)
+
+
+def test_ca2d_bitplane_many_generations_more_than_resident_ctas(gpu, oracle):
+    """700 generations on a small grid: more generations than CTAs the device keeps resident."""
+    rng = np.random.default_rng(5)
+    arr = synth(rng, (96, 80), 0.5, 1)
+    want = oracle.ca2d_run(arr.copy(), 0x8, 0xC, 1, 1, oracle_lib.NEIGH_M1, 700, side=96)      # Life: B3/S23
+    gpu.ca2d_step(_ca(gpu, 0x8, 0xC, 1, 1, oracle_lib.NEIGH_M1), arr, side=96, steps=700, engine=BITPLANE)
+    assert np.array_equal(arr, want)
+    assert arr.any()
+
+
+def test_ca2d_engines_agree_1024(gpu):
+    rng = np.random.default_rng(6)
+    arr = synth(rng, (1024, 1024), 0.55, 4)
+    a, b = arr.copy(), arr.copy()
+    gpu.ca2d_step(gpu.CA_TEST, a, steps=12, engine=BITPLANE)
+    gpu.ca2d_step(gpu.CA_TEST, b, steps=12, engine=WAVEFRONT)
+    assert np.array_equal(a, b)
+
+
+def test_ca2d_bitplane_rejects_what_it_cannot_run(gpu):
+    arr = np.ones((64, 64), np.uint8)
+    with pytest.raises(gpu.ClapcaError):          # partial sweep
+        gpu.ca2d_step(gpu.CA_TEST, arr, side=40, steps=1, engine=BITPLANE)
+    with pytest.raises(gpu.ClapcaError):          # value-comparing neighbourhood with decay
+        gpu.ca2d_step(_ca(gpu, 0xC, 0x180, 4, True, oracle_lib.NEIGH_MV), arr, steps=1, engine=BITPLANE)
+
+
+def test_ca2d_cfg3_full_width_strip_vs_oracle(gpu, oracle):
+    """BASELINE config 3 geometry in one dimension: rows of 16384 cells (16 warps per CTA), 64 of them, 100
+    generations of the binary cave rule, bit-exact against the oracle."""
+    rng = np.random.default_rng(7)
+    arr = synth(rng, (16384, 64), 0.45, 1)
+    want = oracle.ca2d_run(arr.copy(), CAVE_BIN["born"], CAVE_BIN["surv"], 1, 1, oracle_lib.NEIGH_M1, 100, side=16384)
+    gpu.ca2d_step(_ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1), arr, side=16384, steps=100, engine=BITPLANE)
+    assert np.array_equal(arr, want)
+    assert arr.any() and not arr.all()
+
+
+def test_ca2d_cfg3_16384_generations_compose(gpu):
+    """BASELINE config 3 at full size (16384^2, 100 generations), too large for the oracle in seconds: the fused
+    100-generation run must equal 60 then 40 generations (different pipeline depths over the same data), and the
+    on-device population count must match the downloaded grid."""
+    rng = np.random.default_rng(8)
+    side = 16384
+    arr = (rng.random((side, side), dtype=np.float32) < 0.45).astype(np.uint8)
+    ca = _ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1)
+    grid = gpu.Grid(side, side, 1)
+    grid.upload(arr)
+    grid.run2d(ca, 100)
+    st = grid.stats()
+    assert st["engine"] == "bitplane" and st["planes"] == 1
+    a = np.empty_like(arr)
+    grid.download(a)
+    grid.upload(arr)
+    grid.run2d(ca, 60)
+    grid.run2d(ca, 40)
+    b = np.empty_like(arr)
+    grid.download(b)
+    assert np.array_equal(a, b)
+    assert grid.count() == int(np.count_nonzero(a)) and 0 < grid.count() < side * side
+
+
 # ---- noise ----------------------------------------------------------------------------------------
 
 def test_noise_bake_golden_exact(gpu, oracle):
