@@ -37,6 +37,9 @@ WORKLOADS = {
     "ca3d_1024": (1024, 1024, 1024, 50, 7),
     "ca3d_512": (512, 512, 512, 50, 7),
     "ca3d_128": (128, 128, 128, 10, 7),
+    # per-GPU shares of the 2048^3 volume as stand-alone volumes (scaling diagnostics)
+    "ca3d_2048_z1024": (2048, 2048, 1024, 50, 7),
+    "ca3d_2048_z256": (2048, 2048, 256, 50, 7),
 }
 # BASELINE config 3: binary cave-smoothing rule, 1 bit per cell in the 2D bit-plane engine
 CA2D_WORKLOADS = {

@@ -44,7 +44,7 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     auto kern = ca3d_sweep_kernel<P, WPL, TheRule>;
     /* small CTAs: co-residency is bounded by registers, 128-thread granularity wastes the least of the file */
     int threads = 128;
-    if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) threads = v; }
+    if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) threads = v; }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
     if (e != cudaSuccess) return e;

@@ -54,8 +54,10 @@ struct Bp3Params {
     int nsweeps;            /* number of work items */
     uint32_t epoch;         /* run number, upper half of the ghost-row tags */
     int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
+    int prefetch_rows;      /* > 0: prefetch.L2 the own record this many rows ahead (HBM -> L2 latency) */
     unsigned *ticket;       /* next sweep to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
+    unsigned long long *diag;   /* optional: [0] cycles waiting on counters, [1] on ghost tags, [2] in work items */
     uint32_t surv, born;    /* rule masks (run-time rule only) */
     uint32_t bornval;       /* (nr_states - 1) & 0xff */
     long long spin_limit;   /* watchdog budget in clock ticks per wait */
@@ -188,12 +190,14 @@ struct Sweep3 {
         uint32_t vmask[WPL];
         const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load */
         uint32_t *rec;                              /* lane-adjusted own record of the current row */
+        const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead */
         uint32_t *push_dn, *push_up;                /* lane-adjusted peer ghost rows of the current row */
         const int *flagp;                           /* the producer counter this lane polls (lanes 0..2) */
         int have;                                   /* min over the producers' published row counts */
         int next_raise;                             /* next row count at which the own counter is raised */
         int dn_mode, up_mode;
         uint32_t tag_dn, tag_up, tag_out;
+        long long waited_flag, waited_tag;          /* diagnostics: cycles spent in the slow paths */
     };
 
     /* false = watchdog fired / abort requested */
@@ -218,6 +222,7 @@ struct Sweep3 {
                 }
             }
         }
+        if (t0) st.waited_flag += dp_clock() - t0;
         dp_syncwarp();          /* the polling lanes acquired; the warp barrier extends it to every lane */
         return true;
     }
@@ -232,7 +237,7 @@ struct Sweep3 {
      * Ghost rows (see bp3_types.h): {word, tag} pairs written by the neighbouring GPU.  Re-read until every
      * pair of this lane -- and of the whole warp -- carries the expected tag.  false = watchdog / abort.
      */
-    CA_MDEV bool load_h_tagged(const Bp3Params &p, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL])
+    CA_MDEV bool load_h_tagged(const Bp3Params &p, St &st, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL])
     {
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
@@ -245,8 +250,10 @@ struct Sweep3 {
                 h[q1 / WPL][q1 % WPL] = v.z;
                 ok = ok && v.y == expect && v.w == expect;
             }
-            if (dp_all(ok))
+            if (dp_all(ok)) {
+                if (t0) st.waited_tag += dp_clock() - t0;
                 return true;
+            }
             if (spins == 0) t0 = dp_clock();
             dp_nanosleep(100);
             if ((spins & 63u) == 63u) {
@@ -272,7 +279,7 @@ struct Sweep3 {
     }
 
     /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
-    CA_MDEV bool load_side(const Bp3Params &p, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
+    CA_MDEV bool load_side(const Bp3Params &p, St &st, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
     {
         if (mode == SRC_LOCAL) {
             LaneVec<WPL>::ld(src, h[0]);
@@ -281,7 +288,7 @@ struct Sweep3 {
         } else if (mode == SRC_NONE) {
             zero2(h);
         } else {
-            if (!load_h_tagged(p, src, tag, h)) return false;
+            if (!load_h_tagged(p, st, src, tag, h)) return false;
             src += GHW;
         }
         return true;
@@ -350,14 +357,19 @@ struct Sweep3 {
         }
 
         /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
+        if (st.pf) {
+            if (y + p.prefetch_rows < H)
+                dp_prefetch_l2(st.pf);
+            st.pf += RECW;
+        }
         if (y + 2 <= y1) {          /* row y1 is still needed (as "row y+1" of the last step), y1+1 is not */
             if (y + 2 < H) {
                 if (!wait_rows(p, st, y + 3 < H ? y + 3 : H))
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
-                if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
+                if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
+                if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
             } else {
                 zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
                 zero_s(st.so[A]);
@@ -414,18 +426,6 @@ struct Sweep3 {
             LaneVec<WPL>::st(st.rec + (2 + q) * RWP, st.so[B][q]);
         st.rec += RECW;
         /*
-         * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
-         * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).
-         */
-        if (st.push_dn) {
-            store_h_tagged(st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
-            st.push_dn += GHW;
-        }
-        if (st.push_up) {
-            store_h_tagged(st.push_up, st.tag_out, st.hn[0], st.hn[1]);
-            st.push_up += GHW;
-        }
-        /*
          * Local consumers: warp barrier (orders every lane's row stores before lane 0), then ONE
          * release store of the counter (MEMBAR.GPU + store).  Raised every flag_rows rows.
          */
@@ -436,6 +436,19 @@ struct Sweep3 {
             dp_syncwarp();
             if (lane == 0)
                 dp_st_release(myprog, y + 1);
+        }
+        /*
+         * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
+         * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).  They are issued AFTER the
+         * counter's release so that its MEMBAR never waits for this row's NVLink round trip.
+         */
+        if (st.push_dn) {
+            store_h_tagged(st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
+            st.push_dn += GHW;
+        }
+        if (st.push_up) {
+            store_h_tagged(st.push_up, st.tag_out, st.hn[0], st.hn[1]);
+            st.push_up += GHW;
         }
         return true;
     }
@@ -458,6 +471,8 @@ struct Sweep3 {
         st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 * WPL : WPL)
                            : nullptr;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
+        st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
+              ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
         st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
         st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
         st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
@@ -473,6 +488,8 @@ struct Sweep3 {
             st.have = (fdn || fup || fown) ? 0 : 0x7fffffff;
         }
         st.next_raise = (y0 / p.flag_rows + 1) * p.flag_rows;
+        st.waited_flag = st.waited_tag = 0;
+        const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
 
@@ -500,18 +517,18 @@ struct Sweep3 {
 
         /* ---- fill the windows: rows y0-1 (slot 2), y0 (slot 0), y0+1 (slot 1) ---- */
         if (y0 > 0) {
-            if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
-            if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
+            if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
+            if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
             load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
         } else {
             zero2(st.hd[2]); zero2(st.hu[2]); zero2(st.hn);
         }
-        if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
-        if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
+        if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
+        if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
         load_own_s<0>(st, st.so[0]);
         if (y0 + 1 < H) {
-            if (!load_side(p, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
-            if (!load_side(p, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
+            if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
+            if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
             load_own_h<1>(st, st.ho);
             load_own_s<1>(st, st.so[1]);
         } else {
@@ -532,6 +549,11 @@ struct Sweep3 {
         }
         if (y < y1) {
             if (!step<1>(p, st, y, y1, myprog)) return false;
+        }
+        if (p.diag && lane == 0) {
+            dp_atomic_add64(p.diag + 0, (unsigned long long)st.waited_flag);
+            dp_atomic_add64(p.diag + 1, (unsigned long long)st.waited_tag);
+            dp_atomic_add64(p.diag + 2, (unsigned long long)(dp_clock() - t_item));
         }
         return true;
     }
@@ -556,8 +578,9 @@ struct Sweep3 {
     }
 };
 
+/* 128-thread CTAs; the register cap keeps 5 (2 words per lane) / 6 (1 word per lane) CTAs per SM resident */
 template <int P, int WPL, class Rule>
-CA_GLOBAL void __launch_bounds__(256) ca3d_sweep_kernel(Bp3Params p)
+CA_GLOBAL void __launch_bounds__(128, (P == 3 && WPL == 2) ? 5 : ((P <= 4 && WPL == 1) ? 6 : 1)) ca3d_sweep_kernel(Bp3Params p)
 {
     Sweep3<P, WPL, Rule>::kernel_body(p);
 }

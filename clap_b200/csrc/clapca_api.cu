@@ -47,6 +47,28 @@ int fail(int code, const char *fmt, ...)
                         "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+/* control words of a sweep launch: [0] ticket, [1] err, [4..9] three 64-bit diagnostic cycle counters */
+static const int kTicketWords = 16;
+
+static bool diag_enabled()
+{
+    const char *e = getenv("CLAPCA_DIAG");
+    return e && atoi(e) != 0;
+}
+
+/* CLAPCA_DIAG=1: where the persistent warps of the last sweep launch spent their cycles */
+static void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t stream, int rank)
+{
+    if (!diag_enabled())
+        return;
+    unsigned long long d[3] = { 0, 0, 0 };
+    if (cudaMemcpyAsync(d, d_ticket + 4, sizeof(d), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+        return;
+    fprintf(stderr, "clapca diag [%s rank %d]: in items %.3e cycles, waiting on counters %.1f %%, on ghost tags %.1f %%\n",
+            what, rank, (double)d[2], d[2] ? 100.0 * d[0] / d[2] : 0.0, d[2] ? 100.0 * d[1] / d[2] : 0.0);
+}
+
 struct Ctx {
     int device = -1;
     int sms = 0;
@@ -226,7 +248,7 @@ int clapca_grid_create(clapca_grid **out, int64_t d0, int64_t d1, int64_t d2)
     memset(&g->stats, 0, sizeof(g->stats));
     g->stream = g_ctx.stream;
     cudaError_t e = cudaMalloc(&g->cells, g->n);
-    if (e == cudaSuccess) e = cudaMalloc(&g->ticket, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&g->ticket, kTicketWords * sizeof(unsigned));
     for (int i = 0; i < 4 && e == cudaSuccess; i++)
         e = cudaEventCreate(&g->ev[i]);
     if (e != cudaSuccess) {
@@ -465,7 +487,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
             g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = oc.key();
         }
         CU(cudaMemsetAsync(g->prog, 0, (size_t)G * Z * sizeof(int), g->stream));
-        CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
+        CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
 
         Bp3Params p;
         memset(&p, 0, sizeof(p));
@@ -477,8 +499,10 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.nsweeps = g->n_items;
         p.flag_rows = kFlagRows;
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
+        if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
+        p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;
         p.surv = surv; p.born = born; p.bornval = bornval;
         p.spin_limit = 4000000000LL;        /* ~2 s of SM clock in a single wait */
         Bp3LaunchInfo info;
@@ -488,6 +512,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         done += G;
     }
     CU(cudaEventRecord(g->ev[2], g->stream));
+    diag_report("grid", g->ticket, g->stream, 0);
 
     CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
     ca3d_unpack_kernel<<<grid_blocks_for((size_t)Z * H * ((W + 31) / 32), 256, 16), 256, 0, g->stream>>>(L);
@@ -631,7 +656,7 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
             g->planes_prog = nullptr;       /* the 3D plane descriptors cached on this grid are stale now */
         }
         CU(cudaMemsetAsync(g->prog, 0, (size_t)G * sizeof(int), g->stream));
-        CU(cudaMemsetAsync(g->ticket, 0, 2 * sizeof(unsigned), g->stream));
+        CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
         Bp2Params p;
         memset(&p, 0, sizeof(p));
         p.rows = g->rows;
@@ -797,7 +822,7 @@ int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_glo
     if (e == cudaSuccess) e = cudaMemset(s->halo, 0, s->hl.total_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&s->prog, (size_t)s->Gcap * zl * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&s->planes, zl * sizeof(Bp3Plane));
-    if (e == cudaSuccess) e = cudaMalloc(&s->ticket, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&s->ticket, kTicketWords * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_pop, sizeof(unsigned long long));
     for (int i = 0; i < 5 && e == cudaSuccess; i++)
         e = cudaEventCreate(&s->ev[i]);
@@ -957,7 +982,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
         }
     }
     CU(cudaMemsetAsync(s->prog, 0, (size_t)s->Gcap * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
-    CU(cudaMemsetAsync(s->ticket, 0, 2 * sizeof(unsigned), s->stream));
+    CU(cudaMemsetAsync(s->ticket, 0, kTicketWords * sizeof(unsigned), s->stream));
     CU(cudaEventRecord(s->ev[1], s->stream));
     CU(cudaStreamSynchronize(s->stream));
     s->prepared = true;
@@ -988,8 +1013,10 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.flag_rows = kFlagRows;
         p.epoch = s->epoch;
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
+        if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
         p.ticket = s->ticket;
         p.err = (int *)(s->ticket + 1);
+        p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
         p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
         p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
         Bp3LaunchInfo info;
@@ -997,6 +1024,7 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         workers = info.workers;
     }
     CU(cudaEventRecord(s->ev[3], s->stream));
+    diag_report("slab", s->ticket, s->stream, s->geo.rank);
     CU(cudaMemsetAsync(s->d_pop, 0, sizeof(unsigned long long), s->stream));
     if (s->Zl) {
         Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };

@@ -90,6 +90,7 @@ CA_DEV void dp_fence_sys()                        { asm volatile("fence.acq_rel.
 CA_DEV void dp_fence_release()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_nanosleep(unsigned ns)             { __nanosleep(ns); }
+CA_DEV void dp_prefetch_l2(const void *p)         { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 CA_DEV long long dp_clock()                       { return clock64(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return atomicAdd(p, 1u); }
 CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -195,6 +196,7 @@ CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __
 CA_DEV void dp_st_flag_sys(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 CA_DEV void dp_fence_acquire()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV void dp_nanosleep(unsigned)                { emu_yield(); }
+CA_DEV void dp_prefetch_l2(const void *)          { }
 CA_DEV long long dp_clock()                       { return emu_clock(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
 CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
