@@ -144,6 +144,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[workload]["bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -297,7 +306,7 @@ def run_ca2d(args, torch, clap_b200, dev, local):
                          "(%.0f MiB, larger than L2) before every step" % (cells / 2 ** 20),
                    "population": pop},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "ca2d_sweep_kernel (all generations fused)", "kernel_ms": kernel_ms,
+                     "traffic": ncu_traffic(args.workload), "kernel": "ca2d_sweep_kernel (all generations fused)", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_update": bytes_per_update, "peak_source": peak_src,
                      "note": "dependency-latency bound: the in-place sweep order leaves a chain of side + 2*generations "
                              "row steps"},
@@ -375,7 +384,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = updates * 2.0 / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "ca3d_sweep_kernel (all generations fused)",
+                "traffic": ncu_traffic(args.workload), "kernel": "ca3d_sweep_kernel (all generations fused)",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_update": 2.0, "peak_source": peak_src}
 
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------

@@ -49,6 +49,8 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    /* fewer resident warps run faster each: worth it when the dependency DAG, not the SM count, bounds the parallelism */
+    if (p.max_ctas_per_sm > 0 && per_sm > p.max_ctas_per_sm) per_sm = p.max_ctas_per_sm;
     int blocks = per_sm * sms;
     if (p.nsweeps >= 0) {
         const int need = (p.nsweeps + threads / 32 - 1) / (threads / 32);

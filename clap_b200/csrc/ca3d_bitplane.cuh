@@ -61,6 +61,7 @@ struct Bp3Params {
     uint32_t surv, born;    /* rule masks (run-time rule only) */
     uint32_t bornval;       /* (nr_states - 1) & 0xff */
     long long spin_limit;   /* watchdog budget in clock ticks per wait */
+    int max_ctas_per_sm;    /* host side only: > 0 caps the resident CTAs per SM of the launch */
 };
 
 /* ---- rules ---------------------------------------------------------------- */
