@@ -3,6 +3,7 @@
  * and all (P, WPL) variants, and provides its cooperative launcher.
  */
 #include <stdlib.h>
+#include <algorithm>
 #include "bp3_launch.h"
 
 #ifndef BP3_RULE
@@ -43,8 +44,14 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
 {
     auto kern = ca3d_sweep_kernel<P, WPL, TheRule>;
     /* small CTAs: co-residency is bounded by registers, 128-thread granularity wastes the least of the file */
-    int threads = 128;
+    int threads = 128, wpc = 4;             /* threads and WORKER warps per CTA */
     if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) threads = v; }
+    wpc = threads / 32;
+    if (p.pub_workers > 0) {
+        /* publisher mode: pub_workers worker warps + the publisher warp per CTA */
+        wpc = std::min(std::min(p.pub_workers, (int)BP3_MAX_PUB_WORKERS), Bp3Bounds<P, WPL>::kMaxThreads / 32 - 1);
+        threads = 32 * (wpc + 1);
+    }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
     if (e != cudaSuccess) return e;
@@ -53,7 +60,7 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     if (p.max_ctas_per_sm > 0 && per_sm > p.max_ctas_per_sm) per_sm = p.max_ctas_per_sm;
     int blocks = per_sm * sms;
     if (p.nsweeps >= 0) {
-        const int need = (p.nsweeps + threads / 32 - 1) / (threads / 32);
+        const int need = (p.nsweeps + wpc - 1) / wpc;
         if (blocks > need) blocks = need;
     }
     if (blocks < 1) blocks = 1;
@@ -63,12 +70,13 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     if (info) {
         info->blocks = blocks;
         info->threads = threads;
-        info->workers = blocks * (threads / 32);
+        info->workers = blocks * wpc;
         info->regs = fa.numRegs;
     }
     if (p.nsweeps < 0)
         return cudaSuccess;             /* occupancy query (bp3_max_workers) */
     Bp3Params pp = p;
+    pp.pub_workers = p.pub_workers > 0 ? wpc : 0;
     void *args[] = { &pp };
     /* cooperative launch: fails instead of silently running a non-co-resident grid */
     return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(threads), args, 0, stream);

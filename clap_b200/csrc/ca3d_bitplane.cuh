@@ -62,7 +62,26 @@ struct Bp3Params {
     uint32_t bornval;       /* (nr_states - 1) & 0xff */
     long long spin_limit;   /* watchdog budget in clock ticks per wait */
     int max_ctas_per_sm;    /* host side only: > 0 caps the resident CTAs per SM of the launch */
+    int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
 };
+
+/*
+ * Publisher mode.  Raising a progress counter needs a gpu-scope release, and MEMBAR.GPU on a two-die B200
+ * costs a few microseconds -- the time of two row steps.  A worker that fences itself can therefore only
+ * afford a counter update every ~8 rows, which makes every consumer trail its producer by ~10 rows and
+ * bounds the number of sweeps the dependency DAG lets run concurrently (the limit that matters once a
+ * rank owns only G/N sweeps per dependency level).  In publisher mode the workers never fence at gpu
+ * scope: after the stores of a row they bump `done` in a shared-memory mailbox (CTA-scope release: cheap),
+ * and one extra warp per CTA loops { read all mailboxes; ONE fence.acq_rel.gpu; store the counters that
+ * moved }.  Release cumulativity (worker stores -> CTA-scope release/acquire -> gpu-scope fence -> counter)
+ * makes the rows visible before the counter, exactly like bar.sync + thread 0 fencing in a grid barrier.
+ */
+struct PubSlot {
+    unsigned long long flag;    /* global counter of the sweep the worker is on (int *) */
+    int done;                   /* rows completed (worker-written) */
+    int pub;                    /* rows published (publisher-written; worker resets it between items) */
+};
+enum { BP3_MAX_PUB_WORKERS = 23 };
 
 /* ---- rules ---------------------------------------------------------------- */
 
@@ -193,6 +212,7 @@ struct Sweep3 {
         uint32_t *rec;                              /* lane-adjusted own record of the current row */
         const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead */
         uint32_t *push_dn, *push_up;                /* lane-adjusted peer ghost rows of the current row */
+        PubSlot *slot;                              /* publisher mode: this worker's mailbox (else nullptr) */
         const int *flagp;                           /* the producer counter this lane polls (lanes 0..2) */
         int have;                                   /* min over the producers' published row counts */
         int next_raise;                             /* next row count at which the own counter is raised */
@@ -435,8 +455,14 @@ struct Sweep3 {
             st.next_raise += p.flag_rows;
         if (at_mark || y + 1 == y1) {
             dp_syncwarp();
-            if (lane == 0)
-                dp_st_release(myprog, y + 1);
+            if (lane == 0) {
+                if (st.slot) {
+                    dp_fence_cta();
+                    dp_st_volatile(&st.slot->done, y + 1);
+                } else {
+                    dp_st_release(myprog, y + 1);
+                }
+            }
         }
         /*
          * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
@@ -455,7 +481,7 @@ struct Sweep3 {
     }
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
-    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1)
+    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
@@ -513,6 +539,19 @@ struct Sweep3 {
             }
             dp_syncwarp();
         }
+        /*
+         * Publisher mode: hand the mailbox over to this sweep.  The previous item ended with pub == done, so
+         * the publisher is idle on this slot; it reads pub, then done, then flag -- written here in the
+         * opposite order -- so it can never pair an old row count with the new counter address.
+         */
+        st.slot = slot;
+        if (slot && lane == 0) {
+            dp_st_volatile64(&slot->flag, (unsigned long long)(size_t)myprog);
+            dp_fence_cta();
+            dp_st_volatile(&slot->done, y0);
+            dp_fence_cta();
+            dp_st_volatile(&slot->pub, y0);
+        }
         if (!wait_rows(p, st, y0 + 2 < H ? y0 + 2 : H))
             return false;
 
@@ -551,6 +590,13 @@ struct Sweep3 {
         if (y < y1) {
             if (!step<1>(p, st, y, y1, myprog)) return false;
         }
+        /* publisher mode: the mailbox is reused by the next item only once the last rows are out */
+        if (slot) {
+            if (lane == 0)
+                while (dp_ld_volatile(&slot->pub) < y1)
+                    dp_nanosleep(20);
+            dp_syncwarp();
+        }
         if (p.diag && lane == 0) {
             dp_atomic_add64(p.diag + 0, (unsigned long long)st.waited_flag);
             dp_atomic_add64(p.diag + 1, (unsigned long long)st.waited_tag);
@@ -559,7 +605,8 @@ struct Sweep3 {
         return true;
     }
 
-    CA_MDEV void kernel_body(const Bp3Params &p)
+    /* the worker loop: claim items in dependency order until the list is exhausted */
+    CA_MDEV void work_loop(const Bp3Params &p, PubSlot *slot)
     {
         const int lane = dp_lane();
         for (;;) {
@@ -573,15 +620,82 @@ struct Sweep3 {
             if (t >= (unsigned)p.nsweeps)
                 break;
             int4 it = p.order[t];
-            if (!run_segment(p, it.x, it.y, it.z, it.w))
+            if (!run_segment(p, it.x, it.y, it.z, it.w, slot))
                 break;
+        }
+    }
+
+    /* publisher warp: lane i serves the mailbox of worker warp i; one gpu-scope fence per pass for all of them */
+    CA_MDEV void publish_loop(PubSlot *slots, int *nexit, int nw)
+    {
+        const int lane = dp_lane();
+        PubSlot *my = slots + (lane < nw ? lane : 0);
+        for (;;) {
+            int pb = 0, d = 0;
+            if (lane < nw) {
+                pb = dp_ld_volatile(&my->pub);
+                dp_fence_cta();
+                d = dp_ld_volatile(&my->done);
+            }
+            const bool need = d > pb;
+            if (dp_any(need)) {
+                unsigned long long f = 0;
+                if (need) {
+                    dp_fence_cta();
+                    f = dp_ld_volatile64(&my->flag);
+                }
+                dp_fence_release();                     /* fence.acq_rel.gpu: the ONE expensive instruction */
+                if (need) {
+                    dp_st_flag((int *)(size_t)f, d);
+                    dp_st_volatile(&my->pub, d);
+                }
+            } else {
+                if (dp_all(dp_ld_volatile(nexit) >= nw))        /* warp-uniform: the lanes read at different times */
+                    break;
+                dp_nanosleep(40);
+            }
+        }
+    }
+
+    CA_MDEV void kernel_body(const Bp3Params &p)
+    {
+        if (p.pub_workers <= 0) {
+            work_loop(p, nullptr);
+            return;
+        }
+        CA_SHARED(PubSlot, slots, BP3_MAX_PUB_WORKERS + 1);     /* last entry: exit counter */
+        int *nexit = &slots[BP3_MAX_PUB_WORKERS].done;
+        const int nw = dp_block_threads() / 32 - 1;
+        const int w = dp_warp_in_block();
+        if (dp_thread() <= BP3_MAX_PUB_WORKERS) {
+            slots[dp_thread()].flag = 0ull;
+            slots[dp_thread()].done = 0;
+            slots[dp_thread()].pub = 0;
+        }
+        dp_syncblock();
+        if (w < nw) {
+            work_loop(p, slots + w);
+            dp_syncwarp();
+            if (dp_lane() == 0)
+                dp_atomic_add_cta(nexit, 1);
+        } else {
+            publish_loop(slots, nexit, nw);
         }
     }
 };
 
-/* 128-thread CTAs; the register cap keeps 5 (2 words per lane) / 6 (1 word per lane) CTAs per SM resident */
+/*
+ * Self-publishing mode: 128-thread CTAs, 5 (2 words per lane) / 6 (1 word per lane) of them per SM.
+ * Publisher mode: one CTA of up to 640 / 768 threads per SM (19 / 23 workers + the publisher).  The register
+ * cap is the same either way: 65536 / 640 = 102, 65536 / 768 = 85.
+ */
+template <int P, int WPL>
+struct Bp3Bounds {
+    static constexpr int kMaxThreads = (P == 3 && WPL == 2) ? 640 : ((P <= 4 && WPL == 1) ? 768 : 160);
+};
+
 template <int P, int WPL, class Rule>
-CA_GLOBAL void __launch_bounds__(128, (P == 3 && WPL == 2) ? 5 : ((P <= 4 && WPL == 1) ? 6 : 1)) ca3d_sweep_kernel(Bp3Params p)
+CA_GLOBAL void __launch_bounds__(Bp3Bounds<P, WPL>::kMaxThreads, 1) ca3d_sweep_kernel(Bp3Params p)
 {
     Sweep3<P, WPL, Rule>::kernel_body(p);
 }

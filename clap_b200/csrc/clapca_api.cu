@@ -501,6 +501,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
         if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
         if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
+        if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;
@@ -1016,6 +1017,7 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
         if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
         if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
+        if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
         p.ticket = s->ticket;
         p.err = (int *)(s->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;

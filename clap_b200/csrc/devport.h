@@ -88,6 +88,14 @@ CA_DEV void dp_st_flag_sys(int *p, int v)
 CA_DEV void dp_fence_sys()                        { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 /* fence.acq_rel.gpu (MEMBAR.ALL.GPU); __threadfence() would be the heavier fence.sc */
 CA_DEV void dp_fence_release()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+/* CTA-scope mailboxes in shared memory: volatile accesses ordered by fence.acq_rel.cta (MEMBAR.CTA: cheap) */
+CA_DEV void dp_fence_cta()                        { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+CA_DEV int  dp_ld_volatile(const int *p)          { return *(const volatile int *)p; }
+CA_DEV void dp_st_volatile(int *p, int v)         { *(volatile int *)p = v; }
+CA_DEV unsigned long long dp_ld_volatile64(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+CA_DEV void dp_st_volatile64(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
+CA_DEV void dp_atomic_add_cta(int *p, int v)      { atomicAdd(p, v); }
+CA_DEV bool dp_any(bool p)                        { return __any_sync(CA_FULL, p); }
 CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_nanosleep(unsigned ns)             { __nanosleep(ns); }
 CA_DEV void dp_prefetch_l2(const void *p)         { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
@@ -191,6 +199,13 @@ CA_DEV int  dp_reduce_min(int v)
     return v;
 }
 CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV void dp_fence_cta()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+CA_DEV int  dp_ld_volatile(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV void dp_st_volatile(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV unsigned long long dp_ld_volatile64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV void dp_st_volatile64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV void dp_atomic_add_cta(int *p, int v)      { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+CA_DEV bool dp_any(bool p)                        { return emu_ballot(p) != 0u; }
 CA_DEV void dp_fence_sys()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV void dp_st_flag_sys(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }

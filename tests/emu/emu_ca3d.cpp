@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers]]]]]]]
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
  *            10   = run-time rule with random masks
  *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
@@ -41,6 +41,12 @@ typedef Rule3Const<RANGE(0, 6), B(1) | B(3), 2> R8;
 template <int P, int WPL, class Rule>
 static void launch_sweep(const Bp3Params &p, int warps)
 {
+    if (p.pub_workers > 0) {
+        /* publisher mode: CTAs of pub_workers worker warps + 1 publisher warp */
+        const int blocks = (warps + p.pub_workers - 1) / p.pub_workers;
+        emu_launch(blocks, (p.pub_workers + 1) * 32, [&]() { Sweep3<P, WPL, Rule>::kernel_body(p); });
+        return;
+    }
     emu_launch(1, warps * 32, [&]() { Sweep3<P, WPL, Rule>::kernel_body(p); });
 }
 
@@ -96,6 +102,7 @@ int main(int argc, char **argv)
     int segL = argc > 13 ? atoi(argv[13]) : 0;       /* rows per work item, 0 = planner default */
     int flagRows = argc > 14 ? atoi(argv[14]) : 2;   /* rows per progress-counter update */
     int genBatch = argc > 15 ? atoi(argv[15]) : 0;   /* > 0: generation-batched diagonal order, -1: time-key order */
+    int pubWorkers = argc > 16 ? atoi(argv[16]) : 0; /* > 0: publisher mode, worker warps per CTA */
 
     unsigned surv, born, nr;
     if (nca <= 9) {
@@ -195,6 +202,7 @@ int main(int argc, char **argv)
         k.p.order = k.order.data();
         k.p.nsweeps = (int)k.order.size();
         k.p.flag_rows = flagRows;
+        k.p.pub_workers = pubWorkers;
         k.p.ticket = &k.ticket;
         k.p.err = &err;
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;

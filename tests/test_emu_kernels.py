@@ -93,6 +93,24 @@ def test_ca3d_generation_batched_diagonal_order(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 1, -1, 2),        # 2 CTAs of 2 workers + 1 publisher, time-key order
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 2, -1, 4),
+    (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 1, -1, 1),       # one worker and its publisher
+    (64, 33, 6, 9, 10, 4, 2, 1, 9, 7, 1, 0, 4, 5, 0, 3),         # row segments: mailbox handed over mid-sweep
+    (45, 20, 12, 7, 7, 3, 1, 1, 3, 5, 1, 0, 0, 2, 3, 5),         # generation-batched diagonals
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 5, 2, 2, 5, 2, 0, 3),         # 2 ranks, ghost rows + publisher
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 3, 3, 2, 16, 1, 0, 2),        # 3 ranks, ragged last block
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 2, 4, 1, 7, 1, 0, 1),        # 4 ranks, every plane is an edge
+    (20, 5, 3, 4, 7, 3, 1, 1, 4, 2, 4, 1, 1, 1, 0, 2),           # ranks without any plane
+])
+def test_ca3d_publisher_warps(emu_bin, args):
+    """Publisher mode: workers bump a shared-memory mailbox after every row, one extra warp per CTA does the
+    gpu-scope fence and raises the global counters for all of them."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
 # ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
 
 @pytest.mark.parametrize("args", [
