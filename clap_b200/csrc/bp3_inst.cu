@@ -42,15 +42,20 @@ typedef Rule3Dyn TheRule;                                                       
 template <int P, int WPL>
 static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, Bp3LaunchInfo *info)
 {
-    auto kern = ca3d_sweep_kernel<P, WPL, TheRule>;
+    auto kern = p.team > 0 ? ca3d_team_kernel<P, WPL, TheRule> : ca3d_sweep_kernel<P, WPL, TheRule>;
     /* small CTAs: co-residency is bounded by registers, 128-thread granularity wastes the least of the file */
     int threads = 128, wpc = 4;             /* threads and WORKER warps per CTA */
     if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) threads = v; }
     wpc = threads / 32;
-    if (p.pub_workers > 0) {
+    if (p.pub_workers > 0 && p.team <= 0) {
         /* publisher mode: pub_workers worker warps + the publisher warp per CTA */
         wpc = std::min(std::min(p.pub_workers, (int)BP3_MAX_PUB_WORKERS), Bp3Bounds<P, WPL>::kMaxThreads / 32 - 1);
         threads = 32 * (wpc + 1);
+    }
+    if (p.team > 0) {
+        /* team mode: one CTA = `team` warps sweeping a group of consecutive planes; an item occupies a whole CTA */
+        wpc = std::min(p.team, bp3_team_cap(P, WPL));
+        threads = 32 * wpc;
     }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
@@ -60,7 +65,7 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     if (p.max_ctas_per_sm > 0 && per_sm > p.max_ctas_per_sm) per_sm = p.max_ctas_per_sm;
     int blocks = per_sm * sms;
     if (p.nsweeps >= 0) {
-        const int need = (p.nsweeps + wpc - 1) / wpc;
+        const int need = p.team > 0 ? p.nsweeps : (p.nsweeps + wpc - 1) / wpc;
         if (blocks > need) blocks = need;
     }
     if (blocks < 1) blocks = 1;
@@ -76,7 +81,8 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     if (p.nsweeps < 0)
         return cudaSuccess;             /* occupancy query (bp3_max_workers) */
     Bp3Params pp = p;
-    pp.pub_workers = p.pub_workers > 0 ? wpc : 0;
+    pp.pub_workers = (p.pub_workers > 0 && p.team <= 0) ? wpc : 0;
+    pp.team = p.team > 0 ? wpc : 0;
     void *args[] = { &pp };
     /* cooperative launch: fails instead of silently running a non-co-resident grid */
     return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(threads), args, 0, stream);

@@ -248,6 +248,44 @@ inline void bp3_make_items_batched(const std::vector<Bp3Plane> &planes, int Zg, 
     }
 }
 
+/*
+ * Team mode (ca3d_bitplane.cuh): an item is a GROUP of up to T consecutive planes of one z-block at one
+ * generation, WorkItem{ first local plane, g, number of planes, H }.  Group (z0..z0+n-1, g) needs the group
+ * holding z0-1 at g, the group holding z0+n at g-1 and itself at g-1; the key z0 + (T+1) g orders all three
+ * before it for any grouping with n <= T (z0' >= z0 - T; z0 + n + (T+1)(g-1) < z0 + (T+1) g), and it is a
+ * function of global coordinates, so every rank's list is a sub-sequence of ONE global linear extension of
+ * the dependency order: the globally first unfinished group is always running or next in line on its rank.
+ */
+inline void bp3_make_items_team(const std::vector<Bp3Plane> &planes, int H, int G, int T,
+                                std::vector<WorkItem> &items)
+{
+    items.clear();
+    if (G <= 0 || planes.empty())
+        return;
+    if (T < 1) T = 1;
+    struct Group { int l0, n, z0; };
+    std::vector<Group> groups;
+    for (size_t l = 0; l < planes.size();) {
+        size_t e = l + 1;
+        /* extend while the next local plane is the next global plane of the same z-block (its "below" is local) */
+        while (e < planes.size() && (int)(e - l) < T && planes[e].zglobal == planes[e - 1].zglobal + 1 &&
+               planes[e].dn_rows && !(planes[e].ghost_mask & 1u))
+            e++;
+        groups.push_back(Group{ (int)l, (int)(e - l), planes[l].zglobal });
+        l = e;
+    }
+    std::vector<std::pair<long long, WorkItem>> tmp;
+    tmp.reserve(groups.size() * (size_t)G);
+    for (int g = 0; g < G; g++)
+        for (const Group &gr : groups)
+            tmp.push_back({ ((long long)gr.z0 + (long long)(T + 1) * g) * 65536 + g, WorkItem{ gr.l0, g, gr.n, H } });
+    std::sort(tmp.begin(), tmp.end(),
+              [](const std::pair<long long, WorkItem> &a, const std::pair<long long, WorkItem> &b) {
+                  return a.first < b.first;
+              });
+    for (auto &t : tmp) items.push_back(t.second);
+}
+
 /* segment length: long enough that a band offers ~2x more independent items than there are workers */
 inline int bp3_segment_rows(int Zg, int H, int G, int workers)
 {

@@ -63,7 +63,23 @@ struct Bp3Params {
     long long spin_limit;   /* watchdog budget in clock ticks per wait */
     int max_ctas_per_sm;    /* host side only: > 0 caps the resident CTAs per SM of the launch */
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
+    int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
+    int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
 };
+
+/*
+ * Team mode.  With one warp per sweep and gpu-scope counters, plane z+1 trails plane z by flag_rows + ~3 rows
+ * (the counter period plus the MEMBAR.GPU / poll latency), and that hop -- paid Z times in a row -- bounds how
+ * many sweeps the dependency DAG lets run at once: G * H / hop.  One GPU has fewer warps than that; eight
+ * GPUs sharing one volume do not.  In team mode a work item is a GROUP of up to `team` consecutive planes of
+ * one generation, swept by the warps of ONE CTA: warp w takes plane z0 + w and follows warp w - 1 through a
+ * shared-memory row counter raised after EVERY row (CTA-scope release: MEMBAR.CTA + STS, tens of cycles), so
+ * inside a team the hop is the 3 rows the data dependency itself asks for.  The row data still travels
+ * through L2 (st.cg / ld.cg by warps of the same SM, ordered by the CTA-scope release/acquire pair).  Only
+ * the team's last plane hands over to another CTA (or GPU) through the gpu-scope counter / ghost tags, and
+ * every plane keeps raising its gpu-scope counter every flag_rows rows for the next generation's readers.
+ */
+enum { BP3_MAX_TEAM = 24 };
 
 /*
  * Publisher mode.  Raising a progress counter needs a gpu-scope release, and MEMBAR.GPU on a two-die B200
@@ -213,17 +229,23 @@ struct Sweep3 {
         const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead */
         uint32_t *push_dn, *push_up;                /* lane-adjusted peer ghost rows of the current row */
         PubSlot *slot;                              /* publisher mode: this worker's mailbox (else nullptr) */
+        const int *sdn;                             /* team mode: shared-memory row counter of the plane below (else nullptr) */
+        int *sown;                                  /* team mode: own shared-memory row counter (nullptr: nobody follows) */
+        int have_s;                                 /* rows the plane below has published through sdn */
+        int flag_period;                            /* rows between two raises of the own gpu-scope counter */
         const int *flagp;                           /* the producer counter this lane polls (lanes 0..2) */
         int have;                                   /* min over the producers' published row counts */
         int next_raise;                             /* next row count at which the own counter is raised */
         int dn_mode, up_mode;
         uint32_t tag_dn, tag_up, tag_out;
-        long long waited_flag, waited_tag;          /* diagnostics: cycles spent in the slow paths */
+        long long waited_flag, waited_tag, waited_team;     /* diagnostics: cycles spent in the slow paths */
     };
 
     /* false = watchdog fired / abort requested */
     CA_MDEV bool wait_rows(const Bp3Params &p, St &st, int need)
     {
+        if (st.sdn && st.have_s < need && !wait_team(p, st, need))
+            return false;
         if (st.have >= need)
             return true;
         long long t0 = 0;
@@ -245,6 +267,35 @@ struct Sweep3 {
         }
         if (t0) st.waited_flag += dp_clock() - t0;
         dp_syncwarp();          /* the polling lanes acquired; the warp barrier extends it to every lane */
+        return true;
+    }
+
+    /*
+     * Team mode: rows of the plane below, swept by the previous warp of this CTA.  Every lane reads the same
+     * shared-memory word (a broadcast), the vote keeps the warp converged, and every lane acquires for itself.
+     */
+    CA_MDEV bool wait_team(const Bp3Params &p, St &st, int need)
+    {
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            const int v = dp_ld_volatile(st.sdn);
+            if (dp_all(v >= need)) {
+                st.have_s = dp_reduce_min(v);
+                break;
+            }
+            if (spins == 0) t0 = dp_clock();
+            if ((spins & 1023u) == 1023u) {
+                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
+                if (!dp_all(!bad)) {
+                    if (dp_lane() == 0)
+                        dp_atomic_max(p.err, 3);
+                    return false;
+                }
+            }
+            dp_team_pause();
+        }
+        if (t0) st.waited_team += dp_clock() - t0;
+        dp_fence_cta();
         return true;
     }
 
@@ -452,15 +503,21 @@ struct Sweep3 {
          */
         const bool at_mark = (y + 1 == st.next_raise);
         if (at_mark)
-            st.next_raise += p.flag_rows;
-        if (at_mark || y + 1 == y1) {
+            st.next_raise += st.flag_period;
+        if (at_mark || y + 1 == y1 || st.sown) {
             dp_syncwarp();
             if (lane == 0) {
-                if (st.slot) {
+                if (st.sown) {                      /* team mode: the next warp of this CTA follows row by row */
                     dp_fence_cta();
-                    dp_st_volatile(&st.slot->done, y + 1);
-                } else {
-                    dp_st_release(myprog, y + 1);
+                    dp_st_volatile(st.sown, y + 1);
+                }
+                if (at_mark || y + 1 == y1) {
+                    if (st.slot) {
+                        dp_fence_cta();
+                        dp_st_volatile(&st.slot->done, y + 1);
+                    } else {
+                        dp_st_release(myprog, y + 1);
+                    }
                 }
             }
         }
@@ -481,7 +538,8 @@ struct Sweep3 {
     }
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
-    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot)
+    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
+                             const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
@@ -508,14 +566,19 @@ struct Sweep3 {
 
         /* ---- producers (ghost sources are synchronised by their row tags, not by counters) ---- */
         {
-            const int *fdn = st.dn_mode == SRC_LOCAL ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
+            /* team mode: the plane below is followed through shared memory, not through its gpu-scope counter */
+            const int *fdn = (st.dn_mode == SRC_LOCAL && !sdn) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
             const int *fup = (g > 0 && st.up_mode == SRC_LOCAL) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
             const int *fown = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
             st.flagp = lane == 0 ? fdn : (lane == 1 ? fup : (lane == 2 ? fown : nullptr));
             st.have = (fdn || fup || fown) ? 0 : 0x7fffffff;
         }
-        st.next_raise = (y0 / p.flag_rows + 1) * p.flag_rows;
-        st.waited_flag = st.waited_tag = 0;
+        st.sdn = sdn;
+        st.sown = sown;
+        st.have_s = 0;
+        st.flag_period = (team_edge && p.edge_flag_rows > 0) ? p.edge_flag_rows : p.flag_rows;
+        st.next_raise = (y0 / st.flag_period + 1) * st.flag_period;
+        st.waited_flag = st.waited_tag = st.waited_team = 0;
         const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
@@ -601,6 +664,7 @@ struct Sweep3 {
             dp_atomic_add64(p.diag + 0, (unsigned long long)st.waited_flag);
             dp_atomic_add64(p.diag + 1, (unsigned long long)st.waited_tag);
             dp_atomic_add64(p.diag + 2, (unsigned long long)(dp_clock() - t_item));
+            dp_atomic_add64(p.diag + 3, (unsigned long long)st.waited_team);
         }
         return true;
     }
@@ -657,6 +721,35 @@ struct Sweep3 {
         }
     }
 
+    /*
+     * Team mode: the CTA claims one group of planes at a time (item = first local plane, generation, number of
+     * planes); warp w sweeps plane w of the group, warps beyond the group's size sit the item out.
+     */
+    CA_MDEV void team_loop(const Bp3Params &p)
+    {
+        CA_SHARED(int, sm, BP3_MAX_TEAM + 1);       /* row counters of the team's warps, then the claimed ticket */
+        const int w = dp_warp_in_block();
+        for (;;) {
+            if (dp_thread() == 0) {
+                unsigned t = dp_atomic_inc(p.ticket);
+                if (dp_ld_flag(p.err) != 0)
+                    t = 0xffffffffu;
+                sm[BP3_MAX_TEAM] = (int)t;
+            }
+            if (dp_thread() < BP3_MAX_TEAM)
+                sm[dp_thread()] = 0;
+            dp_syncblock();
+            const unsigned t = (unsigned)dp_ld_volatile(&sm[BP3_MAX_TEAM]);
+            if (t >= (unsigned)p.nsweeps)
+                break;
+            const int4 it = p.order[t];
+            if (w < it.z)
+                run_segment(p, it.x + w, it.y, 0, p.H, nullptr, w > 0 ? sm + (w - 1) : nullptr,
+                            w + 1 < it.z ? sm + w : nullptr, w + 1 == it.z);
+            dp_syncblock();                         /* the counters are cleared for the next item */
+        }
+    }
+
     CA_MDEV void kernel_body(const Bp3Params &p)
     {
         if (p.pub_workers <= 0) {
@@ -694,10 +787,32 @@ struct Bp3Bounds {
     static constexpr int kMaxThreads = (P == 3 && WPL == 2) ? 640 : ((P <= 4 && WPL == 1) ? 768 : 160);
 };
 
+/*
+ * Team mode is a kernel of its own (one CTA per SM): 512 threads leave every thread 128 registers -- the row
+ * loop of the common variants then needs no spills -- and the widest variants run 256-thread teams.
+ */
+template <int P, int WPL>
+struct Bp3TeamBounds {
+    static constexpr int kMaxThreads = (P <= 4 && WPL <= 2) ? 512 : 256;
+};
+
+/* largest team (warps per CTA) of a variant */
+inline int bp3_team_cap(int P, int WPL)
+{
+    const int t = ((P <= 4 && WPL <= 2) ? 512 : 256) / 32;
+    return t < BP3_MAX_TEAM ? t : (int)BP3_MAX_TEAM;
+}
+
 template <int P, int WPL, class Rule>
 CA_GLOBAL void __launch_bounds__(Bp3Bounds<P, WPL>::kMaxThreads, 1) ca3d_sweep_kernel(Bp3Params p)
 {
     Sweep3<P, WPL, Rule>::kernel_body(p);
+}
+
+template <int P, int WPL, class Rule>
+CA_GLOBAL void __launch_bounds__(Bp3TeamBounds<P, WPL>::kMaxThreads, 1) ca3d_team_kernel(Bp3Params p)
+{
+    Sweep3<P, WPL, Rule>::team_loop(p);
 }
 
 } // namespace clapca

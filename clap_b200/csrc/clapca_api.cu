@@ -47,7 +47,7 @@ int fail(int code, const char *fmt, ...)
                         "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-/* control words of a sweep launch: [0] ticket, [1] err, [4..9] three 64-bit diagnostic cycle counters */
+/* control words of a sweep launch: [0] ticket, [1] err, [4..11] four 64-bit diagnostic cycle counters */
 static const int kTicketWords = 16;
 
 static bool diag_enabled()
@@ -61,12 +61,13 @@ static void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t
 {
     if (!diag_enabled())
         return;
-    unsigned long long d[3] = { 0, 0, 0 };
+    unsigned long long d[4] = { 0, 0, 0, 0 };
     if (cudaMemcpyAsync(d, d_ticket + 4, sizeof(d), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
         cudaStreamSynchronize(stream) != cudaSuccess)
         return;
-    fprintf(stderr, "clapca diag [%s rank %d]: in items %.3e cycles, waiting on counters %.1f %%, on ghost tags %.1f %%\n",
-            what, rank, (double)d[2], d[2] ? 100.0 * d[0] / d[2] : 0.0, d[2] ? 100.0 * d[1] / d[2] : 0.0);
+    fprintf(stderr, "clapca diag [%s rank %d]: in items %.3e cycles, waiting on counters %.1f %%, on ghost tags %.1f %%, "
+            "on team-mates %.1f %%\n", what, rank, (double)d[2], d[2] ? 100.0 * d[0] / d[2] : 0.0,
+            d[2] ? 100.0 * d[1] / d[2] : 0.0, d[2] ? 100.0 * d[3] / d[2] : 0.0);
 }
 
 struct Ctx {
@@ -366,17 +367,47 @@ static const int kMaxFusedGenerations = 4096;
 
 /* work-item claim order of the bit-plane sweep (see bp_plan.h) */
 struct OrderCfg {
-    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals */
+    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals, 3 plane teams */
     int seg_rows;       /* mode 1 */
     int gen_batch;      /* mode 2 */
-    int key() const { return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : 0)); }
+    int team;           /* mode 3: planes per group = warps per CTA */
+    int key() const { return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? team : 0))); }
 };
+
+/*
+ * Team mode (ca3d_bitplane.cuh): warps per CTA = planes per work item; 0 = one warp per sweep.  Default: teams
+ * of 16 for the variants whose register budget allows 512-thread CTAs.  Measured on B200 at 2048^3, coral
+ * (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms, and in the low-parallelism regime that
+ * a rank of an 8-GPU run sees (6 generations' worth of sweeps per dependency level) 35.2 -> 16.4 ms.
+ */
+static int team_config(int P, int WPL)
+{
+    int t = bp3_team_cap(P, WPL) >= 16 ? 16 : 0;
+    if (const char *e = getenv("CLAPCA_TEAM")) t = atoi(e);
+    if (t <= 0) return 0;
+    return std::min(t, bp3_team_cap(P, WPL));
+}
+
+static void sweep_knobs(Bp3Params &p, int team)
+{
+    p.flag_rows = kFlagRows;
+    if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
+    if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
+    if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
+    if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
+    p.team = team;
+    if (const char *e = getenv("CLAPCA_EDGE_FLAG_ROWS")) p.edge_flag_rows = std::max(0, atoi(e));
+}
 
 static const int kGenBatch = 16;
 
-static OrderCfg order_config(int Z, int H, int G, int max_workers)
+static OrderCfg order_config(int Z, int H, int G, int max_workers, int team)
 {
-    OrderCfg oc = { 0, 0, kGenBatch };
+    OrderCfg oc = { 0, 0, kGenBatch, team };
+    if (team > 0) {
+        oc.mode = 3;
+        return oc;
+    }
     if (const char *e = getenv("CLAPCA_ORDER")) { int v = atoi(e); if (v >= 0 && v <= 2) oc.mode = v; }
     if (oc.mode == 1) {
         oc.seg_rows = bp3_segment_rows(Z, H, G, max_workers);
@@ -391,7 +422,8 @@ static OrderCfg order_config(int Z, int H, int G, int max_workers)
 static void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                        std::vector<WorkItem> &items)
 {
-    if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
+    if (oc.mode == 3) bp3_make_items_team(planes, H, G, oc.team, items);
+    else if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
     else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
     else bp3_make_items_timekey(planes, H, G, items);
 }
@@ -472,7 +504,8 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
          * for smaller batches and for smaller volumes) -- the kernel is bound by the ALU pipe (LOP3), not by HBM.
          * CLAPCA_ORDER=1 selects the skewed row segments; CLAPCA_GEN_BATCH / CLAPCA_SEG_ROWS tune them.
          */
-        const OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms));
+        const int team = team_config(P, WPL);
+        const OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms), team);
         if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != oc.key()) {
             std::vector<WorkItem> items;
             make_items(oc, planes, Z, H, G, items);
@@ -497,11 +530,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.prog = g->prog;
         p.order = g->order;
         p.nsweeps = g->n_items;
-        p.flag_rows = kFlagRows;
-        if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
-        if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
-        if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
-        if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
+        sweep_knobs(p, team);
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;
@@ -783,7 +812,7 @@ struct clapca_slab {
     std::vector<Bp3Plane> h_planes;
     int4 *order = nullptr;
     size_t order_bytes = 0;
-    int n_items = 0, order_G = -1;
+    int n_items = 0, order_G = -1, team = -1;
     unsigned *ticket = nullptr;
     unsigned long long *d_pop = nullptr;
     cudaStream_t stream = nullptr;
@@ -953,9 +982,11 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     for (int i = 0; i < 9; i++)
         if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { s->rule = i; break; }
 
-    if (s->order_G != steps) {
+    const int team = team_config(s->P, s->WPL);
+    if (s->order_G != steps || s->team != team) {
         std::vector<WorkItem> items;
-        const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms));
+        const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms), team);
+        s->team = team;
         make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items);
         void *p = s->order;
         if (int rc = ensure_bytes(&p, &s->order_bytes, (items.size() ? items.size() : 1) * sizeof(int4))) {
@@ -1012,12 +1043,8 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.prog = s->prog;
         p.order = s->order;
         p.nsweeps = s->n_items;
-        p.flag_rows = kFlagRows;
         p.epoch = s->epoch;
-        if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
-        if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
-        if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
-        if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
+        sweep_knobs(p, s->team);
         p.ticket = s->ticket;
         p.err = (int *)(s->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;

@@ -98,6 +98,8 @@ CA_DEV void dp_atomic_add_cta(int *p, int v)      { atomicAdd(p, v); }
 CA_DEV bool dp_any(bool p)                        { return __any_sync(CA_FULL, p); }
 CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_nanosleep(unsigned ns)             { __nanosleep(ns); }
+/* polling a shared-memory counter of a sibling warp: give the issue slots away for a moment */
+CA_DEV void dp_team_pause()                       { __nanosleep(20); }
 CA_DEV void dp_prefetch_l2(const void *p)         { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 CA_DEV long long dp_clock()                       { return clock64(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return atomicAdd(p, 1u); }
@@ -211,6 +213,7 @@ CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __
 CA_DEV void dp_st_flag_sys(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 CA_DEV void dp_fence_acquire()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV void dp_nanosleep(unsigned)                { emu_yield(); }
+CA_DEV void dp_team_pause()                       { emu_yield(); }
 CA_DEV void dp_prefetch_l2(const void *)          { }
 CA_DEV long long dp_clock()                       { return emu_clock(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }

@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers]]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows]]]]]]]]]
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
  *            10   = run-time rule with random masks
  *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
@@ -41,6 +41,12 @@ typedef Rule3Const<RANGE(0, 6), B(1) | B(3), 2> R8;
 template <int P, int WPL, class Rule>
 static void launch_sweep(const Bp3Params &p, int warps)
 {
+    if (p.team > 0) {
+        /* team mode: CTAs of `team` warps, each CTA sweeps a group of consecutive planes */
+        const int blocks = (warps + p.team - 1) / p.team;
+        emu_launch(blocks, p.team * 32, [&]() { Sweep3<P, WPL, Rule>::team_loop(p); });
+        return;
+    }
     if (p.pub_workers > 0) {
         /* publisher mode: CTAs of pub_workers worker warps + 1 publisher warp */
         const int blocks = (warps + p.pub_workers - 1) / p.pub_workers;
@@ -103,6 +109,8 @@ int main(int argc, char **argv)
     int flagRows = argc > 14 ? atoi(argv[14]) : 2;   /* rows per progress-counter update */
     int genBatch = argc > 15 ? atoi(argv[15]) : 0;   /* > 0: generation-batched diagonal order, -1: time-key order */
     int pubWorkers = argc > 16 ? atoi(argv[16]) : 0; /* > 0: publisher mode, worker warps per CTA */
+    int team = argc > 17 ? atoi(argv[17]) : 0;       /* > 0: team mode, warps (= planes of a group) per CTA */
+    int edgeFlagRows = argc > 18 ? atoi(argv[18]) : 0;
 
     unsigned surv, born, nr;
     if (nca <= 9) {
@@ -182,7 +190,9 @@ int main(int argc, char **argv)
                          rk[(r + ranks - 1) % ranks].halo.data() };
         bp3_build_planes(k.geo, ptr, k.hl, H, RWP, NP, k.planes);
         std::vector<WorkItem> items;
-        if (genBatch > 0)
+        if (team > 0)
+            bp3_make_items_team(k.planes, H, G, team, items);
+        else if (genBatch > 0)
             bp3_make_items_batched(k.planes, Z, H, G, genBatch, items);
         else if (genBatch < 0)
             bp3_make_items_timekey(k.planes, H, G, items);
@@ -203,6 +213,8 @@ int main(int argc, char **argv)
         k.p.nsweeps = (int)k.order.size();
         k.p.flag_rows = flagRows;
         k.p.pub_workers = pubWorkers;
+        k.p.team = team;
+        k.p.edge_flag_rows = edgeFlagRows;
         k.p.ticket = &k.ticket;
         k.p.err = &err;
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;

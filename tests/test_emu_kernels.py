@@ -111,6 +111,25 @@ def test_ca3d_publisher_warps(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 8, 1, 0, 0, 2, 0, 0, 4),              # 2 CTAs of 4 warps, groups of 4 planes
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 3, 1, 0, 0, 8, 0, 0, 3, 2),           # a single CTA: the claim order alone
+    (64, 33, 7, 9, 10, 4, 2, 1, 9, 12, 1, 0, 0, 4, 0, 0, 5, 1),          # ragged last group, edge plane raised every row
+    (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 3, 0, 0, 1),             # teams of one warp
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 24, 1, 0, 0, 8, 0, 0, 24),            # team larger than the volume
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 6, 2, 2, 0, 2, 0, 0, 3),              # 2 ranks, z-blocks of 2 planes < team
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 8, 3, 5, 0, 4, 0, 0, 4, 1),           # 3 ranks, blocks of 5 = groups of 4 + 1
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 4, 4, 1, 0, 2, 0, 0, 2),             # 4 ranks, every plane is an edge
+    (20, 5, 3, 4, 7, 3, 1, 1, 4, 4, 4, 1, 0, 1, 0, 0, 2),                # ranks without any plane
+    (33, 5, 9, 4, 8, 8, 1, 2, 3, 6, 2, 4, 0, 2, 0, 0, 3),                # ca3d_make seed (255s), 2 ranks
+])
+def test_ca3d_plane_teams(emu_bin, args):
+    """Team mode: a CTA sweeps a group of consecutive planes, warp w follows warp w-1 through a shared-memory
+    row counter raised after every row; only group edges use gpu-scope counters / ghost tags."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
 # ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
 
 @pytest.mark.parametrize("args", [

@@ -119,6 +119,37 @@ def test_ca3d_engines_agree_256cube(gpu):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("team", [1, 3, 16])
+def test_ca3d_team_mode_vs_oracle(gpu, oracle, monkeypatch, team):
+    """Team mode (CLAPCA_TEAM: one CTA sweeps a group of consecutive planes, warps follow each other through
+    shared-memory row counters) against the oracle on ragged shapes, 255-valued cells and every plane count."""
+    monkeypatch.setenv("CLAPCA_TEAM", str(team))
+    rng = np.random.default_rng(400 + team)
+    for shape, nca in (((1, 1, 1), 7), ((33, 6, 5), 0), ((100, 17, 11), 3), ((130, 9, 40), 7), ((70, 40, 37), 6),
+                       ((1500, 24, 9), 7), ((2048, 30, 20), 8), ((4096, 12, 5), 7), ((64, 20, 35), 2)):
+        d0, d1, d2 = shape
+        vol = synth(rng, (d2, d1, d0), 0.4, 6, with255=(nca == 6))
+        want = vol.copy()
+        s, b, n = oracle.ca3d_rule(nca)
+        wpop = oracle.ca3d_run(want, s, b, n, 7)
+        pop = gpu.ca3d_run(vol, nca, 7, engine=BITPLANE)
+        assert pop == wpop and np.array_equal(vol, want), (team, shape, nca)
+
+
+def test_ca3d_team_mode_agrees_with_sweep_mode_512(gpu, monkeypatch):
+    """No CPU in the loop: team mode == one-warp-per-sweep mode at 2048 x 512 x 300, 12 generations."""
+    rng = np.random.default_rng(16)
+    vol = synth(rng, (300, 512, 2048))
+    a, b = vol.copy(), vol.copy()
+    monkeypatch.setenv("CLAPCA_TEAM", "0")
+    pa = gpu.ca3d_run(a, 7, 12, engine=BITPLANE)
+    monkeypatch.setenv("CLAPCA_TEAM", "16")
+    monkeypatch.setenv("CLAPCA_EDGE_FLAG_ROWS", "2")
+    pb = gpu.ca3d_run(b, 7, 12, engine=BITPLANE)
+    assert pa == pb == int(np.count_nonzero(a))
+    assert np.array_equal(a, b)
+
+
 def test_ca3d_generations_compose_large(gpu):
     """Size-independent property at 1024 x 1024 x 96: G1 then G2 generations == G1 + G2 in one fused run."""
     rng = np.random.default_rng(15)
