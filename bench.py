@@ -48,6 +48,14 @@ CA2D_WORKLOADS = {
     "ca2d_4096": (4096, 100, 0x1E0, 0x1F0, 1, True),
     "ca2d_16384_cavetest": (16384, 100, 3 << 2, 3 << 7, 4, True),      # multi-state ca_test rule (terrain.c:391-398)
 }
+# BASELINE config 5 (+ the noise.c bake): per-lattice-point field evaluation
+FIELD_WORKLOADS = {
+    # name: (kind, size)
+    "terrain_8192": ("terrain", 8192),      # terrain.c:447-467 heightmap, maze = ca2d_generate(&ca_test, 1024, 4)
+    "terrain_1024": ("terrain", 1024),
+    "noise_256": ("noise", 256),            # noise_grad3d_bake_rgba8(256, 4, 2.0, 0.5, 37.0, 0xc14d)
+    "noise_64": ("noise", 64),              # the engine's default bake (noise.c:309-317)
+}
 SEED = 0xC1A9
 CHUNK_PLANES = 64
 
@@ -58,7 +66,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ca3d_2048", choices=sorted(WORKLOADS) + sorted(CA2D_WORKLOADS))
+    ap.add_argument("--workload", default="ca3d_2048", choices=sorted(WORKLOADS) + sorted(CA2D_WORKLOADS) + sorted(FIELD_WORKLOADS))
     ap.add_argument("--engine", default="auto", choices=["auto", "wavefront", "bitplane"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -316,6 +324,145 @@ def run_ca2d(args, torch, clap_b200, dev, local):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workloads: BASELINE config 5 (terrain.c heightmap) and the noise.c gradient bake
+# ------------------------------------------------------------------------------------------------
+def run_fields(args, torch, clap_b200, dev, local):
+    import ctypes
+    import numpy as np
+    from ctypes import byref, c_float, c_void_p
+    from clap_b200 import _lib
+    from clap_b200.ca import Rand48
+    kind, size = FIELD_WORKLOADS[args.workload]
+    lib = _lib.lib()
+    peak, peak_src = measured_peak()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > L2 (126 MB): written between steps
+    TSEED, NSEED = 12345, 0xC14D
+
+    if kind == "terrain":
+        nr_v, mside = size, size // 8
+        units = nr_v * nr_v
+        maze = clap_b200.ca2d_generate(clap_b200.CA_TEST, mside, 4, Rand48(7))      # terrain.c:434
+        d_maze = torch.from_numpy(maze).to(dev)
+        d_map0 = torch.empty(units, dtype=torch.float32, device=dev)
+        d_map = torch.empty(units, dtype=torch.float32, device=dev)
+        bytes_per_unit, unit, metric = 8.0, "Mvertex/s", "terrain heightmap vertices/s"
+        kernel = "terrain_heightmap_kernel (+ terrain_map0_kernel for the lattice)"
+        desc = (f"{args.workload}: terrain.c:447-467 map fill, nr_v {nr_v}, seed {TSEED}, maze = ca2d_generate(&ca_test, "
+                f"{mside}, 4) after srand48(7), 4 octaves")
+
+        def step():
+            a, b = c_float(), c_float()
+            _lib.check(lib, lib.clapca_terrain_heightmap_device(c_void_p(d_map.data_ptr()), c_void_p(d_map0.data_ptr()),
+                                                                TSEED, nr_v, 0.0, c_void_p(d_maze.data_ptr()), mside,
+                                                                1.0, 4, byref(a), byref(b)))
+            return a.value + b.value, b.value, 2 if os.environ.get("CLAPCA_TERRAIN_DIRECT") else 3
+
+        host_out = torch.empty(units, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            _lib.check(lib, lib.clapca_terrain_heightmap(c_void_p(host_out.data_ptr()), TSEED, nr_v, 0.0,
+                                                         maze.ctypes.data_as(c_void_p), mside, 1.0, 4))
+        h2d, d2h = maze.nbytes, units * 4
+    else:
+        units = size ** 3
+        period = 37.0 if size == 256 else 64.0
+        d_out = torch.empty(units, dtype=torch.int32, device=dev)
+        bytes_per_unit, unit, metric = 4.0, "Mvoxel/s", "noise gradient bake voxels/s"
+        kernel = "noise_bake_kernel"
+        desc = f"{args.workload}: noise_grad3d_bake_rgba8({size}, 4, 2.0, 0.5, {period}, 0xc14d) (noise.c:222-270)"
+
+        def step():
+            a = c_float()
+            _lib.check(lib, lib.clapca_noise_bake_device(c_void_p(d_out.data_ptr()), size, 4, 2.0, 0.5, period, NSEED,
+                                                         byref(a)))
+            return a.value, a.value, 1
+
+        host_out = torch.empty(units, dtype=torch.int32, pin_memory=True)
+
+        def e2e_step():
+            _lib.check(lib, lib.clapca_noise_grad3d_bake_rgba8(c_void_p(host_out.data_ptr()), size, 4, 2.0, 0.5, period,
+                                                               NSEED))
+        h2d, d2h = 0, units * 4
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    tot_ms = ker_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t, k, n = step()
+        tot_ms += t; ker_ms += k; launches += n
+    clocks = sampler.stop()
+    ms_per_step, kernel_ms = tot_ms / args.steps, ker_ms / args.steps
+    achieved = units * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
+
+    e2e = None
+    if not args.no_e2e:
+        n = max(1, min(args.steps, 3))
+        e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / n
+        e2e = {"value": units / dt / 1e6, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": n}
+
+    cpu = None
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        ref, port = oracle_lib.ref(), oracle_lib.port()
+        kind_cpu = "reference" if ref is not None else "port"
+        if kind == "terrain":
+            # the lattice in full (cheap), then as many vertex rows of the SAME map as the budget allows
+            rows = int(max(8, min(nr_v, args.cpu_seconds * 1.9e6 / nr_v)))
+            t0 = time.perf_counter()
+            map0 = ref.terrain_map0(TSEED, nr_v) if ref is not None else port.terrain_map0(TSEED, nr_v)
+            t1 = time.perf_counter()
+            if ref is not None:
+                buf, _ = ref._boxed(np.ascontiguousarray(maze, np.uint8))
+                out = np.zeros((nr_v, nr_v), np.float32)
+                ref.lib.ref_terrain_heightmap(TSEED, nr_v, map0.ctypes.data_as(c_void_p), 0.0, buf.ctypes.data + 12, 0,
+                                              rows, out.ctypes.data_as(c_void_p))
+            else:
+                port.terrain_heightmap(map0, 0.0, maze, 0, rows)
+            t2 = time.perf_counter()
+            per_vertex = (t1 - t0) / units + (t2 - t1) / (rows * nr_v)
+            cpu = {"value": 1.0 / per_vertex / 1e6, "unit": unit, "cores": 1, "kind": kind_cpu,
+                   "sample": f"lattice map0 in full ({t1 - t0:.1f} s) + vertex rows 0..{rows - 1} of the same {nr_v}^2 map "
+                             f"({t2 - t1:.1f} s) on one core of {os.cpu_count()}; per-vertex cost is uniform"}
+        else:
+            cs = min(size, 128)
+            cperiod = period * cs / size            # same step (= eps) per voxel as the full workload
+            t0 = time.perf_counter()
+            if ref is not None:
+                ref.noise_bake(cs, 4, 2.0, 0.5, cperiod, NSEED)
+            else:
+                port.noise_bake(cs, 4, 2.0, 0.5, cperiod, NSEED)
+            dt = time.perf_counter() - t0
+            cpu = {"value": cs ** 3 / dt / 1e6, "unit": unit, "cores": 1, "kind": kind_cpu,
+                   "sample": f"noise_grad3d_bake_rgba8({cs}, 4, 2.0, 0.5, {cperiod}, 0xc14d): same lattice step per voxel, "
+                             f"{dt:.1f} s on one core of {os.cpu_count()}"}
+
+    line = {
+        "metric": metric, "value": units / (ms_per_step * 1e-3) / 1e6, "unit": unit, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "l2": "a 512 MiB buffer (> L2) is rewritten between timed steps"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.workload), "kernel": kernel, "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_update": bytes_per_unit, "peak_source": peak_src,
+                     "note": "nominally output-bound (HBM), in practice ALU/SFU-bound: see DESIGN.md section 4"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
@@ -342,6 +489,10 @@ def main():
     if args.workload in CA2D_WORKLOADS:
         if rank == 0:
             run_ca2d(args, torch, clap_b200, dev, local)        # fits L2 of one GPU: replicas only
+        return
+    if args.workload in FIELD_WORKLOADS:
+        if rank == 0:
+            run_fields(args, torch, clap_b200, dev, local)      # independent per point: replicas only
         return
     d0, d1, d2, gens, rule_index = WORKLOADS[args.workload]
     rule = ca3d_rule(rule_index)

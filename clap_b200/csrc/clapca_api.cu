@@ -79,6 +79,9 @@ struct Ctx {
     /* small device scalars shared by the helpers below */
     unsigned long long *d_count = nullptr;
     unsigned *d_max = nullptr;
+    /* terrain: table of get_avg_height() (field_kernels.cuh), kept between calls */
+    void *d_smooth = nullptr;
+    size_t smooth_bytes = 0;
 } g_ctx;
 
 int need_init()
@@ -215,6 +218,7 @@ void clapca_shutdown(void)
     cudaDeviceSynchronize();
     if (g_ctx.d_count) cudaFree(g_ctx.d_count);
     if (g_ctx.d_max) cudaFree(g_ctx.d_max);
+    if (g_ctx.d_smooth) cudaFree(g_ctx.d_smooth);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
 }
@@ -1208,8 +1212,21 @@ int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsign
     CU(cudaGetLastError());
     CU(cudaEventRecord(e1, g_ctx.stream));
     if (d_map) {
-        TerrainParams p = { (float *)d_map, (const float *)d_map0, (const uint8_t *)d_maze, nr_v, mside, ty, amp, oct };
-        terrain_heightmap_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
+        TerrainParams p = { (float *)d_map, (const float *)d_map0, (const uint8_t *)d_maze, nr_v, mside, ty, amp, oct,
+                            nullptr };
+        const char *direct = getenv("CLAPCA_TERRAIN_DIRECT");       /* diagnostics: evaluate the 3x3 kernel per use */
+        if (!(direct && atoi(direct) > 0)) {
+            const size_t sn = ((size_t)nr_v + 1) * ((size_t)nr_v + 1);
+            if (int rc = ensure_bytes(&g_ctx.d_smooth, &g_ctx.smooth_bytes, sn * sizeof(float))) return rc;
+            terrain_smooth_kernel<<<grid_blocks_for(sn, 256, 8), 256, 0, g_ctx.stream>>>(p, (float *)g_ctx.d_smooth);
+            CU(cudaGetLastError());
+            p.smooth = (const float *)g_ctx.d_smooth;
+        }
+        /* tabulated blend factors need 2^(oct-1) <= 8 distinct fractions (the reference fixes OCTAVES = 4) */
+        if (p.smooth && (d_maze || (oct >= 0 && oct <= 4)))
+            terrain_heightmap_tab_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
+        else
+            terrain_heightmap_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(e2, g_ctx.stream));

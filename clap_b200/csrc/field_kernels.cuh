@@ -42,13 +42,22 @@ __device__ __forceinline__ float fk_linf(float a, float b, float blend)
     return (float)((double)a * (1.0 - (double)blend) + (double)bb);
 }
 
-/* cosf_interp(): core/interp.h:35-42 */
-__device__ __forceinline__ float fk_cosf_interp(float a, float b, float blend)
+/* cosf_interp(): core/interp.h:35-42, split into the blend factor and the mix so the factor can be tabulated */
+__device__ __forceinline__ float fk_cos_factor(float blend)
 {
     float theta = (float)((double)blend * CLAPCA_PI);
-    float f = (float)((1.0 - (double)cosf(theta)) / 2.0);
+    return (float)((1.0 - (double)cosf(theta)) / 2.0);
+}
+
+__device__ __forceinline__ float fk_cos_mix(float a, float b, float f)
+{
     float bf = b * f;
     return (float)((double)a * (1.0 - (double)f) + (double)bf);
+}
+
+__device__ __forceinline__ float fk_cosf_interp(float a, float b, float blend)
+{
+    return fk_cos_mix(a, b, fk_cos_factor(blend));
 }
 
 /* hash31(): core/noise.h:9-17 */
@@ -181,6 +190,7 @@ struct TerrainParams {
     unsigned nr_v, mside;
     float ty, amp;
     int oct;
+    const float *smooth;        /* (nr_v+1)^2 table of get_avg_height(), or NULL: evaluate it per use */
 };
 
 /* get_mapped_rand_height(): core/terrain.c:21-33 */
@@ -210,13 +220,34 @@ __device__ __forceinline__ float fk_smooth3x3(const TerrainParams &p, int x, int
     return corners + sides + self;
 }
 
+/*
+ * get_avg_height() is a pure function of the integer lattice point, and get_height() only ever asks for
+ * points 0..nr_v (x * freq with freq <= 1, plus one): tabulating it once -- same float operations in the
+ * same order, so the same bits -- turns the 36 lattice reads of an interpolation into 4 table reads.
+ */
+__global__ void __launch_bounds__(256) terrain_smooth_kernel(TerrainParams p, float *smooth)
+{
+    const unsigned side = p.nr_v + 1;
+    const size_t n = (size_t)side * side;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        smooth[i] = fk_smooth3x3(p, (int)(i / side), (int)(i % side));
+}
+
+__device__ __forceinline__ float fk_avg_height(const TerrainParams &p, int x, int z)
+{
+    if (p.smooth)
+        return __ldg(p.smooth + (size_t)x * (p.nr_v + 1) + z);
+    return fk_smooth3x3(p, x, z);
+}
+
 /* get_interp_height(): core/terrain.c:56-71 */
 __device__ __forceinline__ float fk_interp_height(const TerrainParams &p, float x, float z)
 {
     int ix = (int)floor((double)x), iz = (int)floor((double)z);
     float fx = x - (float)ix, fz = z - (float)iz;
-    float v1 = fk_smooth3x3(p, ix, iz), v2 = fk_smooth3x3(p, ix + 1, iz);
-    float v3 = fk_smooth3x3(p, ix, iz + 1), v4 = fk_smooth3x3(p, ix + 1, iz + 1);
+    float v1 = fk_avg_height(p, ix, iz), v2 = fk_avg_height(p, ix + 1, iz);
+    float v3 = fk_avg_height(p, ix, iz + 1), v4 = fk_avg_height(p, ix + 1, iz + 1);
     return fk_cosf_interp(fk_cosf_interp(v1, v2, fx), fk_cosf_interp(v3, v4, fx), fz);
 }
 
@@ -265,6 +296,66 @@ __global__ void __launch_bounds__(256) terrain_heightmap_kernel(TerrainParams p)
             h = fk_octave_height(p, i, j, p.amp, p.oct);
         }
         p.map[idx] = h;
+    }
+}
+
+/*
+ * Table-driven map fill (the default): same arithmetic, far fewer instructions.
+ *   - get_avg_height() comes from the smooth table (terrain_smooth_kernel);
+ *   - get_height() samples octave i at x * 2^i / 2^(oct-1): the fractional parts are multiples of 1 / 2^(oct-1), and
+ *     the maze blend fractions are multiples of 1/8 (MAZE_FAC), so every cosf() of the fill has one of a handful of
+ *     arguments.  The blend factors are tabulated per CTA in shared memory by the SAME device function the direct
+ *     kernel calls (fk_cos_factor), hence the same bits; only powf(1.5, avg) is still evaluated per vertex.
+ * D = 2^(oct-1) <= 8 (the reference fixes OCTAVES = 4, terrain.c:73).
+ */
+__global__ void __launch_bounds__(256) terrain_heightmap_tab_kernel(TerrainParams p)
+{
+    __shared__ float f_oct[8];          /* factor(k / D) */
+    __shared__ float f_frac[8];         /* factor(k / 8): |fi - fj| */
+    __shared__ float f_edge[8];         /* factor(2 * (k / 8) - 1): blend toward the x / y maze neighbour */
+    const int oct = p.maze ? 4 : p.oct;
+    const int D = 1 << (oct > 0 ? oct - 1 : 0);
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        f_oct[k] = fk_cos_factor((float)k / (float)D);
+        float fr = fmodf((float)k, 8.f) / 8;
+        f_frac[k] = fk_cos_factor(fr);
+        f_edge[k] = fk_cos_factor(2 * fr - 1);
+    }
+    __syncthreads();
+
+    const size_t n = (size_t)p.nr_v * p.nr_v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float d = (float)ldexp(1.0, oct - 1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx / p.nr_v), j = (int)(idx % p.nr_v);
+        float amp0 = p.amp, avg = 0.f;
+        if (p.maze) {
+            const int ki = i & 7, kj = j & 7;                   /* fmodf(i, 8) for i >= 0 */
+            const int mi = i >> 3, mj = j >> 3;
+            int cn = fk_maze(p, mi, mj);
+            int xn = fk_maze(p, ki >= 4 ? mi + 1 : mi - 1, mj);
+            int yn = fk_maze(p, mi, kj >= 4 ? mj + 1 : mj - 1);
+            float xa = cn > xn ? (float)cn : fk_cos_mix((float)cn, (float)xn, f_edge[ki]);
+            float ya = cn > yn ? (float)cn : fk_cos_mix((float)cn, (float)yn, f_edge[kj]);
+            avg = fk_cos_mix(xa, ya, f_frac[ki > kj ? ki - kj : kj - ki]);
+            amp0 = powf(1.5f, avg);
+        }
+        float total = 0;
+        for (int o = 0; o < oct; o++) {
+            float freq = (float)(ldexp(1.0, o) / (double)d);
+            float amp = (float)(ldexp(1.0, -o) * (double)amp0);
+            float x = (float)i * freq, z = (float)j * freq;
+            int ix = (int)floorf(x), iz = (int)floorf(z);       /* x >= 0: floor() of the promoted value is the same */
+            float fx = x - (float)ix, fz = z - (float)iz;
+            float gx = f_oct[(int)(fx * (float)D)], gz = f_oct[(int)(fz * (float)D)];
+            const float *row0 = p.smooth + (size_t)ix * (p.nr_v + 1) + iz;
+            const float *row1 = row0 + (p.nr_v + 1);
+            float v1 = __ldg(row0), v2 = __ldg(row1), v3 = __ldg(row0 + 1), v4 = __ldg(row1 + 1);
+            total += fk_cos_mix(fk_cos_mix(v1, v2, gx), fk_cos_mix(v3, v4, gx), gz) * amp;
+        }
+        float h = p.ty + total;
+        p.map[idx] = p.maze ? h + avg : h;
     }
 }
 

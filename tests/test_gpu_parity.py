@@ -384,6 +384,20 @@ def test_terrain_heightmap_golden(gpu):
     _field_close(gpu.terrain_heightmap(12345, 128, 0.0, g["maze_16"]), g["heightmap_128"])
 
 
+def test_terrain_smooth_table_is_bit_identical_to_direct_evaluation(gpu, monkeypatch):
+    """The get_avg_height() table (terrain_smooth_kernel) and the tabulated cosine blend factors
+    (terrain_heightmap_tab_kernel) must not change a single bit of the map: same float operations in the same order
+    as evaluating the 3x3 kernel and cosf() at every use (terrain.c:35-71, interp.h:35-42)."""
+    g = np.load(os.path.join(G, "terrain.npz"))
+    for nr_v, maze, octv in ((128, g["maze_16"], 4), (131, None, 4), (1024, None, 4), (200, None, 1), (77, None, 3),
+                             (96, None, 6)):        # 6 octaves: 32 distinct fractions, no factor table
+        a = gpu.terrain_heightmap(12345, nr_v, 0.5, maze, 1.25, octv)
+        monkeypatch.setenv("CLAPCA_TERRAIN_DIRECT", "1")
+        b = gpu.terrain_heightmap(12345, nr_v, 0.5, maze, 1.25, octv)
+        monkeypatch.delenv("CLAPCA_TERRAIN_DIRECT")
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nr_v, octv)
+
+
 def test_terrain_survey_spot_values_1024(gpu):
     g = np.load(os.path.join(G, "terrain.npz"))
     m = gpu.terrain_map0(12345, 1024)
