@@ -539,6 +539,8 @@ def main():
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_update": 2.0, "peak_source": peak_src}
 
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------
+    # clapca_grid_run3d_streamed: host -> device -> host as one pipeline (H2D chunks, pack / sweep / unpack items of
+    # ONE launch, D2H chunks); the result is checked against the device-resident run's.
     e2e = None
     if not args.no_e2e:
         host_in = torch.empty(cells, dtype=torch.uint8, pin_memory=True)
@@ -546,16 +548,24 @@ def main():
         host_in.copy_(seed_dev.reshape(-1))
         torch.cuda.synchronize()
         n_e2e = max(1, min(args.steps, 3))
+        streamed = False
         for i in range(1 + n_e2e):
             if i == 1:
                 t0 = time.perf_counter()
-            grid.upload(host_in.data_ptr())
-            pop_e = grid.run3d(rule, gens, engine=engine)
-            grid.download(host_out.data_ptr())
+            pop_e = grid.run3d_streamed(rule, gens, host_in.data_ptr(), host_out.data_ptr(), max_value=5)
+            streamed = grid.stats()["streamed"]
         dt = (time.perf_counter() - t0) / n_e2e
         assert pop_e == pop, "end-to-end population differs from the device-resident run"
+        # the device-resident result, downloaded over the (no longer needed) input buffer, must equal the streamed one
+        grid.upload(seed_dev.data_ptr())
+        grid.run3d(rule, gens, engine=engine)
+        grid.download(host_in.data_ptr())
+        assert torch.equal(host_in, host_out), "streamed result differs from the device-resident run"
         e2e = {"value": updates / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": cells,
-               "d2h_bytes_per_step": cells + 8, "ms_per_step": dt * 1e3, "steps": n_e2e}
+               "d2h_bytes_per_step": cells + 8, "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "pipeline": "streamed: H2D chunks | pack+sweep+unpack in one launch | D2H chunks" if streamed
+                           else "upload, run, download one after the other",
+               "verified_equal_to_resident_run": True}
         del host_in, host_out
 
     cpu = None
@@ -569,6 +579,8 @@ def main():
         "config": {"workload": f"{args.workload}: ca3d_run {d0}x{d1}x{d2} uint8, {gens} generations, rule {rule.name}, "
                                f"seed P(alive)=1/4 values 1..5",
                    "engine": st["engine"], "planes": st["planes"], "workers": st["workers"],
+                   "layout": "pack / unpack fused into the sweep launch" if st["launches"] == 2 else
+                             "separate pack / unpack kernels",
                    "l2": "input volume (%.1f GiB) is larger than L2; state is reset from a pristine device copy "
                          "before every step" % (cells / 2 ** 30),
                    "population": pop, "wall_s_timed_region": wall},

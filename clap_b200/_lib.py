@@ -28,7 +28,7 @@ class ClapcaError(RuntimeError):
 
 class RunStats(Structure):
     _fields_ = [("total_ms", c_float), ("kernel_ms", c_float), ("launches", c_int), ("engine", c_int),
-                ("planes", c_int), ("workers", c_int)]
+                ("planes", c_int), ("workers", c_int), ("streamed", c_int)]
 
 
 # every symbol include/clapca.h declares: (restype, argtypes)
@@ -55,6 +55,8 @@ SIGNATURES = {
     "clapca_grid_device_ptr": (c_void_p, [c_void_p]),
     "clapca_grid_stream": (c_void_p, [c_void_p]),
     "clapca_grid_run3d": (c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_int, c_int, POINTER(c_int64)]),
+    "clapca_grid_run3d_streamed": (c_int, [c_void_p, c_void_p, c_void_p, c_uint, c_uint32, c_uint32, c_uint32, c_int,
+                                           POINTER(c_int64)]),
     "clapca_grid_run2d": (c_int, [c_void_p, c_int64, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, c_int]),
     "clapca_grid_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "clapca_grid_last_stats": (c_int, [c_void_p, POINTER(RunStats)]),

@@ -152,6 +152,19 @@ class Grid:
                                                      int(steps), engine, byref(pop)))
         return pop.value
 
+    def run3d_streamed(self, rule, steps, host_in, host_out, max_value=255):
+        """clapca_grid_run3d_streamed(): host -> device -> host as one pipeline (upload, all generations and download
+        overlap inside one sweep launch when the buffers are page-locked).  host_in / host_out: numpy uint8 arrays
+        or raw addresses (pinned torch tensors' data_ptr()); max_value bounds the input cells (255 is always safe)."""
+        rule = rule if isinstance(rule, CellAutomaton) else ca3d_rule(int(rule))
+        pin = host_in.ctypes.data if isinstance(host_in, np.ndarray) else int(host_in)
+        pout = host_out.ctypes.data if isinstance(host_out, np.ndarray) else int(host_out)
+        pop = c_int64(0)
+        check(self._lib, self._lib.clapca_grid_run3d_streamed(self._h, c_void_p(pin), c_void_p(pout), int(max_value),
+                                                              rule.surv_mask, rule.born_mask, rule.nr_states,
+                                                              int(steps), byref(pop)))
+        return pop.value
+
     def run2d(self, ca, steps, side=None, engine=ENGINE_AUTO):
         side = self.dims[0] if side is None else int(side)
         check(self._lib, self._lib.clapca_grid_run2d(self._h, side, ca.born_mask, ca.surv_mask, ca.nr_states,
@@ -167,4 +180,4 @@ class Grid:
         check(self._lib, self._lib.clapca_grid_last_stats(self._h, byref(st)))
         return {"total_ms": st.total_ms, "kernel_ms": st.kernel_ms, "launches": st.launches,
                 "engine": _lib.ENGINE_NAMES.get(st.engine, str(st.engine)), "planes": st.planes,
-                "workers": st.workers}
+                "workers": st.workers, "streamed": bool(st.streamed)}

@@ -198,11 +198,17 @@ inline void bp3_make_items(const std::vector<Bp3Plane> &planes, int Zg, int H, i
  * so claimed items rarely stall on each other; the price is that consecutive generations of a plane
  * run far apart and the volume streams through HBM once per generation.
  */
-inline void bp3_make_items_timekey(const std::vector<Bp3Plane> &planes, int H, int G, std::vector<WorkItem> &items)
+inline void bp3_make_items_timekey(const std::vector<Bp3Plane> &planes, int H, int G, std::vector<WorkItem> &items,
+                                   bool layout_items = false)
 {
     std::vector<std::pair<long long, WorkItem>> tmp;
-    tmp.reserve(planes.size() * (size_t)G);
-    for (int g = 0; g < G; g++)
+    tmp.reserve(planes.size() * (size_t)(G + 2));
+    /*
+     * layout_items (ca3d_bitplane.cuh): every plane gets a pack item at "generation -1" and an unpack item at
+     * "generation G".  The same key orders them: pack (z,-1) and (z+1,-1) precede sweep (z,0), unpack (z,G)
+     * follows sweep (z,G-1).
+     */
+    for (int g = layout_items ? -1 : 0; g < (layout_items ? G + 1 : G); g++)
         for (size_t l = 0; l < planes.size(); l++)
             tmp.push_back({ (2LL * planes[l].zglobal + 4LL * g) * 65536 + g, WorkItem{ (int)l, g, 0, H } });
     std::sort(tmp.begin(), tmp.end(),
@@ -257,7 +263,7 @@ inline void bp3_make_items_batched(const std::vector<Bp3Plane> &planes, int Zg, 
  * the dependency order: the globally first unfinished group is always running or next in line on its rank.
  */
 inline void bp3_make_items_team(const std::vector<Bp3Plane> &planes, int H, int G, int T,
-                                std::vector<WorkItem> &items)
+                                std::vector<WorkItem> &items, bool layout_items = false)
 {
     items.clear();
     if (G <= 0 || planes.empty())
@@ -275,8 +281,9 @@ inline void bp3_make_items_team(const std::vector<Bp3Plane> &planes, int H, int 
         l = e;
     }
     std::vector<std::pair<long long, WorkItem>> tmp;
-    tmp.reserve(groups.size() * (size_t)G);
-    for (int g = 0; g < G; g++)
+    tmp.reserve(groups.size() * (size_t)(G + 2));
+    /* layout_items: pack groups at "generation -1", unpack groups at "generation G"; the key orders them as well */
+    for (int g = layout_items ? -1 : 0; g < (layout_items ? G + 1 : G); g++)
         for (const Group &gr : groups)
             tmp.push_back({ ((long long)gr.z0 + (long long)(T + 1) * g) * 65536 + g, WorkItem{ gr.l0, g, gr.n, H } });
     std::sort(tmp.begin(), tmp.end(),

@@ -65,7 +65,32 @@ struct Bp3Params {
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
     int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
+    /*
+     * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
+     * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
+     */
+    int layout_items;       /* != 0: items with g == -1 pack a plane, items with g == G unpack it; prog has a row -1 */
+    uint8_t *io_cells;      /* reference-layout cells of the local planes, (z*H + y)*W + x */
+    const int *in_ready;    /* chunks of io_chunk planes that have landed in io_cells (raised by the copy stream) */
+    int *out_done;          /* [Z] = io_epoch once the plane's final cells are back in io_cells (host-mapped memory) */
+    int io_chunk;           /* planes per H2D chunk */
+    int io_epoch;           /* run number written into out_done */
+    unsigned long long *population;     /* += non-zero cells of every unpacked plane */
 };
+
+/*
+ * Layout items.  With layout_items set the claim order holds two more item kinds around the G sweep
+ * generations of every plane: "generation -1" PACKS the plane (uint8 cells -> row record, publishing
+ * prog[-1][z] so that sweep (z,0) and (z-1,0) wait for it exactly as they wait for a previous generation),
+ * and "generation G" UNPACKS it (row record -> uint8 cells + population) as soon as sweep (z,G-1) is done.
+ * A pack item first waits until the copy engine has delivered the plane's chunk (in_ready, raised by a
+ * stream-ordered 4-byte copy after each chunk's H2D copy); an unpack item stores the run's epoch into
+ * out_done[z] -- host-mapped memory -- after a system-scope fence, and the host thread inside the C-ABI call
+ * issues a chunk's D2H copy as soon as all of its planes carry the epoch.  Upload, all
+ * generations and download of a volume then overlap inside ONE launch: the sweep follows the H2D front a
+ * few planes behind and the D2H follows the last generation.  Cells whose value does not fit the P state
+ * planes of the launched variant raise err = 4 (the host picks P from the caller's bound and verifies here).
+ */
 
 /*
  * Team mode.  With one warp per sweep and gpu-scope counters, plane z+1 trails plane z by flag_rows + ~3 rows
@@ -568,8 +593,10 @@ struct Sweep3 {
         {
             /* team mode: the plane below is followed through shared memory, not through its gpu-scope counter */
             const int *fdn = (st.dn_mode == SRC_LOCAL && !sdn) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
-            const int *fup = (g > 0 && st.up_mode == SRC_LOCAL) ? pl.up_flag + (size_t)(g - 1) * pl.up_gstride : nullptr;
-            const int *fown = g > 0 ? p.prog + (size_t)(g - 1) * Z + z : nullptr;
+            /* layout items: "generation -1" is the pack item of a plane, counted in row -1 of the table */
+            const bool prev = g > 0 || p.layout_items;
+            const int *fup = (prev && st.up_mode == SRC_LOCAL) ? pl.up_flag + ((long long)g - 1) * (long long)pl.up_gstride : nullptr;
+            const int *fown = prev ? p.prog + ((long long)g - 1) * Z + z : nullptr;
             st.flagp = lane == 0 ? fdn : (lane == 1 ? fup : (lane == 2 ? fown : nullptr));
             st.have = (fdn || fup || fown) ? 0 : 0x7fffffff;
         }
@@ -669,6 +696,174 @@ struct Sweep3 {
         return true;
     }
 
+    /* ---- layout items: one warp converts one plane -------------------------------------------------------- */
+
+    /* poll *flag (written by the copy stream or by other SMs) until it reaches `need`; false = watchdog / abort */
+    CA_MDEV bool wait_word(const Bp3Params &p, const int *flag, int need, bool sys, int code)
+    {
+        const int lane = dp_lane();
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            int v = 0x7fffffff;
+            if (lane == 0)
+                v = sys ? dp_ld_flag_sys(flag) : dp_ld_acquire(flag);
+            if (dp_reduce_min(v) >= need)
+                break;
+            if (spins == 0) t0 = dp_clock();
+            dp_nanosleep(200);
+            if ((spins & 127u) == 127u) {
+                /* the copy engine may take its time: 16 x the budget of a dataflow wait */
+                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > 16 * p.spin_limit;
+                if (!dp_all(!bad)) {
+                    if (lane == 0)
+                        dp_atomic_max(p.err, code);
+                    return false;
+                }
+            }
+        }
+        if (sys)
+            dp_fence_sys();
+        dp_syncwarp();
+        return true;
+    }
+
+    /* uint8 cells of plane z -> row records; publishes prog[-1][z] */
+    CA_MDEV bool pack_plane(const Bp3Params &p, int z)
+    {
+        const int lane = dp_lane();
+        const int H = p.H, W = p.W;
+        if (p.in_ready && !wait_word(p, p.in_ready, z / p.io_chunk + 1, true, 5))
+            return false;
+        int *myprog = p.prog - p.Z + z;
+        const uint8_t *src = p.io_cells + (size_t)z * H * W;
+        uint32_t *rec = p.rows + (size_t)z * H * RECW + lane * WPL;
+        const bool vec = (W & 15) == 0;
+        constexpr uint32_t kOver = (P >= 8) ? 0u : (((0xffu << P) & 0xffu) * 0x01010101u);
+        uint32_t over = 0u;
+        for (int y = 0; y < H; y++, src += W, rec += RECW) {
+            uint32_t s[P][WPL], a[WPL], h0[WPL], h1[WPL];
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                const int x0 = 32 * (lane * WPL + j);
+#pragma unroll
+                for (int q = 0; q < P; q++) s[q][j] = 0u;
+                if (vec && x0 + 32 <= W) {
+                    const uint4 lo = dp_ld_cg(reinterpret_cast<const uint4 *>(src + x0));
+                    const uint4 hi = dp_ld_cg(reinterpret_cast<const uint4 *>(src + x0 + 16));
+                    const uint32_t r[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        over |= r[k];
+#pragma unroll
+                        for (int q = 0; q < P; q++)
+                            s[q][j] |= ((((r[k] >> q) & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+                    }
+                } else {
+                    for (int i = 0; i < 32 && x0 + i < W; i++) {
+                        const uint32_t v = dp_ld_cg(src + x0 + i);
+                        over |= v;
+#pragma unroll
+                        for (int q = 0; q < P; q++) s[q][j] |= ((v >> q) & 1u) << i;
+                    }
+                }
+                a[j] = 0u;
+#pragma unroll
+                for (int q = 0; q < P; q++) a[j] |= s[q][j];
+            }
+            bp_hsum<WPL>(a, h0, h1);
+            LaneVec<WPL>::st(rec, h0);
+            LaneVec<WPL>::st(rec + RWP, h1);
+#pragma unroll
+            for (int q = 0; q < P; q++)
+                LaneVec<WPL>::st(rec + (2 + q) * RWP, s[q]);
+            if (((y + 1) & 31) == 0 || y + 1 == H) {
+                dp_syncwarp();
+                if (lane == 0)
+                    dp_st_release(myprog, y + 1);
+            }
+        }
+        if (!dp_all((over & kOver) == 0u)) {
+            if (lane == 0)
+                dp_atomic_max(p.err, 4);
+            return false;
+        }
+        return true;
+    }
+
+    /* row records of plane z after the last generation -> uint8 cells, population, out_done[z] */
+    CA_MDEV bool unpack_plane(const Bp3Params &p, int z)
+    {
+        const int lane = dp_lane();
+        const int H = p.H, W = p.W;
+        if (p.G > 0 && !wait_word(p, p.prog + (size_t)(p.G - 1) * p.Z + z, H, false, 6))
+            return false;
+        if (p.G <= 0 && !wait_word(p, p.prog - p.Z + z, H, false, 6))
+            return false;
+        uint8_t *dst = p.io_cells + (size_t)z * H * W;
+        const uint32_t *rec = p.rows + (size_t)z * H * RECW + lane * WPL;
+        const bool vec = (W & 15) == 0;
+        unsigned pop = 0u;
+        for (int y = 0; y < H; y++, dst += W, rec += RECW) {
+            uint32_t s[P][WPL];
+#pragma unroll
+            for (int q = 0; q < P; q++)
+                LaneVec<WPL>::ld(rec + (2 + q) * RWP, s[q]);
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                const int x0 = 32 * (lane * WPL + j);
+                uint32_t alive = 0u;
+#pragma unroll
+                for (int q = 0; q < P; q++) alive |= s[q][j];
+                pop += (unsigned)dp_popc(alive);
+                if (vec && x0 + 32 <= W) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        uint32_t v = 0u;
+#pragma unroll
+                        for (int q = 0; q < P; q++)
+                            v |= ((((s[q][j] >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) << q;
+                        r[k] = v;
+                    }
+                    dp_st_cg(reinterpret_cast<uint4 *>(dst + x0), make_uint4(r[0], r[1], r[2], r[3]));
+                    dp_st_cg(reinterpret_cast<uint4 *>(dst + x0 + 16), make_uint4(r[4], r[5], r[6], r[7]));
+                } else {
+                    for (int i = 0; i < 32 && x0 + i < W; i++) {
+                        uint32_t v = 0u;
+#pragma unroll
+                        for (int q = 0; q < P; q++) v |= ((s[q][j] >> i) & 1u) << q;
+                        dst[x0 + i] = (uint8_t)v;
+                    }
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1)
+            pop += dp_shfl_down(pop, o);
+        dp_syncwarp();
+        if (lane == 0) {
+            if (p.population)
+                dp_atomic_add64(p.population, (unsigned long long)pop);
+            if (p.out_done) {
+                dp_fence_sys();             /* the cells must be visible to the copy engine before the word moves */
+                dp_st_flag_sys(p.out_done + z, p.io_epoch);
+            }
+        }
+        return true;
+    }
+
+    /* dispatch on the item kind: g == -1 pack, g == G unpack (layout items), else a sweep segment */
+    CA_MDEV bool run_item(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
+                          const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
+    {
+        if (p.layout_items) {
+            if (g < 0)
+                return pack_plane(p, z);
+            if (g >= p.G)
+                return unpack_plane(p, z);
+        }
+        return run_segment(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+    }
+
     /* the worker loop: claim items in dependency order until the list is exhausted */
     CA_MDEV void work_loop(const Bp3Params &p, PubSlot *slot)
     {
@@ -684,7 +879,7 @@ struct Sweep3 {
             if (t >= (unsigned)p.nsweeps)
                 break;
             int4 it = p.order[t];
-            if (!run_segment(p, it.x, it.y, it.z, it.w, slot))
+            if (!run_item(p, it.x, it.y, it.z, it.w, slot))
                 break;
         }
     }
@@ -744,8 +939,8 @@ struct Sweep3 {
                 break;
             const int4 it = p.order[t];
             if (w < it.z)
-                run_segment(p, it.x + w, it.y, 0, p.H, nullptr, w > 0 ? sm + (w - 1) : nullptr,
-                            w + 1 < it.z ? sm + w : nullptr, w + 1 == it.z);
+                run_item(p, it.x + w, it.y, 0, p.H, nullptr, w > 0 ? sm + (w - 1) : nullptr,
+                         w + 1 < it.z ? sm + w : nullptr, w + 1 == it.z);
             dp_syncblock();                         /* the counters are cleared for the next item */
         }
     }

@@ -76,6 +76,7 @@ struct Ctx {
     size_t mem = 0;
     int coop = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;     /* copy streams of the streamed ca3d run */
     /* small device scalars shared by the helpers below */
     unsigned long long *d_count = nullptr;
     unsigned *d_max = nullptr;
@@ -162,9 +163,22 @@ struct clapca_grid {
     const void *planes_prog = nullptr;
     int planes_NP = -1, planes_RWP = -1;
     unsigned *ticket = nullptr;     /* [0] ticket, [1] err (as int) */
+    /* streamed runs (layout items of the sweep kernel): chunk-arrival word and per-plane done flags */
+    int *d_in_ready = nullptr;      /* device: chunks landed, written by 4-byte copies on the H2D stream */
+    int *h_io = nullptr;            /* pinned + mapped: [0, d2) done flags, then the chunk ordinals 1, 2, ... */
+    size_t h_io_count = 0;
+    int io_epoch = 0;
+    cudaEvent_t ev_io = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     clapca_run_stats stats;
+};
+
+/* host buffers of a streamed run */
+struct StreamIO {
+    const uint8_t *host_in;
+    uint8_t *host_out;
+    unsigned max_value;
 };
 
 extern "C" {
@@ -204,6 +218,8 @@ int clapca_init(int device)
     if (!g_ctx.coop)
         return fail(CLAPCA_ERR_CUDA, "device %d does not support cooperative launch", device);
     CU(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g_ctx.stream_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g_ctx.stream_out, cudaStreamNonBlocking));
     CU(cudaMalloc(&g_ctx.d_count, sizeof(unsigned long long)));
     CU(cudaMalloc(&g_ctx.d_max, sizeof(unsigned)));
     g_ctx.device = device;
@@ -220,6 +236,8 @@ void clapca_shutdown(void)
     if (g_ctx.d_max) cudaFree(g_ctx.d_max);
     if (g_ctx.d_smooth) cudaFree(g_ctx.d_smooth);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.stream_in) cudaStreamDestroy(g_ctx.stream_in);
+    if (g_ctx.stream_out) cudaStreamDestroy(g_ctx.stream_out);
     g_ctx = Ctx();
 }
 
@@ -275,6 +293,9 @@ int clapca_grid_destroy(clapca_grid *g)
     if (g->order) cudaFree(g->order);
     if (g->planes) cudaFree(g->planes);
     if (g->ticket) cudaFree(g->ticket);
+    if (g->d_in_ready) cudaFree(g->d_in_ready);
+    if (g->h_io) cudaFreeHost(g->h_io);
+    if (g->ev_io) cudaEventDestroy(g->ev_io);
     for (int i = 0; i < 4; i++)
         if (g->ev[i]) cudaEventDestroy(g->ev[i]);
     delete g;
@@ -424,28 +445,68 @@ static OrderCfg order_config(int Z, int H, int G, int max_workers, int team)
 }
 
 static void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
-                       std::vector<WorkItem> &items)
+                       std::vector<WorkItem> &items, bool layout_items)
 {
-    if (oc.mode == 3) bp3_make_items_team(planes, H, G, oc.team, items);
+    if (oc.mode == 3) bp3_make_items_team(planes, H, G, oc.team, items, layout_items);
     else if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
     else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
-    else bp3_make_items_timekey(planes, H, G, items);
+    else bp3_make_items_timekey(planes, H, G, items, layout_items);
 }
 
+/* CLAPCA_FUSED_LAYOUT=1: device-resident runs also convert the layout inside the sweep launch (layout items) */
+static bool fused_layout_default()
+{
+    const char *e = getenv("CLAPCA_FUSED_LAYOUT");
+    return e && atoi(e) != 0;
+}
+
+/* planes per H2D chunk of a streamed run: ~32 MiB; CLAPCA_IO_CHUNK_MB / CLAPCA_IO_CHUNK_PLANES override */
+static int io_chunk_planes(size_t plane_bytes, int Z)
+{
+    size_t mb = 32;
+    if (const char *e = getenv("CLAPCA_IO_CHUNK_MB")) { int v = atoi(e); if (v > 0) mb = (size_t)v; }
+    size_t c = (mb << 20) / std::max<size_t>(plane_bytes, 1);
+    if (const char *e = getenv("CLAPCA_IO_CHUNK_PLANES")) { int v = atoi(e); if (v > 0) c = (size_t)v; }
+    if (c < 1) c = 1;
+    if (c > (size_t)Z) c = (size_t)Z;
+    while (((size_t)Z + c - 1) / c > 4096) c *= 2;         /* bounded number of copies */
+    return (int)c;
+}
+
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
+/*
+ * The bit-plane engine on a device-resident grid.  io == nullptr: the cells are in g->cells and the result
+ * goes back there.  io != nullptr ("streamed"): the cells are in pinned HOST memory; upload, every generation
+ * and download run as one pipeline inside a single sweep launch (layout items, ca3d_bitplane.cuh): chunks of
+ * planes are copied in on one copy stream, each followed by a 4-byte copy that tells the kernel's pack items
+ * the chunk has landed, and the calling thread issues a chunk's D2H copy on a second copy stream as soon as
+ * the kernel's unpack items have flagged all of its planes in host-mapped memory.
+ */
 static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps,
-                          int64_t *population)
+                          int64_t *population, const StreamIO *io)
 {
     const int W = (int)g->d0, H = (int)g->d1, Z = (int)g->d2;
     const int WPL = bp_wpl_for(W);
     const uint32_t bornval = (nr_states - 1u) & 0xffu;
 
+    CU(cudaEventRecord(g->ev[0], g->stream));
     /* largest value that can ever occur decides the number of state planes */
     unsigned maxv = 0;
-    CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
-    max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&maxv, g_ctx.d_max, sizeof(maxv), cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
+    if (io) {
+        maxv = io->max_value;           /* the caller's bound; the pack items verify it (err = 4) */
+    } else {
+        CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+        max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&maxv, g_ctx.d_max, sizeof(maxv), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+    }
     if (born && bornval > maxv) maxv = bornval;
     const int P = bp_planes_for(maxv);
     const int NP = P + 2, RWP = 32 * WPL;
@@ -461,34 +522,65 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         g->rows = (uint32_t *)p;
     }
 
+    const int team = team_config(P, WPL);
+    /* layout items need whole-plane items and all generations in one launch */
+    bool fused = io != nullptr || fused_layout_default();
+    if (fused && steps > kMaxFusedGenerations) {
+        if (io) return fail(CLAPCA_ERR_UNSUPPORTED, "streamed run: at most %d generations", kMaxFusedGenerations);
+        fused = false;
+    }
+
     unsigned long long *d_pop = g_ctx.d_count;
     Bp3Layout L = { g->cells, g->rows, W, H, Z, P, RWP, d_pop };
     const size_t nwords = (size_t)Z * H * RWP;
+    const size_t plane_bytes = (size_t)W * H;
+    const int chunk = io_chunk_planes(plane_bytes, Z);
+    const int nchunks = (Z + chunk - 1) / chunk;
 
-    CU(cudaEventRecord(g->ev[0], g->stream));
-    ca3d_pack_kernel<<<grid_blocks_for(nwords, 256, 16), 256, 0, g->stream>>>(L);
-    CU(cudaGetLastError());
+    if (io) {
+        if (!g->d_in_ready) CU(cudaMalloc(&g->d_in_ready, 64));
+        if (!g->ev_io) CU(cudaEventCreateWithFlags(&g->ev_io, cudaEventDisableTiming));
+        const size_t want = (size_t)Z + nchunks;
+        if (g->h_io_count < want) {
+            if (g->h_io) cudaFreeHost(g->h_io);
+            g->h_io = nullptr;
+            g->h_io_count = 0;
+            CU(cudaHostAlloc((void **)&g->h_io, want * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+            memset(g->h_io, 0, want * sizeof(int));
+            g->h_io_count = want;
+            g->io_epoch = 0;
+        }
+        for (int c = 0; c < nchunks; c++) g->h_io[Z + c] = c + 1;
+        g->io_epoch++;
+    }
+
+    if (!fused) {
+        ca3d_pack_kernel<<<grid_blocks_for(nwords, 256, 16), 256, 0, g->stream>>>(L);
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(g->ev[1], g->stream));
 
     int launches = 0, workers = 0;
     for (int done = 0; done < steps;) {
         const int G = std::min(steps - done, kMaxFusedGenerations);
         {
+            /* [G + 1][Z]: row 0 is "generation -1" (the pack items of a fused run), p.prog points at row 1 */
             size_t have = g->prog_count * sizeof(int);
             void *p = g->prog;
-            if (int rc = ensure_bytes(&p, &have, (size_t)G * Z * sizeof(int))) { g->prog = nullptr; return rc; }
+            if (int rc = ensure_bytes(&p, &have, (size_t)(G + 1) * Z * sizeof(int))) { g->prog = nullptr; return rc; }
             g->prog = (int *)p;
             g->prog_count = have / sizeof(int);
         }
+        int *prog = g->prog + Z;
         /* per-plane source descriptors: on one GPU every neighbour plane is local (one z-block, no ghosts) */
         std::vector<Bp3Plane> planes;
         {
             SlabGeom geo = { Z, 1, 0, Z };
-            SlabPtrs ptr = { g->rows, g->prog, nullptr, nullptr, nullptr };
+            SlabPtrs ptr = { g->rows, prog, nullptr, nullptr, nullptr };
             HaloLayout hl = slab_halo_layout(geo, H, RWP);
             bp3_build_planes(geo, ptr, hl, H, RWP, NP, planes);
         }
-        if (g->planes_rows != g->rows || g->planes_prog != g->prog || g->planes_NP != NP || g->planes_RWP != RWP ||
+        if (g->planes_rows != g->rows || g->planes_prog != prog || g->planes_NP != NP || g->planes_RWP != RWP ||
             g->planes_bytes < planes.size() * sizeof(Bp3Plane)) {
             void *p = g->planes;
             if (int rc = ensure_bytes(&p, &g->planes_bytes, planes.size() * sizeof(Bp3Plane))) {
@@ -499,7 +591,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
             CU(cudaMemcpyAsync(g->planes, planes.data(), planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice,
                                g->stream));
             CU(cudaStreamSynchronize(g->stream));
-            g->planes_rows = g->rows; g->planes_prog = g->prog; g->planes_NP = NP; g->planes_RWP = RWP;
+            g->planes_rows = g->rows; g->planes_prog = prog; g->planes_NP = NP; g->planes_RWP = RWP;
         }
         /*
          * Claim order (bp_plan.h).  Default: time-key order.  Measured on B200 at 2048^3 x 50
@@ -508,11 +600,15 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
          * for smaller batches and for smaller volumes) -- the kernel is bound by the ALU pipe (LOP3), not by HBM.
          * CLAPCA_ORDER=1 selects the skewed row segments; CLAPCA_GEN_BATCH / CLAPCA_SEG_ROWS tune them.
          */
-        const int team = team_config(P, WPL);
-        const OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms), team);
-        if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != oc.key()) {
+        OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms), team);
+        if (fused && oc.mode != 0 && oc.mode != 3) {
+            if (io) oc.mode = 0;                    /* layout items exist for whole-plane orders only */
+            else return fail(CLAPCA_ERR_UNSUPPORTED, "CLAPCA_FUSED_LAYOUT needs the time-key or the team order");
+        }
+        const int okey = oc.key() + (fused ? 50000000 : 0);
+        if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != okey) {
             std::vector<WorkItem> items;
-            make_items(oc, planes, Z, H, G, items);
+            make_items(oc, planes, Z, H, G, items, fused);
             static_assert(sizeof(WorkItem) == sizeof(int4), "WorkItem must alias int4");
             void *p = g->order;
             if (int rc = ensure_bytes(&p, &g->order_bytes, items.size() * sizeof(int4))) { g->order = nullptr; return rc; }
@@ -521,9 +617,9 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
                                g->stream));
             CU(cudaStreamSynchronize(g->stream));       /* `items` is a stack vector */
             g->n_items = (int)items.size();
-            g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = oc.key();
+            g->order_Z = Z; g->order_H = H; g->order_G = G; g->order_L = okey;
         }
-        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * Z * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)(G + 1) * Z * sizeof(int), g->stream));
         CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
 
         Bp3Params p;
@@ -531,7 +627,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.rows = g->rows;
         p.planes = g->planes;
         p.W = W; p.H = H; p.Z = Z; p.G = G; p.RWP = RWP;
-        p.prog = g->prog;
+        p.prog = prog;
         p.order = g->order;
         p.nsweeps = g->n_items;
         sweep_knobs(p, team);
@@ -540,6 +636,23 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;
         p.surv = surv; p.born = born; p.bornval = bornval;
         p.spin_limit = 4000000000LL;        /* ~2 s of SM clock in a single wait */
+        if (fused) {
+            p.layout_items = 1;
+            p.io_cells = g->cells;
+            p.io_chunk = chunk;
+            p.population = d_pop;
+            CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
+        }
+        if (io) {
+            int *h_io_dev = nullptr;
+            CU(cudaHostGetDevicePointer((void **)&h_io_dev, g->h_io, 0));
+            p.in_ready = g->d_in_ready;
+            p.out_done = h_io_dev;
+            p.io_epoch = g->io_epoch;
+            CU(cudaMemsetAsync(g->d_in_ready, 0, sizeof(int), g->stream));
+            CU(cudaEventRecord(g->ev_io, g->stream));
+            CU(cudaStreamWaitEvent(g_ctx.stream_in, g->ev_io, 0));
+        }
         Bp3LaunchInfo info;
         CU(bp3_launch(rule, P, WPL, p, g_ctx.sms, g->stream, &info));
         launches++;
@@ -547,11 +660,67 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         done += G;
     }
     CU(cudaEventRecord(g->ev[2], g->stream));
+
+    if (io) {
+        /* H2D: every chunk, then its ordinal into the word the pack items poll (stream order = arrival order) */
+        for (int c = 0; c < nchunks; c++) {
+            const size_t off = (size_t)c * chunk * plane_bytes;
+            const size_t len = (size_t)std::min(chunk, Z - c * chunk) * plane_bytes;
+            CU(cudaMemcpyAsync(g->cells + off, io->host_in + off, len, cudaMemcpyHostToDevice, g_ctx.stream_in));
+            CU(cudaMemcpyAsync(g->d_in_ready, g->h_io + Z + c, sizeof(int), cudaMemcpyHostToDevice, g_ctx.stream_in));
+        }
+        /* D2H: this thread follows the unpack items plane by plane and releases a chunk's copy when it is whole */
+        volatile const int *flag = g->h_io;
+        const int epoch = g->io_epoch;
+        bool kernel_done = false, stuck = false;
+        unsigned spins = 0;
+        for (int c = 0; c < nchunks && !stuck;) {
+            const int z0 = c * chunk, z1 = std::min(Z, z0 + chunk);
+            bool ready = true;
+            for (int z = z0; z < z1; z++)
+                if (flag[z] != epoch) { ready = false; break; }
+            if (ready) {
+                const size_t off = (size_t)z0 * plane_bytes;
+                CU(cudaMemcpyAsync(io->host_out + off, g->cells + off, (size_t)(z1 - z0) * plane_bytes,
+                                   cudaMemcpyDeviceToHost, g_ctx.stream_out));
+                c++;
+                continue;
+            }
+            if (kernel_done) { stuck = true; break; }     /* the launch ended without finishing this chunk */
+            if ((++spins & 255u) == 0u) {
+                cudaError_t e = cudaStreamQuery(g->stream);
+                if (e == cudaSuccess) kernel_done = true;   /* one more look at the flags, then give up */
+                else if (e != cudaErrorNotReady) return fail(CLAPCA_ERR_CUDA, "streamed run: %s", cudaGetErrorString(e));
+            }
+            cpu_relax();
+        }
+        CU(cudaStreamSynchronize(g_ctx.stream_in));
+        CU(cudaStreamSynchronize(g_ctx.stream_out));
+        CU(cudaEventRecord(g->ev[3], g->stream));
+        unsigned long long pop = 0;
+        int err = 0;
+        CU(cudaMemcpyAsync(&pop, d_pop, sizeof(pop), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaMemcpyAsync(&err, g->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        diag_report("grid (streamed)", g->ticket, g->stream, 0);
+        if (err == 4)
+            return fail(CLAPCA_ERR_ARG, "streamed run: a cell value exceeds max_value = %u", io->max_value);
+        if (err || stuck)
+            return fail(CLAPCA_ERR_TIMEOUT, "ca3d bit-plane engine (streamed): dataflow watchdog fired (err=%d)", err);
+        if (population) *population = (int64_t)pop;
+        g->stats.launches = launches;
+        g->stats.engine = CLAPCA_ENGINE_BITPLANE;
+        g->stats.planes = P;
+        g->stats.workers = workers;
+        return CLAPCA_OK;
+    }
     diag_report("grid", g->ticket, g->stream, 0);
 
-    CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
-    ca3d_unpack_kernel<<<grid_blocks_for((size_t)Z * H * ((W + 31) / 32), 256, 16), 256, 0, g->stream>>>(L);
-    CU(cudaGetLastError());
+    if (!fused) {
+        CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
+        ca3d_unpack_kernel<<<grid_blocks_for((size_t)Z * H * ((W + 31) / 32), 256, 16), 256, 0, g->stream>>>(L);
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(g->ev[3], g->stream));
 
     unsigned long long pop = 0;
@@ -562,11 +731,18 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     if (err)
         return fail(CLAPCA_ERR_TIMEOUT, "ca3d bit-plane engine: dataflow watchdog fired (err=%d)", err);
     if (population) *population = (int64_t)pop;
-    g->stats.launches = launches + 2;
+    g->stats.launches = launches + (fused ? 1 : 3);     /* + max scan (+ pack, unpack) */
     g->stats.engine = CLAPCA_ENGINE_BITPLANE;
     g->stats.planes = P;
     g->stats.workers = workers;
     return CLAPCA_OK;
+}
+
+/* shapes / step counts the bit-plane engine takes */
+static bool bp3_supported(const clapca_grid *g, int steps)
+{
+    return g->d0 <= 4096 && g->d1 < (1 << 30) && g->d2 < (1 << 30) &&
+           (double)g->d2 * (double)std::min(steps, kMaxFusedGenerations) < 2.0e9;
 }
 
 int clapca_grid_run3d(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_states, int steps, int engine,
@@ -582,15 +758,14 @@ int clapca_grid_run3d(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_
         if (population) *population = pop;
         return CLAPCA_OK;
     }
-    const bool bp_ok = g->d0 <= 4096 && g->d1 < (1 << 30) && g->d2 < (1 << 30) &&
-                       (double)g->d2 * (double)std::min(steps, kMaxFusedGenerations) < 2.0e9;
+    const bool bp_ok = bp3_supported(g, steps);
     if (engine == CLAPCA_ENGINE_AUTO)
         engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
     if (engine == CLAPCA_ENGINE_BITPLANE) {
         if (!bp_ok)
             return fail(CLAPCA_ERR_UNSUPPORTED, "bit-plane engine handles rows of at most 4096 cells (d0 = %lld)",
                         (long long)g->d0);
-        if (int rc = run3d_bitplane(g, surv, born, nr_states, steps, population)) return rc;
+        if (int rc = run3d_bitplane(g, surv, born, nr_states, steps, population, nullptr)) return rc;
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, g->ev[0], g->ev[3]));
         g->stats.total_ms = ms;
@@ -607,6 +782,42 @@ int clapca_grid_run3d(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t nr_
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
     g->stats.kernel_ms = g->stats.total_ms = ms;
+    return CLAPCA_OK;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int clapca_grid_run3d_streamed(clapca_grid *g, const uint8_t *host_in, uint8_t *host_out, unsigned max_value,
+                               uint32_t surv, uint32_t born, uint32_t nr_states, int steps, int64_t *population)
+{
+    if (int rc = need_init()) return rc;
+    if (!g || !host_in || !host_out) return fail(CLAPCA_ERR_ARG, "grid_run3d_streamed: NULL argument");
+    if (steps < 0) return fail(CLAPCA_ERR_ARG, "grid_run3d_streamed: negative step count");
+    if (max_value > 255u) return fail(CLAPCA_ERR_ARG, "grid_run3d_streamed: max_value %u > 255", max_value);
+    const char *e = getenv("CLAPCA_STREAMED");
+    const bool pipelined = steps > 0 && steps <= kMaxFusedGenerations && bp3_supported(g, steps) &&
+                           !(e && atoi(e) == 0) && is_pinned_host(host_in) && is_pinned_host(host_out);
+    if (!pipelined) {
+        /* pageable buffers / shapes outside the bit-plane engine: the same three steps one after the other */
+        if (int rc = clapca_grid_upload(g, host_in)) return rc;
+        if (int rc = clapca_grid_run3d(g, surv, born, nr_states, steps, CLAPCA_ENGINE_AUTO, population)) return rc;
+        return clapca_grid_download(g, host_out);
+    }
+    memset(&g->stats, 0, sizeof(g->stats));
+    StreamIO io = { host_in, host_out, max_value };
+    if (int rc = run3d_bitplane(g, surv, born, nr_states, steps, population, &io)) return rc;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+    g->stats.kernel_ms = g->stats.total_ms = ms;
+    g->stats.streamed = 1;
     return CLAPCA_OK;
 }
 
@@ -991,7 +1202,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
         std::vector<WorkItem> items;
         const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms), team);
         s->team = team;
-        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items);
+        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items, false);
         void *p = s->order;
         if (int rc = ensure_bytes(&p, &s->order_bytes, (items.size() ? items.size() : 1) * sizeof(int4))) {
             s->order = nullptr;

@@ -151,6 +151,22 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born_mask, uint32_t
 int clapca_grid_count(clapca_grid *g, int64_t *population);
 
 /*
+ * ca3d_run() (core/ca3d.c:124-142) from host memory to host memory as ONE pipeline: the volume is copied in
+ * chunk by chunk while the sweep kernel already runs, the kernel itself converts the layout plane by plane
+ * (no separate pack / unpack pass), every generation follows the upload front a few planes behind, and
+ * finished planes are copied out while later planes are still being swept -- H2D, all generations and D2H of
+ * one volume overlap instead of adding up.  host_in / host_out are d0*d1*d2 uint8 cells in the reference
+ * layout (core/xyarray.c:43) and may be the same buffer.  `max_value` is an upper bound on the input cells
+ * (it fixes the number of state bit planes before the data has arrived); the kernel verifies it and the call
+ * fails with CLAPCA_ERR_ARG -- output undefined -- if a cell exceeds it; 255 is always safe.  Buffers that
+ * are not page-locked (cudaHostAlloc / cudaHostRegister), and shapes the bit-plane engine does not take, run
+ * the same three steps one after the other; the result is identical either way.
+ */
+int clapca_grid_run3d_streamed(clapca_grid *g, const uint8_t *host_in, uint8_t *host_out, unsigned max_value,
+                               uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states, int steps,
+                               int64_t *population);
+
+/*
  * Timing of the last *_run on this grid, measured with CUDA events on the
  * grid's stream: total device milliseconds, the share spent in the
  * generation kernel(s) alone (excludes layout pack/unpack and the count), the
@@ -163,6 +179,7 @@ typedef struct clapca_run_stats {
     int     engine;
     int     planes;          /* bit planes used by the bit-plane engine (0 otherwise) */
     int     workers;         /* persistent warps (bit-plane) / threads per wavefront step */
+    int     streamed;        /* 1: the run overlapped H2D / sweep / D2H (clapca_grid_run3d_streamed) */
 } clapca_run_stats;
 int clapca_grid_last_stats(clapca_grid *g, clapca_run_stats *st);
 

@@ -4,7 +4,11 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows]]]]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows [layout [chunk]]]]]]]]]]]
+ *   layout   1 = layout items (pack / unpack run as work items of the sweep launch, cells resident),
+ *            2 = layout items fed by a "copy engine" thread that delivers the cells chunk by chunk and raises
+ *                in_ready, while a second thread drains finished chunks as their planes' out_done words show the epoch
+ *            (single rank, time-key or team order)
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
  *            10   = run-time rule with random masks
  *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
@@ -14,6 +18,8 @@
 #include <string.h>
 #include <vector>
 #include <thread>
+#include <chrono>
+#include <algorithm>
 #include "emu_runtime.h"
 #include "../../clap_b200/csrc/ca3d_bitplane.cuh"
 #include "../../clap_b200/csrc/ca3d_layout.cuh"
@@ -111,6 +117,12 @@ int main(int argc, char **argv)
     int pubWorkers = argc > 16 ? atoi(argv[16]) : 0; /* > 0: publisher mode, worker warps per CTA */
     int team = argc > 17 ? atoi(argv[17]) : 0;       /* > 0: team mode, warps (= planes of a group) per CTA */
     int edgeFlagRows = argc > 18 ? atoi(argv[18]) : 0;
+    int layout = argc > 19 ? atoi(argv[19]) : 0;
+    int chunk = argc > 20 ? atoi(argv[20]) : 2;
+    if (layout && (ranks != 1 || (team <= 0 && genBatch >= 0))) {
+        fprintf(stderr, "layout items: single rank, time-key (genbatch -1) or team order\n");
+        return 2;
+    }
 
     unsigned surv, born, nr;
     if (nca <= 9) {
@@ -162,6 +174,8 @@ int main(int argc, char **argv)
         std::vector<int> prog;
         std::vector<Bp3Plane> planes;
         std::vector<int4> order;
+        std::vector<int> out_done;
+        int in_ready = 0;
         unsigned ticket = 0;
         unsigned long long pop = 0;
         Bp3Params p;
@@ -181,26 +195,26 @@ int main(int argc, char **argv)
         }
         k.rows.assign((size_t)(Zl ? Zl : 1) * H * NP * RWP, 0xdeadbeefu);
         k.halo.assign(k.hl.total_words, 0u);
-        k.prog.assign((size_t)Gcap * (Zl ? Zl : 1), 0);
+        k.prog.assign((size_t)(Gcap + 1) * (Zl ? Zl : 1), 0);       /* row 0 = "generation -1" of the layout items */
     }
     for (int r = 0; r < ranks; r++) {
         Rank &k = rk[r];
         const int Zl = k.geo.local_planes();
-        SlabPtrs ptr = { k.rows.data(), k.prog.data(), k.halo.data(), rk[(r + 1) % ranks].halo.data(),
+        SlabPtrs ptr = { k.rows.data(), k.prog.data() + (Zl ? Zl : 1), k.halo.data(), rk[(r + 1) % ranks].halo.data(),
                          rk[(r + ranks - 1) % ranks].halo.data() };
         bp3_build_planes(k.geo, ptr, k.hl, H, RWP, NP, k.planes);
         std::vector<WorkItem> items;
         if (team > 0)
-            bp3_make_items_team(k.planes, H, G, team, items);
+            bp3_make_items_team(k.planes, H, G, team, items, layout != 0);
         else if (genBatch > 0)
             bp3_make_items_batched(k.planes, Z, H, G, genBatch, items);
         else if (genBatch < 0)
-            bp3_make_items_timekey(k.planes, H, G, items);
+            bp3_make_items_timekey(k.planes, H, G, items, layout != 0);
         else
             bp3_make_items(k.planes, Z, H, G, segL > 0 ? segL : bp3_segment_rows(Z, H, G, warps), items);
         k.order.resize(items.size());
         for (size_t i = 0; i < items.size(); i++) k.order[i] = make_int4(items[i].z, items[i].g, items[i].y0, items[i].y1);
-        if (Zl) {
+        if (Zl && !layout) {
             Bp3Layout L = { k.cells.data(), k.rows.data(), W, H, Zl, P, RWP, &k.pop };
             emu_launch(2, 64, [&]() { ca3d_pack_kernel(L); });
         }
@@ -208,7 +222,7 @@ int main(int argc, char **argv)
         k.p.rows = k.rows.data();
         k.p.planes = k.planes.data();
         k.p.W = W; k.p.H = H; k.p.Z = Zl; k.p.G = G; k.p.RWP = RWP;
-        k.p.prog = k.prog.data();
+        k.p.prog = k.prog.data() + (Zl ? Zl : 1);
         k.p.order = k.order.data();
         k.p.nsweeps = (int)k.order.size();
         k.p.flag_rows = flagRows;
@@ -219,6 +233,16 @@ int main(int argc, char **argv)
         k.p.err = &err;
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;
         k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
+        if (layout) {
+            k.out_done.assign(Zl + 1, 0);
+            k.p.layout_items = 1;
+            k.p.io_cells = k.cells.data();
+            k.p.in_ready = layout == 2 ? &k.in_ready : nullptr;
+            k.p.out_done = k.out_done.data();
+            k.p.io_chunk = chunk;
+            k.p.io_epoch = 3;
+            k.p.population = &k.pop;
+        }
     }
     /* halo init: the first plane of every block but the first seeds the ghost plane above the previous block */
     const uint32_t epoch = 7;
@@ -232,8 +256,37 @@ int main(int argc, char **argv)
             emu_launch(1, 64, [&]() { halo_seed_kernel(dst, src, H, RWP, NP, WPL, epoch << 16); });
         }
     }
+    std::vector<uint8_t> host_in, host_out;
+    if (layout == 2) {
+        /* the cells only arrive while the kernel runs: start from garbage */
+        host_in = rk[0].cells;
+        host_out.assign(n, 0xEE);
+        memset(rk[0].cells.data(), 0xA5, rk[0].cells.size());
+    }
     if (G > 0) {
         std::vector<std::thread> ths;
+        if (layout == 2) {
+            Rank &k = rk[0];
+            const size_t plane = (size_t)W * H;
+            const int nchunks = (Z + chunk - 1) / chunk;
+            ths.emplace_back([&, plane, nchunks]() {            /* "H2D copy stream": memcpy, then the 32-bit write */
+                for (int c = 0; c < nchunks; c++) {
+                    std::this_thread::sleep_for(std::chrono::microseconds(300));
+                    const int z0 = c * chunk, z1 = std::min(Z, z0 + chunk);
+                    memcpy(k.cells.data() + z0 * plane, host_in.data() + z0 * plane, (z1 - z0) * plane);
+                    __atomic_store_n(&k.in_ready, c + 1, __ATOMIC_SEQ_CST);
+                }
+            });
+            ths.emplace_back([&, plane, nchunks]() {            /* "D2H copy stream": 32-bit wait, then memcpy */
+                for (int c = 0; c < nchunks; c++) {
+                    const int z0 = c * chunk, z1 = std::min(Z, z0 + chunk);
+                    for (int z = z0; z < z1; z++)
+                        while (__atomic_load_n(&k.out_done[z], __ATOMIC_SEQ_CST) != 3 && !__atomic_load_n(&err, __ATOMIC_SEQ_CST))
+                            std::this_thread::yield();
+                    memcpy(host_out.data() + z0 * plane, k.cells.data() + z0 * plane, (z1 - z0) * plane);
+                }
+            });
+        }
         for (int r = 0; r < ranks; r++)
             ths.emplace_back([&, r]() {
                 const Bp3Params &p = rk[r].p;
@@ -253,7 +306,17 @@ int main(int argc, char **argv)
     }
     std::vector<uint8_t> got(n, 0xEE);
     unsigned long long pop = 0;
-    for (int r = 0; r < ranks; r++) {
+    if (layout) {
+        Rank &k = rk[0];
+        for (int z = 0; z < Z; z++)
+            if (k.out_done[z] != 3) {
+                printf("FAIL out_done[%d]=%d\n", z, k.out_done[z]);
+                return 1;
+            }
+        got = layout == 2 ? host_out : k.cells;
+        pop = k.pop;
+    }
+    for (int r = 0; r < ranks && !layout; r++) {
         Rank &k = rk[r];
         const int Zl = k.geo.local_planes();
         if (!Zl) continue;

@@ -130,6 +130,27 @@ def test_ca3d_plane_teams(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows layout chunk
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1, 0, 0, 0, 1, 2),        # time-key order, cells resident
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1, 0, 0, 0, 2, 3),        # ... fed / drained chunk by chunk
+    (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 3, -1, 0, 0, 0, 2, 16),      # one worker: the claim order alone
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 8, 1, 0, 0, 2, 0, 0, 4, 0, 1, 2),         # plane teams, cells resident
+    (45, 20, 13, 5, 7, 3, 1, 1, 3, 8, 1, 0, 0, 2, 0, 0, 4, 0, 2, 4),         # teams, ragged last group and chunk
+    (64, 33, 7, 9, 10, 4, 2, 1, 9, 12, 1, 0, 0, 4, 0, 0, 5, 1, 2, 2),        # 2 words per lane, 16-byte row path
+    (48, 12, 10, 3, 2, 8, 1, 2, 5, 1, 1, 0, 0, 3, 0, 0, 1, 0, 2, 1),         # ca3d_make seed (255s), 8 planes
+    (2048, 3, 5, 2, 7, 3, 2, 0, 9, 4, 1, 0, 0, 2, -1, 0, 0, 0, 2, 2),        # BASELINE config-4 row width
+    (1030, 2, 3, 2, 0, 3, 2, 1, 8, 3, 1, 0, 0, 2, -1, 0, 0, 0, 2, 1),        # ragged row end inside a word
+    (96, 4, 5, 5, 7, 3, 4, 1, 7, 4, 1, 0, 0, 2, 0, 0, 3, 0, 2, 2),           # 4 words per lane
+    (1, 1, 1, 3, 7, 3, 1, 1, 5, 2, 1, 0, 0, 2, -1, 0, 0, 0, 2, 1),
+])
+def test_ca3d_layout_items_streamed(emu_bin, args):
+    """Layout items: pack ("generation -1") and unpack ("generation G") run as work items of the sweep launch; a
+    feeder thread plays the H2D copy stream (cells arrive chunk by chunk, then the in_ready word moves) and a
+    drainer thread plays the host side of the D2H (copies a chunk out once its planes carry the epoch)."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
 # ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
 
 @pytest.mark.parametrize("args", [

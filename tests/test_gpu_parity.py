@@ -100,6 +100,112 @@ def test_ca3d_wide_rows_thin_slab_vs_oracle(gpu, oracle):
         assert np.array_equal(vol, want), d0
 
 
+# ---- ca3d: layout items of the sweep launch (fused pack / unpack, streamed host -> device -> host run) ----
+
+def _pinned(shape):
+    import torch
+    t = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+    return t, t.numpy()
+
+
+@pytest.mark.parametrize("shape,nca,steps,chunk_planes", [
+    ((45, 20, 12), 7, 5, 1), ((64, 33, 7), 0, 9, 2), ((33, 6, 5), 3, 6, 0), ((100, 17, 11), 6, 6, 3),
+    ((1500, 12, 6), 7, 4, 2), ((2048, 40, 18), 7, 4, 4), ((4096, 8, 5), 8, 3, 1), ((1, 1, 1), 7, 3, 0),
+])
+def test_ca3d_streamed_vs_oracle(gpu, oracle, monkeypatch, shape, nca, steps, chunk_planes):
+    """clapca_grid_run3d_streamed with page-locked buffers: H2D chunks, pack / sweep / unpack items and D2H chunks
+    overlap inside one launch; the result must be the oracle's, for one-plane chunks as well as for one big one."""
+    if chunk_planes:
+        monkeypatch.setenv("CLAPCA_IO_CHUNK_PLANES", str(chunk_planes))
+    d0, d1, d2 = shape
+    rng = np.random.default_rng(d0 + 7 * d1 + 31 * d2)
+    keep_in, host_in = _pinned((d2, d1, d0))
+    keep_out, host_out = _pinned((d2, d1, d0))
+    host_in[...] = synth(rng, (d2, d1, d0), 0.4, 6)
+    host_out[...] = 0xEE
+    want = host_in.copy()
+    s, b, n = oracle.ca3d_rule(nca)
+    wpop = oracle.ca3d_run(want, s, b, n, steps)
+    grid = gpu.Grid(d0, d1, d2)
+    for _ in range(2):                              # twice: the epoch / counters of a grid are reused
+        pop = grid.run3d_streamed(nca, steps, host_in, host_out, max_value=6)
+        assert grid.stats()["streamed"]
+        assert pop == wpop and np.array_equal(host_out, want), (shape, nca)
+        host_out[...] = 0xEE
+    grid.close()
+
+
+def test_ca3d_streamed_in_place_255_and_bound_violation(gpu, oracle, monkeypatch):
+    monkeypatch.setenv("CLAPCA_IO_CHUNK_PLANES", "2")
+    oracle.ca3d_make(16, 8, 4, 42)
+    seed = oracle.ca3d_make(48, 40, 24, 42)         # ca3d_prune leaves 255s: 8 state planes
+    keep, host = _pinned(seed.shape)
+    host[...] = seed
+    want = seed.copy()
+    s, b, n = oracle.ca3d_rule(7)
+    wpop = oracle.ca3d_run(want, s, b, n, 6)
+    grid = gpu.Grid(48, 40, 24)
+    assert grid.run3d_streamed(7, 6, host, host, max_value=255) == wpop        # in place
+    assert np.array_equal(host, want)
+    host[...] = seed
+    with pytest.raises(gpu.ClapcaError) as ei:      # a bound below the data: detected by the pack items, never wrong
+        grid.run3d_streamed(7, 6, host, host, max_value=5)
+    assert ei.value.status == 2
+    host[...] = seed                                # the grid stays usable
+    assert grid.run3d_streamed(7, 6, host, host, max_value=255) == wpop
+    assert np.array_equal(host, want)
+    grid.close()
+
+
+def test_ca3d_streamed_pageable_buffers_take_the_sequential_path(gpu, oracle):
+    rng = np.random.default_rng(77)
+    vol = synth(rng, (9, 14, 50))
+    want = vol.copy()
+    s, b, n = oracle.ca3d_rule(7)
+    wpop = oracle.ca3d_run(want, s, b, n, 5)
+    out = np.zeros_like(vol)
+    grid = gpu.Grid(50, 14, 9)
+    assert grid.run3d_streamed(7, 5, vol, out, max_value=5) == wpop
+    assert not grid.stats()["streamed"]
+    assert np.array_equal(out, want)
+    grid.close()
+
+
+@pytest.mark.parametrize("team", ["16", "0"])
+def test_ca3d_streamed_matches_resident_run_medium(gpu, monkeypatch, team):
+    """512 x 512 x 192, 20 generations: beyond the oracle's reach in seconds -- the streamed pipeline (many chunks,
+    all SMs busy, team and one-warp-per-sweep kernels) against the device-resident run with separate layout kernels."""
+    monkeypatch.setenv("CLAPCA_TEAM", team)
+    monkeypatch.setenv("CLAPCA_IO_CHUNK_PLANES", "8")
+    rng = np.random.default_rng(5)
+    shape = (192, 512, 512)
+    keep_in, host_in = _pinned(shape)
+    keep_out, host_out = _pinned(shape)
+    host_in[...] = synth(rng, shape)
+    ref = host_in.copy()
+    rpop = gpu.ca3d_run(ref, 7, 20, engine=BITPLANE)
+    grid = gpu.Grid(512, 512, 192)
+    assert grid.run3d_streamed(7, 20, host_in, host_out, max_value=5) == rpop
+    assert np.array_equal(host_out, ref)
+    grid.close()
+
+
+@pytest.mark.parametrize("team", ["16", "0"])
+def test_ca3d_fused_layout_resident_vs_oracle(gpu, oracle, monkeypatch, team):
+    """CLAPCA_FUSED_LAYOUT=1: the device-resident run converts the layout inside the sweep launch too."""
+    monkeypatch.setenv("CLAPCA_FUSED_LAYOUT", "1")
+    monkeypatch.setenv("CLAPCA_TEAM", team)
+    rng = np.random.default_rng(21)
+    for shape, nca in (((100, 17, 11), 7), ((64, 33, 40), 2), ((2048, 12, 6), 7)):
+        d0, d1, d2 = shape
+        vol = synth(rng, (d2, d1, d0), 0.4, 6, with255=(nca == 2))
+        want = vol.copy()
+        s, b, n = oracle.ca3d_rule(nca)
+        wpop = oracle.ca3d_run(want, s, b, n, 6)
+        assert gpu.ca3d_run(vol, nca, 6, engine=BITPLANE) == wpop
+        assert np.array_equal(vol, want), shape
+
+
 def test_ca3d_zero_steps_and_population(gpu):
     rng = np.random.default_rng(13)
     vol = synth(rng, (8, 9, 10))
