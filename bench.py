@@ -53,6 +53,8 @@ FIELD_WORKLOADS = {
     # name: (kind, size)
     "terrain_8192": ("terrain", 8192),      # terrain.c:447-467 heightmap, maze = ca2d_generate(&ca_test, 1024, 4)
     "terrain_1024": ("terrain", 1024),
+    "terrain_mesh_8192": ("mesh", 8192),    # terrain.c:479-516 vertex / normal / uv / index buffers from the heightmap
+    "terrain_mesh_1024": ("mesh", 1024),
     "noise_256": ("noise", 256),            # noise_grad3d_bake_rgba8(256, 4, 2.0, 0.5, 37.0, 0xc14d)
     "noise_64": ("noise", 64),              # the engine's default bake (noise.c:309-317)
 }
@@ -363,6 +365,47 @@ def run_fields(args, torch, clap_b200, dev, local):
             _lib.check(lib, lib.clapca_terrain_heightmap(c_void_p(host_out.data_ptr()), TSEED, nr_v, 0.0,
                                                          maze.ctypes.data_as(c_void_p), mside, 1.0, 4))
         h2d, d2h = maze.nbytes, units * 4
+    elif kind == "mesh":
+        nr_v, mside = size, size // 8
+        units = nr_v * nr_v
+        quads = (nr_v - 1) * (nr_v - 1)
+        maze = clap_b200.ca2d_generate(clap_b200.CA_TEST, mside, 4, Rand48(7))
+        d_maze = torch.from_numpy(maze).to(dev)
+        d_map0 = torch.empty(units, dtype=torch.float32, device=dev)
+        d_map = torch.empty(units, dtype=torch.float32, device=dev)
+        _lib.check(lib, lib.clapca_terrain_heightmap_device(c_void_p(d_map.data_ptr()), c_void_p(d_map0.data_ptr()), TSEED,
+                                                            nr_v, 0.0, c_void_p(d_maze.data_ptr()), mside, 1.0, 4, None, None))
+        del d_map0
+        d_vx = torch.empty(units * 3, dtype=torch.float32, device=dev)
+        d_norm = torch.empty(units * 3, dtype=torch.float32, device=dev)
+        d_tx = torch.empty(units * 2, dtype=torch.float32, device=dev)
+        d_idx = torch.empty(quads * 6, dtype=torch.int16, device=dev)
+        # per vertex: 4 B of map read, 12 + 12 + 8 B of vertex / normal / uv written, 12 B of indices per quad
+        bytes_per_unit, unit, metric = 36.0 + 12.0 * quads / units, "Mvertex/s", "terrain mesh vertices/s"
+        kernel = "terrain_mesh_vertex_kernel + terrain_mesh_index_kernel"
+        desc = (f"{args.workload}: terrain.c:479-516 mesh buffers (vx, norm, tx, idx) of the {nr_v}^2 heightmap of "
+                f"terrain_{nr_v}, origin (0,0,0), side {nr_v // 4}")
+        side = float(nr_v // 4)
+
+        def step():
+            a = c_float()
+            _lib.check(lib, lib.clapca_terrain_mesh_device(c_void_p(d_map.data_ptr()), nr_v, 0.0, 0.0, 0.0, side,
+                                                           c_void_p(d_vx.data_ptr()), c_void_p(d_norm.data_ptr()),
+                                                           c_void_p(d_tx.data_ptr()), c_void_p(d_idx.data_ptr()), byref(a)))
+            return a.value, a.value, 2
+
+        host_map = torch.empty(units, dtype=torch.float32, pin_memory=True)
+        host_map.copy_(d_map)
+        h_vx = torch.empty(units * 3, dtype=torch.float32, pin_memory=True)
+        h_norm = torch.empty(units * 3, dtype=torch.float32, pin_memory=True)
+        h_tx = torch.empty(units * 2, dtype=torch.float32, pin_memory=True)
+        h_idx = torch.empty(quads * 6, dtype=torch.int16, pin_memory=True)
+
+        def e2e_step():
+            _lib.check(lib, lib.clapca_terrain_mesh(c_void_p(host_map.data_ptr()), nr_v, 0.0, 0.0, 0.0, side,
+                                                    c_void_p(h_vx.data_ptr()), c_void_p(h_norm.data_ptr()),
+                                                    c_void_p(h_tx.data_ptr()), c_void_p(h_idx.data_ptr())))
+        h2d, d2h = units * 4, units * 32 + quads * 12
     else:
         units = size ** 3
         period = 37.0 if size == 256 else 64.0
@@ -435,6 +478,21 @@ def run_fields(args, torch, clap_b200, dev, local):
             cpu = {"value": 1.0 / per_vertex / 1e6, "unit": unit, "cores": 1, "kind": kind_cpu,
                    "sample": f"lattice map0 in full ({t1 - t0:.1f} s) + vertex rows 0..{rows - 1} of the same {nr_v}^2 map "
                              f"({t2 - t1:.1f} s) on one core of {os.cpu_count()}; per-vertex cost is uniform"}
+        elif kind == "mesh":
+            # the mesh stage has no reachable reference entry point (it sits inside terrain_init_square_landscape);
+            # the oracle port restates it and its normals are pinned to the reference's calc_normal()
+            hm = host_map.numpy().reshape(nr_v, nr_v)
+            rows = int(max(8, min(nr_v, args.cpu_seconds * 2.0e7 / nr_v)))
+            vx = np.zeros((units, 3), np.float32); nm = np.zeros((units, 3), np.float32)
+            txx = np.zeros((units, 2), np.float32); ix = np.zeros(quads * 6, np.uint16)
+            t0 = time.perf_counter()
+            port.lib.ora_terrain_mesh(hm.ctypes.data_as(c_void_p), nr_v, 0.0, 0.0, 0.0, side, 0, rows,
+                                      vx.ctypes.data_as(c_void_p), nm.ctypes.data_as(c_void_p),
+                                      txx.ctypes.data_as(c_void_p), ix.ctypes.data_as(c_void_p))
+            dt = time.perf_counter() - t0
+            kind_cpu = "port"
+            cpu = {"value": rows * nr_v / dt / 1e6, "unit": unit, "cores": 1, "kind": kind_cpu,
+                   "sample": f"vertex rows 0..{rows - 1} of the same {nr_v}^2 mesh, {dt:.1f} s on one core of {os.cpu_count()}"}
         else:
             cs = min(size, 128)
             cperiod = period * cs / size            # same step (= eps) per voxel as the full workload
@@ -456,7 +514,8 @@ def run_fields(args, torch, clap_b200, dev, local):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args.workload), "kernel": kernel, "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_update": bytes_per_unit, "peak_source": peak_src,
-                     "note": "nominally output-bound (HBM), in practice ALU/SFU-bound: see DESIGN.md section 4"},
+                     "note": "HBM-bound: one coalesced pass over the map and the output buffers" if kind == "mesh" else
+                             "nominally output-bound (HBM), in practice ALU/SFU-bound: see DESIGN.md section 4"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

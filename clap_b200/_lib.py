@@ -76,6 +76,10 @@ SIGNATURES = {
                                          POINTER(c_float)]),
     "clapca_terrain_heightmap_device": (c_int, [c_void_p, c_void_p, c_long, c_uint, c_float, c_void_p, c_uint,
                                                 c_float, c_int, POINTER(c_float), POINTER(c_float)]),
+    "clapca_terrain_mesh": (c_int, [c_void_p, c_uint, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "clapca_terrain_mesh_device": (c_int, [c_void_p, c_uint, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, POINTER(c_float)]),
     "clapca_device_alloc": (c_void_p, [c_size_t]),
     "clapca_device_free": (c_int, [c_void_p]),
     "clapca_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_size_t]),

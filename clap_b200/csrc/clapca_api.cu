@@ -1485,5 +1485,61 @@ int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty, con
     return rc;
 }
 
+/* ---- terrain mesh ------------------------------------------------------------ */
+
+int clapca_terrain_mesh_device(const void *d_map, unsigned nr_v, float x, float y, float z, float side,
+                               void *d_vx, void *d_norm, void *d_tx, void *d_idx, float *kernel_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_map || nr_v < 1 || nr_v > 46340)
+        return fail(CLAPCA_ERR_ARG, "terrain_mesh: bad arguments (nr_v %u)", nr_v);
+    TerrainMeshParams p = { (const float *)d_map, nr_v, x, y, z, side, (float *)d_vx, (float *)d_norm, (float *)d_tx,
+                            (unsigned short *)d_idx };
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, g_ctx.stream));
+    if (d_vx || d_norm || d_tx) {
+        const unsigned tiles = (nr_v + 31) / 32;
+        terrain_mesh_vertex_kernel<<<dim3(tiles, tiles), dim3(32, 32), 0, g_ctx.stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    if (d_idx && nr_v > 1) {
+        const size_t quads = (size_t)(nr_v - 1) * (nr_v - 1);
+        terrain_mesh_index_kernel<<<grid_blocks_for(quads, 256, 8), 256, 0, g_ctx.stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e1, g_ctx.stream));
+    int rc = timed_sync(e0, e1, kernel_ms);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
+                        float *vx, float *norm, float *tx, unsigned short *idx)
+{
+    if (int rc = need_init()) return rc;
+    if (!map || nr_v < 1 || nr_v > 46340)
+        return fail(CLAPCA_ERR_ARG, "terrain_mesh: bad arguments (nr_v %u)", nr_v);
+    const size_t nv = (size_t)nr_v * nr_v, nq = (size_t)(nr_v - 1) * (nr_v - 1);
+    const size_t bytes[5] = { nv * 4, vx ? nv * 12 : 0, norm ? nv * 12 : 0, tx ? nv * 8 : 0, idx ? nq * 12 : 0 };
+    void *d[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    int rc = CLAPCA_OK;
+    for (int i = 0; i < 5 && !rc; i++)
+        if (bytes[i]) {
+            cudaError_t e = cudaMalloc(&d[i], bytes[i]);
+            if (e != cudaSuccess) rc = fail(CLAPCA_ERR_NOMEM, "terrain_mesh: %s", cudaGetErrorString(e));
+        }
+    if (!rc) rc = clapca_memcpy_h2d(d[0], map, bytes[0]);
+    if (!rc) rc = clapca_terrain_mesh_device(d[0], nr_v, x, y, z, side, d[1], d[2], d[3], d[4], nullptr);
+    void *host[5] = { nullptr, vx, norm, tx, idx };
+    for (int i = 1; i < 5 && !rc; i++)
+        if (bytes[i]) rc = clapca_memcpy_d2h(host[i], d[i], bytes[i]);
+    for (int i = 0; i < 5; i++)
+        if (d[i]) cudaFree(d[i]);
+    return rc;
+}
+
 #pragma GCC visibility pop
 } /* extern "C" */

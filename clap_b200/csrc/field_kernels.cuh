@@ -359,5 +359,81 @@ __global__ void __launch_bounds__(256) terrain_heightmap_tab_kernel(TerrainParam
     }
 }
 
+/* ---- terrain mesh: core/terrain.c:93-110 (calc_normal), :479-519 (vertex / normal / uv / index buffers) -------- */
+
+struct TerrainMeshParams {
+    const float *map;           /* t->map, nr_v * nr_v, map[a*nr_v + b] */
+    unsigned nr_v;
+    float x, y, z, side;        /* terrain origin and edge length (terrain.c:441-445) */
+    float *vx, *norm, *tx;      /* 3, 3, 2 floats per vertex (any may be NULL) */
+    unsigned short *idx;        /* 6 per quad */
+};
+
+/*
+ * Vertex it = i*nr_v + j reads the map TRANSPOSED -- map[j*nr_v + i], and calc_normal(t, n, j, i) its four
+ * neighbours (terrain.c:497-500) -- so a CTA stages a 32 x 32 map tile plus a one-cell halo in shared memory with
+ * coalesced row reads and then walks it column-wise: consecutive threads produce consecutive vertices.
+ * Arithmetic is the reference's, operation by operation (no FMA contraction in this translation unit):
+ * calc_normal() zeroes the neighbour beyond an edge (its torus indices are computed but never used),
+ * vec3_norm() is k = (float)(1.0 / (double)sqrtf(n.n)) then three float products (linmath.h:48-62).
+ */
+__global__ void __launch_bounds__(1024) terrain_mesh_vertex_kernel(TerrainMeshParams p)
+{
+    __shared__ float tile[34][35];
+    const int nr = (int)p.nr_v;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;      /* map row (= vertex j) / map column (= vertex i) origin */
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 34; r += 32)
+        for (int c = tx; c < 34; c += 32) {
+            const int a = a0 + r - 1, b = b0 + c - 1;
+            tile[r][c] = (a >= 0 && a < nr && b >= 0 && b < nr) ? p.map[(size_t)a * nr + b] : 0.f;
+        }
+    __syncthreads();
+    const int j = a0 + tx, i = b0 + ty;                         /* j fastest: it = i*nr_v + j is contiguous per warp */
+    if (i >= nr || j >= nr)
+        return;
+    const size_t it = (size_t)i * nr + j;
+    const float den = (float)p.nr_v - 1;
+    if (p.vx) {
+        p.vx[it * 3 + 0] = p.x + (float)j / den * p.side;
+        p.vx[it * 3 + 1] = p.y + tile[tx + 1][ty + 1];
+        p.vx[it * 3 + 2] = p.z + (float)i / den * p.side;
+    }
+    if (p.norm) {
+        /* calc_normal(t, n, x = j, z = i): hl/hr along the first map index, hd/hu along the second */
+        const float hl = tile[tx][ty + 1], hr = tile[tx + 2][ty + 1];
+        const float hd = tile[tx + 1][ty], hu = tile[tx + 1][ty + 2];
+        const float n0 = hl - hr, n1 = 2.f, n2 = hd - hu;
+        float dot = 0.f;
+        dot += n0 * n0;
+        dot += n1 * n1;
+        dot += n2 * n2;
+        const float k = (float)(1.0 / (double)sqrtf(dot));
+        p.norm[it * 3 + 0] = n0 * k;
+        p.norm[it * 3 + 1] = n1 * k;
+        p.norm[it * 3 + 2] = n2 * k;
+    }
+    if (p.tx) {
+        p.tx[it * 2 + 0] = (float)j * 32 / den;
+        p.tx[it * 2 + 1] = (float)i * 32 / den;
+    }
+}
+
+/* two triangles per quad, indices truncated to unsigned short exactly like the reference's buffer (terrain.c:503-516) */
+__global__ void __launch_bounds__(256) terrain_mesh_index_kernel(TerrainMeshParams p)
+{
+    const size_t q = (size_t)p.nr_v - 1;
+    const size_t n = q * q;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += stride) {
+        const unsigned i = (unsigned)(it / q), j = (unsigned)(it % q);
+        const unsigned tl = i * p.nr_v + j, tr = tl + 1, bl = (i + 1) * p.nr_v + j, br = bl + 1;
+        uint32_t *out = reinterpret_cast<uint32_t *>(p.idx + it * 6);       /* 12 bytes per quad: 4-byte aligned */
+        out[0] = (tl & 0xffffu) | (bl << 16);
+        out[1] = (tr & 0xffffu) | (tr << 16);
+        out[2] = (bl & 0xffffu) | (br << 16);
+    }
+}
+
 } // namespace clapca
 #endif

@@ -50,3 +50,22 @@ def terrain_heightmap(seed, nr_v, y=0.0, maze=None, amp=1.0, octaves=4):
         mptr, mside = None, 0
     check(lib, lib.clapca_terrain_heightmap(out.ctypes.data_as(c_void_p), seed, nr_v, y, mptr, mside, amp, octaves))
     return out
+
+
+def terrain_mesh(hmap, x=0.0, y=0.0, z=0.0, side=1.0, indices=True):
+    """Mesh buffers of terrain_init_square_landscape(): core/terrain.c:479-516 with calc_normal() (:93-110).
+    ``hmap`` is t->map (float32[nr_v, nr_v]).  Returns (vx[n, 3], norm[n, 3], tx[n, 2], idx) with n = nr_v^2 and
+    idx = uint16[6 * (nr_v - 1)^2] (None when ``indices`` is false) -- truncated to 16 bits like the reference's."""
+    lib = _lib.lib()
+    hmap = np.ascontiguousarray(hmap, dtype=np.float32)
+    if hmap.ndim != 2 or hmap.shape[0] != hmap.shape[1]:
+        raise ValueError("hmap must be a square 2-D float32 array")
+    nr_v = hmap.shape[0]
+    n = nr_v * nr_v
+    vx, norm = np.empty((n, 3), dtype=np.float32), np.empty((n, 3), dtype=np.float32)
+    tx = np.empty((n, 2), dtype=np.float32)
+    idx = np.empty(6 * (nr_v - 1) * (nr_v - 1), dtype=np.uint16) if indices else None
+    check(lib, lib.clapca_terrain_mesh(hmap.ctypes.data_as(c_void_p), nr_v, x, y, z, side, vx.ctypes.data_as(c_void_p),
+                                       norm.ctypes.data_as(c_void_p), tx.ctypes.data_as(c_void_p),
+                                       idx.ctypes.data_as(c_void_p) if indices else None))
+    return vx, norm, tx, idx

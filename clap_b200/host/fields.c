@@ -55,3 +55,21 @@ float *clap_terrain_heightmap(long seed, unsigned int nr_v, float y, unsigned ch
         shim_fatal("clapca_terrain_heightmap", rc);
     return map;
 }
+
+void clap_terrain_mesh(const float *map, unsigned int nr_v, float x, float y, float z, float side,
+                       float **vx, float **norm, float **tx, unsigned short **idx)
+{
+    size_t total = (size_t)nr_v * nr_v;
+    size_t quads = nr_v ? (size_t)(nr_v - 1) * (nr_v - 1) : 0;
+    int rc;
+
+    /* the reference returns NULL when one of these allocations fails (terrain.c:487-488); here that is fatal */
+    *vx = shim_alloc_zeroed(total * 3 * sizeof(float));
+    *norm = shim_alloc_zeroed(total * 3 * sizeof(float));
+    *tx = shim_alloc_zeroed(total * 2 * sizeof(float));
+    *idx = shim_alloc_zeroed((quads ? quads : 1) * 6 * sizeof(unsigned short));
+    shim_require_gpu();
+    rc = clapca_terrain_mesh(map, nr_v, x, y, z, side, *vx, *norm, *tx, *idx);
+    if (rc != CLAPCA_OK)
+        shim_fatal("clapca_terrain_mesh", rc);
+}

@@ -17,4 +17,12 @@ float *clap_terrain_map0(long seed, unsigned int nr_v);
  */
 float *clap_terrain_heightmap(long seed, unsigned int nr_v, float y, unsigned char *maze);
 
+/*
+ * Mesh buffers (terrain.c:479-516, calc_normal :93-110) from the finished map: *vx / *norm get 3 floats per
+ * vertex, *tx 2, *idx 6 unsigned shorts per quad, each a malloc()ed buffer the caller frees -- what the
+ * reference hands to mesh_attr_add().  `x,y,z,side` are the arguments of terrain_init_square_landscape().
+ */
+void clap_terrain_mesh(const float *map, unsigned int nr_v, float x, float y, float z, float side,
+                       float **vx, float **norm, float **tx, unsigned short **idx);
+
 #endif

@@ -128,6 +128,17 @@ int clapca_terrain_map0(float *map0, long seed, unsigned nr_v);
 int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty,
                              const uint8_t *maze, unsigned mside, float amp, int oct);
 
+/*
+ * Terrain mesh buffers: core/terrain.c:479-519 with calc_normal() (:93-110).  From the nr_v x nr_v
+ * heightmap t->map: vx[it*3..] = { x + j/(nr_v-1)*side, y + map[j*nr_v+i], z + i/(nr_v-1)*side },
+ * norm[it*3..] = normalised { hl-hr, 2, hd-hu } (neighbours beyond an edge count as 0),
+ * tx[it*2..] = { 32 j/(nr_v-1), 32 i/(nr_v-1) } for it = i*nr_v + j, and idx = two triangles per quad
+ * (6 * (nr_v-1)^2 entries, truncated to unsigned short like the reference's buffer, terrain.h:13).
+ * Any output pointer may be NULL.
+ */
+int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
+                        float *vx, float *norm, float *tx, unsigned short *idx);
+
 /* ---- device-resident grids (benchmarks, pipelines, multi-GPU slabs) ------ */
 
 typedef struct clapca_grid clapca_grid;
@@ -224,6 +235,9 @@ int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacuna
 int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsigned nr_v, float ty,
                                     const void *d_maze, unsigned mside, float amp, int oct,
                                     float *map0_ms, float *map_ms);
+/* the mesh buffers straight from a device-resident heightmap (all pointers are device memory; outputs may be NULL) */
+int clapca_terrain_mesh_device(const void *d_map, unsigned nr_v, float x, float y, float z, float side,
+                               void *d_vx, void *d_norm, void *d_tx, void *d_idx, float *kernel_ms);
 void *clapca_device_alloc(size_t bytes);
 int   clapca_device_free(void *p);
 int   clapca_memcpy_h2d(void *dst, const void *src, size_t bytes);

@@ -506,6 +506,71 @@ void ora_terrain_heightmap(unsigned nr_v, const float *map0, float ty, const uin
         }
 }
 
+/*
+ * calc_normal(): core/terrain.c:93-110.  The torus indices left/right/up/down are used only
+ * away from the edges; at an edge the neighbour height counts as 0.  vec3_norm() is
+ * linmath.h:48-62: p = 0; p += v[i]*v[i]; k = 1.0 / sqrtf(p) (double division, stored to float);
+ * r[i] = v[i] * k.
+ */
+static void p_calc_normal(const float *map, int nr, float n[3], int x, int z)
+{
+    float hl = x == 0 ? 0 : map[(size_t)(x - 1) * nr + z];
+    float hr = x == nr - 1 ? 0 : map[(size_t)(x + 1) * nr + z];
+    float hd = z == 0 ? 0 : map[(size_t)x * nr + (z - 1)];
+    float hu = z == nr - 1 ? 0 : map[(size_t)x * nr + (z + 1)];
+    float v[3] = { hl - hr, 2.f, hd - hu };
+    float p = 0.f;
+    for (int i = 0; i < 3; i++)
+        p += v[i] * v[i];
+    float k = 1.0 / sqrtf(p);
+    for (int i = 0; i < 3; i++)
+        n[i] = v[i] * k;
+}
+
+/*
+ * Mesh buffers of terrain_init_square_landscape(): core/terrain.c:479-516 (vertex rows [i0,i1),
+ * quad rows [i0, min(i1, nr_v-1))).  Outputs are indexed from the start of the full buffers.
+ */
+void ora_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
+                      unsigned i0, unsigned i1, float *vx, float *norm, float *tx, unsigned short *idx)
+{
+    const int nr = (int)nr_v;
+    for (int i = (int)i0; i < (int)i1; i++)
+        for (int j = 0; j < nr; j++) {
+            size_t it = (size_t)i * nr + j;
+            float n[3];
+            if (vx) {
+                vx[it * 3 + 0] = x + (float)j / ((float)nr_v - 1) * side;
+                vx[it * 3 + 1] = y + map[(size_t)j * nr + i];
+                vx[it * 3 + 2] = z + (float)i / ((float)nr_v - 1) * side;
+            }
+            if (norm) {
+                p_calc_normal(map, nr, n, j, i);
+                norm[it * 3 + 0] = n[0];
+                norm[it * 3 + 1] = n[1];
+                norm[it * 3 + 2] = n[2];
+            }
+            if (tx) {
+                tx[it * 2 + 0] = (float)j * 32 / ((float)nr_v - 1);
+                tx[it * 2 + 1] = (float)i * 32 / ((float)nr_v - 1);
+            }
+        }
+    if (!idx)
+        return;
+    for (int i = (int)i0; i < (int)i1 && i < nr - 1; i++)
+        for (int j = 0; j < nr - 1; j++) {
+            size_t it = ((size_t)i * (nr - 1) + j) * 6;
+            int top_left = i * nr + j, top_right = top_left + 1;
+            int bottom_left = (i + 1) * nr + j, bottom_right = bottom_left + 1;
+            idx[it + 0] = (unsigned short)top_left;
+            idx[it + 1] = (unsigned short)bottom_left;
+            idx[it + 2] = (unsigned short)top_right;
+            idx[it + 3] = (unsigned short)top_right;
+            idx[it + 4] = (unsigned short)bottom_left;
+            idx[it + 5] = (unsigned short)bottom_right;
+        }
+}
+
 /* FNV-1a 64 over a byte buffer (fixture fingerprints) */
 uint64_t ora_fnv1a64(const void *buf, size_t n)
 {

@@ -57,5 +57,9 @@ void  ora_terrain_field(unsigned nr_v, const float *map0, float ty, float amp, i
 void  ora_terrain_heightmap(unsigned nr_v, const float *map0, float ty, const uint8_t *maze,
                             unsigned mside, unsigned i0, unsigned i1, float *map);
 
+/* mesh buffers, core/terrain.c:93-110,479-516; any output may be NULL */
+void  ora_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
+                       unsigned i0, unsigned i1, float *vx, float *norm, float *tx, unsigned short *idx);
+
 uint64_t ora_fnv1a64(const void *buf, size_t n);
 #endif

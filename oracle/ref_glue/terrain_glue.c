@@ -74,5 +74,24 @@ void ref_terrain_heightmap(long seed, unsigned int nr_v, float *map0, float ty, 
     }
 }
 
+/*
+ * Normals of the mesh stage: drives the reference's own calc_normal() (terrain.c:93-110) in the order and
+ * with the argument swap of the vertex loop at terrain.c:493-500 (vertex it = i*nr_v + j uses calc_normal(t, n, j, i)).
+ */
+void ref_terrain_normals(unsigned int nr_v, float *map, float *norm)
+{
+    struct terrain t = { .nr_vert = nr_v, .map = map };
+    size_t it = 0;
+
+    for (unsigned int i = 0; i < nr_v; i++)
+        for (unsigned int j = 0; j < nr_v; j++, it++) {
+            vec3 n;
+            calc_normal(&t, n, j, i);
+            norm[it * 3 + 0] = n[0];
+            norm[it * 3 + 1] = n[1];
+            norm[it * 3 + 2] = n[2];
+        }
+}
+
 const struct cell_automaton *ref_ca_test(void) { return &ca_test; }
 const struct cell_automaton *ref_ca_instor(int i) { return &ca_instors[i]; }

@@ -116,6 +116,13 @@ def main():
     out["survey_map_sum"] = np.float64(f1024.astype(np.float64).sum())
     np.savez_compressed(os.path.join(HERE, "terrain.npz"), **out)
 
+    # ---- terrain mesh stage: the reference's calc_normal() over the golden heightmap -------
+    mesh = {"normals_128": ref.terrain_normals(out["heightmap_128"])}
+    rough = (np.random.default_rng(3).random((37, 37)) * 40 - 20).astype(np.float32)
+    mesh["rough_37"] = rough
+    mesh["normals_rough_37"] = ref.terrain_normals(rough)
+    np.savez_compressed(os.path.join(HERE, "terrain_mesh.npz"), **mesh)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

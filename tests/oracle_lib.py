@@ -40,6 +40,8 @@ class Port:
         lib.ora_terrain_map0.argtypes = [c_long, c_uint, c_void_p]
         lib.ora_terrain_field.argtypes = [c_uint, c_void_p, c_float, c_float, c_int, c_uint, c_uint, c_void_p]
         lib.ora_terrain_heightmap.argtypes = [c_uint, c_void_p, c_float, c_void_p, c_uint, c_uint, c_uint, c_void_p]
+        lib.ora_terrain_mesh.argtypes = [c_void_p, c_uint, c_float, c_float, c_float, c_float, c_uint, c_uint,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]
         lib.ora_fnv1a64.restype = c_uint64
         lib.ora_fnv1a64.argtypes = [c_void_p, c_size_t]
 
@@ -113,6 +115,16 @@ class Port:
         self.lib.ora_terrain_heightmap(nr_v, _vp(map0), ty, _vp(maze), maze.shape[0], i0,
                                        nr_v if i1 is None else i1, _vp(out))
         return out
+
+    def terrain_mesh(self, hmap, x, y, z, side):
+        """(vx[n,3], norm[n,3], tx[n,2], idx[6*(nr_v-1)^2]) of core/terrain.c:479-516"""
+        hmap = np.ascontiguousarray(hmap, np.float32)
+        nr_v = hmap.shape[0]
+        n = nr_v * nr_v
+        vx, norm, tx = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 2), np.float32)
+        idx = np.zeros(6 * (nr_v - 1) * (nr_v - 1), np.uint16)
+        self.lib.ora_terrain_mesh(_vp(hmap), nr_v, x, y, z, side, 0, nr_v, _vp(vx), _vp(norm), _vp(tx), _vp(idx))
+        return vx, norm, tx, idx
 
     def fnv(self, arr):
         arr = np.ascontiguousarray(arr)
@@ -207,6 +219,14 @@ class Ref:
         nr_v = map0.shape[0]
         out = np.zeros((nr_v, nr_v), np.float32)
         self.lib.ref_terrain_field(seed, nr_v, _vp(map0), ty, amp, octv, 0, nr_v, _vp(out))
+        return out
+
+    def terrain_normals(self, hmap):
+        """the reference's calc_normal() (terrain.c:93-110) for every vertex, in mesh order"""
+        hmap = np.ascontiguousarray(hmap, np.float32)
+        nr_v = hmap.shape[0]
+        out = np.zeros((nr_v * nr_v, 3), np.float32)
+        self.lib.ref_terrain_normals(c_uint(nr_v), _vp(hmap), _vp(out))
         return out
 
     def terrain_heightmap(self, seed, map0, ty, maze):

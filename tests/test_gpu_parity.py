@@ -138,13 +138,14 @@ def test_ca3d_streamed_vs_oracle(gpu, oracle, monkeypatch, shape, nca, steps, ch
 def test_ca3d_streamed_in_place_255_and_bound_violation(gpu, oracle, monkeypatch):
     monkeypatch.setenv("CLAPCA_IO_CHUNK_PLANES", "2")
     oracle.ca3d_make(16, 8, 4, 42)
-    seed = oracle.ca3d_make(48, 40, 24, 42)         # ca3d_prune leaves 255s: 8 state planes
+    seed = oracle.ca3d_make(48, 12, 10, 42)         # ca3d_prune leaves 255s here: 8 state planes
+    assert int((seed == 255).sum()) > 0
     keep, host = _pinned(seed.shape)
     host[...] = seed
     want = seed.copy()
     s, b, n = oracle.ca3d_rule(7)
     wpop = oracle.ca3d_run(want, s, b, n, 6)
-    grid = gpu.Grid(48, 40, 24)
+    grid = gpu.Grid(48, 12, 10)
     assert grid.run3d_streamed(7, 6, host, host, max_value=255) == wpop        # in place
     assert np.array_equal(host, want)
     host[...] = seed
@@ -526,3 +527,47 @@ def test_terrain_cfg5_rows_vs_oracle(gpu, oracle):
     for i0 in (0, 4093, 8188):
         want = oracle.terrain_heightmap(map0, 0.0, maze, i0=i0, i1=i0 + 4)
         _field_close(got[i0:i0 + 4], want[i0:i0 + 4])
+
+
+# ---- terrain mesh stage: core/terrain.c:93-110 (calc_normal), :479-516 (vertex / normal / uv / index buffers) ----
+
+MESH_RTOL = 1e-5        # north_star tolerance for float fields; the kernels mirror the float ops, so 0 ulp is expected
+
+
+def _mesh_check(got, want, what):
+    for name, a, b in zip(("vx", "norm", "tx"), got[:3], want[:3]):
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=MESH_RTOL, atol=1e-7), (what, name, float(np.abs(a - b).max()))
+        exact = float((a.view(np.uint32) == b.view(np.uint32)).mean())
+        assert exact > 0.999, (what, name, exact)
+    assert np.array_equal(got[3], want[3]), (what, "idx")
+
+
+def test_terrain_mesh_golden_normals(gpu):
+    t = np.load(os.path.join(G, "terrain.npz"))
+    m = np.load(os.path.join(G, "terrain_mesh.npz"))
+    _, norm, _, _ = gpu.terrain_mesh(t["heightmap_128"], 10.0, -2.0, 5.0, 300.0)
+    assert np.allclose(norm, m["normals_128"], rtol=MESH_RTOL, atol=1e-7)
+    _, norm, _, _ = gpu.terrain_mesh(m["rough_37"])
+    assert np.allclose(norm, m["normals_rough_37"], rtol=MESH_RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("nr_v", [1, 2, 3, 31, 32, 33, 100, 300, 1000])
+def test_terrain_mesh_vs_oracle(gpu, oracle, nr_v):
+    """Ragged tile edges, a single vertex, and nr_v > 256 where the reference's unsigned-short indices wrap."""
+    rng = np.random.default_rng(nr_v)
+    hmap = (rng.random((nr_v, nr_v)) * 30 - 10).astype(np.float32)
+    got = gpu.terrain_mesh(hmap, 3.5, -1.25, 100.0, 777.0)
+    want = oracle.terrain_mesh(hmap, 3.5, -1.25, 100.0, 777.0)
+    _mesh_check(got, want, nr_v)
+
+
+def test_terrain_mesh_from_the_generated_heightmap_4096(gpu, oracle):
+    """The pipeline the engine runs: cave maze -> heightmap -> mesh, at a size the oracle still does in seconds."""
+    from clap_b200.ca import Rand48
+    nr_v = 4096
+    maze = gpu.ca2d_generate(gpu.CA_TEST, nr_v // 8, 4, Rand48(7))
+    hmap = gpu.terrain_heightmap(12345, nr_v, 0.0, maze)
+    got = gpu.terrain_mesh(hmap, 0.0, 0.0, 0.0, 2048.0)
+    want = oracle.terrain_mesh(hmap, 0.0, 0.0, 0.0, 2048.0)
+    _mesh_check(got, want, nr_v)

@@ -157,3 +157,33 @@ def test_oracle_vs_reference_fields(oracle, reference):
     a = oracle.terrain_heightmap(m, 1.5, maze)
     b = reference.terrain_heightmap(777, m, 1.5, maze)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_terrain_mesh_normals_golden(oracle):
+    """Mesh stage (core/terrain.c:93-110,479-516): the port's normals against the reference's calc_normal() outputs
+    committed in golden/terrain_mesh.npz, and the trivially restated vertex / uv / index formulas at a few spots."""
+    t = np.load(os.path.join(G, "terrain.npz"))
+    m = np.load(os.path.join(G, "terrain_mesh.npz"))
+    vx, norm, tx, idx = oracle.terrain_mesh(t["heightmap_128"], 10.0, -2.0, 5.0, 300.0)
+    assert np.array_equal(norm.view(np.uint32), m["normals_128"].view(np.uint32))
+    _, norm2, _, _ = oracle.terrain_mesh(m["rough_37"], 0.0, 0.0, 0.0, 1.0)
+    assert np.array_equal(norm2.view(np.uint32), m["normals_rough_37"].view(np.uint32))
+    nr = 128
+    i, j = 5, 77
+    it = i * nr + j
+    f = np.float32
+    assert vx[it, 0] == f(10.0) + f(j) / (f(nr) - f(1)) * f(300.0)
+    assert vx[it, 1] == f(-2.0) + t["heightmap_128"][j, i]
+    assert vx[it, 2] == f(5.0) + f(i) / (f(nr) - f(1)) * f(300.0)
+    assert tx[it, 0] == f(j) * f(32) / (f(nr) - f(1)) and tx[it, 1] == f(i) * f(32) / (f(nr) - f(1))
+    q = (i * (nr - 1) + j) * 6
+    assert idx[q:q + 6].tolist() == [it, it + nr, it + 1, it + 1, it + nr, it + nr + 1]
+    assert np.allclose(np.linalg.norm(norm.astype(np.float64), axis=1), 1.0, atol=1e-6)
+
+
+def test_terrain_mesh_port_vs_reference_normals(oracle, reference):
+    rng = np.random.default_rng(8)
+    for nr in (1, 2, 3, 50, 131):
+        hmap = (rng.random((nr, nr)) * 9 - 4).astype(np.float32)
+        _, norm, _, _ = oracle.terrain_mesh(hmap, 0.0, 0.0, 0.0, 1.0)
+        assert np.array_equal(norm.view(np.uint32), reference.terrain_normals(hmap).view(np.uint32)), nr

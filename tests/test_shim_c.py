@@ -65,6 +65,15 @@ int main(void)
     free(tex);
     float *m0 = clap_terrain_map0(12345, 64);
     printf("map0 %016llx\n", (unsigned long long)fnv((unsigned char *)m0, 64 * 64 * 4));
+    /* the mesh stage of terrain.c:479-516, fed with the lattice as a stand-in height field */
+    float *vx, *norm, *tx;
+    unsigned short *idx;
+    clap_terrain_mesh(m0, 64, 1.0f, 2.0f, 3.0f, 50.0f, &vx, &norm, &tx, &idx);
+    printf("mesh %016llx %016llx %016llx %016llx\n", (unsigned long long)fnv((unsigned char *)vx, 64 * 64 * 12),
+           (unsigned long long)fnv((unsigned char *)norm, 64 * 64 * 12),
+           (unsigned long long)fnv((unsigned char *)tx, 64 * 64 * 8),
+           (unsigned long long)fnv((unsigned char *)idx, 63 * 63 * 12));
+    free(vx); free(norm); free(tx); free(idx);
     free(m0);
     return 0;
 }
@@ -96,3 +105,5 @@ def test_reference_style_c_program(oracle):
     assert out["noise"] == "%016x" % oracle.fnv(g["bake_16_p5"])
     t = np.load(os.path.join(ROOT, "tests", "golden", "terrain.npz"))
     assert out["map0"] == "%016x" % oracle.fnv(t["map0_64_seed12345"])
+    want = oracle.terrain_mesh(t["map0_64_seed12345"], 1.0, 2.0, 3.0, 50.0)
+    assert out["mesh"].split() == ["%016x" % oracle.fnv(a) for a in want]
