@@ -285,7 +285,7 @@ struct Sweep3 {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
-                        dp_atomic_max(p.err, 1);
+                        dp_set_error(p.err, 1);
                     return false;
                 }
             }
@@ -313,7 +313,7 @@ struct Sweep3 {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
-                        dp_atomic_max(p.err, 3);
+                        dp_set_error(p.err, 3);
                     return false;
                 }
             }
@@ -357,7 +357,7 @@ struct Sweep3 {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
-                        dp_atomic_max(p.err, 2);
+                        dp_set_error(p.err, 2);
                     return false;
                 }
             }
@@ -622,7 +622,7 @@ struct Sweep3 {
                     bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                     if (!dp_all(!bad)) {
                         if (lane == 0)
-                            dp_atomic_max(p.err, 1);
+                            dp_set_error(p.err, 1);
                         return false;
                     }
                 }
@@ -716,7 +716,7 @@ struct Sweep3 {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > 16 * p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (lane == 0)
-                        dp_atomic_max(p.err, code);
+                        dp_set_error(p.err, code);
                     return false;
                 }
             }
@@ -784,7 +784,7 @@ struct Sweep3 {
         }
         if (!dp_all((over & kOver) == 0u)) {
             if (lane == 0)
-                dp_atomic_max(p.err, 4);
+                dp_set_error(p.err, 4);
             return false;
         }
         return true;

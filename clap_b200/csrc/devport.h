@@ -105,6 +105,8 @@ CA_DEV long long dp_clock()                       { return clock64(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return atomicAdd(p, 1u); }
 CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 CA_DEV void dp_atomic_max(int *p, int v)          { atomicMax(p, v); }
+/* error words: the FIRST non-zero code sticks (later bail-outs are consequences of it) */
+CA_DEV void dp_set_error(int *p, int v)           { atomicCAS(p, 0, v); }
 CA_DEV int  dp_popc(uint32_t v)                   { return __popc(v); }
 CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s) { return __funnelshift_l(lo, hi, s); }
 CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, s); }
@@ -223,6 +225,11 @@ CA_DEV void dp_atomic_max(int *p, int v)
     int o = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED))
         ;
+}
+CA_DEV void dp_set_error(int *p, int v)
+{
+    int o = 0;
+    __atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED);
 }
 CA_DEV int  dp_popc(uint32_t v)                   { return __builtin_popcount(v); }
 CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s)

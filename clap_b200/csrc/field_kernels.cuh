@@ -377,9 +377,28 @@ struct TerrainMeshParams {
  * calc_normal() zeroes the neighbour beyond an edge (its torus indices are computed but never used),
  * vec3_norm() is k = (float)(1.0 / (double)sqrtf(n.n)) then three float products (linmath.h:48-62).
  */
+/*
+ * One warp = 32 consecutive vertices of one output row; it stages each attribute in shared memory and writes it
+ * back as whole 16-byte vectors (96 floats = 24 float4 for vx / norm, 16 for tx), so the 12-byte vertex stride
+ * never reaches the memory system as strided 4-byte stores.
+ */
+__device__ __forceinline__ void fk_flush_row(float *dst, const float *st, int nfloats, bool vec, int lane)
+{
+    __syncwarp();
+    if (vec && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+        if (lane < nfloats / 4)
+            reinterpret_cast<float4 *>(dst)[lane] = reinterpret_cast<const float4 *>(st)[lane];
+    } else {
+        for (int k = lane; k < nfloats; k += 32)
+            dst[k] = st[k];
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(1024) terrain_mesh_vertex_kernel(TerrainMeshParams p)
 {
     __shared__ float tile[34][35];
+    __shared__ __align__(16) float stage[32][96];
     const int nr = (int)p.nr_v;
     const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;      /* map row (= vertex j) / map column (= vertex i) origin */
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -390,32 +409,45 @@ __global__ void __launch_bounds__(1024) terrain_mesh_vertex_kernel(TerrainMeshPa
         }
     __syncthreads();
     const int j = a0 + tx, i = b0 + ty;                         /* j fastest: it = i*nr_v + j is contiguous per warp */
-    if (i >= nr || j >= nr)
-        return;
-    const size_t it = (size_t)i * nr + j;
+    if (i >= nr)
+        return;                                                 /* the whole warp */
+    const bool live = j < nr;
+    const int count = nr - a0 < 32 ? nr - a0 : 32;              /* vertices of this warp */
+    const size_t it0 = (size_t)i * nr + a0;
+    const bool vec = count == 32 && (nr & 3) == 0;              /* 16-byte aligned rows of 96 / 64 floats */
     const float den = (float)p.nr_v - 1;
+    float *st = stage[ty];
     if (p.vx) {
-        p.vx[it * 3 + 0] = p.x + (float)j / den * p.side;
-        p.vx[it * 3 + 1] = p.y + tile[tx + 1][ty + 1];
-        p.vx[it * 3 + 2] = p.z + (float)i / den * p.side;
+        if (live) {
+            st[tx * 3 + 0] = p.x + (float)j / den * p.side;
+            st[tx * 3 + 1] = p.y + tile[tx + 1][ty + 1];
+            st[tx * 3 + 2] = p.z + (float)i / den * p.side;
+        }
+        fk_flush_row(p.vx + it0 * 3, st, count * 3, vec, tx);
     }
     if (p.norm) {
-        /* calc_normal(t, n, x = j, z = i): hl/hr along the first map index, hd/hu along the second */
-        const float hl = tile[tx][ty + 1], hr = tile[tx + 2][ty + 1];
-        const float hd = tile[tx + 1][ty], hu = tile[tx + 1][ty + 2];
-        const float n0 = hl - hr, n1 = 2.f, n2 = hd - hu;
-        float dot = 0.f;
-        dot += n0 * n0;
-        dot += n1 * n1;
-        dot += n2 * n2;
-        const float k = (float)(1.0 / (double)sqrtf(dot));
-        p.norm[it * 3 + 0] = n0 * k;
-        p.norm[it * 3 + 1] = n1 * k;
-        p.norm[it * 3 + 2] = n2 * k;
+        if (live) {
+            /* calc_normal(t, n, x = j, z = i): hl/hr along the first map index, hd/hu along the second */
+            const float hl = tile[tx][ty + 1], hr = tile[tx + 2][ty + 1];
+            const float hd = tile[tx + 1][ty], hu = tile[tx + 1][ty + 2];
+            const float n0 = hl - hr, n1 = 2.f, n2 = hd - hu;
+            float dot = 0.f;
+            dot += n0 * n0;
+            dot += n1 * n1;
+            dot += n2 * n2;
+            const float k = (float)(1.0 / (double)sqrtf(dot));
+            st[tx * 3 + 0] = n0 * k;
+            st[tx * 3 + 1] = n1 * k;
+            st[tx * 3 + 2] = n2 * k;
+        }
+        fk_flush_row(p.norm + it0 * 3, st, count * 3, vec, tx);
     }
     if (p.tx) {
-        p.tx[it * 2 + 0] = (float)j * 32 / den;
-        p.tx[it * 2 + 1] = (float)i * 32 / den;
+        if (live) {
+            st[tx * 2 + 0] = (float)j * 32 / den;
+            st[tx * 2 + 1] = (float)i * 32 / den;
+        }
+        fk_flush_row(p.tx + it0 * 2, st, count * 2, vec, tx);
     }
 }
 
