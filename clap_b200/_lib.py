@@ -7,7 +7,7 @@ GPU is usable, importing the binding works but the first call raises ``ClapcaErr
 import ctypes
 import os
 from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int64, c_long, c_size_t,
-                    c_uint, c_uint32, c_void_p)
+                    c_uint, c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
@@ -44,6 +44,9 @@ SIGNATURES = {
     "clapca_ca3d_rule": (c_int, [c_int, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
     "clapca_ca2d_run": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_uint32, c_uint32, c_uint32, c_int, c_int,
                                 c_int, c_int]),
+    "clapca_ca2d_generate": (c_int, [c_void_p, c_int64, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, c_int,
+                                     c_uint64, POINTER(c_uint64)]),
+    "clapca_grid_seed2d": (c_int, [c_void_p, c_int64, c_uint32, c_uint64, POINTER(c_uint64)]),
     "clapca_noise_grad3d_bake_rgba8": (c_int, [c_void_p, c_size_t, c_int, c_float, c_float, c_float, c_uint32]),
     "clapca_noise_fbm3": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_float, c_int, c_uint32]),
     "clapca_terrain_map0": (c_int, [c_void_p, c_long, c_uint]),

@@ -98,10 +98,15 @@ def ca2d_seed(ca, side, rng):
 
 
 def ca2d_generate(ca, side, steps, rng, engine=ENGINE_AUTO):
-    """ca2d_generate(): core/ca2d.c:79-98 with an explicit rand48 stream instead of libc's global."""
-    arr = ca2d_seed(ca, side, rng)
-    if steps > 0:
-        ca2d_step(ca, arr, side, steps, engine)
+    """ca2d_generate(): core/ca2d.c:79-98 with an explicit rand48 stream instead of libc's global.  Seeding and
+    the generations both run on the device (clapca_ca2d_generate); ``rng`` is left where side*side lrand48()
+    calls would have left it.  (:func:`ca2d_seed` is the same seeding loop on the host.)"""
+    lib = _lib.lib()
+    arr = np.empty((side, side), dtype=np.uint8)
+    after = ctypes.c_uint64(0)
+    check(lib, lib.clapca_ca2d_generate(arr.ctypes.data_as(c_void_p), side, ca.born_mask, ca.surv_mask, ca.nr_states,
+                                        int(ca.decay), ca.neigh, int(steps), engine, rng.x, byref(after)))
+    rng.x = int(after.value)
     return arr
 
 
@@ -164,6 +169,13 @@ class Grid:
                                                               rule.surv_mask, rule.born_mask, rule.nr_states,
                                                               int(steps), byref(pop)))
         return pop.value
+
+    def seed2d(self, ca, rng, side=None):
+        """clapca_grid_seed2d(): the seeding loop of ca2d_generate() into this device-resident grid."""
+        side = self.dims[0] if side is None else int(side)
+        after = ctypes.c_uint64(0)
+        check(self._lib, self._lib.clapca_grid_seed2d(self._h, side, ca.nr_states, rng.x, byref(after)))
+        rng.x = int(after.value)
 
     def run2d(self, ca, steps, side=None, engine=ENGINE_AUTO):
         side = self.dims[0] if side is None else int(side)

@@ -116,5 +116,75 @@ CA_GLOBAL void ca2d_unpack_kernel(Bp2Layout L)
         dp_atomic_add64(L.population, pop);
 }
 
+/* ---- device-side seeding: ca2d_generate()'s fill loop, core/ca2d.c:86-90 ------------------------------- */
+
+/*
+ * glibc lrand48(): X' = (a X + c) mod 2^48 with a = 0x5DEECE66D, c = 0xB, result X' >> 17.  The affine map
+ * composes, so the state n steps ahead is G X + C with (G, C) from O(log n) squarings (Brown's arbitrary-stride
+ * jump): every cell can start from the same 48-bit state the host's stream is in.
+ */
+struct Rand48Jump { unsigned long long G, C; };
+
+CA_HOSTDEV Rand48Jump r48_jump(unsigned long long n)
+{
+    const unsigned long long M = (1ull << 48) - 1;
+    unsigned long long h = 0x5DEECE66Dull, f = 0xBull, G = 1ull, C = 0ull;
+    while (n) {
+        if (n & 1ull) {
+            G = (G * h) & M;
+            C = (C * h + f) & M;
+        }
+        f = (f * (h + 1ull)) & M;
+        h = (h * h) & M;
+        n >>= 1;
+    }
+    Rand48Jump j = { G, C };
+    return j;
+}
+
+CA_HOSTDEV unsigned long long r48_advance(unsigned long long x, unsigned long long n)
+{
+    const Rand48Jump j = r48_jump(n);
+    return (j.G * x + j.C) & ((1ull << 48) - 1);
+}
+
+#ifndef CLAPCA_EMU
+/*
+ * The reference draws one lrand48() % 8 per cell in x-OUTER / y-inner order and stores cell (x,y) at
+ * arr[y*w + x]: draw number k = x*side + y.  A thread jumps to the first draw of a run of 32 consecutive y of one
+ * x and iterates; the CTA's 32 (x) x 256 (y) tile goes through shared memory so the stores run along x.
+ */
+__global__ void __launch_bounds__(256) ca2d_seed_kernel(uint8_t *cells, int w, int side, uint32_t nr_states,
+                                                        unsigned long long x0)
+{
+    __shared__ __align__(16) uint8_t tile[256][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xb = blockIdx.x * 32, yb = blockIdx.y * 256;
+    const int x = xb + lane, ys = yb + 32 * warp;
+    const unsigned long long M = (1ull << 48) - 1;
+    if (x < side && ys < side) {
+        unsigned long long st = r48_advance(x0, (unsigned long long)x * side + ys);
+        for (int s = 0; s < 32; s++) {
+            st = (st * 0x5DEECE66Dull + 0xBull) & M;
+            const uint32_t v = (uint32_t)(st >> 17) & 7u;               /* lrand48() % 8 */
+            tile[32 * warp + s][lane] = v <= nr_states ? (uint8_t)nr_states : (uint8_t)0;
+        }
+    }
+    __syncthreads();
+    const int y = yb + threadIdx.x;
+    if (y >= side)
+        return;
+    uint8_t *dst = cells + (size_t)y * w + xb;
+    if (xb + 32 <= side && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tile[threadIdx.x]);
+        reinterpret_cast<uint4 *>(dst)[0] = src[0];
+        reinterpret_cast<uint4 *>(dst)[1] = src[1];
+    } else {
+        for (int i = 0; i < 32 && xb + i < side; i++)
+            dst[i] = tile[threadIdx.x][i];
+    }
+}
+#endif
+
 } // namespace clapca
 #endif

@@ -83,6 +83,9 @@ struct Ctx {
     /* terrain: table of get_avg_height() (field_kernels.cuh), kept between calls */
     void *d_smooth = nullptr;
     size_t smooth_bytes = 0;
+    /* grow-only device staging of the one-shot field calls (cudaMalloc / cudaFree of GBs per call costs more than the kernels) */
+    void *scratch[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t scratch_bytes[5] = { 0, 0, 0, 0, 0 };
 } g_ctx;
 
 int need_init()
@@ -235,6 +238,8 @@ void clapca_shutdown(void)
     if (g_ctx.d_count) cudaFree(g_ctx.d_count);
     if (g_ctx.d_max) cudaFree(g_ctx.d_max);
     if (g_ctx.d_smooth) cudaFree(g_ctx.d_smooth);
+    for (int i = 0; i < 5; i++)
+        if (g_ctx.scratch[i]) cudaFree(g_ctx.scratch[i]);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.stream_in) cudaStreamDestroy(g_ctx.stream_in);
     if (g_ctx.stream_out) cudaStreamDestroy(g_ctx.stream_out);
@@ -1010,6 +1015,48 @@ int clapca_ca2d_run(uint8_t *arr, int64_t w, int64_t h, int64_t side, uint32_t b
     return rc;
 }
 
+/*
+ * Seeding loop of ca2d_generate() (core/ca2d.c:86-90) on the device: draw k = x*side + y of the caller's
+ * lrand48() stream decides cell (x,y).  Cells outside side x side are zero, like the reference's fresh xyarray.
+ */
+int clapca_grid_seed2d(clapca_grid *g, int64_t side, uint32_t nr_states, uint64_t rand48_state,
+                       uint64_t *rand48_state_after)
+{
+    if (int rc = need_init()) return rc;
+    if (!g) return fail(CLAPCA_ERR_ARG, "grid_seed2d: NULL grid");
+    if (g->d2 != 1 || side < 0 || side > g->d0 || side > g->d1 || side > 46340)
+        return fail(CLAPCA_ERR_ARG, "grid_seed2d: side %lld does not fit the %lld x %lld grid", (long long)side,
+                    (long long)g->d0, (long long)g->d1);
+    rand48_state &= (1ull << 48) - 1;
+    if (side != g->d0 || side != g->d1)
+        CU(cudaMemsetAsync(g->cells, 0, g->n, g->stream));
+    if (side > 0) {
+        dim3 grid((unsigned)((side + 31) / 32), (unsigned)((side + 255) / 256));
+        ca2d_seed_kernel<<<grid, 256, 0, g->stream>>>(g->cells, (int)g->d0, (int)side, nr_states,
+                                                      (unsigned long long)rand48_state);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(g->stream));
+    if (rand48_state_after)
+        *rand48_state_after = r48_advance(rand48_state, (unsigned long long)side * (unsigned long long)side);
+    return CLAPCA_OK;
+}
+
+int clapca_ca2d_generate(uint8_t *arr, int64_t side, uint32_t born, uint32_t surv, uint32_t nr_states, int decay,
+                         int neigh, int steps, int engine, uint64_t rand48_state, uint64_t *rand48_state_after)
+{
+    if (int rc = need_init()) return rc;
+    if (!arr || side < 1) return fail(CLAPCA_ERR_ARG, "ca2d_generate: bad arguments");
+    clapca_grid *g = nullptr;
+    int rc = clapca_grid_create(&g, side, side, 1);
+    if (rc) return rc;
+    rc = clapca_grid_seed2d(g, side, nr_states, rand48_state, rand48_state_after);
+    if (!rc && steps > 0) rc = clapca_grid_run2d(g, side, born, surv, nr_states, decay, neigh, steps, engine);
+    if (!rc) rc = clapca_grid_download(g, arr);
+    clapca_grid_destroy(g);
+    return rc;
+}
+
 
 /* ---- multi-GPU z-block slabs ------------------------------------------------------ */
 
@@ -1472,16 +1519,18 @@ int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty, con
     if (!map) return fail(CLAPCA_ERR_ARG, "terrain_heightmap: NULL output");
     size_t bytes = (size_t)nr_v * nr_v * sizeof(float);
     void *d_map = nullptr, *d_map0 = nullptr, *d_maze = nullptr;
-    CU(cudaMalloc(&d_map, bytes ? bytes : 4));
-    cudaError_t e = cudaMalloc(&d_map0, bytes ? bytes : 4);
-    if (e == cudaSuccess && maze) e = cudaMalloc(&d_maze, (size_t)mside * mside);
-    int rc = e == cudaSuccess ? CLAPCA_OK : fail(CLAPCA_ERR_NOMEM, "terrain_heightmap: %s", cudaGetErrorString(e));
-    if (!rc && maze) rc = clapca_memcpy_h2d(d_maze, maze, (size_t)mside * mside);
+    if (int rc = ensure_bytes(&g_ctx.scratch[0], &g_ctx.scratch_bytes[0], bytes ? bytes : 4)) return rc;
+    if (int rc = ensure_bytes(&g_ctx.scratch[1], &g_ctx.scratch_bytes[1], bytes ? bytes : 4)) return rc;
+    d_map = g_ctx.scratch[0];
+    d_map0 = g_ctx.scratch[1];
+    int rc = CLAPCA_OK;
+    if (maze) {
+        if (int rc2 = ensure_bytes(&g_ctx.scratch[2], &g_ctx.scratch_bytes[2], (size_t)mside * mside)) return rc2;
+        d_maze = g_ctx.scratch[2];
+        rc = clapca_memcpy_h2d(d_maze, maze, (size_t)mside * mside);
+    }
     if (!rc) rc = clapca_terrain_heightmap_device(d_map, d_map0, seed, nr_v, ty, d_maze, mside, amp, oct, nullptr, nullptr);
     if (!rc) rc = clapca_memcpy_d2h(map, d_map, bytes);
-    cudaFree(d_map);
-    cudaFree(d_map0);
-    cudaFree(d_maze);
     return rc;
 }
 
@@ -1501,7 +1550,7 @@ int clapca_terrain_mesh_device(const void *d_map, unsigned nr_v, float x, float 
     CU(cudaEventRecord(e0, g_ctx.stream));
     if (d_vx || d_norm || d_tx) {
         const unsigned tiles = (nr_v + 31) / 32;
-        terrain_mesh_vertex_kernel<<<dim3(tiles, tiles), dim3(32, 32), 0, g_ctx.stream>>>(p);
+        terrain_mesh_vertex_kernel<<<dim3(tiles, tiles), dim3(32, 8), 0, g_ctx.stream>>>(p);
         CU(cudaGetLastError());
     }
     if (d_idx && nr_v > 1) {
@@ -1525,19 +1574,16 @@ int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float
     const size_t nv = (size_t)nr_v * nr_v, nq = (size_t)(nr_v - 1) * (nr_v - 1);
     const size_t bytes[5] = { nv * 4, vx ? nv * 12 : 0, norm ? nv * 12 : 0, tx ? nv * 8 : 0, idx ? nq * 12 : 0 };
     void *d[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    int rc = CLAPCA_OK;
-    for (int i = 0; i < 5 && !rc; i++)
+    for (int i = 0; i < 5; i++)
         if (bytes[i]) {
-            cudaError_t e = cudaMalloc(&d[i], bytes[i]);
-            if (e != cudaSuccess) rc = fail(CLAPCA_ERR_NOMEM, "terrain_mesh: %s", cudaGetErrorString(e));
+            if (int rc = ensure_bytes(&g_ctx.scratch[i], &g_ctx.scratch_bytes[i], bytes[i])) return rc;
+            d[i] = g_ctx.scratch[i];
         }
-    if (!rc) rc = clapca_memcpy_h2d(d[0], map, bytes[0]);
+    int rc = clapca_memcpy_h2d(d[0], map, bytes[0]);
     if (!rc) rc = clapca_terrain_mesh_device(d[0], nr_v, x, y, z, side, d[1], d[2], d[3], d[4], nullptr);
     void *host[5] = { nullptr, vx, norm, tx, idx };
     for (int i = 1; i < 5 && !rc; i++)
         if (bytes[i]) rc = clapca_memcpy_d2h(host[i], d[i], bytes[i]);
-    for (int i = 0; i < 5; i++)
-        if (d[i]) cudaFree(d[i]);
     return rc;
 }
 

@@ -395,59 +395,62 @@ __device__ __forceinline__ void fk_flush_row(float *dst, const float *st, int nf
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(1024) terrain_mesh_vertex_kernel(TerrainMeshParams p)
+__global__ void __launch_bounds__(256) terrain_mesh_vertex_kernel(TerrainMeshParams p)
 {
     __shared__ float tile[34][35];
-    __shared__ __align__(16) float stage[32][96];
+    __shared__ __align__(16) float stage[8][96];
     const int nr = (int)p.nr_v;
     const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;      /* map row (= vertex j) / map column (= vertex i) origin */
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int r = ty; r < 34; r += 32)
+    const int tx = threadIdx.x, ty = threadIdx.y;               /* 32 x 8 threads: a warp per output row, 4 rows each */
+    for (int r = ty; r < 34; r += 8)
         for (int c = tx; c < 34; c += 32) {
             const int a = a0 + r - 1, b = b0 + c - 1;
             tile[r][c] = (a >= 0 && a < nr && b >= 0 && b < nr) ? p.map[(size_t)a * nr + b] : 0.f;
         }
     __syncthreads();
-    const int j = a0 + tx, i = b0 + ty;                         /* j fastest: it = i*nr_v + j is contiguous per warp */
-    if (i >= nr)
-        return;                                                 /* the whole warp */
+    const int j = a0 + tx;                                      /* j fastest: it = i*nr_v + j is contiguous per warp */
     const bool live = j < nr;
-    const int count = nr - a0 < 32 ? nr - a0 : 32;              /* vertices of this warp */
-    const size_t it0 = (size_t)i * nr + a0;
+    const int count = nr - a0 < 32 ? nr - a0 : 32;              /* vertices of a warp's row */
     const bool vec = count == 32 && (nr & 3) == 0;              /* 16-byte aligned rows of 96 / 64 floats */
     const float den = (float)p.nr_v - 1;
     float *st = stage[ty];
-    if (p.vx) {
-        if (live) {
-            st[tx * 3 + 0] = p.x + (float)j / den * p.side;
-            st[tx * 3 + 1] = p.y + tile[tx + 1][ty + 1];
-            st[tx * 3 + 2] = p.z + (float)i / den * p.side;
+    for (int ci = ty; ci < 32; ci += 8) {
+        const int i = b0 + ci;
+        if (i >= nr)
+            break;                                              /* the whole warp */
+        const size_t it0 = (size_t)i * nr + a0;
+        if (p.vx) {
+            if (live) {
+                st[tx * 3 + 0] = p.x + (float)j / den * p.side;
+                st[tx * 3 + 1] = p.y + tile[tx + 1][ci + 1];
+                st[tx * 3 + 2] = p.z + (float)i / den * p.side;
+            }
+            fk_flush_row(p.vx + it0 * 3, st, count * 3, vec, tx);
         }
-        fk_flush_row(p.vx + it0 * 3, st, count * 3, vec, tx);
-    }
-    if (p.norm) {
-        if (live) {
-            /* calc_normal(t, n, x = j, z = i): hl/hr along the first map index, hd/hu along the second */
-            const float hl = tile[tx][ty + 1], hr = tile[tx + 2][ty + 1];
-            const float hd = tile[tx + 1][ty], hu = tile[tx + 1][ty + 2];
-            const float n0 = hl - hr, n1 = 2.f, n2 = hd - hu;
-            float dot = 0.f;
-            dot += n0 * n0;
-            dot += n1 * n1;
-            dot += n2 * n2;
-            const float k = (float)(1.0 / (double)sqrtf(dot));
-            st[tx * 3 + 0] = n0 * k;
-            st[tx * 3 + 1] = n1 * k;
-            st[tx * 3 + 2] = n2 * k;
+        if (p.norm) {
+            if (live) {
+                /* calc_normal(t, n, x = j, z = i): hl/hr along the first map index, hd/hu along the second */
+                const float hl = tile[tx][ci + 1], hr = tile[tx + 2][ci + 1];
+                const float hd = tile[tx + 1][ci], hu = tile[tx + 1][ci + 2];
+                const float n0 = hl - hr, n1 = 2.f, n2 = hd - hu;
+                float dot = 0.f;
+                dot += n0 * n0;
+                dot += n1 * n1;
+                dot += n2 * n2;
+                const float k = (float)(1.0 / (double)sqrtf(dot));
+                st[tx * 3 + 0] = n0 * k;
+                st[tx * 3 + 1] = n1 * k;
+                st[tx * 3 + 2] = n2 * k;
+            }
+            fk_flush_row(p.norm + it0 * 3, st, count * 3, vec, tx);
         }
-        fk_flush_row(p.norm + it0 * 3, st, count * 3, vec, tx);
-    }
-    if (p.tx) {
-        if (live) {
-            st[tx * 2 + 0] = (float)j * 32 / den;
-            st[tx * 2 + 1] = (float)i * 32 / den;
+        if (p.tx) {
+            if (live) {
+                st[tx * 2 + 0] = (float)j * 32 / den;
+                st[tx * 2 + 1] = (float)i * 32 / den;
+            }
+            fk_flush_row(p.tx + it0 * 2, st, count * 2, vec, tx);
         }
-        fk_flush_row(p.tx + it0 * 2, st, count * 2, vec, tx);
     }
 }
 

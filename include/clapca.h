@@ -98,6 +98,18 @@ int clapca_ca2d_run(uint8_t *arr, int64_t w, int64_t h, int64_t side,
                     int decay, int neigh, int steps, int engine);
 
 /*
+ * ca2d_generate(): core/ca2d.c:79-98 with the seeding loop (:86-90) on the device as well.  The
+ * reference draws one lrand48() % 8 per cell from the process-wide stream in x-outer / y-inner order;
+ * `rand48_state` is that stream's current 48-bit state X (what seed48() reports), every cell jumps
+ * ahead to its own draw (the LCG's affine map composes), and *rand48_state_after is the state after the
+ * side*side draws so the caller can put the stream where the reference would have left it.  Then
+ * `steps` generations; `arr` receives the side x side grid (index y*side + x).
+ */
+int clapca_ca2d_generate(uint8_t *arr, int64_t side, uint32_t born_mask, uint32_t surv_mask,
+                         uint32_t nr_states, int decay, int neigh, int steps, int engine,
+                         uint64_t rand48_state, uint64_t *rand48_state_after);
+
+/*
  * noise_grad3d_bake_rgba8(): core/noise.c:222-270.  Fills out[size^3 * 4]
  * (x fastest, RGBA8, A = 0) with the normalised central-difference gradient
  * of the periodic fBm field (hash31 / value_noise3d_periodic / fbm3_periodic,
@@ -160,6 +172,9 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born_mask, uint32_t
                       uint32_t nr_states, int decay, int neigh, int steps, int engine);
 /* xyzarray_count(): core/xyarray.c:68-78 */
 int clapca_grid_count(clapca_grid *g, int64_t *population);
+/* the seeding loop of ca2d_generate() (core/ca2d.c:86-90) into a device-resident 2D grid; see clapca_ca2d_generate */
+int clapca_grid_seed2d(clapca_grid *g, int64_t side, uint32_t nr_states, uint64_t rand48_state,
+                       uint64_t *rand48_state_after);
 
 /*
  * ca3d_run() (core/ca3d.c:124-142) from host memory to host memory as ONE pipeline: the volume is copied in

@@ -53,6 +53,7 @@ int main(void)
             count += xyarray_get(map, x, y);
     if (!count) return 2;
     printf("ca2d %d %016llx\n", count, (unsigned long long)fnv(map, 256 * 256));
+    printf("next %ld\n", lrand48());          /* the stream continues where 256 * 256 draws leave it */
     /* the instantiator pass of terrain.c:473-477 */
     const struct cell_automaton tree = { .name = "cool tree", .born_mask = 0x1e, .surv_mask = 0xff,
                                          .nr_states = 20, .neigh_2d = ca2d_neigh_mv };
@@ -99,6 +100,10 @@ def test_reference_style_c_program(oracle):
     import oracle_lib
     cave = oracle.ca2d_run(oracle.ca2d_seed(256, 4, 1234), 3 << 2, 3 << 7, 4, 1, oracle_lib.NEIGH_M1, 5)
     assert out["ca2d"].split() == [str(int(cave.sum())), "%016x" % oracle.fnv(cave)]
+    st = oracle.srand48(1234)
+    for _ in range(256 * 256):
+        oracle.lrand48(st)
+    assert int(out["next"]) == oracle.lrand48(st)
     oracle.ca2d_run(cave, 0x1e, 0xff, 20, 0, oracle_lib.NEIGH_MV, 1)
     assert out["tree"] == "%016x" % oracle.fnv(cave)
     g = np.load(os.path.join(ROOT, "tests", "golden", "noise.npz"))
