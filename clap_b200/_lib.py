@@ -83,6 +83,11 @@ SIGNATURES = {
                                     c_void_p]),
     "clapca_terrain_mesh_device": (c_int, [c_void_p, c_uint, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                                            c_void_p, c_void_p, POINTER(c_float)]),
+    "clapca_terrain_instantiators": (c_int, [c_void_p, c_uint, POINTER(c_uint32), c_int, c_void_p, c_uint, c_float, c_float,
+                                             c_float, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "clapca_terrain_instantiators_device": (c_int, [c_void_p, c_uint, POINTER(c_uint32), c_int, c_void_p, c_uint, c_float,
+                                                    c_float, c_float, c_void_p, c_size_t, POINTER(c_size_t),
+                                                    POINTER(c_float)]),
     "clapca_device_alloc": (c_void_p, [c_size_t]),
     "clapca_device_free": (c_int, [c_void_p]),
     "clapca_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -1587,5 +1587,72 @@ int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float
     return rc;
 }
 
+/* ---- instantiator extraction ----------------------------------------------------- */
+
+int clapca_terrain_instantiators_device(const void *d_maze, unsigned mside, const uint32_t *nr_states, int nkinds,
+                                        const void *d_map, unsigned nr_v, float x, float z, float side,
+                                        void *d_out, size_t cap, size_t *count, float *kernel_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_maze || !d_map || !nr_states || !count || mside < 1 || mside > 8192 || nkinds < 1 || nkinds > 4 || nr_v < 2 ||
+        nr_v > 46340 || (cap && !d_out))
+        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: bad arguments (mside %u, kinds %d, nr_v %u)", mside, nkinds,
+                    nr_v);
+    if ((unsigned long long)mside * 8ull > nr_v)
+        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: maze of %u cells of 8 vertices does not fit %u vertices",
+                    mside, nr_v);
+    InstorParams p;
+    memset(&p, 0, sizeof(p));
+    p.maze = (const uint8_t *)d_maze;
+    p.mside = mside;
+    for (int k = 0; k < nkinds; k++) p.kinds[k] = nr_states[k];
+    p.nkinds = nkinds;
+    p.map = (const float *)d_map;
+    p.nr_v = nr_v;
+    p.x = x; p.z = z; p.side = side;
+    p.tside = (unsigned)side;
+    if (int rc = ensure_bytes(&g_ctx.scratch[4], &g_ctx.scratch_bytes[4], ((size_t)mside + 1) * sizeof(unsigned))) return rc;
+    p.counts = (unsigned *)g_ctx.scratch[4];
+    p.out = (int4 *)d_out;
+    p.cap = cap;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, g_ctx.stream));
+    const unsigned blocks = (mside + 7) / 8;
+    instor_count_kernel<<<blocks, 256, 0, g_ctx.stream>>>(p);
+    instor_scan_kernel<<<1, 1024, 0, g_ctx.stream>>>(p.counts, mside);
+    instor_emit_kernel<<<blocks, 256, 0, g_ctx.stream>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e1, g_ctx.stream));
+    unsigned total = 0;
+    CU(cudaMemcpyAsync(&total, p.counts + mside, sizeof(total), cudaMemcpyDeviceToHost, g_ctx.stream));
+    int rc = timed_sync(e0, e1, kernel_ms);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *count = total;
+    return rc;
+}
+
+int clapca_terrain_instantiators(const uint8_t *maze, unsigned mside, const uint32_t *nr_states, int nkinds,
+                                 const float *map, unsigned nr_v, float x, float z, float side,
+                                 clapca_instor *out, size_t cap, size_t *count)
+{
+    if (int rc = need_init()) return rc;
+    if (!maze || !map || !count || (cap && !out))
+        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: NULL argument");
+    const size_t mbytes = (size_t)mside * mside, hbytes = (size_t)nr_v * nr_v * sizeof(float);
+    if (int rc = ensure_bytes(&g_ctx.scratch[0], &g_ctx.scratch_bytes[0], hbytes ? hbytes : 4)) return rc;
+    if (int rc = ensure_bytes(&g_ctx.scratch[2], &g_ctx.scratch_bytes[2], mbytes ? mbytes : 4)) return rc;
+    if (int rc = ensure_bytes(&g_ctx.scratch[3], &g_ctx.scratch_bytes[3], cap ? cap * sizeof(clapca_instor) : 16)) return rc;
+    int rc = clapca_memcpy_h2d(g_ctx.scratch[0], map, hbytes);
+    if (!rc) rc = clapca_memcpy_h2d(g_ctx.scratch[2], maze, mbytes);
+    if (!rc) rc = clapca_terrain_instantiators_device(g_ctx.scratch[2], mside, nr_states, nkinds, g_ctx.scratch[0], nr_v, x, z,
+                                                      side, g_ctx.scratch[3], cap, count, nullptr);
+    if (!rc && cap && *count)
+        rc = clapca_memcpy_d2h(out, g_ctx.scratch[3], std::min(cap, *count) * sizeof(clapca_instor));
+    return rc;
+}
+
 #pragma GCC visibility pop
 } /* extern "C" */

@@ -470,5 +470,136 @@ __global__ void __launch_bounds__(256) terrain_mesh_index_kernel(TerrainMeshPara
     }
 }
 
+/* ---- instantiator extraction: core/terrain.c:555-570 with terrain_height() (:336-379), barrycentric() (interp.h:49-56) ---- */
+
+struct InstorParams {
+    const uint8_t *maze;        /* mside x mside xyarray payload after the ca_instors[] passes (terrain.c:473-477) */
+    unsigned mside;
+    uint32_t kinds[4];          /* ca_instors[k].nr_states: a cell equal to it spawns an instantiator of kind k */
+    int nkinds;
+    const float *map;           /* t->map */
+    unsigned nr_v;
+    float x, z, side;           /* arguments of terrain_init_square_landscape() */
+    unsigned tside;             /* t->side = (unsigned)side (terrain.h:19, terrain.c:443) */
+    unsigned *counts;           /* [mside + 1]: matches per maze column i, then their exclusive scan (last = total) */
+    int4 *out;                  /* { kind, dx, dy, dz } as bit patterns */
+    unsigned long long cap;
+};
+
+/* interp.h:49-56, operation by operation */
+__device__ __forceinline__ float fk_barrycentric(const float p1[3], const float p2[3], const float p3[3], float px, float pz)
+{
+    float det = (p2[2] - p3[2]) * (p1[0] - p3[0]) + (p3[0] - p2[0]) * (p1[2] - p3[2]);
+    float l1 = ((p2[2] - p3[2]) * (px - p3[0]) + (p3[0] - p2[0]) * (pz - p3[2])) / det;
+    float l2 = ((p3[2] - p1[2]) * (px - p3[0]) + (p1[0] - p3[0]) * (pz - p3[2])) / det;
+    float l3 = 1.0f - l1 - l2;
+    return l1 * p1[1] + l2 * p2[1] + l3 * p3[1];
+}
+
+/* terrain_height(): core/terrain.c:336-379 (t->y plays no part; t->side is the truncated unsigned) */
+__device__ __forceinline__ float fk_terrain_height(const InstorParams &p, float x, float z)
+{
+    const int nr = (int)p.nr_v;
+    float square = (float)p.tside / (float)(p.nr_v - 1u);
+    float tx = x - p.x, tz = z - p.z;
+    int gridx = (int)floorf(tx / square), gridz = (int)floorf(tz / square);
+    float xoff = (tx - square * (float)gridx) / square;
+    float zoff = (tz - square * (float)gridz) / square;
+    if (x < p.x || x > p.x + (float)p.tside || z < p.z || z > p.z + (float)p.tside)
+        return 0.f;
+    const float h00 = p.map[(size_t)gridx * nr + gridz], h10 = p.map[(size_t)(gridx + 1) * nr + gridz];
+    const float h01 = p.map[(size_t)gridx * nr + gridz + 1];
+    if (xoff <= 1 - zoff) {
+        const float p1[3] = { 0, h00, 0 }, p2[3] = { 1, h10, 0 }, p3[3] = { 0, h01, 1 };
+        return fk_barrycentric(p1, p2, p3, xoff, zoff);
+    }
+    const float h11 = p.map[(size_t)(gridx + 1) * nr + gridz + 1];
+    const float p1[3] = { 1, h10, 0 }, p2[3] = { 1, h11, 1 }, p3[3] = { 0, h01, 1 };
+    return fk_barrycentric(p1, p2, p3, xoff, zoff);
+}
+
+__device__ __forceinline__ unsigned fk_instor_matches(const InstorParams &p, unsigned cell)
+{
+    unsigned m = 0;
+    for (int k = 0; k < p.nkinds; k++)
+        m |= (unsigned)(cell == p.kinds[k]) << k;
+    return m;
+}
+
+/* pass 1: one warp per maze column i (the reference's OUTER loop index): number of instantiators it spawns */
+__global__ void __launch_bounds__(256) instor_count_kernel(InstorParams p)
+{
+    const unsigned i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= p.mside)
+        return;
+    unsigned n = 0;
+    for (unsigned j = lane; j < p.mside; j += 32)
+        n += __popc(fk_instor_matches(p, p.maze[(size_t)j * p.mside + i]));     /* xyarray_get(maze, i, j) */
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0)
+        p.counts[i] = n;
+}
+
+/* pass 2: exclusive scan of the per-column counts in place, total in counts[mside] (one CTA: mside <= 5792) */
+__global__ void __launch_bounds__(1024) instor_scan_kernel(unsigned *counts, unsigned n)
+{
+    __shared__ unsigned part[1024];
+    const unsigned per = (n + 1023) / 1024, t = threadIdx.x;
+    const unsigned lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
+    unsigned sum = 0;
+    for (unsigned k = lo; k < hi; k++) sum += counts[k];
+    part[t] = sum;
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1) {
+        unsigned v = t >= d ? part[t - d] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned run = part[t] - sum;                       /* exclusive prefix of this thread's slice */
+    for (unsigned k = lo; k < hi; k++) {
+        unsigned c = counts[k];
+        counts[k] = run;
+        run += c;
+    }
+    if (t == 1023)
+        counts[n] = part[1023];
+}
+
+/* pass 3: the records, in the reference's order: i outer, j inner, kind innermost */
+__global__ void __launch_bounds__(256) instor_emit_kernel(InstorParams p)
+{
+    const unsigned i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= p.mside)
+        return;
+    unsigned long long base = p.counts[i];
+    if (p.counts[i + 1] == p.counts[i])
+        return;
+    const float den = (float)(p.nr_v - 1u);
+    for (unsigned j0 = 0; j0 < p.mside; j0 += 32) {
+        const unsigned j = j0 + lane;
+        const unsigned m = j < p.mside ? fk_instor_matches(p, p.maze[(size_t)j * p.mside + i]) : 0u;
+        unsigned n = __popc(m), incl = n;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        unsigned long long at = base + incl - n;
+        if (m) {
+            /* terrain.c:563-565 */
+            const float dx = p.x + (float)((double)i + 0.5) * 8 * p.side / den;
+            const float dz = p.z + (float)((double)j + 0.5) * 8 * p.side / den;
+            const float dy = fk_terrain_height(p, dx, dz);
+            for (int k = 0; k < p.nkinds; k++)
+                if ((m >> k) & 1u) {
+                    if (at < p.cap)
+                        p.out[at] = make_int4(k, __float_as_int(dx), __float_as_int(dy), __float_as_int(dz));
+                    at++;
+                }
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
 } // namespace clapca
 #endif

@@ -1,5 +1,5 @@
 """Field evaluation: the noise.c fBm-gradient bake and the terrain.c heightmap chain."""
-from ctypes import c_void_p
+from ctypes import POINTER, byref, c_size_t, c_uint32, c_void_p
 
 import numpy as np
 
@@ -69,3 +69,25 @@ def terrain_mesh(hmap, x=0.0, y=0.0, z=0.0, side=1.0, indices=True):
                                        norm.ctypes.data_as(c_void_p), tx.ctypes.data_as(c_void_p),
                                        idx.ctypes.data_as(c_void_p) if indices else None))
     return vx, norm, tx, idx
+
+
+INSTOR_DTYPE = np.dtype([("kind", np.int32), ("dx", np.float32), ("dy", np.float32), ("dz", np.float32)])
+
+
+def terrain_instantiators(maze, nr_states, hmap, x=0.0, z=0.0, side=1.0):
+    """Instantiator extraction of terrain_init_square_landscape(): core/terrain.c:555-570 with terrain_height()
+    (:336-379).  ``maze`` is the cave grid after the ca_instors passes, ``nr_states`` the values that spawn an
+    instantiator (one per kind, e.g. (20, 21) for ca_instors[]), ``hmap`` is t->map.  Returns a structured array
+    (kind, dx, dy, dz) in the reference's list order."""
+    lib = _lib.lib()
+    maze = np.ascontiguousarray(maze, dtype=np.uint8)
+    hmap = np.ascontiguousarray(hmap, dtype=np.float32)
+    kinds = (c_uint32 * len(nr_states))(*[int(v) for v in nr_states])
+    n = c_size_t(0)
+    args = (maze.ctypes.data_as(c_void_p), maze.shape[0], kinds, len(nr_states), hmap.ctypes.data_as(c_void_p),
+            hmap.shape[0], x, z, side)
+    check(lib, lib.clapca_terrain_instantiators(*args, None, 0, byref(n)))
+    out = np.zeros(n.value, dtype=INSTOR_DTYPE)
+    if n.value:
+        check(lib, lib.clapca_terrain_instantiators(*args, out.ctypes.data_as(c_void_p), n.value, byref(n)))
+    return out

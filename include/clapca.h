@@ -151,6 +151,23 @@ int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty,
 int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
                         float *vx, float *norm, float *tx, unsigned short *idx);
 
+/*
+ * Instantiator extraction: core/terrain.c:555-570.  After the ca_instors[] passes over the maze
+ * (terrain.c:473-477) every maze cell (i outer, j inner) whose value equals nr_states[k] spawns an
+ * instantiator of kind k at dx = x + (i+0.5)*8*side/(nr_v-1), dz likewise with j, dy =
+ * terrain_height(t, dx, dz) (terrain.c:336-379: barycentric interpolation of t->map, interp.h:49-56).
+ * Records come out in the reference's list order.  *count receives the number found; at most `cap`
+ * are written (call with cap == 0 to size the buffer).
+ */
+typedef struct clapca_instor {
+    int32_t kind;                 /* index into the caller's rule table (ca_instors[], terrain.c:400-415) */
+    float   dx, dy, dz;
+} clapca_instor;
+
+int clapca_terrain_instantiators(const uint8_t *maze, unsigned mside, const uint32_t *nr_states, int nkinds,
+                                 const float *map, unsigned nr_v, float x, float z, float side,
+                                 clapca_instor *out, size_t cap, size_t *count);
+
 /* ---- device-resident grids (benchmarks, pipelines, multi-GPU slabs) ------ */
 
 typedef struct clapca_grid clapca_grid;
@@ -253,6 +270,10 @@ int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsign
 /* the mesh buffers straight from a device-resident heightmap (all pointers are device memory; outputs may be NULL) */
 int clapca_terrain_mesh_device(const void *d_map, unsigned nr_v, float x, float y, float z, float side,
                                void *d_vx, void *d_norm, void *d_tx, void *d_idx, float *kernel_ms);
+/* the same from a device-resident maze and heightmap (d_out: device array of clapca_instor) */
+int clapca_terrain_instantiators_device(const void *d_maze, unsigned mside, const uint32_t *nr_states, int nkinds,
+                                        const void *d_map, unsigned nr_v, float x, float z, float side,
+                                        void *d_out, size_t cap, size_t *count, float *kernel_ms);
 void *clapca_device_alloc(size_t bytes);
 int   clapca_device_free(void *p);
 int   clapca_memcpy_h2d(void *dst, const void *src, size_t bytes);

@@ -571,6 +571,74 @@ void ora_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z
         }
 }
 
+/* barrycentric(): core/interp.h:49-56 */
+static float p_barrycentric(const float p1[3], const float p2[3], const float p3[3], const float pos[2])
+{
+    float det = (p2[2] - p3[2]) * (p1[0] - p3[0]) + (p3[0] - p2[0]) * (p1[2] - p3[2]);
+    float l1  = ((p2[2] - p3[2]) * (pos[0] - p3[0]) + (p3[0] - p2[0]) * (pos[1] - p3[2])) / det;
+    float l2  = ((p3[2] - p1[2]) * (pos[0] - p3[0]) + (p1[0] - p3[0]) * (pos[1] - p3[2])) / det;
+    float l3  = 1.0f - l1 - l2;
+    return l1 * p1[1] + l2 * p2[1] + l3 * p3[1];
+}
+
+/* terrain_height(): core/terrain.c:336-379; t->side is an unsigned int (terrain.h:19) */
+float ora_terrain_height(const float *map, unsigned nr_vert, float t_x, float t_z, unsigned t_side, float x, float z)
+{
+    float square = (float)t_side / (nr_vert - 1);
+    float tx = x - t_x;
+    float tz = z - t_z;
+    int gridx = floorf(tx / square);
+    int gridz = floorf(tz / square);
+    float xoff = (tx - square * gridx) / square;
+    float zoff = (tz - square * gridz) / square;
+    float pos[2] = { xoff, zoff };
+
+    if (!map)
+        return 0;
+    if (x < t_x || x > t_x + t_side || z < t_z || z > t_z + t_side)
+        return 0;
+    if (xoff <= 1 - zoff) {
+        float p1[3] = { 0, map[(size_t)gridx * nr_vert + gridz], 0 };
+        float p2[3] = { 1, map[(size_t)(gridx + 1) * nr_vert + gridz], 0 };
+        float p3[3] = { 0, map[(size_t)gridx * nr_vert + gridz + 1], 1 };
+        return p_barrycentric(p1, p2, p3, pos);
+    } else {
+        float p1[3] = { 1, map[(size_t)(gridx + 1) * nr_vert + gridz], 0 };
+        float p2[3] = { 1, map[(size_t)(gridx + 1) * nr_vert + gridz + 1], 1 };
+        float p3[3] = { 0, map[(size_t)gridx * nr_vert + gridz + 1], 1 };
+        return p_barrycentric(p1, p2, p3, pos);
+    }
+}
+
+/*
+ * Instantiator loop of terrain_init_square_landscape(): core/terrain.c:555-570.  out = records of
+ * { kind, dx, dy, dz } (4 x 32 bit); returns the number found, writes at most cap.
+ */
+size_t ora_terrain_instantiators(const uint8_t *maze, unsigned mside, const unsigned *nr_states, int nkinds,
+                                 const float *map, unsigned nr_v, float x, float z, float side,
+                                 void *out, size_t cap)
+{
+    grid_t mz = { (uint8_t *)maze, mside, mside, 1 };
+    struct rec { int32_t kind; float dx, dy, dz; } *o = out;
+    size_t n = 0;
+
+    for (int i = 0; i < (int)mside; i++)
+        for (int j = 0; j < (int)mside; j++)
+            for (int ca = 0; ca < nkinds; ca++)
+                if ((unsigned)g_get(&mz, i, j, 0) == nr_states[ca]) {
+                    float dx = x + (float)(i + 0.5) * 8 * side / (nr_v - 1);
+                    float dz = z + (float)(j + 0.5) * 8 * side / (nr_v - 1);
+                    if (n < cap) {
+                        o[n].kind = ca;
+                        o[n].dx = dx;
+                        o[n].dz = dz;
+                        o[n].dy = ora_terrain_height(map, nr_v, x, z, (unsigned)side, dx, dz);
+                    }
+                    n++;
+                }
+    return n;
+}
+
 /* FNV-1a 64 over a byte buffer (fixture fingerprints) */
 uint64_t ora_fnv1a64(const void *buf, size_t n)
 {

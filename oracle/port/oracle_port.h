@@ -61,5 +61,11 @@ void  ora_terrain_heightmap(unsigned nr_v, const float *map0, float ty, const ui
 void  ora_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
                        unsigned i0, unsigned i1, float *vx, float *norm, float *tx, unsigned short *idx);
 
+/* terrain_height() core/terrain.c:336-379 and the instantiator loop :555-570 */
+float  ora_terrain_height(const float *map, unsigned nr_vert, float t_x, float t_z, unsigned t_side, float x, float z);
+size_t ora_terrain_instantiators(const uint8_t *maze, unsigned mside, const unsigned *nr_states, int nkinds,
+                                 const float *map, unsigned nr_v, float x, float z, float side,
+                                 void *out, size_t cap);
+
 uint64_t ora_fnv1a64(const void *buf, size_t n);
 #endif

@@ -93,5 +93,12 @@ void ref_terrain_normals(unsigned int nr_v, float *map, float *norm)
         }
 }
 
+/* the reference's own terrain_height() (terrain.c:336-379) on a caller-supplied map */
+float ref_terrain_height(float *map, unsigned int nr_v, float t_x, float t_z, unsigned int t_side, float x, float z)
+{
+    struct terrain t = { .nr_vert = nr_v, .map = map, .x = t_x, .z = t_z, .side = t_side };
+    return terrain_height(&t, x, z);
+}
+
 const struct cell_automaton *ref_ca_test(void) { return &ca_test; }
 const struct cell_automaton *ref_ca_instor(int i) { return &ca_instors[i]; }

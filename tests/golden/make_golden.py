@@ -121,6 +121,10 @@ def main():
     rough = (np.random.default_rng(3).random((37, 37)) * 40 - 20).astype(np.float32)
     mesh["rough_37"] = rough
     mesh["normals_rough_37"] = ref.terrain_normals(rough)
+    # terrain_height() (terrain.c:336-379) of the reference at seeded points, inside and outside the square
+    pts = (np.random.default_rng(4).random((400, 2)) * 340 - 20).astype(np.float32) + np.float32([10.0, 5.0])
+    mesh["height_pts"] = pts
+    mesh["heights_128_x10_z5_side300"] = ref.terrain_height(out["heightmap_128"], 10.0, 5.0, 300, pts)
     np.savez_compressed(os.path.join(HERE, "terrain_mesh.npz"), **mesh)
 
     for f in sorted(os.listdir(HERE)):

@@ -42,6 +42,11 @@ class Port:
         lib.ora_terrain_heightmap.argtypes = [c_uint, c_void_p, c_float, c_void_p, c_uint, c_uint, c_uint, c_void_p]
         lib.ora_terrain_mesh.argtypes = [c_void_p, c_uint, c_float, c_float, c_float, c_float, c_uint, c_uint,
                                          c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.ora_terrain_height.restype = c_float
+        lib.ora_terrain_height.argtypes = [c_void_p, c_uint, c_float, c_float, c_uint, c_float, c_float]
+        lib.ora_terrain_instantiators.restype = c_size_t
+        lib.ora_terrain_instantiators.argtypes = [c_void_p, c_uint, c_void_p, c_int, c_void_p, c_uint, c_float, c_float,
+                                                  c_float, c_void_p, c_size_t]
         lib.ora_fnv1a64.restype = c_uint64
         lib.ora_fnv1a64.argtypes = [c_void_p, c_size_t]
 
@@ -125,6 +130,23 @@ class Port:
         idx = np.zeros(6 * (nr_v - 1) * (nr_v - 1), np.uint16)
         self.lib.ora_terrain_mesh(_vp(hmap), nr_v, x, y, z, side, 0, nr_v, _vp(vx), _vp(norm), _vp(tx), _vp(idx))
         return vx, norm, tx, idx
+
+    def terrain_height(self, hmap, t_x, t_z, t_side, pts):
+        hmap = np.ascontiguousarray(hmap, np.float32)
+        return np.array([self.lib.ora_terrain_height(_vp(hmap), hmap.shape[0], t_x, t_z, int(t_side), float(x), float(z))
+                         for x, z in pts], np.float32)
+
+    def terrain_instantiators(self, maze, nr_states, hmap, x, z, side):
+        """structured array (kind, dx, dy, dz) of core/terrain.c:555-570"""
+        maze = np.ascontiguousarray(maze, np.uint8)
+        hmap = np.ascontiguousarray(hmap, np.float32)
+        kinds = np.array(nr_states, np.uint32)
+        dt = np.dtype([("kind", np.int32), ("dx", np.float32), ("dy", np.float32), ("dz", np.float32)])
+        args = (_vp(maze), maze.shape[0], _vp(kinds), len(kinds), _vp(hmap), hmap.shape[0], x, z, side)
+        n = self.lib.ora_terrain_instantiators(*args, None, 0)
+        out = np.zeros(n, dt)
+        self.lib.ora_terrain_instantiators(*args, _vp(out), n)
+        return out
 
     def fnv(self, arr):
         arr = np.ascontiguousarray(arr)
@@ -220,6 +242,14 @@ class Ref:
         out = np.zeros((nr_v, nr_v), np.float32)
         self.lib.ref_terrain_field(seed, nr_v, _vp(map0), ty, amp, octv, 0, nr_v, _vp(out))
         return out
+
+    def terrain_height(self, hmap, t_x, t_z, t_side, pts):
+        """the reference's terrain_height() (terrain.c:336-379) at the points pts[n, 2] = (x, z)"""
+        hmap = np.ascontiguousarray(hmap, np.float32)
+        self.lib.ref_terrain_height.restype = c_float
+        self.lib.ref_terrain_height.argtypes = [c_void_p, c_uint, c_float, c_float, c_uint, c_float, c_float]
+        return np.array([self.lib.ref_terrain_height(_vp(hmap), hmap.shape[0], t_x, t_z, int(t_side), float(x), float(z))
+                         for x, z in pts], np.float32)
 
     def terrain_normals(self, hmap):
         """the reference's calc_normal() (terrain.c:93-110) for every vertex, in mesh order"""

@@ -626,3 +626,42 @@ def test_ca2d_generate_16384_seed_row_samples(gpu, oracle):
     for x in range(6):
         col = np.where(vals[x * side:(x + 1) * side] <= 1, 1, 0).astype(np.uint8)
         assert np.array_equal(got[:, x], col), x
+
+
+# ---- instantiator extraction: core/terrain.c:555-570 with terrain_height() (:336-379) ----
+
+def _instor_check(got, want):
+    assert got.shape == want.shape
+    assert np.array_equal(got["kind"], want["kind"])
+    for f in ("dx", "dy", "dz"):
+        assert np.allclose(got[f], want[f], rtol=MESH_RTOL, atol=1e-6), f
+        assert float((got[f].view(np.uint32) == want[f].view(np.uint32)).mean()) > 0.999, f
+
+
+@pytest.mark.parametrize("nr_v,density", [(8, 0.5), (64, 0.0), (64, 1.0), (128, 0.1), (264, 0.02), (1000, 0.3)])
+def test_terrain_instantiators_vs_oracle(gpu, oracle, nr_v, density):
+    rng = np.random.default_rng(nr_v)
+    mside = nr_v // 8
+    maze = rng.integers(0, 20, (mside, mside)).astype(np.uint8)
+    hit = rng.random((mside, mside)) < density
+    maze[hit] = rng.integers(20, 22, int(hit.sum())).astype(np.uint8)
+    hmap = (rng.random((nr_v, nr_v)) * 30 - 10).astype(np.float32)
+    got = gpu.terrain_instantiators(maze, (20, 21), hmap, -12.5, 40.0, 500.0)
+    want = oracle.terrain_instantiators(maze, (20, 21), hmap, -12.5, 40.0, 500.0)
+    assert len(want) == int(hit.sum())
+    _instor_check(got, want)
+
+
+def test_terrain_instantiators_full_pipeline_2048(gpu, oracle):
+    """terrain.c:434-570 end to end: cave maze, heightmap, the two ca_instors passes, then the extraction."""
+    from clap_b200.ca import Rand48
+    nr_v = 2048
+    maze = gpu.ca2d_generate(gpu.CA_TEST, nr_v // 8, 4, Rand48(7))
+    hmap = gpu.terrain_heightmap(12345, nr_v, 0.0, maze)
+    for ca in gpu.CA_INSTORS:
+        gpu.ca2d_step(ca, maze, nr_v // 8)
+    kinds = tuple(ca.nr_states for ca in gpu.CA_INSTORS)
+    got = gpu.terrain_instantiators(maze, kinds, hmap, 0.0, 0.0, 1024.0)
+    want = oracle.terrain_instantiators(maze, kinds, hmap, 0.0, 0.0, 1024.0)
+    assert len(want) > 0
+    _instor_check(got, want)

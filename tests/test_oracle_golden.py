@@ -187,3 +187,34 @@ def test_terrain_mesh_port_vs_reference_normals(oracle, reference):
         hmap = (rng.random((nr, nr)) * 9 - 4).astype(np.float32)
         _, norm, _, _ = oracle.terrain_mesh(hmap, 0.0, 0.0, 0.0, 1.0)
         assert np.array_equal(norm.view(np.uint32), reference.terrain_normals(hmap).view(np.uint32)), nr
+
+
+def test_terrain_height_and_instantiators_golden(oracle):
+    """terrain_height() (core/terrain.c:336-379) against the reference's values in golden/terrain_mesh.npz, and the
+    instantiator loop (:555-570) on a small hand-checkable maze."""
+    t = np.load(os.path.join(G, "terrain.npz"))
+    m = np.load(os.path.join(G, "terrain_mesh.npz"))
+    h = oracle.terrain_height(t["heightmap_128"], 10.0, 5.0, 300, m["height_pts"])
+    assert np.array_equal(h.view(np.uint32), m["heights_128_x10_z5_side300"].view(np.uint32))
+    assert (h == 0).sum() > 10 and (h != 0).sum() > 200            # points outside the square read 0
+    maze = np.zeros((16, 16), np.uint8)
+    maze[3, 5] = 20         # xyarray_get(maze, i=5, j=3)
+    maze[9, 5] = 21
+    maze[0, 7] = 20
+    maze[2, 2] = 19
+    rec = oracle.terrain_instantiators(maze, (20, 21), t["heightmap_128"], 10.0, 5.0, 300.0)
+    assert rec["kind"].tolist() == [0, 1, 0]                        # i outer, j inner: (5,3) (5,9) (7,0)
+    f = np.float32
+    assert rec["dx"][0] == f(10.0) + f(5.5) * f(8) * f(300.0) / f(127) and rec["dz"][0] == f(5.0) + f(3.5) * f(8) * f(300.0) / f(127)
+    want = oracle.terrain_height(t["heightmap_128"], 10.0, 5.0, 300, np.stack([rec["dx"], rec["dz"]], 1))
+    assert np.array_equal(rec["dy"].view(np.uint32), want.view(np.uint32)) and (rec["dy"] != 0).all()
+
+
+def test_terrain_height_port_vs_reference(oracle, reference):
+    rng = np.random.default_rng(10)
+    for nr, side in ((50, 77), (131, 1000), (9, 3)):
+        hmap = (rng.random((nr, nr)) * 9 - 4).astype(np.float32)
+        pts = (rng.random((300, 2)) * side * 1.2 - side * 0.1).astype(np.float32) + np.float32([-3.0, 8.0])
+        a = oracle.terrain_height(hmap, -3.0, 8.0, side, pts)
+        b = reference.terrain_height(hmap, -3.0, 8.0, side, pts)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), nr
