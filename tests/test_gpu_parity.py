@@ -633,12 +633,14 @@ def test_ca2d_generate_16384_seed_row_samples(gpu, oracle):
 def _instor_check(got, want):
     assert got.shape == want.shape
     assert np.array_equal(got["kind"], want["kind"])
+    if len(want) == 0:
+        return
     for f in ("dx", "dy", "dz"):
         assert np.allclose(got[f], want[f], rtol=MESH_RTOL, atol=1e-6), f
         assert float((got[f].view(np.uint32) == want[f].view(np.uint32)).mean()) > 0.999, f
 
 
-@pytest.mark.parametrize("nr_v,density", [(8, 0.5), (64, 0.0), (64, 1.0), (128, 0.1), (264, 0.02), (1000, 0.3)])
+@pytest.mark.parametrize("nr_v,density", [(8, 1.0), (16, 0.5), (64, 0.0), (64, 1.0), (128, 0.1), (264, 0.02), (1000, 0.3)])
 def test_terrain_instantiators_vs_oracle(gpu, oracle, nr_v, density):
     rng = np.random.default_rng(nr_v)
     mside = nr_v // 8
