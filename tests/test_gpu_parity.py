@@ -667,3 +667,25 @@ def test_terrain_instantiators_full_pipeline_2048(gpu, oracle):
     want = oracle.terrain_instantiators(maze, kinds, hmap, 0.0, 0.0, 1024.0)
     assert len(want) > 0
     _instor_check(got, want)
+
+
+def test_ca2d_cfg3_full_size_reference_fingerprint(gpu, oracle):
+    """BASELINE config 3 at FULL size against the unmodified reference: srand48(1); ca2d_generate(cave rule, 16384,
+    100) took the reference a quarter of an hour on one core (tests/golden/make_golden_cfg3.py); its fingerprints
+    are committed in golden/cfg3_16384.json.  Seeding and all 100 generations run on the device here."""
+    import json
+    from clap_b200.ca import Rand48
+    with open(os.path.join(G, "cfg3_16384.json")) as f:
+        cfg = json.load(f)
+    assert "cave_bin_16384_x100_seed1" in cfg
+    for name, c in cfg.items():
+        r = c["rule"]
+        ca = gpu.CellAutomaton(name, born_mask=r["born"], surv_mask=r["surv"], nr_states=r["nr"], decay=bool(r["decay"]),
+                               neigh=r["neigh"])
+        for steps, key in ((0, "seed_grid"), (c["steps"], "final_grid")):
+            got = gpu.ca2d_generate(ca, c["side"], steps, Rand48(c["srand48"]))
+            want = c[key]
+            assert int(np.count_nonzero(got)) == want["population"], (name, key)
+            for row, h in want["rows"].items():
+                assert "%016x" % oracle.fnv(got[int(row)]) == h, (name, key, row)
+            assert "%016x" % oracle.fnv(got) == want["fnv1a64"], (name, key)
