@@ -25,7 +25,10 @@ namespace clapca {
  * so a consumer that reads {word, tag} atomically knows which version it got
  * and simply re-reads until the expected tag shows up (the LL protocol of
  * collective libraries).  A lane's 2*WPL words of a ghost row are the pairs
- * {H0[0..WPL), H1[0..WPL)} at ghost + r * stride + lane * 4 * WPL.
+ * {H0[0..WPL), H1[0..WPL)}, two pairs per 16-byte vector; vector i of lane l sits
+ * at 16-byte index r * stride/4 + 32 * i + l, so every warp-wide store of a row is
+ * ONE contiguous 512-byte burst on NVLink (16-byte scattered peer stores are what
+ * the link is worst at).
  */
 struct Bp3Plane {
     const uint32_t *dn_rows, *up_rows;      /* NULL: outside the volume (reads 0) */

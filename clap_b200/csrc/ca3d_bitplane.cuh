@@ -263,6 +263,7 @@ struct Sweep3 {
         int next_raise;                             /* next row count at which the own counter is raised */
         int dn_mode, up_mode;
         uint32_t tag_dn, tag_up, tag_out;
+        uint32_t bad_dn, bad_up;                    /* != 0 in some lane: the ghost row fetched one step ago carried a stale tag */
         long long waited_flag, waited_tag, waited_team;     /* diagnostics: cycles spent in the slow paths */
     };
 
@@ -341,7 +342,7 @@ struct Sweep3 {
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < WPL; i++) {             /* pairs 2i, 2i+1 of this lane */
-                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + i);
+                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);      /* vector i of every lane is contiguous */
                 const int q0 = 2 * i, q1 = 2 * i + 1;   /* pair index -> (plane, word) = (q / WPL, q % WPL) */
                 h[q0 / WPL][q0 % WPL] = v.x;
                 h[q1 / WPL][q1 % WPL] = v.z;
@@ -371,8 +372,38 @@ struct Sweep3 {
             const int q0 = 2 * i, q1 = 2 * i + 1;
             const uint32_t a = (q0 / WPL) ? h1[q0 % WPL] : h0[q0 % WPL];
             const uint32_t b = (q1 / WPL) ? h1[q1 % WPL] : h0[q1 % WPL];
-            dp_st_cg(reinterpret_cast<uint4 *>(dst) + i, make_uint4(a, tag, b, tag));
+            dp_st_cg(reinterpret_cast<uint4 *>(dst) + 32 * i, make_uint4(a, tag, b, tag));      /* one 512-byte burst per warp */
         }
+    }
+
+    /*
+     * In-loop variant: the row fetched here is not needed before the NEXT row step, so the loads are only issued;
+     * the data words go straight into the window registers and the tags are folded into one word per lane that
+     * settle_side() looks at a whole row step later.  Checking the tags on the spot (load -> compare -> vote)
+     * would put the L2 latency of a remotely written line on the critical path of every row of an edge plane --
+     * and in team mode the other warps of the CTA follow the edge plane row by row.
+     */
+    CA_MDEV void fetch_h_tagged(const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
+    {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
+            const int q0 = 2 * i, q1 = 2 * i + 1;
+            h[q0 / WPL][q0 % WPL] = v.x;
+            h[q1 / WPL][q1 % WPL] = v.z;
+            acc |= (v.y ^ expect) | (v.w ^ expect);
+        }
+        bad = acc;
+    }
+
+    /* the row fetched by fetch_h_tagged() one step ago is about to be used: re-read it if a tag was stale */
+    CA_MDEV bool settle_side(const Bp3Params &p, St &st, const uint32_t *next, uint32_t tag, uint32_t &bad, uint32_t h[2][WPL])
+    {
+        if (dp_all(bad == 0u))
+            return true;
+        bad = 0u;
+        return load_h_tagged(p, st, next - GHW, tag, h);
     }
 
     /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
@@ -427,6 +458,10 @@ struct Sweep3 {
         const uint32_t bornval = Rule::bornval(p);
         uint32_t k[WPL][5], ao[WPL], ge2[WPL];
 
+        /* ghost rows y+1 were only fetched during the previous step: make sure they carried the right tags */
+        if (st.dn_mode == SRC_GHOST && !settle_side(p, st, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
+        if (st.up_mode == SRC_GHOST && !settle_side(p, st, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
+
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
@@ -465,8 +500,18 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
-                if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
+                if (st.dn_mode == SRC_GHOST) {
+                    fetch_h_tagged(st.dn, st.tag_dn, st.hd[A], st.bad_dn);
+                    st.dn += GHW;
+                } else if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
+                    return false;
+                }
+                if (st.up_mode == SRC_GHOST) {
+                    fetch_h_tagged(st.up, st.tag_up, st.hu[A], st.bad_up);
+                    st.up += GHW;
+                } else if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
+                    return false;
+                }
             } else {
                 zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
                 zero_s(st.so[A]);
@@ -576,15 +621,15 @@ struct Sweep3 {
         const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
         st.dn_mode = !pl.dn_rows ? SRC_NONE : ((pl.ghost_mask & 1u) ? SRC_GHOST : SRC_LOCAL);
         st.up_mode = !pl.up_rows ? SRC_NONE : ((pl.ghost_mask & 2u) ? SRC_GHOST : SRC_LOCAL);
-        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 * WPL : WPL)
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 : WPL)
                            : nullptr;
-        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 * WPL : WPL)
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 : WPL)
                            : nullptr;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
         st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
               ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
-        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
-        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 * WPL : nullptr;
+        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
+        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
         st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
         st.tag_up = (p.epoch << 16) | (uint32_t)g;          /* plane above: still generation g-1 */
         st.tag_out = (p.epoch << 16) | (uint32_t)(g + 1);
@@ -606,6 +651,7 @@ struct Sweep3 {
         st.flag_period = (team_edge && p.edge_flag_rows > 0) ? p.edge_flag_rows : p.flag_rows;
         st.next_raise = (y0 / st.flag_period + 1) * st.flag_period;
         st.waited_flag = st.waited_tag = st.waited_team = 0;
+        st.bad_dn = st.bad_up = 0u;
         const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);

@@ -162,7 +162,8 @@ CA_GLOBAL void halo_seed_kernel(uint32_t *dst, const uint32_t *src, int H, int R
         const int lane = q / (2 * WPL), k = q % (2 * WPL);
         const int plane = k / WPL, j = k % WPL;
         const uint32_t v = src[(size_t)y * NP * RWP + (size_t)plane * RWP + lane * WPL + j];
-        uint32_t *d = dst + (size_t)y * 4 * RWP + (size_t)q * 2;
+        /* pair k of the lane lives in 16-byte vector k / 2 of that lane: vector u of all lanes is contiguous */
+        uint32_t *d = dst + (size_t)y * 4 * RWP + ((size_t)(k / 2) * 32 + lane) * 4 + (size_t)(k & 1) * 2;
         dp_st_cg(reinterpret_cast<uint2 *>(d), make_uint2(v, tag));
     }
 }
