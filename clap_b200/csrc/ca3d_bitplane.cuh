@@ -65,6 +65,8 @@ struct Bp3Params {
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
     int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
+    int ghost_scatter;      /* diagnostics: != 0 keeps a lane's ghost vectors adjacent (16-byte scattered peer stores) */
+    int ghost_eager;        /* diagnostics: != 0 validates ghost tags right after the load instead of one row later */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -342,7 +344,7 @@ struct Sweep3 {
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < WPL; i++) {             /* pairs 2i, 2i+1 of this lane */
-                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);      /* vector i of every lane is contiguous */
+                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + (p.ghost_scatter ? i : 32 * i));   /* vector i of every lane is contiguous */
                 const int q0 = 2 * i, q1 = 2 * i + 1;   /* pair index -> (plane, word) = (q / WPL, q % WPL) */
                 h[q0 / WPL][q0 % WPL] = v.x;
                 h[q1 / WPL][q1 % WPL] = v.z;
@@ -365,14 +367,14 @@ struct Sweep3 {
         }
     }
 
-    CA_MDEV void store_h_tagged(uint32_t *dst, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
+    CA_MDEV void store_h_tagged(const Bp3Params &p, uint32_t *dst, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
     {
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
             const int q0 = 2 * i, q1 = 2 * i + 1;
             const uint32_t a = (q0 / WPL) ? h1[q0 % WPL] : h0[q0 % WPL];
             const uint32_t b = (q1 / WPL) ? h1[q1 % WPL] : h0[q1 % WPL];
-            dp_st_cg(reinterpret_cast<uint4 *>(dst) + 32 * i, make_uint4(a, tag, b, tag));      /* one 512-byte burst per warp */
+            dp_st_cg(reinterpret_cast<uint4 *>(dst) + (p.ghost_scatter ? i : 32 * i), make_uint4(a, tag, b, tag));   /* one 512-byte burst per warp */
         }
     }
 
@@ -383,12 +385,12 @@ struct Sweep3 {
      * would put the L2 latency of a remotely written line on the critical path of every row of an edge plane --
      * and in team mode the other warps of the CTA follow the edge plane row by row.
      */
-    CA_MDEV void fetch_h_tagged(const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
+    CA_MDEV void fetch_h_tagged(const Bp3Params &p, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
     {
         uint32_t acc = 0u;
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
-            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
+            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + (p.ghost_scatter ? i : 32 * i));
             const int q0 = 2 * i, q1 = 2 * i + 1;
             h[q0 / WPL][q0 % WPL] = v.x;
             h[q1 / WPL][q1 % WPL] = v.z;
@@ -407,13 +409,14 @@ struct Sweep3 {
     }
 
     /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
+    template <bool EDGE>
     CA_MDEV bool load_side(const Bp3Params &p, St &st, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
     {
         if (mode == SRC_LOCAL) {
             LaneVec<WPL>::ld(src, h[0]);
             LaneVec<WPL>::ld(src + RWP, h[1]);
             src += RECW;
-        } else if (mode == SRC_NONE) {
+        } else if (!EDGE || mode == SRC_NONE) {
             zero2(h);
         } else {
             if (!load_h_tagged(p, st, src, tag, h)) return false;
@@ -449,7 +452,7 @@ struct Sweep3 {
      * sit in slots (M+2)%3 / M / (M+1)%3, own state rows y / y+1 in slots M / (M+1)%3; row y+2 is
      * prefetched into slot (M+2)%3 once row y-1 has been consumed.
      */
-    template <int M>
+    template <int M, bool EDGE>
     CA_MDEV bool step(const Bp3Params &p, St &st, int y, int y1, int *myprog)
     {
         constexpr int A = (M + 2) % 3, B = M, C = (M + 1) % 3;
@@ -459,8 +462,10 @@ struct Sweep3 {
         uint32_t k[WPL][5], ao[WPL], ge2[WPL];
 
         /* ghost rows y+1 were only fetched during the previous step: make sure they carried the right tags */
-        if (st.dn_mode == SRC_GHOST && !settle_side(p, st, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
-        if (st.up_mode == SRC_GHOST && !settle_side(p, st, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
+        if (EDGE) {
+            if (st.dn_mode == SRC_GHOST && !settle_side(p, st, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
+            if (st.up_mode == SRC_GHOST && !settle_side(p, st, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
+        }
 
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
 #pragma unroll
@@ -500,16 +505,16 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (st.dn_mode == SRC_GHOST) {
-                    fetch_h_tagged(st.dn, st.tag_dn, st.hd[A], st.bad_dn);
+                if (EDGE && st.dn_mode == SRC_GHOST && !p.ghost_eager) {
+                    fetch_h_tagged(p, st.dn, st.tag_dn, st.hd[A], st.bad_dn);
                     st.dn += GHW;
-                } else if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
+                } else if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
                     return false;
                 }
-                if (st.up_mode == SRC_GHOST) {
-                    fetch_h_tagged(st.up, st.tag_up, st.hu[A], st.bad_up);
+                if (EDGE && st.up_mode == SRC_GHOST && !p.ghost_eager) {
+                    fetch_h_tagged(p, st.up, st.tag_up, st.hu[A], st.bad_up);
                     st.up += GHW;
-                } else if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
+                } else if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
                     return false;
                 }
             } else {
@@ -596,20 +601,36 @@ struct Sweep3 {
          * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).  They are issued AFTER the
          * counter's release so that its MEMBAR never waits for this row's NVLink round trip.
          */
-        if (st.push_dn) {
-            store_h_tagged(st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
+        if (EDGE && st.push_dn) {
+            store_h_tagged(p, st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
             st.push_dn += GHW;
         }
-        if (st.push_up) {
-            store_h_tagged(st.push_up, st.tag_out, st.hn[0], st.hn[1]);
+        if (EDGE && st.push_up) {
+            store_h_tagged(p, st.push_up, st.tag_out, st.hn[0], st.hn[1]);
             st.push_up += GHW;
         }
         return true;
     }
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
+    /*
+     * Planes at a z-block edge (a ghost source or a peer to feed: multi-GPU runs only) take the EDGE instantiation
+     * of the row loop; every other plane -- all of them on one GPU -- runs a loop without a single ghost
+     * instruction in it.  The kernel is bound by instruction issue, and the edge code (tag polling loops inlined at
+     * every load site) costs the plain loop 30 % when it merely sits in its instruction stream.
+     */
     CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
                              const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
+    {
+        const Bp3Plane &pl = p.planes[z];
+        if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows)
+            return run_rows<true>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+        return run_rows<false>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+    }
+
+    template <bool EDGE>
+    CA_MDEV bool run_rows(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
+                          const int *sdn, int *sown, bool team_edge)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
@@ -621,15 +642,15 @@ struct Sweep3 {
         const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
         st.dn_mode = !pl.dn_rows ? SRC_NONE : ((pl.ghost_mask & 1u) ? SRC_GHOST : SRC_LOCAL);
         st.up_mode = !pl.up_rows ? SRC_NONE : ((pl.ghost_mask & 2u) ? SRC_GHOST : SRC_LOCAL);
-        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 : WPL)
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? (p.ghost_scatter ? 4 * WPL : 4) : WPL)
                            : nullptr;
-        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 : WPL)
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? (p.ghost_scatter ? 4 * WPL : 4) : WPL)
                            : nullptr;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
         st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
               ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
-        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
-        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
+        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * (p.ghost_scatter ? 4 * WPL : 4) : nullptr;
+        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * (p.ghost_scatter ? 4 * WPL : 4) : nullptr;
         st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
         st.tag_up = (p.epoch << 16) | (uint32_t)g;          /* plane above: still generation g-1 */
         st.tag_out = (p.epoch << 16) | (uint32_t)(g + 1);
@@ -693,18 +714,18 @@ struct Sweep3 {
 
         /* ---- fill the windows: rows y0-1 (slot 2), y0 (slot 0), y0+1 (slot 1) ---- */
         if (y0 > 0) {
-            if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
-            if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
+            if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
+            if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
             load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
         } else {
             zero2(st.hd[2]); zero2(st.hu[2]); zero2(st.hn);
         }
-        if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
-        if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
+        if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
+        if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
         load_own_s<0>(st, st.so[0]);
         if (y0 + 1 < H) {
-            if (!load_side(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
-            if (!load_side(p, st, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
+            if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
+            if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
             load_own_h<1>(st, st.ho);
             load_own_s<1>(st, st.so[1]);
         } else {
@@ -715,16 +736,16 @@ struct Sweep3 {
 
         int y = y0;
         for (; y + 3 <= y1; y += 3) {
-            if (!step<0>(p, st, y, y1, myprog)) return false;
-            if (!step<1>(p, st, y + 1, y1, myprog)) return false;
-            if (!step<2>(p, st, y + 2, y1, myprog)) return false;
+            if (!step<0, EDGE>(p, st, y, y1, myprog)) return false;
+            if (!step<1, EDGE>(p, st, y + 1, y1, myprog)) return false;
+            if (!step<2, EDGE>(p, st, y + 2, y1, myprog)) return false;
         }
         if (y < y1) {
-            if (!step<0>(p, st, y, y1, myprog)) return false;
+            if (!step<0, EDGE>(p, st, y, y1, myprog)) return false;
             y++;
         }
         if (y < y1) {
-            if (!step<1>(p, st, y, y1, myprog)) return false;
+            if (!step<1, EDGE>(p, st, y, y1, myprog)) return false;
         }
         /* publisher mode: the mailbox is reused by the next item only once the last rows are out */
         if (slot) {

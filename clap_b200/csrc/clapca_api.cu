@@ -427,6 +427,8 @@ static void sweep_knobs(Bp3Params &p, int team)
     if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
     p.team = team;
     if (const char *e = getenv("CLAPCA_EDGE_FLAG_ROWS")) p.edge_flag_rows = std::max(0, atoi(e));
+    if (const char *e = getenv("CLAPCA_GHOST_SCATTER")) p.ghost_scatter = atoi(e) != 0;
+    if (const char *e = getenv("CLAPCA_GHOST_EAGER")) p.ghost_eager = atoi(e) != 0;
 }
 
 static const int kGenBatch = 16;
@@ -1272,7 +1274,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
             if (!pl.push_dn_rows) continue;
             halo_seed_kernel<<<grid_blocks_for((size_t)s->H * 2 * s->RWP, 256, 4), 256, 0, s->stream>>>(
                 pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->WPL,
-                s->epoch << 16);
+                s->epoch << 16, getenv("CLAPCA_GHOST_SCATTER") && atoi(getenv("CLAPCA_GHOST_SCATTER")) != 0);
             CU(cudaGetLastError());
         }
     }
