@@ -65,8 +65,7 @@ struct Bp3Params {
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
     int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
-    int ghost_scatter;      /* diagnostics: != 0 keeps a lane's ghost vectors adjacent (16-byte scattered peer stores) */
-    int ghost_eager;        /* diagnostics: != 0 validates ghost tags right after the load instead of one row later */
+    int edge_loop;          /* != 0: some plane of this launch has a ghost source / feeds a peer (multi-GPU): see run_segment */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -265,7 +264,6 @@ struct Sweep3 {
         int next_raise;                             /* next row count at which the own counter is raised */
         int dn_mode, up_mode;
         uint32_t tag_dn, tag_up, tag_out;
-        uint32_t bad_dn, bad_up;                    /* != 0 in some lane: the ghost row fetched one step ago carried a stale tag */
         long long waited_flag, waited_tag, waited_team;     /* diagnostics: cycles spent in the slow paths */
     };
 
@@ -344,7 +342,7 @@ struct Sweep3 {
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < WPL; i++) {             /* pairs 2i, 2i+1 of this lane */
-                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + (p.ghost_scatter ? i : 32 * i));   /* vector i of every lane is contiguous */
+                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);   /* vector i of every lane is contiguous */
                 const int q0 = 2 * i, q1 = 2 * i + 1;   /* pair index -> (plane, word) = (q / WPL, q % WPL) */
                 h[q0 / WPL][q0 % WPL] = v.x;
                 h[q1 / WPL][q1 % WPL] = v.z;
@@ -374,38 +372,8 @@ struct Sweep3 {
             const int q0 = 2 * i, q1 = 2 * i + 1;
             const uint32_t a = (q0 / WPL) ? h1[q0 % WPL] : h0[q0 % WPL];
             const uint32_t b = (q1 / WPL) ? h1[q1 % WPL] : h0[q1 % WPL];
-            dp_st_cg(reinterpret_cast<uint4 *>(dst) + (p.ghost_scatter ? i : 32 * i), make_uint4(a, tag, b, tag));   /* one 512-byte burst per warp */
+            dp_st_cg(reinterpret_cast<uint4 *>(dst) + 32 * i, make_uint4(a, tag, b, tag));   /* one 512-byte burst per warp */
         }
-    }
-
-    /*
-     * In-loop variant: the row fetched here is not needed before the NEXT row step, so the loads are only issued;
-     * the data words go straight into the window registers and the tags are folded into one word per lane that
-     * settle_side() looks at a whole row step later.  Checking the tags on the spot (load -> compare -> vote)
-     * would put the L2 latency of a remotely written line on the critical path of every row of an edge plane --
-     * and in team mode the other warps of the CTA follow the edge plane row by row.
-     */
-    CA_MDEV void fetch_h_tagged(const Bp3Params &p, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
-    {
-        uint32_t acc = 0u;
-#pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + (p.ghost_scatter ? i : 32 * i));
-            const int q0 = 2 * i, q1 = 2 * i + 1;
-            h[q0 / WPL][q0 % WPL] = v.x;
-            h[q1 / WPL][q1 % WPL] = v.z;
-            acc |= (v.y ^ expect) | (v.w ^ expect);
-        }
-        bad = acc;
-    }
-
-    /* the row fetched by fetch_h_tagged() one step ago is about to be used: re-read it if a tag was stale */
-    CA_MDEV bool settle_side(const Bp3Params &p, St &st, const uint32_t *next, uint32_t tag, uint32_t &bad, uint32_t h[2][WPL])
-    {
-        if (dp_all(bad == 0u))
-            return true;
-        bad = 0u;
-        return load_h_tagged(p, st, next - GHW, tag, h);
     }
 
     /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
@@ -461,11 +429,7 @@ struct Sweep3 {
         const uint32_t bornval = Rule::bornval(p);
         uint32_t k[WPL][5], ao[WPL], ge2[WPL];
 
-        /* ghost rows y+1 were only fetched during the previous step: make sure they carried the right tags */
-        if (EDGE) {
-            if (st.dn_mode == SRC_GHOST && !settle_side(p, st, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
-            if (st.up_mode == SRC_GHOST && !settle_side(p, st, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
-        }
+
 
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
 #pragma unroll
@@ -505,18 +469,8 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (EDGE && st.dn_mode == SRC_GHOST && !p.ghost_eager) {
-                    fetch_h_tagged(p, st.dn, st.tag_dn, st.hd[A], st.bad_dn);
-                    st.dn += GHW;
-                } else if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
-                    return false;
-                }
-                if (EDGE && st.up_mode == SRC_GHOST && !p.ghost_eager) {
-                    fetch_h_tagged(p, st.up, st.tag_up, st.hu[A], st.bad_up);
-                    st.up += GHW;
-                } else if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
-                    return false;
-                }
+                if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
+                if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
             } else {
                 zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
                 zero_s(st.so[A]);
@@ -614,16 +568,17 @@ struct Sweep3 {
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
     /*
-     * Planes at a z-block edge (a ghost source or a peer to feed: multi-GPU runs only) take the EDGE instantiation
-     * of the row loop; every other plane -- all of them on one GPU -- runs a loop without a single ghost
-     * instruction in it.  The kernel is bound by instruction issue, and the edge code (tag polling loops inlined at
-     * every load site) costs the plain loop 30 % when it merely sits in its instruction stream.
+     * The row loop exists twice.  A launch in which some plane has a ghost source or feeds a peer (multi-GPU)
+     * runs the EDGE instantiation for EVERY plane; a single-GPU launch runs a loop without a single ghost
+     * instruction in it.  The kernel is bound by instruction issue and fetch: measured on B200 at 2048^3 x 50,
+     * the plain loop takes 119.3 ms where the loop carrying the (never executed) ghost paths takes 121-122 ms,
+     * more inlined tag-polling code in the same loop cost 30 %, and mixing the two instantiations inside one CTA
+     * (edge planes EDGE, their team-mates plain) was the slowest of all -- one hot loop per launch it is.
      */
     CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
                              const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
     {
-        const Bp3Plane &pl = p.planes[z];
-        if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows)
+        if (p.edge_loop)
             return run_rows<true>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
         return run_rows<false>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
     }
@@ -642,15 +597,15 @@ struct Sweep3 {
         const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
         st.dn_mode = !pl.dn_rows ? SRC_NONE : ((pl.ghost_mask & 1u) ? SRC_GHOST : SRC_LOCAL);
         st.up_mode = !pl.up_rows ? SRC_NONE : ((pl.ghost_mask & 2u) ? SRC_GHOST : SRC_LOCAL);
-        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? (p.ghost_scatter ? 4 * WPL : 4) : WPL)
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 : WPL)
                            : nullptr;
-        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? (p.ghost_scatter ? 4 * WPL : 4) : WPL)
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 : WPL)
                            : nullptr;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
         st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
               ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
-        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * (p.ghost_scatter ? 4 * WPL : 4) : nullptr;
-        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * (p.ghost_scatter ? 4 * WPL : 4) : nullptr;
+        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
+        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
         st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
         st.tag_up = (p.epoch << 16) | (uint32_t)g;          /* plane above: still generation g-1 */
         st.tag_out = (p.epoch << 16) | (uint32_t)(g + 1);
@@ -672,7 +627,6 @@ struct Sweep3 {
         st.flag_period = (team_edge && p.edge_flag_rows > 0) ? p.edge_flag_rows : p.flag_rows;
         st.next_raise = (y0 / st.flag_period + 1) * st.flag_period;
         st.waited_flag = st.waited_tag = st.waited_team = 0;
-        st.bad_dn = st.bad_up = 0u;
         const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);

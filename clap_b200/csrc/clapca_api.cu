@@ -427,8 +427,6 @@ static void sweep_knobs(Bp3Params &p, int team)
     if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
     p.team = team;
     if (const char *e = getenv("CLAPCA_EDGE_FLAG_ROWS")) p.edge_flag_rows = std::max(0, atoi(e));
-    if (const char *e = getenv("CLAPCA_GHOST_SCATTER")) p.ghost_scatter = atoi(e) != 0;
-    if (const char *e = getenv("CLAPCA_GHOST_EAGER")) p.ghost_eager = atoi(e) != 0;
 }
 
 static const int kGenBatch = 16;
@@ -1274,7 +1272,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
             if (!pl.push_dn_rows) continue;
             halo_seed_kernel<<<grid_blocks_for((size_t)s->H * 2 * s->RWP, 256, 4), 256, 0, s->stream>>>(
                 pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->WPL,
-                s->epoch << 16, getenv("CLAPCA_GHOST_SCATTER") && atoi(getenv("CLAPCA_GHOST_SCATTER")) != 0);
+                s->epoch << 16);
             CU(cudaGetLastError());
         }
     }
@@ -1314,6 +1312,8 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
         p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
         p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
+        for (const Bp3Plane &pl : s->h_planes)
+            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) { p.edge_loop = 1; break; }
         Bp3LaunchInfo info;
         CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
         workers = info.workers;

@@ -19,6 +19,16 @@ from .rules import CellAutomaton, ca3d_rule
 DEFAULT_BLOCK_PLANES = 16
 
 
+def default_block_planes(d2, nranks):
+    """z-block size of the scaling bench.  Every z-block edge costs the team that owns it (its edge plane polls ghost
+    tags and pushes rows over NVLink while 15 team-mates follow it row by row), every block adds pipeline depth:
+    measured on 2 x B200 at 2048^3 x 50 (profiles/r01_knobs_multi_team_blocks_n2.txt) the sweep takes 85 / 85 / 80 /
+    74 ms with blocks of 16 / 32 / 64 / 128 planes.  Hence: blocks of 128 planes, but at least two blocks per rank
+    so that the fill of the rank pipeline, (nranks - 1) / (generations * blocks per rank), stays small."""
+    per_rank = max(1, -(-int(d2) // max(1, int(nranks))))
+    return max(1, min(128, max(16, per_rank // 2), per_rank))
+
+
 # ---- pure host-side planning (mirrors SlabGeom in csrc/bp_plan.h; unit-tested on CPU) -----------------
 
 def plan_blocks(d2, nranks, block_planes):
@@ -156,7 +166,7 @@ def run_sharded_bench(args, workload, synth_planes):
     dev = torch.device("cuda", local)
     d0, d1, d2, gens, rule_index = workload
     rule = ca3d_rule(rule_index)
-    block = int(os.environ.get("CLAPCA_BLOCK_PLANES", DEFAULT_BLOCK_PLANES))
+    block = int(os.environ.get("CLAPCA_BLOCK_PLANES", default_block_planes(d2, world)))
 
     vol = ShardedVolume(d0, d1, d2, rank, world, gens, 5, block, torch_all_gather_bytes(dist, dev))
     # synthetic seed, generated block by block so every rank produces exactly the cells a single GPU would

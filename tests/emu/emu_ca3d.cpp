@@ -233,6 +233,8 @@ int main(int argc, char **argv)
         k.p.err = &err;
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;
         k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
+        for (const Bp3Plane &pl : k.planes)
+            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) k.p.edge_loop = 1;
         if (layout) {
             k.out_done.assign(Zl + 1, 0);
             k.p.layout_items = 1;
