@@ -40,5 +40,13 @@ struct Bp3Plane {
     int zglobal;                            /* global z of this plane */
 };
 
+/* arguments of the layout kernels (ca3d_layout.cuh): reference-layout cells <-> row records */
+struct Bp3Layout {
+    uint8_t *cells;         /* reference layout, z*W*H + y*W + x */
+    uint32_t *rows;         /* row records */
+    int W, H, Z, P, RWP;
+    unsigned long long *population;     /* unpack: number of non-zero cells */
+};
+
 } // namespace clapca
 #endif

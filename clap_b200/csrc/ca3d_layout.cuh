@@ -8,17 +8,13 @@
 #define CLAPCA_CA3D_LAYOUT_CUH
 
 #include "devport.h"
+#include "bp3_types.h"
 
 namespace clapca {
 
 /* ---- layout conversion ------------------------------------------------------- */
 
-struct Bp3Layout {
-    uint8_t *cells;         /* reference layout, z*W*H + y*W + x */
-    uint32_t *rows;         /* row records */
-    int W, H, Z, P, RWP;
-    unsigned long long *population;     /* unpack: number of non-zero cells */
-};
+/* struct Bp3Layout: bp3_types.h */
 
 
 /* gather bit q of each of 4 packed cells (bytes) into a nibble: cell k -> bit k */

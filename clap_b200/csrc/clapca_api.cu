@@ -1,32 +1,28 @@
 /*
  * clapca_api.cu -- the C ABI of libclapca_cuda (include/clapca.h): device
- * context, device-resident grids, engine selection and kernel launches.
+ * context, device-resident grids, ca3d / ca2d engine selection and kernel
+ * launches (multi-GPU slabs: api_slab.cu, noise / terrain fields: api_fields.cu).
  * Everything here runs on the GPU or fails; there is no host fallback.
  */
-#include <cuda_runtime.h>
 #include <cooperative_groups.h>
-#include <stdio.h>
-#include <stdarg.h>
-#include <stdlib.h>
-#include <string.h>
-#include <string>
-#include <vector>
-#include <new>
 
-#include "../../include/clapca.h"
-#include "bp3_launch.h"
+#include "api_internal.h"
 #include "bp2_launch.h"
 #include "ca2d_layout.cuh"
 #include "ca3d_layout.cuh"
 #include "ca_wavefront.cuh"
-#include "field_kernels.cuh"
-#include "bp_plan.h"
 
 using namespace clapca;
+using namespace clapca::api;
 
 namespace {
-
 thread_local std::string g_err;
+}
+
+namespace clapca {
+namespace api {
+
+Ctx g_ctx;
 
 int fail(int code, const char *fmt, ...)
 {
@@ -39,25 +35,14 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CU(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess)                                                               \
-            return fail(e__ == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA, \
-                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-/* control words of a sweep launch: [0] ticket, [1] err, [4..11] four 64-bit diagnostic cycle counters */
-static const int kTicketWords = 16;
-
-static bool diag_enabled()
+bool diag_enabled()
 {
     const char *e = getenv("CLAPCA_DIAG");
     return e && atoi(e) != 0;
 }
 
 /* CLAPCA_DIAG=1: where the persistent warps of the last sweep launch spent their cycles */
-static void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t stream, int rank)
+void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t stream, int rank)
 {
     if (!diag_enabled())
         return;
@@ -70,24 +55,6 @@ static void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t
             d[2] ? 100.0 * d[1] / d[2] : 0.0, d[2] ? 100.0 * d[3] / d[2] : 0.0);
 }
 
-struct Ctx {
-    int device = -1;
-    int sms = 0;
-    size_t mem = 0;
-    int coop = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream_in = nullptr, stream_out = nullptr;     /* copy streams of the streamed ca3d run */
-    /* small device scalars shared by the helpers below */
-    unsigned long long *d_count = nullptr;
-    unsigned *d_max = nullptr;
-    /* terrain: table of get_avg_height() (field_kernels.cuh), kept between calls */
-    void *d_smooth = nullptr;
-    size_t smooth_bytes = 0;
-    /* grow-only device staging of the one-shot field calls (cudaMalloc / cudaFree of GBs per call costs more than the kernels) */
-    void *scratch[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    size_t scratch_bytes[5] = { 0, 0, 0, 0, 0 };
-} g_ctx;
-
 int need_init()
 {
     if (g_ctx.device < 0)
@@ -95,7 +62,7 @@ int need_init()
     return CLAPCA_OK;
 }
 
-int grid_blocks_for(size_t work_items, int threads, int per_sm_cap = 8)
+int grid_blocks_for(size_t work_items, int threads, int per_sm_cap)
 {
     size_t b = (work_items + threads - 1) / threads;
     size_t cap = (size_t)g_ctx.sms * per_sm_cap;        /* grid-stride: a multiple of the SM count */
@@ -120,7 +87,8 @@ const uint32_t kCas[9][3] = {
     { RANGE(0, 6), B(1) | B(3), 2 },
 };
 
-} // namespace
+} // namespace api
+} // namespace clapca
 
 namespace clapca {
 cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream,
@@ -377,7 +345,12 @@ static int run3d_wavefront(clapca_grid *g, uint32_t surv, uint32_t born, uint32_
     return CLAPCA_OK;
 }
 
-static int ensure_bytes(void **ptr, size_t *have, size_t want)
+#pragma GCC visibility pop
+} /* extern "C" */
+
+/* ---- helpers shared with api_slab.cu / api_fields.cu (api_internal.h) ---- */
+
+int clapca::api::ensure_bytes(void **ptr, size_t *have, size_t want)
 {
     if (*have >= want)
         return CLAPCA_OK;
@@ -389,20 +362,35 @@ static int ensure_bytes(void **ptr, size_t *have, size_t want)
     return CLAPCA_OK;
 }
 
+int clapca::api::timed_sync(cudaEvent_t a, cudaEvent_t b, float *ms)
+{
+    CU(cudaStreamSynchronize(g_ctx.stream));
+    if (ms) CU(cudaEventElapsedTime(ms, a, b));
+    return CLAPCA_OK;
+}
+
+cudaError_t clapca::api::launch_ca3d_pack(const Bp3Layout &L, cudaStream_t stream)
+{
+    ca3d_pack_kernel<<<grid_blocks_for((size_t)L.Z * L.H * L.RWP, 256, 16), 256, 0, stream>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t clapca::api::launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t stream)
+{
+    ca3d_unpack_kernel<<<grid_blocks_for((size_t)L.Z * L.H * ((L.W + 31) / 32), 256, 16), 256, 0, stream>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t clapca::api::launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, int WPL, uint32_t tag,
+                                          cudaStream_t stream)
+{
+    halo_seed_kernel<<<grid_blocks_for((size_t)H * 2 * RWP, 256, 4), 256, 0, stream>>>(dst, src, H, RWP, NP, WPL, tag);
+    return cudaGetLastError();
+}
+
 /* progress counters are raised every kFlagRows rows: one fence per kFlagRows row steps */
 static const int kFlagRows = 8;
 
-/* generations fused per launch: bounds the progress-counter table, not the result */
-static const int kMaxFusedGenerations = 4096;
-
-/* work-item claim order of the bit-plane sweep (see bp_plan.h) */
-struct OrderCfg {
-    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals, 3 plane teams */
-    int seg_rows;       /* mode 1 */
-    int gen_batch;      /* mode 2 */
-    int team;           /* mode 3: planes per group = warps per CTA */
-    int key() const { return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? team : 0))); }
-};
 
 /*
  * Team mode (ca3d_bitplane.cuh): warps per CTA = planes per work item; 0 = one warp per sweep.  Default: teams
@@ -410,7 +398,7 @@ struct OrderCfg {
  * (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms, and in the low-parallelism regime that
  * a rank of an 8-GPU run sees (6 generations' worth of sweeps per dependency level) 35.2 -> 16.4 ms.
  */
-static int team_config(int P, int WPL)
+int clapca::api::team_config(int P, int WPL)
 {
     int t = bp3_team_cap(P, WPL) >= 16 ? 16 : 0;
     if (const char *e = getenv("CLAPCA_TEAM")) t = atoi(e);
@@ -418,7 +406,7 @@ static int team_config(int P, int WPL)
     return std::min(t, bp3_team_cap(P, WPL));
 }
 
-static void sweep_knobs(Bp3Params &p, int team)
+void clapca::api::sweep_knobs(Bp3Params &p, int team)
 {
     p.flag_rows = kFlagRows;
     if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
@@ -431,7 +419,7 @@ static void sweep_knobs(Bp3Params &p, int team)
 
 static const int kGenBatch = 16;
 
-static OrderCfg order_config(int Z, int H, int G, int max_workers, int team)
+OrderCfg clapca::api::order_config(int Z, int H, int G, int max_workers, int team)
 {
     OrderCfg oc = { 0, 0, kGenBatch, team };
     if (team > 0) {
@@ -449,7 +437,7 @@ static OrderCfg order_config(int Z, int H, int G, int max_workers, int team)
     return oc;
 }
 
-static void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
+void clapca::api::make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                        std::vector<WorkItem> &items, bool layout_items)
 {
     if (oc.mode == 3) bp3_make_items_team(planes, H, G, oc.team, items, layout_items);
@@ -457,6 +445,9 @@ static void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, 
     else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
     else bp3_make_items_timekey(planes, H, G, items, layout_items);
 }
+
+extern "C" {
+#pragma GCC visibility push(default)
 
 /* CLAPCA_FUSED_LAYOUT=1: device-resident runs also convert the layout inside the sweep launch (layout items) */
 static bool fused_layout_default()
@@ -537,7 +528,6 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
 
     unsigned long long *d_pop = g_ctx.d_count;
     Bp3Layout L = { g->cells, g->rows, W, H, Z, P, RWP, d_pop };
-    const size_t nwords = (size_t)Z * H * RWP;
     const size_t plane_bytes = (size_t)W * H;
     const int chunk = io_chunk_planes(plane_bytes, Z);
     const int nchunks = (Z + chunk - 1) / chunk;
@@ -560,8 +550,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     }
 
     if (!fused) {
-        ca3d_pack_kernel<<<grid_blocks_for(nwords, 256, 16), 256, 0, g->stream>>>(L);
-        CU(cudaGetLastError());
+        CU(launch_ca3d_pack(L, g->stream));
     }
     CU(cudaEventRecord(g->ev[1], g->stream));
 
@@ -723,8 +712,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
 
     if (!fused) {
         CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
-        ca3d_unpack_kernel<<<grid_blocks_for((size_t)Z * H * ((W + 31) / 32), 256, 16), 256, 0, g->stream>>>(L);
-        CU(cudaGetLastError());
+        CU(launch_ca3d_unpack(L, g->stream));
     }
     CU(cudaEventRecord(g->ev[3], g->stream));
 
@@ -1058,303 +1046,6 @@ int clapca_ca2d_generate(uint8_t *arr, int64_t side, uint32_t born, uint32_t sur
 }
 
 
-/* ---- multi-GPU z-block slabs ------------------------------------------------------ */
-
-struct clapca_slab {
-    SlabGeom geo;
-    HaloLayout hl;
-    int W, H, P, WPL, RWP, NP, Gcap, Zl;
-    uint8_t *cells = nullptr;           /* local planes, reference layout, local order */
-    uint32_t *rows = nullptr;
-    uint32_t *halo = nullptr;           /* exported to the neighbours */
-    uint32_t *halo_next = nullptr, *halo_prev = nullptr;
-    bool opened_next = false, opened_prev = false;
-    int *prog = nullptr;
-    Bp3Plane *planes = nullptr;
-    std::vector<Bp3Plane> h_planes;
-    int4 *order = nullptr;
-    size_t order_bytes = 0;
-    int n_items = 0, order_G = -1, team = -1;
-    unsigned *ticket = nullptr;
-    unsigned long long *d_pop = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    uint32_t surv = 0, born = 0, nr_states = 0;
-    int G = 0, rule = BP3_RULE_DYN;
-    bool prepared = false;
-    uint32_t epoch = 0;             /* run number: upper half of the ghost-row tags */
-    clapca_run_stats stats;
-};
-
-int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_global, int rank, int nranks,
-                       int block_planes, int max_generations, unsigned max_value)
-{
-    if (int rc = need_init()) return rc;
-    if (!out || d0 < 1 || d1 < 1 || d2_global < 1 || nranks < 1 || rank < 0 || rank >= nranks || block_planes < 1 ||
-        max_generations < 1 || max_generations > kMaxFusedGenerations)
-        return fail(CLAPCA_ERR_ARG, "slab_create: bad arguments");
-    const int WPL = bp_wpl_for((int)d0);
-    if (!WPL || d1 >= (1 << 30) || d2_global >= (1 << 30))
-        return fail(CLAPCA_ERR_UNSUPPORTED, "slab_create: rows of at most 4096 cells are supported (d0 = %lld)",
-                    (long long)d0);
-    clapca_slab *s = new (std::nothrow) clapca_slab();
-    if (!s) return fail(CLAPCA_ERR_NOMEM, "slab_create: host allocation failed");
-    s->geo = SlabGeom{ (int)d2_global, nranks, rank, nranks == 1 ? (int)d2_global : block_planes };
-    s->W = (int)d0; s->H = (int)d1;
-    s->P = bp_planes_for(max_value);
-    s->WPL = WPL; s->RWP = 32 * WPL; s->NP = s->P + 2;
-    s->Gcap = max_generations;
-    s->Zl = s->geo.local_planes();
-    s->hl = slab_halo_layout(s->geo, s->H, s->RWP);
-    s->stream = g_ctx.stream;
-    memset(&s->stats, 0, sizeof(s->stats));
-    const size_t zl = s->Zl ? s->Zl : 1;
-    cudaError_t e = cudaMalloc(&s->cells, zl * s->W * s->H);
-    if (e == cudaSuccess) e = cudaMalloc(&s->rows, zl * s->H * s->NP * s->RWP * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&s->halo, s->hl.total_words * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(s->halo, 0, s->hl.total_words * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&s->prog, (size_t)s->Gcap * zl * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&s->planes, zl * sizeof(Bp3Plane));
-    if (e == cudaSuccess) e = cudaMalloc(&s->ticket, kTicketWords * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_pop, sizeof(unsigned long long));
-    for (int i = 0; i < 5 && e == cudaSuccess; i++)
-        e = cudaEventCreate(&s->ev[i]);
-    if (e != cudaSuccess) {
-        clapca_slab_destroy(s);
-        return fail(e == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA, "slab_create: %s",
-                    cudaGetErrorString(e));
-    }
-    *out = s;
-    return CLAPCA_OK;
-}
-
-int clapca_slab_destroy(clapca_slab *s)
-{
-    if (!s) return CLAPCA_OK;
-    if (s->opened_next && s->halo_next) cudaIpcCloseMemHandle(s->halo_next);
-    if (s->opened_prev && s->halo_prev) cudaIpcCloseMemHandle(s->halo_prev);
-    void *bufs[] = { s->cells, s->rows, s->halo, s->prog, s->planes, s->order, s->ticket, s->d_pop };
-    for (void *b : bufs)
-        if (b) cudaFree(b);
-    for (int i = 0; i < 5; i++)
-        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
-    delete s;
-    return CLAPCA_OK;
-}
-
-int clapca_slab_local_planes(clapca_slab *s, int *n)
-{
-    if (!s || !n) return fail(CLAPCA_ERR_ARG, "slab_local_planes: NULL argument");
-    *n = s->Zl;
-    return CLAPCA_OK;
-}
-
-int clapca_slab_plane_map(clapca_slab *s, int64_t *zglobal)
-{
-    if (!s || !zglobal) return fail(CLAPCA_ERR_ARG, "slab_plane_map: NULL argument");
-    for (int lb = 0; lb < s->geo.local_blocks(); lb++) {
-        const int j = s->geo.global_block(lb), l0 = s->geo.local_z0(lb);
-        for (int i = 0; i < s->geo.block_len(j); i++)
-            zglobal[l0 + i] = s->geo.block_z0(j) + i;
-    }
-    return CLAPCA_OK;
-}
-
-void *clapca_slab_device_ptr(clapca_slab *s) { return s ? s->cells : nullptr; }
-
-int clapca_slab_ipc_handle(clapca_slab *s, void *handle64)
-{
-    if (!s || !handle64) return fail(CLAPCA_ERR_ARG, "slab_ipc_handle: NULL argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, s->halo));
-    memcpy(handle64, &h, sizeof(h));
-    return CLAPCA_OK;
-}
-
-int clapca_slab_connect(clapca_slab *s, const void *handle_next, const void *handle_prev)
-{
-    if (!s) return fail(CLAPCA_ERR_ARG, "slab_connect: NULL slab");
-    const int R = s->geo.R;
-    if (R == 1) {
-        s->halo_next = s->halo_prev = s->halo;
-    } else {
-        if (!handle_next || !handle_prev) return fail(CLAPCA_ERR_ARG, "slab_connect: NULL handle");
-        cudaIpcMemHandle_t hn, hp;
-        memcpy(&hn, handle_next, sizeof(hn));
-        memcpy(&hp, handle_prev, sizeof(hp));
-        void *pn = nullptr, *pp = nullptr;
-        CU(cudaIpcOpenMemHandle(&pn, hn, cudaIpcMemLazyEnablePeerAccess));
-        s->halo_next = (uint32_t *)pn;
-        s->opened_next = true;
-        if (R == 2) {
-            s->halo_prev = s->halo_next;        /* both neighbours are the same rank: one mapping */
-        } else {
-            CU(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
-            s->halo_prev = (uint32_t *)pp;
-            s->opened_prev = true;
-        }
-    }
-    SlabPtrs ptr = { s->rows, s->prog, s->halo, s->halo_next, s->halo_prev };
-    bp3_build_planes(s->geo, ptr, s->hl, s->H, s->RWP, s->NP, s->h_planes);
-    /* progress counters of a generation are Zl apart only when all Gcap generations share one table */
-    if (s->Zl)
-        CU(cudaMemcpy(s->planes, s->h_planes.data(), s->h_planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice));
-    return CLAPCA_OK;
-}
-
-int clapca_slab_upload(clapca_slab *s, const uint8_t *src)
-{
-    if (!s || !src) return fail(CLAPCA_ERR_ARG, "slab_upload: NULL argument");
-    if (s->Zl) {
-        CU(cudaMemcpyAsync(s->cells, src, (size_t)s->Zl * s->W * s->H, cudaMemcpyDefault, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-    }
-    return CLAPCA_OK;
-}
-
-int clapca_slab_download(clapca_slab *s, uint8_t *dst)
-{
-    if (!s || !dst) return fail(CLAPCA_ERR_ARG, "slab_download: NULL argument");
-    if (s->Zl) {
-        CU(cudaMemcpyAsync(dst, s->cells, (size_t)s->Zl * s->W * s->H, cudaMemcpyDefault, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-    }
-    return CLAPCA_OK;
-}
-
-/*
- * Step 1 of a sharded run (all ranks, then a barrier): lay the local planes out as bit-plane row
- * records, seed the neighbour's ghost planes with the H rows of every block's first plane (the
- * "old plane above" of generation 0) and clear the progress counters.
- */
-int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t nr_states, int steps)
-{
-    if (int rc = need_init()) return rc;
-    if (!s) return fail(CLAPCA_ERR_ARG, "slab_prepare: NULL slab");
-    if (s->h_planes.empty() && s->Zl) return fail(CLAPCA_ERR_STATE, "slab_prepare: call clapca_slab_connect first");
-    if (steps < 1 || steps > s->Gcap) return fail(CLAPCA_ERR_ARG, "slab_prepare: steps %d outside 1..%d", steps, s->Gcap);
-    const uint32_t bornval = (nr_states - 1u) & 0xffu;
-    if (born && (bornval >> s->P))
-        return fail(CLAPCA_ERR_ARG, "slab_prepare: rule needs more than the %d state planes of this slab", s->P);
-    s->surv = surv; s->born = born; s->nr_states = nr_states; s->G = steps;
-    s->epoch = (s->epoch + 1) & 0xffffu;        /* every rank prepares the same number of times */
-    if (!s->epoch) s->epoch = 1;
-    s->rule = BP3_RULE_DYN;
-    for (int i = 0; i < 9; i++)
-        if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { s->rule = i; break; }
-
-    const int team = team_config(s->P, s->WPL);
-    if (s->order_G != steps || s->team != team) {
-        std::vector<WorkItem> items;
-        const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms), team);
-        s->team = team;
-        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items, false);
-        void *p = s->order;
-        if (int rc = ensure_bytes(&p, &s->order_bytes, (items.size() ? items.size() : 1) * sizeof(int4))) {
-            s->order = nullptr;
-            return rc;
-        }
-        s->order = (int4 *)p;
-        if (!items.empty())
-            CU(cudaMemcpy(s->order, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-        s->n_items = (int)items.size();
-        s->order_G = steps;
-    }
-    CU(cudaEventRecord(s->ev[0], s->stream));
-    if (s->Zl) {
-        Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };
-        ca3d_pack_kernel<<<grid_blocks_for((size_t)s->Zl * s->H * s->RWP, 256, 16), 256, 0, s->stream>>>(L);
-        CU(cudaGetLastError());
-        /* halo seed: H rows of each block's first plane -> ghost plane above the previous block, tag = seed state */
-        for (size_t l = 0; l < s->h_planes.size(); l++) {
-            const Bp3Plane &pl = s->h_planes[l];
-            if (!pl.push_dn_rows) continue;
-            halo_seed_kernel<<<grid_blocks_for((size_t)s->H * 2 * s->RWP, 256, 4), 256, 0, s->stream>>>(
-                pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->WPL,
-                s->epoch << 16);
-            CU(cudaGetLastError());
-        }
-    }
-    CU(cudaMemsetAsync(s->prog, 0, (size_t)s->Gcap * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
-    CU(cudaMemsetAsync(s->ticket, 0, kTicketWords * sizeof(unsigned), s->stream));
-    CU(cudaEventRecord(s->ev[1], s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    s->prepared = true;
-    return CLAPCA_OK;
-}
-
-/*
- * Step 2 (after the barrier): the fused sweep kernel -- halo rows travel as peer stores inside it --
- * then the layout conversion back and the local population count.
- */
-int clapca_slab_run(clapca_slab *s, int64_t *local_population)
-{
-    if (int rc = need_init()) return rc;
-    if (!s || !s->prepared) return fail(CLAPCA_ERR_STATE, "slab_run: slab is not prepared");
-    s->prepared = false;
-    memset(&s->stats, 0, sizeof(s->stats));
-    CU(cudaEventRecord(s->ev[2], s->stream));
-    int workers = 0;
-    if (s->n_items) {
-        Bp3Params p;
-        memset(&p, 0, sizeof(p));
-        p.rows = s->rows;
-        p.planes = s->planes;
-        p.W = s->W; p.H = s->H; p.Z = s->Zl; p.G = s->G; p.RWP = s->RWP;
-        p.prog = s->prog;
-        p.order = s->order;
-        p.nsweeps = s->n_items;
-        p.epoch = s->epoch;
-        sweep_knobs(p, s->team);
-        p.ticket = s->ticket;
-        p.err = (int *)(s->ticket + 1);
-        p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
-        p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
-        p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
-        for (const Bp3Plane &pl : s->h_planes)
-            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) { p.edge_loop = 1; break; }
-        Bp3LaunchInfo info;
-        CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
-        workers = info.workers;
-    }
-    CU(cudaEventRecord(s->ev[3], s->stream));
-    diag_report("slab", s->ticket, s->stream, s->geo.rank);
-    CU(cudaMemsetAsync(s->d_pop, 0, sizeof(unsigned long long), s->stream));
-    if (s->Zl) {
-        Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };
-        ca3d_unpack_kernel<<<grid_blocks_for((size_t)s->Zl * s->H * ((s->W + 31) / 32), 256, 16), 256, 0, s->stream>>>(L);
-        CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(s->ev[4], s->stream));
-    unsigned long long pop = 0;
-    int err = 0;
-    CU(cudaMemcpyAsync(&pop, s->d_pop, sizeof(pop), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&err, s->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    if (err)
-        return fail(CLAPCA_ERR_TIMEOUT, "slab_run: dataflow watchdog fired on rank %d (err=%d)", s->geo.rank, err);
-    if (local_population) *local_population = (int64_t)pop;
-    float prep = 0, sweep = 0, tail = 0;
-    CU(cudaEventElapsedTime(&prep, s->ev[0], s->ev[1]));
-    CU(cudaEventElapsedTime(&sweep, s->ev[2], s->ev[3]));
-    CU(cudaEventElapsedTime(&tail, s->ev[3], s->ev[4]));
-    s->stats.total_ms = prep + sweep + tail;
-    s->stats.kernel_ms = sweep;
-    s->stats.launches = (s->Zl ? 2 : 0) + (s->n_items ? 1 : 0);
-    s->stats.engine = CLAPCA_ENGINE_BITPLANE;
-    s->stats.planes = s->P;
-    s->stats.workers = workers;
-    return CLAPCA_OK;
-}
-
-int clapca_slab_last_stats(clapca_slab *s, clapca_run_stats *st)
-{
-    if (!s || !st) return fail(CLAPCA_ERR_ARG, "slab_last_stats: NULL argument");
-    *st = s->stats;
-    return CLAPCA_OK;
-}
-
 /* ---- fields ------------------------------------------------------------------- */
 
 void *clapca_device_alloc(size_t bytes)
@@ -1387,273 +1078,6 @@ int clapca_memcpy_d2h(void *dst, const void *src, size_t bytes)
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
     CU(cudaStreamSynchronize(g_ctx.stream));
     return CLAPCA_OK;
-}
-
-static int timed_sync(cudaEvent_t a, cudaEvent_t b, float *ms)
-{
-    CU(cudaStreamSynchronize(g_ctx.stream));
-    if (ms) CU(cudaEventElapsedTime(ms, a, b));
-    return CLAPCA_OK;
-}
-
-int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
-                             float period_units, uint32_t seed, float *kernel_ms)
-{
-    if (int rc = need_init()) return rc;
-    if (!d_out || size < 1 || size > 4096 || octaves < 0 || (int)period_units < 1)
-        return fail(CLAPCA_ERR_ARG, "noise bake: bad arguments (size %zu, octaves %d, period %g)", size, octaves,
-                    (double)period_units);
-    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed };
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
-    size_t voxels = size * size * size;
-    CU(cudaEventRecord(a, g_ctx.stream));
-    noise_bake_kernel<<<grid_blocks_for(voxels, 256, 8), 256, 0, g_ctx.stream>>>(p);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(b, g_ctx.stream));
-    int rc = timed_sync(a, b, kernel_ms);
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    return rc;
-}
-
-int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float lacunarity, float gain,
-                                   float period_units, uint32_t seed)
-{
-    if (int rc = need_init()) return rc;
-    if (!out) return fail(CLAPCA_ERR_ARG, "noise bake: NULL output");
-    size_t bytes = size * size * size * 4;
-    void *d = nullptr;
-    CU(cudaMalloc(&d, bytes ? bytes : 4));
-    int rc = clapca_noise_bake_device(d, size, octaves, lacunarity, gain, period_units, seed, nullptr);
-    if (!rc) rc = clapca_memcpy_d2h(out, d, bytes);
-    cudaFree(d);
-    return rc;
-}
-
-int clapca_noise_fbm3(float *out, const float *xyz, size_t n, int octaves, float lacunarity, float gain,
-                      int period, uint32_t seed)
-{
-    if (int rc = need_init()) return rc;
-    if (!out || !xyz || period < 1) return fail(CLAPCA_ERR_ARG, "noise_fbm3: bad arguments");
-    if (!n) return CLAPCA_OK;
-    float *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMalloc(&d_in, n * 3 * sizeof(float)));
-    cudaError_t e = cudaMalloc(&d_out, n * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(d_in); return fail(CLAPCA_ERR_NOMEM, "noise_fbm3: %s", cudaGetErrorString(e)); }
-    int rc = clapca_memcpy_h2d(d_in, xyz, n * 3 * sizeof(float));
-    if (!rc) {
-        noise_fbm3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_ctx.stream>>>(d_out, d_in, n, octaves, lacunarity,
-                                                                                 gain, period, seed);
-        if (cudaGetLastError() != cudaSuccess) rc = fail(CLAPCA_ERR_CUDA, "noise_fbm3 launch failed");
-    }
-    if (!rc) rc = clapca_memcpy_d2h(out, d_out, n * sizeof(float));
-    cudaFree(d_in);
-    cudaFree(d_out);
-    return rc;
-}
-
-int clapca_terrain_heightmap_device(void *d_map, void *d_map0, long seed, unsigned nr_v, float ty,
-                                    const void *d_maze, unsigned mside, float amp, int oct,
-                                    float *map0_ms, float *map_ms)
-{
-    if (int rc = need_init()) return rc;
-    if (!d_map0 || nr_v < 1 || nr_v > 46340)
-        return fail(CLAPCA_ERR_ARG, "terrain: bad arguments (nr_v %u)", nr_v);
-    if (d_maze && mside < 1) return fail(CLAPCA_ERR_ARG, "terrain: maze without a side length");
-    cudaEvent_t e0, e1, e2;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventCreate(&e2));
-    size_t n = (size_t)nr_v * nr_v;
-    CU(cudaEventRecord(e0, g_ctx.stream));
-    terrain_map0_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>((float *)d_map0, (long long)seed, nr_v);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(e1, g_ctx.stream));
-    if (d_map) {
-        TerrainParams p = { (float *)d_map, (const float *)d_map0, (const uint8_t *)d_maze, nr_v, mside, ty, amp, oct,
-                            nullptr };
-        const char *direct = getenv("CLAPCA_TERRAIN_DIRECT");       /* diagnostics: evaluate the 3x3 kernel per use */
-        if (!(direct && atoi(direct) > 0)) {
-            const size_t sn = ((size_t)nr_v + 1) * ((size_t)nr_v + 1);
-            if (int rc = ensure_bytes(&g_ctx.d_smooth, &g_ctx.smooth_bytes, sn * sizeof(float))) return rc;
-            terrain_smooth_kernel<<<grid_blocks_for(sn, 256, 8), 256, 0, g_ctx.stream>>>(p, (float *)g_ctx.d_smooth);
-            CU(cudaGetLastError());
-            p.smooth = (const float *)g_ctx.d_smooth;
-        }
-        /* tabulated blend factors need 2^(oct-1) <= 8 distinct fractions (the reference fixes OCTAVES = 4) */
-        if (p.smooth && (d_maze || (oct >= 0 && oct <= 4)))
-            terrain_heightmap_tab_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
-        else
-            terrain_heightmap_kernel<<<grid_blocks_for(n, 256, 8), 256, 0, g_ctx.stream>>>(p);
-        CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(e2, g_ctx.stream));
-    int rc = timed_sync(e0, e1, map0_ms);
-    if (!rc && map_ms) {
-        cudaError_t e = cudaEventElapsedTime(map_ms, e1, e2);
-        if (e != cudaSuccess) rc = fail(CLAPCA_ERR_CUDA, "terrain: %s", cudaGetErrorString(e));
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
-    return rc;
-}
-
-int clapca_terrain_map0(float *map0, long seed, unsigned nr_v)
-{
-    if (int rc = need_init()) return rc;
-    if (!map0) return fail(CLAPCA_ERR_ARG, "terrain_map0: NULL output");
-    size_t bytes = (size_t)nr_v * nr_v * sizeof(float);
-    void *d = nullptr;
-    CU(cudaMalloc(&d, bytes ? bytes : 4));
-    int rc = clapca_terrain_heightmap_device(nullptr, d, seed, nr_v, 0.f, nullptr, 0, 0.f, 0, nullptr, nullptr);
-    if (!rc) rc = clapca_memcpy_d2h(map0, d, bytes);
-    cudaFree(d);
-    return rc;
-}
-
-int clapca_terrain_heightmap(float *map, long seed, unsigned nr_v, float ty, const uint8_t *maze, unsigned mside,
-                             float amp, int oct)
-{
-    if (int rc = need_init()) return rc;
-    if (!map) return fail(CLAPCA_ERR_ARG, "terrain_heightmap: NULL output");
-    size_t bytes = (size_t)nr_v * nr_v * sizeof(float);
-    void *d_map = nullptr, *d_map0 = nullptr, *d_maze = nullptr;
-    if (int rc = ensure_bytes(&g_ctx.scratch[0], &g_ctx.scratch_bytes[0], bytes ? bytes : 4)) return rc;
-    if (int rc = ensure_bytes(&g_ctx.scratch[1], &g_ctx.scratch_bytes[1], bytes ? bytes : 4)) return rc;
-    d_map = g_ctx.scratch[0];
-    d_map0 = g_ctx.scratch[1];
-    int rc = CLAPCA_OK;
-    if (maze) {
-        if (int rc2 = ensure_bytes(&g_ctx.scratch[2], &g_ctx.scratch_bytes[2], (size_t)mside * mside)) return rc2;
-        d_maze = g_ctx.scratch[2];
-        rc = clapca_memcpy_h2d(d_maze, maze, (size_t)mside * mside);
-    }
-    if (!rc) rc = clapca_terrain_heightmap_device(d_map, d_map0, seed, nr_v, ty, d_maze, mside, amp, oct, nullptr, nullptr);
-    if (!rc) rc = clapca_memcpy_d2h(map, d_map, bytes);
-    return rc;
-}
-
-/* ---- terrain mesh ------------------------------------------------------------ */
-
-int clapca_terrain_mesh_device(const void *d_map, unsigned nr_v, float x, float y, float z, float side,
-                               void *d_vx, void *d_norm, void *d_tx, void *d_idx, float *kernel_ms)
-{
-    if (int rc = need_init()) return rc;
-    if (!d_map || nr_v < 1 || nr_v > 46340)
-        return fail(CLAPCA_ERR_ARG, "terrain_mesh: bad arguments (nr_v %u)", nr_v);
-    TerrainMeshParams p = { (const float *)d_map, nr_v, x, y, z, side, (float *)d_vx, (float *)d_norm, (float *)d_tx,
-                            (unsigned short *)d_idx };
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, g_ctx.stream));
-    if (d_vx || d_norm || d_tx) {
-        const unsigned tiles = (nr_v + 31) / 32;
-        terrain_mesh_vertex_kernel<<<dim3(tiles, tiles), dim3(32, 8), 0, g_ctx.stream>>>(p);
-        CU(cudaGetLastError());
-    }
-    if (d_idx && nr_v > 1) {
-        const size_t quads = (size_t)(nr_v - 1) * (nr_v - 1);
-        terrain_mesh_index_kernel<<<grid_blocks_for(quads, 256, 8), 256, 0, g_ctx.stream>>>(p);
-        CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(e1, g_ctx.stream));
-    int rc = timed_sync(e0, e1, kernel_ms);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return rc;
-}
-
-int clapca_terrain_mesh(const float *map, unsigned nr_v, float x, float y, float z, float side,
-                        float *vx, float *norm, float *tx, unsigned short *idx)
-{
-    if (int rc = need_init()) return rc;
-    if (!map || nr_v < 1 || nr_v > 46340)
-        return fail(CLAPCA_ERR_ARG, "terrain_mesh: bad arguments (nr_v %u)", nr_v);
-    const size_t nv = (size_t)nr_v * nr_v, nq = (size_t)(nr_v - 1) * (nr_v - 1);
-    const size_t bytes[5] = { nv * 4, vx ? nv * 12 : 0, norm ? nv * 12 : 0, tx ? nv * 8 : 0, idx ? nq * 12 : 0 };
-    void *d[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    for (int i = 0; i < 5; i++)
-        if (bytes[i]) {
-            if (int rc = ensure_bytes(&g_ctx.scratch[i], &g_ctx.scratch_bytes[i], bytes[i])) return rc;
-            d[i] = g_ctx.scratch[i];
-        }
-    int rc = clapca_memcpy_h2d(d[0], map, bytes[0]);
-    if (!rc) rc = clapca_terrain_mesh_device(d[0], nr_v, x, y, z, side, d[1], d[2], d[3], d[4], nullptr);
-    void *host[5] = { nullptr, vx, norm, tx, idx };
-    for (int i = 1; i < 5 && !rc; i++)
-        if (bytes[i]) rc = clapca_memcpy_d2h(host[i], d[i], bytes[i]);
-    return rc;
-}
-
-/* ---- instantiator extraction ----------------------------------------------------- */
-
-int clapca_terrain_instantiators_device(const void *d_maze, unsigned mside, const uint32_t *nr_states, int nkinds,
-                                        const void *d_map, unsigned nr_v, float x, float z, float side,
-                                        void *d_out, size_t cap, size_t *count, float *kernel_ms)
-{
-    if (int rc = need_init()) return rc;
-    if (!d_maze || !d_map || !nr_states || !count || mside < 1 || mside > 8192 || nkinds < 1 || nkinds > 4 || nr_v < 2 ||
-        nr_v > 46340 || (cap && !d_out))
-        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: bad arguments (mside %u, kinds %d, nr_v %u)", mside, nkinds,
-                    nr_v);
-    if ((unsigned long long)mside * 8ull > nr_v)
-        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: maze of %u cells of 8 vertices does not fit %u vertices",
-                    mside, nr_v);
-    InstorParams p;
-    memset(&p, 0, sizeof(p));
-    p.maze = (const uint8_t *)d_maze;
-    p.mside = mside;
-    for (int k = 0; k < nkinds; k++) p.kinds[k] = nr_states[k];
-    p.nkinds = nkinds;
-    p.map = (const float *)d_map;
-    p.nr_v = nr_v;
-    p.x = x; p.z = z; p.side = side;
-    p.tside = (unsigned)side;
-    if (int rc = ensure_bytes(&g_ctx.scratch[4], &g_ctx.scratch_bytes[4], ((size_t)mside + 1) * sizeof(unsigned))) return rc;
-    p.counts = (unsigned *)g_ctx.scratch[4];
-    p.out = (int4 *)d_out;
-    p.cap = cap;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, g_ctx.stream));
-    const unsigned blocks = (mside + 7) / 8;
-    instor_count_kernel<<<blocks, 256, 0, g_ctx.stream>>>(p);
-    instor_scan_kernel<<<1, 1024, 0, g_ctx.stream>>>(p.counts, mside);
-    instor_emit_kernel<<<blocks, 256, 0, g_ctx.stream>>>(p);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(e1, g_ctx.stream));
-    unsigned total = 0;
-    CU(cudaMemcpyAsync(&total, p.counts + mside, sizeof(total), cudaMemcpyDeviceToHost, g_ctx.stream));
-    int rc = timed_sync(e0, e1, kernel_ms);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *count = total;
-    return rc;
-}
-
-int clapca_terrain_instantiators(const uint8_t *maze, unsigned mside, const uint32_t *nr_states, int nkinds,
-                                 const float *map, unsigned nr_v, float x, float z, float side,
-                                 clapca_instor *out, size_t cap, size_t *count)
-{
-    if (int rc = need_init()) return rc;
-    if (!maze || !map || !count || (cap && !out))
-        return fail(CLAPCA_ERR_ARG, "terrain_instantiators: NULL argument");
-    const size_t mbytes = (size_t)mside * mside, hbytes = (size_t)nr_v * nr_v * sizeof(float);
-    if (int rc = ensure_bytes(&g_ctx.scratch[0], &g_ctx.scratch_bytes[0], hbytes ? hbytes : 4)) return rc;
-    if (int rc = ensure_bytes(&g_ctx.scratch[2], &g_ctx.scratch_bytes[2], mbytes ? mbytes : 4)) return rc;
-    if (int rc = ensure_bytes(&g_ctx.scratch[3], &g_ctx.scratch_bytes[3], cap ? cap * sizeof(clapca_instor) : 16)) return rc;
-    int rc = clapca_memcpy_h2d(g_ctx.scratch[0], map, hbytes);
-    if (!rc) rc = clapca_memcpy_h2d(g_ctx.scratch[2], maze, mbytes);
-    if (!rc) rc = clapca_terrain_instantiators_device(g_ctx.scratch[2], mside, nr_states, nkinds, g_ctx.scratch[0], nr_v, x, z,
-                                                      side, g_ctx.scratch[3], cap, count, nullptr);
-    if (!rc && cap && *count)
-        rc = clapca_memcpy_d2h(out, g_ctx.scratch[3], std::min(cap, *count) * sizeof(clapca_instor));
-    return rc;
 }
 
 #pragma GCC visibility pop
