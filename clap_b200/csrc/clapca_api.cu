@@ -518,7 +518,10 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         g->rows = (uint32_t *)p;
     }
 
-    const int team = team_config(P, WPL);
+    int team = team_config(P, WPL);
+    /* CLAPCA_STREAM_TEAM: team size of streamed runs only (the output lags the input by (team + 1) planes per generation) */
+    if (io)
+        if (const char *e = getenv("CLAPCA_STREAM_TEAM")) team = std::max(0, std::min(atoi(e), bp3_team_cap(P, WPL)));
     /* layout items need whole-plane items and all generations in one launch */
     bool fused = io != nullptr || fused_layout_default();
     if (fused && steps > kMaxFusedGenerations) {
