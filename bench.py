@@ -195,7 +195,7 @@ def cpu_reference_sample(np, rule_index, gens_full, budget_s):
         port.ca3d_run(vol, s, b, n, gens)
         dt = time.perf_counter() - t0
     gcups = side ** 3 * gens / dt / 1e9
-    return {"value": gcups, "unit": "GCUPS", "cores": 1, "kind": kind,
+    return {"value": gcups, "unit": "GCUPS", "cores": 1, "kind": kind, "seconds": dt,
             "sample": f"ca3d_run ca_coral on a {side}^3 corner-sized synthetic volume (same P(alive)=1/4, values "
                       f"1..5), {gens} generations, {dt:.1f} s on one core of {os.cpu_count()} (reference path is "
                       f"single-threaded and sequentially dependent)"}
@@ -211,19 +211,21 @@ def run_reference_arm(args):
     d0, d1, d2, gens, rule = WORKLOADS[args.workload]
     total = args.steps + args.warmup
     budget = max(2.0, min(20.0, 150.0 / max(1, total)))
-    vals = []
+    vals, secs = [], []
     base = None
     for i in range(total):
         base = cpu_reference_sample(np, rule, gens, budget)
         if i >= args.warmup:
             vals.append(base["value"])
+            secs.append(base["seconds"])
     v = sum(vals) / len(vals)
     base["value"] = v
     line = {
         "impl": "reference", "metric": "ca3d cell-updates/s", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(secs) / len(secs) * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: ca3d_run {d0}x{d1}x{d2}, {gens} generations, rule ca_coral"},
+        "config": {"workload": f"{args.workload}: ca3d_run {d0}x{d1}x{d2}, {gens} generations, rule ca_coral",
+                   "note": "one step = the bounded sample described in cpu_baseline.sample, not the full volume"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
