@@ -263,6 +263,9 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
         for (const Bp3Plane &pl : s->h_planes)
             if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) { p.edge_loop = 1; break; }
+#if CLAPCA_EDGE_DEFER
+        if (const char *e = getenv("CLAPCA_GHOST_DEFER")) if (p.edge_loop && atoi(e) != 0) p.edge_loop = 2;
+#endif
         Bp3LaunchInfo info;
         CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
         workers = info.workers;

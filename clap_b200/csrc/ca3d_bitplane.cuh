@@ -65,7 +65,8 @@ struct Bp3Params {
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
     int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
-    int edge_loop;          /* != 0: some plane of this launch has a ghost source / feeds a peer (multi-GPU): see run_segment */
+    int edge_loop;          /* != 0: some plane of this launch has a ghost source / feeds a peer (multi-GPU): see run_segment;
+                               2 = the deferred-tag-check loop (only in builds with CLAPCA_EDGE_DEFER) */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -106,6 +107,15 @@ struct Bp3Params {
  * every plane keeps raising its gpu-scope counter every flag_rows rows for the next generation's readers.
  */
 enum { BP3_MAX_TEAM = 24 };
+
+/*
+ * -DCLAPCA_EDGE_DEFER=1 additionally builds a third instantiation of the row loop (edge_loop == 2) in which the
+ * tags of a ghost row are checked one row step AFTER its loads were issued (see fetch_h_tagged); off by default:
+ * not yet measured on hardware, and every instantiation costs build time.  The emulator tests build it.
+ */
+#ifndef CLAPCA_EDGE_DEFER
+#define CLAPCA_EDGE_DEFER 0
+#endif
 
 /*
  * Publisher mode.  Raising a progress counter needs a gpu-scope release, and MEMBAR.GPU on a two-die B200
@@ -264,6 +274,7 @@ struct Sweep3 {
         int next_raise;                             /* next row count at which the own counter is raised */
         int dn_mode, up_mode;
         uint32_t tag_dn, tag_up, tag_out;
+        uint32_t bad_dn, bad_up;                    /* deferred loop: != 0 in some lane = the ghost row fetched a step ago was stale */
         long long waited_flag, waited_tag, waited_team;     /* diagnostics: cycles spent in the slow paths */
     };
 
@@ -376,15 +387,86 @@ struct Sweep3 {
         }
     }
 
+    /*
+     * Deferred loop (EDGE == 2).  The ghost row fetched inside a row step is not needed before the NEXT step, so
+     * the loads are only issued: the data words go straight into the window registers, the tags are folded into one
+     * word per lane, and settle_side() looks at that word a whole row step later -- the L2 latency of a remotely
+     * written line leaves the critical path of the edge plane (which in team mode paces its 15 team-mates).  The
+     * re-read of a stale row is a cold, out-of-line function that returns the row by value: the hot loop only
+     * grows by the fold, one vote and one branch per side (inlining the polling loop at every site made the loop
+     * 16 % longer and the whole kernel 30 % slower).
+     */
+    struct GhostRow {
+        uint32_t w[2 * WPL];
+        int ok;
+    };
+
+    CA_MDEV void fetch_h_tagged(const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
+    {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
+            const int q0 = 2 * i, q1 = 2 * i + 1;
+            h[q0 / WPL][q0 % WPL] = v.x;
+            h[q1 / WPL][q1 % WPL] = v.z;
+            acc |= (v.y ^ expect) | (v.w ^ expect);
+        }
+        bad = acc;
+    }
+
+    CA_MCOLD GhostRow repoll_ghost(const uint32_t *src, uint32_t expect, int *err, long long spin_limit)
+    {
+        GhostRow r;
+        long long t0 = dp_clock();
+        for (unsigned spins = 0;; spins++) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) {
+                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
+                r.w[2 * i] = v.x;
+                r.w[2 * i + 1] = v.z;
+                ok = ok && v.y == expect && v.w == expect;
+            }
+            if (dp_all(ok)) {
+                r.ok = 1;
+                return r;
+            }
+            dp_nanosleep(100);
+            if ((spins & 63u) == 63u) {
+                bool bad = dp_ld_flag(err) != 0 || (dp_clock() - t0) > spin_limit;
+                if (!dp_all(!bad)) {
+                    if (dp_lane() == 0)
+                        dp_set_error(err, 2);
+                    r.ok = 0;
+                    return r;
+                }
+            }
+        }
+    }
+
+    /* the row fetched by fetch_h_tagged() one step ago is about to be used */
+    CA_MDEV bool settle_side(const Bp3Params &p, const uint32_t *next, uint32_t tag, uint32_t &bad, uint32_t h[2][WPL])
+    {
+        if (dp_all(bad == 0u))
+            return true;
+        bad = 0u;
+        const GhostRow r = repoll_ghost(next - GHW, tag, p.err, p.spin_limit);
+#pragma unroll
+        for (int q = 0; q < 2 * WPL; q++)
+            h[q / WPL][q % WPL] = r.w[q];
+        return r.ok != 0;
+    }
+
     /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
-    template <bool EDGE>
+    template <int EDGE>
     CA_MDEV bool load_side(const Bp3Params &p, St &st, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
     {
         if (mode == SRC_LOCAL) {
             LaneVec<WPL>::ld(src, h[0]);
             LaneVec<WPL>::ld(src + RWP, h[1]);
             src += RECW;
-        } else if (!EDGE || mode == SRC_NONE) {
+        } else if (EDGE == 0 || mode == SRC_NONE) {
             zero2(h);
         } else {
             if (!load_h_tagged(p, st, src, tag, h)) return false;
@@ -420,7 +502,7 @@ struct Sweep3 {
      * sit in slots (M+2)%3 / M / (M+1)%3, own state rows y / y+1 in slots M / (M+1)%3; row y+2 is
      * prefetched into slot (M+2)%3 once row y-1 has been consumed.
      */
-    template <int M, bool EDGE>
+    template <int M, int EDGE>
     CA_MDEV bool step(const Bp3Params &p, St &st, int y, int y1, int *myprog)
     {
         constexpr int A = (M + 2) % 3, B = M, C = (M + 1) % 3;
@@ -429,6 +511,10 @@ struct Sweep3 {
         const uint32_t bornval = Rule::bornval(p);
         uint32_t k[WPL][5], ao[WPL], ge2[WPL];
 
+        if (EDGE == 2) {        /* ghost rows y+1 were only fetched during the previous step */
+            if (st.dn_mode == SRC_GHOST && !settle_side(p, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
+            if (st.up_mode == SRC_GHOST && !settle_side(p, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
+        }
 
 
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
@@ -469,8 +555,18 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) return false;
-                if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) return false;
+                if (EDGE == 2 && st.dn_mode == SRC_GHOST) {
+                    fetch_h_tagged(st.dn, st.tag_dn, st.hd[A], st.bad_dn);
+                    st.dn += GHW;
+                } else if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
+                    return false;
+                }
+                if (EDGE == 2 && st.up_mode == SRC_GHOST) {
+                    fetch_h_tagged(st.up, st.tag_up, st.hu[A], st.bad_up);
+                    st.up += GHW;
+                } else if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
+                    return false;
+                }
             } else {
                 zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
                 zero_s(st.so[A]);
@@ -555,11 +651,11 @@ struct Sweep3 {
          * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).  They are issued AFTER the
          * counter's release so that its MEMBAR never waits for this row's NVLink round trip.
          */
-        if (EDGE && st.push_dn) {
+        if (EDGE != 0 && st.push_dn) {
             store_h_tagged(p, st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
             st.push_dn += GHW;
         }
-        if (EDGE && st.push_up) {
+        if (EDGE != 0 && st.push_up) {
             store_h_tagged(p, st.push_up, st.tag_out, st.hn[0], st.hn[1]);
             st.push_up += GHW;
         }
@@ -578,12 +674,16 @@ struct Sweep3 {
     CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
                              const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
     {
+        if constexpr (CLAPCA_EDGE_DEFER != 0) {
+            if (p.edge_loop == 2)
+                return run_rows<2>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+        }
         if (p.edge_loop)
-            return run_rows<true>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
-        return run_rows<false>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+            return run_rows<1>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+        return run_rows<0>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
     }
 
-    template <bool EDGE>
+    template <int EDGE>
     CA_MDEV bool run_rows(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
                           const int *sdn, int *sown, bool team_edge)
     {
@@ -627,6 +727,7 @@ struct Sweep3 {
         st.flag_period = (team_edge && p.edge_flag_rows > 0) ? p.edge_flag_rows : p.flag_rows;
         st.next_raise = (y0 / st.flag_period + 1) * st.flag_period;
         st.waited_flag = st.waited_tag = st.waited_team = 0;
+        st.bad_dn = st.bad_up = 0u;
         const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);

@@ -21,6 +21,7 @@
 
 #define CA_DEV      __device__ __forceinline__
 #define CA_MDEV     __device__ __forceinline__ static      /* static member function */
+#define CA_MCOLD    __device__ __noinline__ static          /* static member function kept out of line (cold paths) */
 #define CA_HOSTDEV  __host__ __device__ __forceinline__
 #define CA_GLOBAL   __global__
 #define CA_FULL     0xffffffffu
@@ -129,6 +130,7 @@ CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
 
 #define CA_DEV      static inline
 #define CA_MDEV     static inline
+#define CA_MCOLD    static
 #define CA_HOSTDEV  static inline
 #define CA_GLOBAL   static
 #define CA_FULL     0xffffffffu

@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows [layout [chunk]]]]]]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows [layout [chunk [ghostdefer]]]]]]]]]]]]
  *   layout   1 = layout items (pack / unpack run as work items of the sweep launch, cells resident),
  *            2 = layout items fed by a "copy engine" thread that delivers the cells chunk by chunk and raises
  *                in_ready, while a second thread drains finished chunks as their planes' out_done words show the epoch
@@ -21,6 +21,7 @@
 #include <chrono>
 #include <algorithm>
 #include "emu_runtime.h"
+#define CLAPCA_EDGE_DEFER 1
 #include "../../clap_b200/csrc/ca3d_bitplane.cuh"
 #include "../../clap_b200/csrc/ca3d_layout.cuh"
 #include "../../clap_b200/csrc/bp_plan.h"
@@ -119,6 +120,7 @@ int main(int argc, char **argv)
     int edgeFlagRows = argc > 18 ? atoi(argv[18]) : 0;
     int layout = argc > 19 ? atoi(argv[19]) : 0;
     int chunk = argc > 20 ? atoi(argv[20]) : 2;
+    int ghostDefer = argc > 21 ? atoi(argv[21]) : 0;    /* != 0: multi-rank runs use the deferred-tag-check row loop */
     if (layout && (ranks != 1 || (team <= 0 && genBatch >= 0))) {
         fprintf(stderr, "layout items: single rank, time-key (genbatch -1) or team order\n");
         return 2;
@@ -234,7 +236,7 @@ int main(int argc, char **argv)
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;
         k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
         for (const Bp3Plane &pl : k.planes)
-            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) k.p.edge_loop = 1;
+            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) k.p.edge_loop = ghostDefer ? 2 : 1;
         if (layout) {
             k.out_done.assign(Zl + 1, 0);
             k.p.layout_items = 1;

@@ -151,6 +151,20 @@ def test_ca3d_layout_items_streamed(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows layout chunk ghostdefer
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 6, 2, 2, 0, 2, 0, 0, 3, 0, 0, 2, 1),          # 2 ranks, z-blocks of 2 planes < team
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 8, 3, 5, 0, 4, 0, 0, 4, 1, 0, 2, 1),          # 3 ranks, blocks of 5 = groups of 4 + 1
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 4, 4, 1, 0, 2, 0, 0, 2, 0, 0, 2, 1),         # 4 ranks, every plane is an edge
+    (64, 37, 12, 6, 7, 3, 2, 1, 9, 5, 2, 2, 5, 2, 0, 0, 0, 0, 0, 2, 1),          # one warp per sweep, row segments, 2 words per lane
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 2, 0, 0, 1, -1, 2, 0, 0, 0, 2, 1),         # publisher warps, time-key order
+])
+def test_ca3d_deferred_ghost_tag_check_loop(emu_bin, args):
+    """The opt-in third instantiation of the row loop (-DCLAPCA_EDGE_DEFER=1, edge_loop == 2): ghost rows are
+    fetched one row step before their tags are looked at, a stale row is re-read by the out-of-line cold path."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
 # ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
 
 @pytest.mark.parametrize("args", [
