@@ -689,3 +689,31 @@ def test_ca2d_cfg3_full_size_reference_fingerprint(gpu, oracle):
             for row, h in want["rows"].items():
                 assert "%016x" % oracle.fnv(got[int(row)]) == h, (name, key, row)
             assert "%016x" % oracle.fnv(got) == want["fnv1a64"], (name, key)
+
+
+def _chain_seed(side=256, seed=2048):
+    rng = np.random.default_rng(seed)
+    return (rng.integers(1, 6, (side, side, side)) * (rng.random((side, side, side)) < 0.25)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name", ["ca_coral", "ca_445m"])
+def test_ca3d_cfg4_chain_256cube_full_50_generations_reference_fingerprint(gpu, oracle, name):
+    """Link (i) of the config-4 parity chain: 256^3, the FULL 50 generations, against the unmodified
+    reference's fingerprint (tests/golden/make_golden_cfg4_chain.py, golden/cfg4_chain_256.json); resident run,
+    then the streamed host -> host run on the same input."""
+    import json
+    with open(os.path.join(G, "cfg4_chain_256.json")) as f:
+        cfg = json.load(f)
+    vol0 = _chain_seed()
+    assert "%016x" % oracle.fnv(vol0) == cfg["seed_fnv1a64"]
+    c = cfg[name]
+    vol = vol0.copy()
+    assert gpu.ca3d_run(vol, c["nca"], c["generations"], engine=BITPLANE) == c["population"]
+    assert "%016x" % oracle.fnv(vol) == c["fnv1a64"]
+    keep_in, host_in = _pinned(vol0.shape)
+    keep_out, host_out = _pinned(vol0.shape)
+    host_in[...] = vol0
+    grid = gpu.Grid(256, 256, 256)
+    assert grid.run3d_streamed(c["nca"], c["generations"], host_in, host_out, max_value=5) == c["population"]
+    assert np.array_equal(host_out, vol)
+    grid.close()

@@ -218,3 +218,18 @@ def test_terrain_height_port_vs_reference(oracle, reference):
         a = oracle.terrain_height(hmap, -3.0, 8.0, side, pts)
         b = reference.terrain_height(hmap, -3.0, 8.0, side, pts)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), nr
+
+
+def test_cfg4_chain_256cube_full_run_port_vs_reference_fingerprint(oracle):
+    """The port on the 256^3 x 50 link of the config-4 parity chain must reproduce the fingerprint the unmodified
+    reference left in golden/cfg4_chain_256.json (about ten seconds of CPU)."""
+    import json
+    with open(os.path.join(G, "cfg4_chain_256.json")) as f:
+        cfg = json.load(f)
+    rng = np.random.default_rng(2048)
+    vol = (rng.integers(1, 6, (256, 256, 256)) * (rng.random((256, 256, 256)) < 0.25)).astype(np.uint8)
+    assert "%016x" % oracle.fnv(vol) == cfg["seed_fnv1a64"] and int(np.count_nonzero(vol)) == cfg["seed_population"]
+    c = cfg["ca_coral"]
+    s, b, n = oracle.ca3d_rule(c["nca"])
+    assert oracle.ca3d_run(vol, s, b, n, c["generations"]) == c["population"]
+    assert "%016x" % oracle.fnv(vol) == c["fnv1a64"]
