@@ -717,3 +717,16 @@ def test_ca3d_cfg4_chain_256cube_full_50_generations_reference_fingerprint(gpu, 
     assert grid.run3d_streamed(c["nca"], c["generations"], host_in, host_out, max_value=5) == c["population"]
     assert np.array_equal(host_out, vol)
     grid.close()
+
+
+def test_ca3d_cfg4_full_plane_thin_slab_vs_oracle(gpu, oracle):
+    """Link (ii) of the config-4 parity chain: planes of the full 2048 x 2048 size -- 2048 rows per
+    sweep, one team of 16 planes -- on a slab thin enough for the 64-bit-index oracle (a few seconds of CPU)."""
+    rng = np.random.default_rng(4096)
+    shape = (16, 2048, 2048)
+    vol = (rng.integers(1, 6, shape) * (rng.random(shape) < 0.25)).astype(np.uint8)
+    want = vol.copy()
+    s, b, n = oracle.ca3d_rule(7)
+    wpop = oracle.ca3d_run(want, s, b, n, 3)
+    assert gpu.ca3d_run(vol, 7, 3, engine=BITPLANE) == wpop
+    assert np.array_equal(vol, want)
