@@ -70,6 +70,9 @@ SIGNATURES = {
     "clapca_slab_device_ptr": (c_void_p, [c_void_p]),
     "clapca_slab_ipc_handle": (c_int, [c_void_p, c_void_p]),
     "clapca_slab_connect": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "clapca_slab_halo_ptr": (c_void_p, [c_void_p]),
+    "clapca_slab_connect_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "clapca_hash_planes": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "clapca_slab_upload": (c_int, [c_void_p, c_void_p]),
     "clapca_slab_download": (c_int, [c_void_p, c_void_p]),
     "clapca_slab_prepare": (c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_int]),

@@ -76,13 +76,20 @@ void diag_report(const char *what, const unsigned *d_ticket, cudaStream_t stream
 
 /* work-item claim order of the bit-plane sweep (see bp_plan.h) */
 struct OrderCfg {
-    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals, 3 plane teams */
+    int mode;           /* 0 time-key, 1 skewed row segments, 2 generation-batched diagonals, 3 tiles (planes x generations) */
     int seg_rows;       /* mode 1 */
     int gen_batch;      /* mode 2 */
-    int team;           /* mode 3: planes per group = warps per CTA */
-    int key() const { return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? team : 0))); }
+    int team;           /* mode 3: compute warps per CTA = tile_z * tile_g */
+    int tile_z, tile_g; /* mode 3: planes / generations per tile */
+    int ctas;           /* mode 3: CTAs the launch keeps resident (bounds tile_g, see bp_plan.h) */
+    int key() const
+    {
+        return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? tile_z * 256 + tile_g : 0)));
+    }
 };
 int team_config(int P, int WPL);
+/* wanted generations per tile for a team of `team` compute warps (CLAPCA_TILE_GENS overrides) */
+int tile_gens_config(int team);
 void sweep_knobs(Bp3Params &p, int team);
 OrderCfg order_config(int Z, int H, int G, int max_workers, int team);
 void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
@@ -91,8 +98,8 @@ void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg,
 /* the layout kernels live in ONE translation unit (clapca_api.cu); these launch them */
 cudaError_t launch_ca3d_pack(const Bp3Layout &L, cudaStream_t stream);
 cudaError_t launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t stream);
-cudaError_t launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, int WPL, uint32_t tag,
-                             cudaStream_t stream);
+cudaError_t launch_max_u8(const uint8_t *cells, size_t n, unsigned *d_max, cudaStream_t stream);
+cudaError_t launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, cudaStream_t stream);
 
 } // namespace api
 } // namespace clapca

@@ -1,6 +1,8 @@
 /*
  * api_slab.cu -- multi-GPU part of the C ABI (include/clapca.h, clapca_slab_*): z-block slabs of one ca3d
- * volume, one process per GPU, halo rows exchanged by peer stores inside the sweep kernel.
+ * volume, one process per GPU (or, for tests, several slabs of one process sharing a device), halo rows exchanged
+ * by peer stores inside the sweep kernel: the service warp of a tile that touches a z-block edge copies finished H
+ * rows into the neighbour's ghost plane and raises the neighbour's progress counter (ca3d_bitplane.cuh).
  */
 #include "api_internal.h"
 
@@ -26,15 +28,18 @@ struct clapca_slab {
     std::vector<Bp3Plane> h_planes;
     int4 *order = nullptr;
     size_t order_bytes = 0;
-    int n_items = 0, order_G = -1, team = -1;
+    int n_items = 0, order_G = -1, team = -1, order_key = -1;
     unsigned *ticket = nullptr;
     unsigned long long *d_pop = nullptr;
-    cudaStream_t stream = nullptr;
+    unsigned *d_max = nullptr;
+    cudaStream_t stream = nullptr;      /* the slab's own stream: slabs of one process run concurrently */
+    int max_ctas = 0;                   /* > 0: CTAs of the sweep launch (ranks sharing one device) */
+    unsigned max_value = 0;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     uint32_t surv = 0, born = 0, nr_states = 0;
     int G = 0, rule = BP3_RULE_DYN;
     bool prepared = false;
-    uint32_t epoch = 0;             /* run number: upper half of the ghost-row tags */
+    uint32_t epoch = 0;             /* run number: its parity selects the bank of ghost counters */
     clapca_run_stats stats;
 };
 
@@ -57,11 +62,12 @@ int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_glo
     s->WPL = WPL; s->RWP = 32 * WPL; s->NP = s->P + 2;
     s->Gcap = max_generations;
     s->Zl = s->geo.local_planes();
-    s->hl = slab_halo_layout(s->geo, s->H, s->RWP);
-    s->stream = g_ctx.stream;
+    s->hl = slab_halo_layout(s->geo, s->H, s->RWP, s->NP, s->Gcap);
+    s->max_value = max_value;
     memset(&s->stats, 0, sizeof(s->stats));
     const size_t zl = s->Zl ? s->Zl : 1;
-    cudaError_t e = cudaMalloc(&s->cells, zl * s->W * s->H);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cells, zl * s->W * s->H);
     if (e == cudaSuccess) e = cudaMalloc(&s->rows, zl * s->H * s->NP * s->RWP * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&s->halo, s->hl.total_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->halo, 0, s->hl.total_words * sizeof(uint32_t));
@@ -69,6 +75,7 @@ int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_glo
     if (e == cudaSuccess) e = cudaMalloc(&s->planes, zl * sizeof(Bp3Plane));
     if (e == cudaSuccess) e = cudaMalloc(&s->ticket, kTicketWords * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_pop, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_max, sizeof(unsigned));
     for (int i = 0; i < 5 && e == cudaSuccess; i++)
         e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess) {
@@ -85,9 +92,11 @@ int clapca_slab_destroy(clapca_slab *s)
     if (!s) return CLAPCA_OK;
     if (s->opened_next && s->halo_next) cudaIpcCloseMemHandle(s->halo_next);
     if (s->opened_prev && s->halo_prev) cudaIpcCloseMemHandle(s->halo_prev);
-    void *bufs[] = { s->cells, s->rows, s->halo, s->prog, s->planes, s->order, s->ticket, s->d_pop };
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void *bufs[] = { s->cells, s->rows, s->halo, s->prog, s->planes, s->order, s->ticket, s->d_pop, s->d_max };
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (s->stream) cudaStreamDestroy(s->stream);
     for (int i = 0; i < 5; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     delete s;
@@ -124,6 +133,18 @@ int clapca_slab_ipc_handle(clapca_slab *s, void *handle64)
     return CLAPCA_OK;
 }
 
+/* this rank's plane descriptors for the bank of ghost counters the next run uses */
+static int slab_build_planes(clapca_slab *s, int bank)
+{
+    SlabPtrs ptr = { s->rows, s->prog, s->halo, s->halo_next, s->halo_prev };
+    bp3_build_planes(s->geo, ptr, s->hl, s->H, s->RWP, s->NP, s->h_planes, bank);
+    if (s->Zl)
+        CU(cudaMemcpyAsync(s->planes, s->h_planes.data(), s->h_planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice,
+                           s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CLAPCA_OK;
+}
+
 int clapca_slab_connect(clapca_slab *s, const void *handle_next, const void *handle_prev)
 {
     if (!s) return fail(CLAPCA_ERR_ARG, "slab_connect: NULL slab");
@@ -147,12 +168,20 @@ int clapca_slab_connect(clapca_slab *s, const void *handle_next, const void *han
             s->opened_prev = true;
         }
     }
-    SlabPtrs ptr = { s->rows, s->prog, s->halo, s->halo_next, s->halo_prev };
-    bp3_build_planes(s->geo, ptr, s->hl, s->H, s->RWP, s->NP, s->h_planes);
-    /* progress counters of a generation are Zl apart only when all Gcap generations share one table */
-    if (s->Zl)
-        CU(cudaMemcpy(s->planes, s->h_planes.data(), s->h_planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice));
-    return CLAPCA_OK;
+    return slab_build_planes(s, 0);
+}
+
+void *clapca_slab_halo_ptr(clapca_slab *s) { return s ? s->halo : nullptr; }
+
+int clapca_slab_connect_local(clapca_slab *s, void *halo_next_rank, void *halo_prev_rank, int max_ctas)
+{
+    if (!s) return fail(CLAPCA_ERR_ARG, "slab_connect_local: NULL slab");
+    if (s->geo.R > 1 && (!halo_next_rank || !halo_prev_rank)) return fail(CLAPCA_ERR_ARG, "slab_connect_local: NULL halo");
+    s->halo_next = s->geo.R > 1 ? (uint32_t *)halo_next_rank : s->halo;
+    s->halo_prev = s->geo.R > 1 ? (uint32_t *)halo_prev_rank : s->halo;
+    s->max_ctas = max_ctas > 0 ? max_ctas : 0;
+    s->order_G = -1;                    /* the tile shape depends on the number of CTAs */
+    return slab_build_planes(s, 0);
 }
 
 int clapca_slab_upload(clapca_slab *s, const uint8_t *src)
@@ -190,16 +219,36 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     if (born && (bornval >> s->P))
         return fail(CLAPCA_ERR_ARG, "slab_prepare: rule needs more than the %d state planes of this slab", s->P);
     s->surv = surv; s->born = born; s->nr_states = nr_states; s->G = steps;
-    s->epoch = (s->epoch + 1) & 0xffffu;        /* every rank prepares the same number of times */
-    if (!s->epoch) s->epoch = 1;
     s->rule = BP3_RULE_DYN;
     for (int i = 0; i < 9; i++)
         if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { s->rule = i; break; }
 
-    const int team = team_config(s->P, s->WPL);
-    if (s->order_G != steps || s->team != team) {
+    /* the cells must fit the state planes chosen at create time: the pack kernel would silently drop the upper bits */
+    if (s->Zl) {
+        unsigned maxv = 0;
+        CU(cudaMemsetAsync(s->d_max, 0, sizeof(unsigned), s->stream));
+        CU(launch_max_u8(s->cells, (size_t)s->Zl * s->W * s->H, s->d_max, s->stream));
+        CU(cudaMemcpyAsync(&maxv, s->d_max, sizeof(maxv), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->P < 8 && (maxv >> s->P))
+            return fail(CLAPCA_ERR_ARG, "slab_prepare: a cell value of %u exceeds the max_value %u given to slab_create "
+                        "(%d state planes)", maxv, s->max_value, s->P);
+    }
+    s->epoch++;                                 /* every rank prepares successfully the same number of times */
+    const int bank = (int)(s->epoch & 1u);
+
+    /* multi-GPU runs are always tiled: the service warp of a tile carries the halo rows (every variant has a team size) */
+    int team = team_config(s->P, s->WPL);
+    if (team <= 0) team = bp3_team_cap(s->P, s->WPL);
+    Bp3Params knobs;
+    memset(&knobs, 0, sizeof(knobs));
+    sweep_knobs(knobs, team);
+    const int max_ctas = s->max_ctas > 0 ? s->max_ctas : knobs.max_ctas;
+    OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms, team, max_ctas), team);
+    /* every rank must settle on the same tile shape: decide it from all ranks' plane lists */
+    oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z);
+    if (s->order_G != steps || s->team != team || s->order_key != oc.key()) {
         std::vector<WorkItem> items;
-        const OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms), team);
         s->team = team;
         make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items, false);
         void *p = s->order;
@@ -212,17 +261,22 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
             CU(cudaMemcpy(s->order, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
         s->n_items = (int)items.size();
         s->order_G = steps;
+        s->order_key = oc.key();
     }
+    /* ghost counters of this run's bank: cleared here, raised by the neighbours only after the barrier that follows */
+    if (int rc = slab_build_planes(s, bank)) return rc;
+    if (s->geo.R > 1)
+        CU(cudaMemsetAsync(s->halo + s->hl.flags + (size_t)bank * s->hl.bank_words(), 0, s->hl.bank_words() * sizeof(int),
+                           s->stream));
     CU(cudaEventRecord(s->ev[0], s->stream));
     if (s->Zl) {
         Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };
         CU(launch_ca3d_pack(L, s->stream));
-        /* halo seed: H rows of each block's first plane -> ghost plane above the previous block, tag = seed state */
+        /* halo seed: H rows of each block's first plane -> ghost plane above the previous block (generation 0's "old plane above") */
         for (size_t l = 0; l < s->h_planes.size(); l++) {
             const Bp3Plane &pl = s->h_planes[l];
             if (!pl.push_dn_rows) continue;
-            CU(launch_halo_seed(pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->WPL,
-                                s->epoch << 16, s->stream));
+            CU(launch_halo_seed(pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->stream));
         }
     }
     CU(cudaMemsetAsync(s->prog, 0, (size_t)s->Gcap * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
@@ -254,18 +308,13 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
         p.prog = s->prog;
         p.order = s->order;
         p.nsweeps = s->n_items;
-        p.epoch = s->epoch;
         sweep_knobs(p, s->team);
+        if (s->max_ctas > 0) p.max_ctas = s->max_ctas;
         p.ticket = s->ticket;
         p.err = (int *)(s->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
         p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
         p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
-        for (const Bp3Plane &pl : s->h_planes)
-            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) { p.edge_loop = 1; break; }
-#if CLAPCA_EDGE_DEFER
-        if (const char *e = getenv("CLAPCA_GHOST_DEFER")) if (p.edge_loop && atoi(e) != 0) p.edge_loop = 2;
-#endif
         Bp3LaunchInfo info;
         CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
         workers = info.workers;

@@ -53,9 +53,9 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
         threads = 32 * (wpc + 1);
     }
     if (p.team > 0) {
-        /* team mode: one CTA = `team` warps sweeping a group of consecutive planes; an item occupies a whole CTA */
+        /* tile mode: one CTA = `team` compute warps sweeping a tile + the service warp; an item occupies a whole CTA */
         wpc = std::min(p.team, bp3_team_cap(P, WPL));
-        threads = 32 * wpc;
+        threads = 32 * (wpc + 1);
     }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
@@ -64,6 +64,8 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     /* fewer resident warps run faster each: worth it when the dependency DAG, not the SM count, bounds the parallelism */
     if (p.max_ctas_per_sm > 0 && per_sm > p.max_ctas_per_sm) per_sm = p.max_ctas_per_sm;
     int blocks = per_sm * sms;
+    /* several ranks sharing one device (tests): each launch keeps to its share of the SMs */
+    if (p.max_ctas > 0 && blocks > p.max_ctas) blocks = p.max_ctas;
     if (p.nsweeps >= 0) {
         const int need = p.team > 0 ? p.nsweeps : (p.nsweeps + wpc - 1) / wpc;
         if (blocks > need) blocks = need;

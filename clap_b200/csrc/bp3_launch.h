@@ -21,8 +21,8 @@ struct Bp3LaunchInfo {
 cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream,
                        Bp3LaunchInfo *info);
 
-/* number of persistent warps a cooperative launch of this variant can keep resident */
-int bp3_max_workers(int rule, int P, int WPL, int sms);
+/* number of persistent (compute) warps a cooperative launch of this variant can keep resident; team > 0: tile mode */
+int bp3_max_workers(int rule, int P, int WPL, int sms, int team = 0, int max_ctas = 0);
 
 #define BP3_DECLARE_RULE(n) \
     cudaError_t bp3_launch_rule##n(int P, int WPL, const Bp3Params &p, int sms, cudaStream_t stream, \

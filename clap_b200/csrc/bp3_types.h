@@ -12,30 +12,29 @@ namespace clapca {
  * Where one plane of this device's slab gets its neighbours from and whom it
  * feeds.  Built on the host (bp_plan.h).
  *
- * Local sources.  Row r of a neighbouring local plane lives at rows + r * stride
- * (words): H0 at +0, H1 at +RWP; its progress counter for generation g at
- * flag[g * gstride].
+ * Sources.  Row r of a neighbouring plane lives at rows + r * RECW (words, RECW =
+ * NP * RWP = the row-record stride of the launched variant): H0 at +0, H1 at
+ * +RWP; its progress counter for generation g at flag[g * gstride].
  *
  * Ghost sources (multi-GPU).  The plane below the first / above the last plane
- * of a z-block belongs to the neighbouring GPU, which stores the H rows of its
- * edge plane straight into a "ghost plane" in this GPU's memory (peer stores
- * over NVLink).  Ghost rows carry no counters and need no fences: every 32-bit
- * data word travels in one aligned 8-byte store together with a tag
- *         tag = epoch << 16 | (generation + 1)        (0 = the seed state)
- * so a consumer that reads {word, tag} atomically knows which version it got
- * and simply re-reads until the expected tag shows up (the LL protocol of
- * collective libraries).  A lane's 2*WPL words of a ghost row are the pairs
- * {H0[0..WPL), H1[0..WPL)}, two pairs per 16-byte vector; vector i of lane l sits
- * at 16-byte index r * stride/4 + 32 * i + l, so every warp-wide store of a row is
- * ONE contiguous 512-byte burst on NVLink (16-byte scattered peer stores are what
- * the link is worst at).
+ * of a z-block belongs to the neighbouring GPU.  Its H rows are mirrored into a
+ * "ghost plane" in THIS GPU's memory -- same record stride as a local plane, only
+ * the H0 | H1 part of a record is ever written -- together with one progress
+ * counter per generation (gstride = 1).  The owner's service warp (tile mode,
+ * ca3d_bitplane.cuh) copies finished rows over NVLink with plain peer stores,
+ * then fence.acq_rel.sys, then the counter, so a ghost plane is an ordinary
+ * source for its consumer: the row loop has no multi-GPU code.  ghost_mask only
+ * tells the consumer to poll that counter at system scope.  The counters exist
+ * in two banks used by alternating runs (the host picks the bank when it builds
+ * the descriptors), so a slow peer still finishing run k can never disturb the
+ * freshly cleared counters of run k+1.
  */
 struct Bp3Plane {
     const uint32_t *dn_rows, *up_rows;      /* NULL: outside the volume (reads 0) */
-    const int *dn_flag, *up_flag;           /* NULL for ghost (tagged) sources */
+    const int *dn_flag, *up_flag;           /* progress counters of the source, generation g at [g * gstride] */
     uint32_t *push_dn_rows, *push_up_rows;  /* peer ghost planes fed by this plane (NULL: none) */
-    uint32_t dn_stride, up_stride, dn_gstride, up_gstride;
-    uint32_t push_dn_stride, push_up_stride;
+    int *push_dn_flag, *push_up_flag;       /* ... and their counters, generation g at [g] */
+    uint32_t dn_gstride, up_gstride;
     uint32_t ghost_mask;                    /* bit 0: dn is a ghost plane, bit 1: up is a ghost plane */
     int zglobal;                            /* global z of this plane */
 };

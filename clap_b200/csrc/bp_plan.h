@@ -62,28 +62,41 @@ struct SlabGeom {
     }
 };
 
-/* size (in 32-bit words) of one ghost plane: H rows of {word, tag} pairs for [H0 | H1] */
-inline size_t slab_ghost_plane_words(int H, int RWP) { return (size_t)H * 4 * RWP; }
-
 /*
- * Layout of a rank's halo region (one device allocation, exported to the two
- * neighbouring ranks): the ghost planes below / above each local block.
- * Offsets in 32-bit words.
+ * Layout of a rank's halo region (one device allocation, exported to the two neighbouring ranks), offsets in
+ * 32-bit words: the ghost planes below / above each local block -- a ghost plane has the record stride of a local
+ * plane (NP * RWP words per row, only H0 | H1 are ever written), so the sweep reads it like any other plane --
+ * followed by their progress counters, [bank][below / above][local block][generation].  Every rank uses the same
+ * layout (nlb_max is the largest number of blocks any rank owns), so a peer's offsets are known without asking.
  */
 struct HaloLayout {
-    size_t ghost_dn, ghost_up, total_words;
-    int nlb_max;
+    size_t gp;                      /* words per ghost plane */
+    size_t ghost_dn, ghost_up;      /* first ghost plane below / above; local block lb at + gp * lb */
+    size_t flags;                   /* counters: bank b at + b * 2 * nlb_max * Gcap ints */
+    size_t total_words;
+    int nlb_max, Gcap;
+    size_t flag_index(int bank, int up, int lb) const
+    {
+        return flags + (((size_t)bank * 2 + (size_t)up) * nlb_max + (size_t)lb) * Gcap;
+    }
+    size_t bank_words() const { return (size_t)2 * nlb_max * Gcap; }
 };
 
-inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP)
+inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP, int NP, int Gcap)
 {
     HaloLayout h;
     h.nlb_max = geo.blocks_per_rank_max();
-    size_t gp = slab_ghost_plane_words(H, RWP);
+    h.Gcap = Gcap > 0 ? Gcap : 1;
+    h.gp = (size_t)H * NP * RWP;
     h.ghost_dn = 0;
-    h.ghost_up = h.ghost_dn + gp * h.nlb_max;
-    h.total_words = h.ghost_up + gp * h.nlb_max;
-    if (h.total_words == 0) h.total_words = 4;
+    h.ghost_up = h.ghost_dn + h.gp * h.nlb_max;
+    h.flags = h.ghost_up + h.gp * h.nlb_max;
+    h.total_words = h.flags + 2 * h.bank_words();
+    if (geo.R == 1) {               /* one rank: no ghosts at all */
+        h.gp = 0;
+        h.ghost_dn = h.ghost_up = h.flags = 0;
+        h.total_words = 4;
+    }
     return h;
 }
 
@@ -96,13 +109,12 @@ struct SlabPtrs {
     uint32_t *halo_prev;    /* halo region of rank (rank - 1 + R) % R, peer-mapped */
 };
 
-/* plane descriptors for every local plane of `geo.rank` */
+/* plane descriptors for every local plane of `geo.rank`; `bank` selects the ghost counters of this run */
 inline void bp3_build_planes(const SlabGeom &geo, const SlabPtrs &ptr, const HaloLayout &hl, int H, int RWP, int NP,
-                             std::vector<Bp3Plane> &out)
+                             std::vector<Bp3Plane> &out, int bank = 0)
 {
     const size_t recw = (size_t)NP * RWP;
     const size_t planew = (size_t)H * recw;
-    const size_t gp = slab_ghost_plane_words(H, RWP);
     const int Zl = geo.local_planes();
     const int nb = geo.nblocks();
     out.assign(Zl, Bp3Plane());
@@ -116,31 +128,31 @@ inline void bp3_build_planes(const SlabGeom &geo, const SlabPtrs &ptr, const Hal
             p.zglobal = geo.block_z0(j) + i;
             if (i > 0) {
                 p.dn_rows = ptr.rows + (size_t)(l - 1) * planew;
-                p.dn_stride = (uint32_t)recw;
                 p.dn_flag = ptr.prog + (l - 1);
                 p.dn_gstride = (uint32_t)Zl;
             } else if (j > 0) {
-                p.dn_rows = ptr.halo + hl.ghost_dn + gp * lb;
-                p.dn_stride = 4u * RWP;
+                p.dn_rows = ptr.halo + hl.ghost_dn + hl.gp * lb;
+                p.dn_flag = (const int *)(ptr.halo + hl.flag_index(bank, 0, lb));
+                p.dn_gstride = 1u;
                 p.ghost_mask |= 1u;
                 /* ... and this plane feeds the ghost plane ABOVE the previous block */
                 const int lbp = (j - 1) / geo.R;
-                p.push_dn_rows = ptr.halo_prev + hl.ghost_up + gp * lbp;
-                p.push_dn_stride = 4u * RWP;
+                p.push_dn_rows = ptr.halo_prev + hl.ghost_up + hl.gp * lbp;
+                p.push_dn_flag = (int *)(ptr.halo_prev + hl.flag_index(bank, 1, lbp));
             }
             if (i + 1 < len) {
                 p.up_rows = ptr.rows + (size_t)(l + 1) * planew;
-                p.up_stride = (uint32_t)recw;
                 p.up_flag = ptr.prog + (l + 1);
                 p.up_gstride = (uint32_t)Zl;
             } else if (j + 1 < nb) {
-                p.up_rows = ptr.halo + hl.ghost_up + gp * lb;
-                p.up_stride = 4u * RWP;
+                p.up_rows = ptr.halo + hl.ghost_up + hl.gp * lb;
+                p.up_flag = (const int *)(ptr.halo + hl.flag_index(bank, 1, lb));
+                p.up_gstride = 1u;
                 p.ghost_mask |= 2u;
                 /* ... and this plane feeds the ghost plane BELOW the next block */
                 const int lbn = (j + 1) / geo.R;
-                p.push_up_rows = ptr.halo_next + hl.ghost_dn + gp * lbn;
-                p.push_up_stride = 4u * RWP;
+                p.push_up_rows = ptr.halo_next + hl.ghost_dn + hl.gp * lbn;
+                p.push_up_flag = (int *)(ptr.halo_next + hl.flag_index(bank, 0, lbn));
             }
         }
     }
@@ -255,42 +267,149 @@ inline void bp3_make_items_batched(const std::vector<Bp3Plane> &planes, int Zg, 
 }
 
 /*
- * Team mode (ca3d_bitplane.cuh): an item is a GROUP of up to T consecutive planes of one z-block at one
- * generation, WorkItem{ first local plane, g, number of planes, H }.  Group (z0..z0+n-1, g) needs the group
- * holding z0-1 at g, the group holding z0+n at g-1 and itself at g-1; the key z0 + (T+1) g orders all three
- * before it for any grouping with n <= T (z0' >= z0 - T; z0 + n + (T+1)(g-1) < z0 + (T+1) g), and it is a
- * function of global coordinates, so every rank's list is a sub-sequence of ONE global linear extension of
- * the dependency order: the globally first unfinished group is always running or next in line on its rank.
+ * Tile mode (ca3d_bitplane.cuh): an item is a TILE of up to Tz consecutive planes of one z-block x up to Tg
+ * consecutive generations, WorkItem{ first local plane, first generation, nz | ng << 8, H }, swept by one CTA.
+ *
+ * Row-level dependencies: (z,g) needs (z-1,g), (z+1,g-1) and (z,g-1).  For a tile X = planes z0..z0+nz-1 x
+ * generation group b that means the tiles holding z0-1 in group b, X's planes in group b-1 -- and, for ng > 1, the
+ * tile holding z0+nz in the SAME group (its first plane at generation g0+j-1 is the "old plane above" of our last
+ * plane at g0+j), which in turn depends on X: mutually dependent tiles advance together row by row and must be
+ * co-resident.  The claim key is z0 + (Tz+1) b.  Everything a row of X can transitively depend on is some
+ * (z', g') with z' <= z0+nz-1+k and g' <= g0+ng-1-k for a k >= 0; the tile holding it has a key of at most
+ * key(X) + Tz + Tg - 2 provided Tg <= Tz + 1 (k more planes cost k keys, every Tg generations back give Tz+1 keys
+ * back).  The key is a function of global coordinates, so every rank's list is a sub-sequence of ONE global order.
+ * Progress: let X be the unfinished tile with the smallest key.  Whatever X waits for is finished or lies in the
+ * key window [key(X), key(X) + Tz + Tg]; every rank claims in key order and nothing below key(X) is unfinished, so
+ * as long as every rank has more CTAs than items inside any such window, all of X's partners get claimed, and then
+ * the row-level DAG lets the earliest unfinished row run.  bp3_tile_shape() picks the largest Tg that satisfies
+ * this for the given number of CTAs (Tg = 1 has no forward dependency at all: the plane groups of round 1).
  */
-inline void bp3_make_items_team(const std::vector<Bp3Plane> &planes, int H, int G, int T,
-                                std::vector<WorkItem> &items, bool layout_items = false)
+inline void bp3_make_items_tile(const std::vector<Bp3Plane> &planes, int H, int G, int Tz, int Tg,
+                                std::vector<WorkItem> &items, bool layout_items = false,
+                                std::vector<long long> *keys_out = nullptr)
 {
     items.clear();
+    if (keys_out) keys_out->clear();
     if (G <= 0 || planes.empty())
         return;
-    if (T < 1) T = 1;
+    if (Tz < 1) Tz = 1;
+    if (Tz > 255) Tz = 255;
+    if (Tg < 1) Tg = 1;
+    if (Tg > 255) Tg = 255;
     struct Group { int l0, n, z0; };
     std::vector<Group> groups;
     for (size_t l = 0; l < planes.size();) {
         size_t e = l + 1;
         /* extend while the next local plane is the next global plane of the same z-block (its "below" is local) */
-        while (e < planes.size() && (int)(e - l) < T && planes[e].zglobal == planes[e - 1].zglobal + 1 &&
+        while (e < planes.size() && (int)(e - l) < Tz && planes[e].zglobal == planes[e - 1].zglobal + 1 &&
                planes[e].dn_rows && !(planes[e].ghost_mask & 1u))
             e++;
         groups.push_back(Group{ (int)l, (int)(e - l), planes[l].zglobal });
         l = e;
     }
+    const int nb = (G + Tg - 1) / Tg;
     std::vector<std::pair<long long, WorkItem>> tmp;
-    tmp.reserve(groups.size() * (size_t)(G + 2));
-    /* layout_items: pack groups at "generation -1", unpack groups at "generation G"; the key orders them as well */
-    for (int g = layout_items ? -1 : 0; g < (layout_items ? G + 1 : G); g++)
-        for (const Group &gr : groups)
-            tmp.push_back({ ((long long)gr.z0 + (long long)(T + 1) * g) * 65536 + g, WorkItem{ gr.l0, g, gr.n, H } });
+    tmp.reserve(groups.size() * (size_t)(nb + 2));
+    /* layout_items: pack groups one "generation group" before the first, unpack groups one after the last */
+    for (int b = layout_items ? -1 : 0; b < (layout_items ? nb + 1 : nb); b++)
+        for (const Group &gr : groups) {
+            const int g0 = b < 0 ? -1 : (b >= nb ? G : b * Tg);
+            const int ng = (b < 0 || b >= nb) ? 1 : std::min(Tg, G - g0);
+            tmp.push_back({ ((long long)gr.z0 + (long long)(Tz + 1) * b) * 65536 + (b + 1),
+                            WorkItem{ gr.l0, g0, gr.n | (ng << 8), H } });
+        }
     std::sort(tmp.begin(), tmp.end(),
               [](const std::pair<long long, WorkItem> &a, const std::pair<long long, WorkItem> &b) {
                   return a.first < b.first;
               });
-    for (auto &t : tmp) items.push_back(t.second);
+    for (auto &t : tmp) {
+        items.push_back(t.second);
+        if (keys_out) keys_out->push_back(t.first >> 16);
+    }
+}
+
+/* the plane list of `geo.rank` with just enough filled in for the grouping of bp3_make_items_tile (no pointers to follow) */
+inline void bp3_topology_planes(const SlabGeom &geo, std::vector<Bp3Plane> &out)
+{
+    static const uint32_t marker = 0;
+    out.assign(geo.local_planes(), Bp3Plane());
+    for (int lb = 0; lb < geo.local_blocks(); lb++) {
+        const int j = geo.global_block(lb);
+        const int l0 = geo.local_z0(lb), len = geo.block_len(j);
+        for (int i = 0; i < len; i++) {
+            Bp3Plane &p = out[l0 + i];
+            p.zglobal = geo.block_z0(j) + i;
+            if (i > 0) {
+                p.dn_rows = &marker;
+            } else if (j > 0) {
+                p.dn_rows = &marker;
+                p.ghost_mask |= 1u;
+            }
+        }
+    }
+}
+
+/* most items of one rank inside any key window [k, k + width] of the tile order */
+inline int bp3_tile_window_items(const std::vector<long long> &keys, long long width)
+{
+    int best = 0;
+    size_t lo = 0;
+    for (size_t hi = 0; hi < keys.size(); hi++) {
+        while (keys[hi] - keys[lo] > width) lo++;
+        best = std::max(best, (int)(hi - lo + 1));
+    }
+    return best;
+}
+
+/*
+ * Shape of the tiles for a team of `team` compute warps: Tz * Tg = team with the largest Tg <= min(want, Tz) for which
+ * `ctas` co-resident CTAs exceed the number of this rank's items inside any window of Tz + Tg keys (see above);
+ * Tg = 1 (plane groups, no forward dependency) always qualifies.  Returns Tg, stores Tz.
+ */
+inline int bp3_tile_shape(const std::vector<Bp3Plane> &planes, int H, int G, int team, int want, int ctas,
+                          bool layout_items, int *Tz_out)
+{
+    if (team < 1) team = 1;
+    std::vector<WorkItem> items;
+    std::vector<long long> keys;
+    for (int Tg = std::max(1, std::min(want, G)); Tg > 1; Tg--) {
+        if (team % Tg) continue;
+        const int Tz = team / Tg;
+        if (Tg > Tz) continue;
+        bp3_make_items_tile(planes, H, G, Tz, Tg, items, layout_items, &keys);
+        if (bp3_tile_window_items(keys, (long long)Tz + Tg) < ctas) {
+            *Tz_out = Tz;
+            return Tg;
+        }
+    }
+    *Tz_out = team;
+    return 1;
+}
+
+/* the same for a sharded volume: every rank must run the same shape, so take the smallest Tg over the ranks' plane lists */
+inline int bp3_tile_shape_all_ranks(const SlabGeom &geo, int H, int G, int team, int want, int ctas, int *Tz_out)
+{
+    int Tg = std::max(1, want), Tz = team;
+    std::vector<Bp3Plane> planes;
+    for (int r = 0; r < geo.R; r++) {
+        SlabGeom g = geo;
+        g.rank = r;
+        bp3_topology_planes(g, planes);
+        Tg = std::min(Tg, bp3_tile_shape(planes, H, G, team, Tg, ctas, false, &Tz));
+    }
+    /* Tg only ever shrinks along the loop and a shape that passed for a larger Tg was not necessarily re-checked
+       for this one on the earlier ranks: confirm, falling back to plane groups */
+    if (Tg > 1) {
+        for (int r = 0; r < geo.R; r++) {
+            SlabGeom g = geo;
+            g.rank = r;
+            bp3_topology_planes(g, planes);
+            int tz = team;
+            if (bp3_tile_shape(planes, H, G, team, Tg, ctas, false, &tz) != Tg) { Tg = 1; break; }
+        }
+    }
+    *Tz_out = Tg > 1 ? team / Tg : team;
+    return Tg;
 }
 
 /* segment length: long enough that a band offers ~2x more independent items than there are workers */

@@ -29,12 +29,16 @@
  * prog[g][z] = rows completed (store after __threadfence), consumers poll it.
  * Sweeps are claimed from a ticket counter in an order that extends the
  * dependency order (key 2z+4g), so with all warps co-resident (cooperative
- * launch) the earliest unfinished sweep can always advance: no deadlock.  All
- * generations of a plane follow each other a few rows apart, so the working
- * set lives in L2 and HBM sees one read and one write of the volume for the
- * whole run (temporal blocking over ALL generations).  The same in-place
- * argument as the reference's makes single buffering safe: a row is only
- * overwritten after every reader of its previous version has passed it.
+ * launch) the earliest unfinished sweep can always advance: no deadlock.  The
+ * same in-place argument as the reference's makes single buffering safe: a row
+ * is only overwritten after every reader of its previous version has passed it.
+ *
+ * HBM traffic depends on how far apart consecutive generations of a plane run.
+ * With one generation per work item the volume streams through HBM once per
+ * generation (measured, round 1: 540 GB for 2048^3 x 50).  In TILE mode (below)
+ * a CTA sweeps a tile of nz planes x ng generations: generation g+1 of a row
+ * runs ~6 row steps after generation g, reads it from L2 and overwrites it
+ * there, so HBM sees one read and one write of the volume per ng generations.
  */
 #ifndef CLAPCA_CA3D_BITPLANE_CUH
 #define CLAPCA_CA3D_BITPLANE_CUH
@@ -50,23 +54,21 @@ struct Bp3Params {
     int W, H, Z, G;         /* cells per row, rows per plane, LOCAL planes, generations */
     int RWP;                /* words per plane-row = 32 * WPL */
     int *prog;              /* [G][Z] rows completed by local sweep (z,g) */
-    const int4 *order;      /* work items in claim order: (local z, g, first row, end row) */
+    const int4 *order;      /* work items in claim order: (local z, g, first row, end row); tile mode: see tile_loop */
     int nsweeps;            /* number of work items */
-    uint32_t epoch;         /* run number, upper half of the ghost-row tags */
     int flag_rows;          /* progress counters are raised every flag_rows rows (and at segment ends) */
     int prefetch_rows;      /* > 0: prefetch.L2 the own record this many rows ahead (HBM -> L2 latency) */
     unsigned *ticket;       /* next sweep to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
-    unsigned long long *diag;   /* optional: [0] cycles waiting on counters, [1] on ghost tags, [2] in work items */
+    unsigned long long *diag;   /* optional: cycles [0] waiting on gpu-scope counters, [1] service warps busy, [2] in work items,
+                                   [3] waiting on tile-mates */
     uint32_t surv, born;    /* rule masks (run-time rule only) */
     uint32_t bornval;       /* (nr_states - 1) & 0xff */
     long long spin_limit;   /* watchdog budget in clock ticks per wait */
     int max_ctas_per_sm;    /* host side only: > 0 caps the resident CTAs per SM of the launch */
+    int max_ctas;           /* host side only: > 0 caps the CTAs of the launch (several ranks sharing one device) */
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
-    int team;               /* > 0: team mode -- a CTA of `team` warps sweeps `team` consecutive planes (see below) */
-    int edge_flag_rows;     /* team mode: counter period of a team's LAST plane (it feeds the next team); 0 = flag_rows */
-    int edge_loop;          /* != 0: some plane of this launch has a ghost source / feeds a peer (multi-GPU): see run_segment;
-                               2 = the deferred-tag-check loop (only in builds with CLAPCA_EDGE_DEFER) */
+    int team;               /* > 0: tile mode -- a CTA of `team` compute warps + ONE service warp sweeps a tile (see below) */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -95,36 +97,38 @@ struct Bp3Params {
  */
 
 /*
- * Team mode.  With one warp per sweep and gpu-scope counters, plane z+1 trails plane z by flag_rows + ~3 rows
- * (the counter period plus the MEMBAR.GPU / poll latency), and that hop -- paid Z times in a row -- bounds how
- * many sweeps the dependency DAG lets run at once: G * H / hop.  One GPU has fewer warps than that; eight
- * GPUs sharing one volume do not.  In team mode a work item is a GROUP of up to `team` consecutive planes of
- * one generation, swept by the warps of ONE CTA: warp w takes plane z0 + w and follows warp w - 1 through a
- * shared-memory row counter raised after EVERY row (CTA-scope release: MEMBAR.CTA + STS, tens of cycles), so
- * inside a team the hop is the 3 rows the data dependency itself asks for.  The row data still travels
- * through L2 (st.cg / ld.cg by warps of the same SM, ordered by the CTA-scope release/acquire pair).  Only
- * the team's last plane hands over to another CTA (or GPU) through the gpu-scope counter / ghost tags, and
- * every plane keeps raising its gpu-scope counter every flag_rows rows for the next generation's readers.
+ * Tile mode.  With one warp per sweep and gpu-scope counters, a consumer trails its producer by flag_rows + ~3 rows
+ * (the counter period plus the MEMBAR.GPU / poll latency); that hop bounds how many sweeps the dependency DAG lets
+ * run at once, and it keeps consecutive generations of a plane so far apart that every generation streams the
+ * volume through HBM.  In tile mode a work item is a TILE of nz consecutive planes x ng consecutive generations,
+ * swept by the warps of ONE CTA: compute warp w = i + nz * j takes plane z0 + i at generation g0 + j.  Its three
+ * producers -- (i-1, j) the new plane below, (i+1, j-1) the old plane above, (i, j-1) its own old state -- are
+ * warps of the same CTA wherever they exist, followed through shared-memory row counters raised after EVERY row
+ * (CTA-scope release: MEMBAR.CTA + STS, tens of cycles): inside a tile the hop is the 3 rows the data dependency
+ * and the one-row software prefetch ask for, plane to plane and generation to generation.  The row data itself
+ * travels through L2 (st.cg / ld.cg by warps of the same SM, ordered by the CTA-scope release / acquire pair), so
+ * generation g0+j+1 of a row finds generation g0+j in L2 and overwrites it there.
+ *
+ * The compute warps never execute a gpu-scope fence and never touch another GPU.  ONE extra "service" warp per CTA
+ * does both for all of them: it watches the shared-memory counters and
+ *   - publishes them to the gpu-scope table prog[g][z] (one fence.acq_rel.gpu per pass, cumulativity makes the rows
+ *     visible before the counter) for the tile's consumers in other CTAs, and
+ *   - for a z-block's edge planes (multi-GPU) copies the finished H rows into the neighbouring GPU's ghost plane
+ *     with plain peer stores over NVLink, then one fence.acq_rel.sys per pass, then the peer's counter.  A ghost
+ *     plane is an ordinary source for its consumer (same record stride, a counter per generation); nothing in the
+ *     row loop knows about GPUs.
+ * Tiles with ng > 1 depend on the NEXT tile in z of the same generation group (its plane z0+nz at generation
+ * g0+j-1 feeds our last plane at g0+j) while that tile depends on ours: the two must be co-resident.  The claim
+ * order (bp_plan.h, bp3_make_items_tile) keeps them a few tickets apart and bounds ng so that every rank always
+ * has more CTAs than items inside that window.
  */
 enum { BP3_MAX_TEAM = 24 };
 
 /*
- * -DCLAPCA_EDGE_DEFER=1 additionally builds a third instantiation of the row loop (edge_loop == 2) in which the
- * tags of a ghost row are checked one row step AFTER its loads were issued (see fetch_h_tagged); off by default:
- * not yet measured on hardware, and every instantiation costs build time.  The emulator tests build it.
- */
-#ifndef CLAPCA_EDGE_DEFER
-#define CLAPCA_EDGE_DEFER 0
-#endif
-
-/*
- * Publisher mode.  Raising a progress counter needs a gpu-scope release, and MEMBAR.GPU on a two-die B200
- * costs a few microseconds -- the time of two row steps.  A worker that fences itself can therefore only
- * afford a counter update every ~8 rows, which makes every consumer trail its producer by ~10 rows and
- * bounds the number of sweeps the dependency DAG lets run concurrently (the limit that matters once a
- * rank owns only G/N sweeps per dependency level).  In publisher mode the workers never fence at gpu
- * scope: after the stores of a row they bump `done` in a shared-memory mailbox (CTA-scope release: cheap),
- * and one extra warp per CTA loops { read all mailboxes; ONE fence.acq_rel.gpu; store the counters that
+ * Publisher mode (one warp per sweep, no tiles).  Raising a progress counter needs a gpu-scope release, and
+ * MEMBAR.GPU on a two-die B200 costs a few microseconds -- the time of two row steps.  In publisher mode the workers
+ * never fence at gpu scope: after the stores of a row they bump `done` in a shared-memory mailbox (CTA-scope release:
+ * cheap), and one extra warp per CTA loops { read all mailboxes; ONE fence.acq_rel.gpu; store the counters that
  * moved }.  Release cumulativity (worker stores -> CTA-scope release/acquire -> gpu-scope fence -> counter)
  * makes the rows visible before the counter, exactly like bar.sync + thread 0 fencing in a grid barrier.
  */
@@ -134,6 +138,12 @@ struct PubSlot {
     int pub;                    /* rows published (publisher-written; worker resets it between items) */
 };
 enum { BP3_MAX_PUB_WORKERS = 23 };
+
+/* tile mode: the shared-memory row counters a compute warp follows / raises (nullptr: that producer is outside the tile) */
+struct TileWire {
+    const int *dn, *up, *own;
+    int *done;
+};
 
 /* ---- rules ---------------------------------------------------------------- */
 
@@ -243,15 +253,14 @@ CA_DEV uint32_t bp_valid_mask(int w, int W)
  *   - the producers' counters are cached as ONE number (`have` = min over the producers); the fast path of
  *     a dependency check is one compare, the slow path polls with ld.acquire in lanes 0..2 and reduces
  *     with redux.min;
- *   - counters are published with st.release every flag_rows rows.
+ *   - there is ONE row loop: ghost planes of a neighbouring GPU look like local planes (same record stride,
+ *     a progress counter per generation), so the loop carries no multi-GPU code at all.
  */
 template <int P, int WPL, class Rule>
 struct Sweep3 {
     static constexpr int NP = P + 2;
     static constexpr int RWP = 32 * WPL;            /* words per plane-row */
     static constexpr int RECW = NP * RWP;           /* words per row record */
-    static constexpr int GHW = 4 * RWP;             /* words per ghost row ({word, tag} pairs of H0|H1) */
-    enum { SRC_NONE = 0, SRC_LOCAL = 1, SRC_GHOST = 2 };
 
     struct St {
         /* slot of row r = (r - y0 + 3) % 3 */
@@ -260,34 +269,32 @@ struct Sweep3 {
         uint32_t ho[2][WPL];                        /* H of own old row y+1 */
         uint32_t hn[2][WPL];                        /* H of own new row y-1 */
         uint32_t vmask[WPL];
-        const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load */
+        const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load; nullptr: outside the volume */
         uint32_t *rec;                              /* lane-adjusted own record of the current row */
         const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead */
-        uint32_t *push_dn, *push_up;                /* lane-adjusted peer ghost rows of the current row */
         PubSlot *slot;                              /* publisher mode: this worker's mailbox (else nullptr) */
-        const int *sdn;                             /* team mode: shared-memory row counter of the plane below (else nullptr) */
-        int *sown;                                  /* team mode: own shared-memory row counter (nullptr: nobody follows) */
-        int have_s;                                 /* rows the plane below has published through sdn */
-        int flag_period;                            /* rows between two raises of the own gpu-scope counter */
-        const int *flagp;                           /* the producer counter this lane polls (lanes 0..2) */
+        const int *sprod;                           /* tile mode: lanes 0..2 = shared-memory row counter of producer dn / up / own */
+        int *sown;                                  /* tile mode: own shared-memory row counter (else nullptr) */
+        int have_s;                                 /* min over the rows the tile-mates have published through sprod */
+        const int *flagp;                           /* the gpu-scope producer counter this lane polls (lanes 0..2) */
+        bool flag_sys;                              /* ... is written by another GPU: poll at system scope */
         int have;                                   /* min over the producers' published row counts */
         int next_raise;                             /* next row count at which the own counter is raised */
-        int dn_mode, up_mode;
-        uint32_t tag_dn, tag_up, tag_out;
-        uint32_t bad_dn, bad_up;                    /* deferred loop: != 0 in some lane = the ghost row fetched a step ago was stale */
-        long long waited_flag, waited_tag, waited_team;     /* diagnostics: cycles spent in the slow paths */
+        long long waited_flag, waited_team;         /* diagnostics: cycles spent in the slow paths */
     };
 
     /* false = watchdog fired / abort requested */
     CA_MDEV bool wait_rows(const Bp3Params &p, St &st, int need)
     {
-        if (st.sdn && st.have_s < need && !wait_team(p, st, need))
+        if (st.have_s < need && !wait_tile(p, st, need))
             return false;
         if (st.have >= need)
             return true;
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
-            int v = st.flagp ? dp_ld_acquire(st.flagp) : 0x7fffffff;
+            int v = 0x7fffffff;
+            if (st.flagp)
+                v = st.flag_sys ? dp_ld_acquire_sys(st.flagp) : dp_ld_acquire(st.flagp);
             st.have = dp_reduce_min(v);
             if (st.have >= need)
                 break;
@@ -308,16 +315,18 @@ struct Sweep3 {
     }
 
     /*
-     * Team mode: rows of the plane below, swept by the previous warp of this CTA.  Every lane reads the same
-     * shared-memory word (a broadcast), the vote keeps the warp converged, and every lane acquires for itself.
+     * Tile mode: rows of the producers that are warps of this CTA.  Lanes 0..2 read the shared-memory counter of
+     * producer dn / up / own (the others contribute "no limit"), redux.min gives the row count all of them have
+     * reached, and every lane acquires for itself.
      */
-    CA_MDEV bool wait_team(const Bp3Params &p, St &st, int need)
+    CA_MDEV bool wait_tile(const Bp3Params &p, St &st, int need)
     {
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
-            const int v = dp_ld_volatile(st.sdn);
-            if (dp_all(v >= need)) {
-                st.have_s = dp_reduce_min(v);
+            const int v = st.sprod ? dp_ld_volatile(st.sprod) : 0x7fffffff;
+            const int m = dp_reduce_min(v);
+            if (m >= need) {
+                st.have_s = m;
                 break;
             }
             if (spins == 0) t0 = dp_clock();
@@ -342,137 +351,16 @@ struct Sweep3 {
         for (int j = 0; j < WPL; j++) h[0][j] = h[1][j] = 0u;
     }
 
-    /*
-     * Ghost rows (see bp3_types.h): {word, tag} pairs written by the neighbouring GPU.  Re-read until every
-     * pair of this lane -- and of the whole warp -- carries the expected tag.  false = watchdog / abort.
-     */
-    CA_MDEV bool load_h_tagged(const Bp3Params &p, St &st, const uint32_t *src, uint32_t expect, uint32_t h[2][WPL])
+    /* next H row of the plane below / above into h; advances the running pointer */
+    CA_MDEV void load_side(const uint32_t *&src, uint32_t h[2][WPL])
     {
-        long long t0 = 0;
-        for (unsigned spins = 0;; spins++) {
-            bool ok = true;
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {             /* pairs 2i, 2i+1 of this lane */
-                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);   /* vector i of every lane is contiguous */
-                const int q0 = 2 * i, q1 = 2 * i + 1;   /* pair index -> (plane, word) = (q / WPL, q % WPL) */
-                h[q0 / WPL][q0 % WPL] = v.x;
-                h[q1 / WPL][q1 % WPL] = v.z;
-                ok = ok && v.y == expect && v.w == expect;
-            }
-            if (dp_all(ok)) {
-                if (t0) st.waited_tag += dp_clock() - t0;
-                return true;
-            }
-            if (spins == 0) t0 = dp_clock();
-            dp_nanosleep(100);
-            if ((spins & 63u) == 63u) {
-                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
-                if (!dp_all(!bad)) {
-                    if (dp_lane() == 0)
-                        dp_set_error(p.err, 2);
-                    return false;
-                }
-            }
-        }
-    }
-
-    CA_MDEV void store_h_tagged(const Bp3Params &p, uint32_t *dst, uint32_t tag, const uint32_t h0[WPL], const uint32_t h1[WPL])
-    {
-#pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            const int q0 = 2 * i, q1 = 2 * i + 1;
-            const uint32_t a = (q0 / WPL) ? h1[q0 % WPL] : h0[q0 % WPL];
-            const uint32_t b = (q1 / WPL) ? h1[q1 % WPL] : h0[q1 % WPL];
-            dp_st_cg(reinterpret_cast<uint4 *>(dst) + 32 * i, make_uint4(a, tag, b, tag));   /* one 512-byte burst per warp */
-        }
-    }
-
-    /*
-     * Deferred loop (EDGE == 2).  The ghost row fetched inside a row step is not needed before the NEXT step, so
-     * the loads are only issued: the data words go straight into the window registers, the tags are folded into one
-     * word per lane, and settle_side() looks at that word a whole row step later -- the L2 latency of a remotely
-     * written line leaves the critical path of the edge plane (which in team mode paces its 15 team-mates).  The
-     * re-read of a stale row is a cold, out-of-line function that returns the row by value: the hot loop only
-     * grows by the fold, one vote and one branch per side (inlining the polling loop at every site made the loop
-     * 16 % longer and the whole kernel 30 % slower).
-     */
-    struct GhostRow {
-        uint32_t w[2 * WPL];
-        int ok;
-    };
-
-    CA_MDEV void fetch_h_tagged(const uint32_t *src, uint32_t expect, uint32_t h[2][WPL], uint32_t &bad)
-    {
-        uint32_t acc = 0u;
-#pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
-            const int q0 = 2 * i, q1 = 2 * i + 1;
-            h[q0 / WPL][q0 % WPL] = v.x;
-            h[q1 / WPL][q1 % WPL] = v.z;
-            acc |= (v.y ^ expect) | (v.w ^ expect);
-        }
-        bad = acc;
-    }
-
-    CA_MCOLD GhostRow repoll_ghost(const uint32_t *src, uint32_t expect, int *err, long long spin_limit)
-    {
-        GhostRow r;
-        long long t0 = dp_clock();
-        for (unsigned spins = 0;; spins++) {
-            bool ok = true;
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                uint4 v = dp_ld_cg(reinterpret_cast<const uint4 *>(src) + 32 * i);
-                r.w[2 * i] = v.x;
-                r.w[2 * i + 1] = v.z;
-                ok = ok && v.y == expect && v.w == expect;
-            }
-            if (dp_all(ok)) {
-                r.ok = 1;
-                return r;
-            }
-            dp_nanosleep(100);
-            if ((spins & 63u) == 63u) {
-                bool bad = dp_ld_flag(err) != 0 || (dp_clock() - t0) > spin_limit;
-                if (!dp_all(!bad)) {
-                    if (dp_lane() == 0)
-                        dp_set_error(err, 2);
-                    r.ok = 0;
-                    return r;
-                }
-            }
-        }
-    }
-
-    /* the row fetched by fetch_h_tagged() one step ago is about to be used */
-    CA_MDEV bool settle_side(const Bp3Params &p, const uint32_t *next, uint32_t tag, uint32_t &bad, uint32_t h[2][WPL])
-    {
-        if (dp_all(bad == 0u))
-            return true;
-        bad = 0u;
-        const GhostRow r = repoll_ghost(next - GHW, tag, p.err, p.spin_limit);
-#pragma unroll
-        for (int q = 0; q < 2 * WPL; q++)
-            h[q / WPL][q % WPL] = r.w[q];
-        return r.ok != 0;
-    }
-
-    /* next H row of the plane below / above into h; advances the running pointer.  false = aborted */
-    template <int EDGE>
-    CA_MDEV bool load_side(const Bp3Params &p, St &st, const uint32_t *&src, int mode, uint32_t tag, uint32_t h[2][WPL])
-    {
-        if (mode == SRC_LOCAL) {
+        if (src) {
             LaneVec<WPL>::ld(src, h[0]);
             LaneVec<WPL>::ld(src + RWP, h[1]);
             src += RECW;
-        } else if (EDGE == 0 || mode == SRC_NONE) {
-            zero2(h);
         } else {
-            if (!load_h_tagged(p, st, src, tag, h)) return false;
-            src += GHW;
+            zero2(h);
         }
-        return true;
     }
 
     /* own record at st.rec + D rows: state planes, and optionally the H planes */
@@ -502,7 +390,7 @@ struct Sweep3 {
      * sit in slots (M+2)%3 / M / (M+1)%3, own state rows y / y+1 in slots M / (M+1)%3; row y+2 is
      * prefetched into slot (M+2)%3 once row y-1 has been consumed.
      */
-    template <int M, int EDGE>
+    template <int M>
     CA_MDEV bool step(const Bp3Params &p, St &st, int y, int y1, int *myprog)
     {
         constexpr int A = (M + 2) % 3, B = M, C = (M + 1) % 3;
@@ -510,12 +398,6 @@ struct Sweep3 {
         const int H = p.H;
         const uint32_t bornval = Rule::bornval(p);
         uint32_t k[WPL][5], ao[WPL], ge2[WPL];
-
-        if (EDGE == 2) {        /* ghost rows y+1 were only fetched during the previous step */
-            if (st.dn_mode == SRC_GHOST && !settle_side(p, st.dn, st.tag_dn, st.bad_dn, st.hd[C])) return false;
-            if (st.up_mode == SRC_GHOST && !settle_side(p, st.up, st.tag_up, st.bad_up, st.hu[C])) return false;
-        }
-
 
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
 #pragma unroll
@@ -555,18 +437,8 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                if (EDGE == 2 && st.dn_mode == SRC_GHOST) {
-                    fetch_h_tagged(st.dn, st.tag_dn, st.hd[A], st.bad_dn);
-                    st.dn += GHW;
-                } else if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[A])) {
-                    return false;
-                }
-                if (EDGE == 2 && st.up_mode == SRC_GHOST) {
-                    fetch_h_tagged(st.up, st.tag_up, st.hu[A], st.bad_up);
-                    st.up += GHW;
-                } else if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[A])) {
-                    return false;
-                }
+                load_side(st.dn, st.hd[A]);
+                load_side(st.up, st.hu[A]);
             } else {
                 zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
                 zero_s(st.so[A]);
@@ -622,70 +494,41 @@ struct Sweep3 {
         for (int q = 0; q < P; q++)
             LaneVec<WPL>::st(st.rec + (2 + q) * RWP, st.so[B][q]);
         st.rec += RECW;
+        if (st.sown) {
+            /*
+             * Tile mode: warp barrier (orders every lane's row stores before lane 0), CTA-scope release, row
+             * counter in shared memory -- after EVERY row.  The service warp carries it to gpu / system scope.
+             */
+            dp_syncwarp();
+            if (lane == 0) {
+                dp_fence_cta();
+                dp_st_volatile(st.sown, y + 1);
+            }
+            return true;
+        }
         /*
-         * Local consumers: warp barrier (orders every lane's row stores before lane 0), then ONE
-         * release store of the counter (MEMBAR.GPU + store).  Raised every flag_rows rows.
+         * One warp per sweep: warp barrier, then ONE release store of the counter (MEMBAR.GPU + store), or the
+         * publisher's mailbox.  Raised every flag_rows rows.
          */
         const bool at_mark = (y + 1 == st.next_raise);
         if (at_mark)
-            st.next_raise += st.flag_period;
-        if (at_mark || y + 1 == y1 || st.sown) {
+            st.next_raise += p.flag_rows;
+        if (at_mark || y + 1 == y1) {
             dp_syncwarp();
             if (lane == 0) {
-                if (st.sown) {                      /* team mode: the next warp of this CTA follows row by row */
+                if (st.slot) {
                     dp_fence_cta();
-                    dp_st_volatile(st.sown, y + 1);
-                }
-                if (at_mark || y + 1 == y1) {
-                    if (st.slot) {
-                        dp_fence_cta();
-                        dp_st_volatile(&st.slot->done, y + 1);
-                    } else {
-                        dp_st_release(myprog, y + 1);
-                    }
+                    dp_st_volatile(&st.slot->done, y + 1);
+                } else {
+                    dp_st_release(myprog, y + 1);
                 }
             }
-        }
-        /*
-         * A z-block's edge plane also feeds the neighbouring GPU's ghost plane: tagged peer stores over
-         * NVLink, fire and forget -- no fence, no counter (the tag travels with every word).  They are issued AFTER the
-         * counter's release so that its MEMBAR never waits for this row's NVLink round trip.
-         */
-        if (EDGE != 0 && st.push_dn) {
-            store_h_tagged(p, st.push_dn, st.tag_out, st.hn[0], st.hn[1]);
-            st.push_dn += GHW;
-        }
-        if (EDGE != 0 && st.push_up) {
-            store_h_tagged(p, st.push_up, st.tag_out, st.hn[0], st.hn[1]);
-            st.push_up += GHW;
         }
         return true;
     }
 
     /* one work item: rows [y0, y1) of plane z at generation g.  false = aborted */
-    /*
-     * The row loop exists twice.  A launch in which some plane has a ghost source or feeds a peer (multi-GPU)
-     * runs the EDGE instantiation for EVERY plane; a single-GPU launch runs a loop without a single ghost
-     * instruction in it.  The kernel is bound by instruction issue and fetch: measured on B200 at 2048^3 x 50,
-     * the plain loop takes 119.3 ms where the loop carrying the (never executed) ghost paths takes 121-122 ms,
-     * more inlined tag-polling code in the same loop cost 30 %, and mixing the two instantiations inside one CTA
-     * (edge planes EDGE, their team-mates plain) was the slowest of all -- one hot loop per launch it is.
-     */
-    CA_MDEV bool run_segment(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
-                             const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
-    {
-        if constexpr (CLAPCA_EDGE_DEFER != 0) {
-            if (p.edge_loop == 2)
-                return run_rows<2>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
-        }
-        if (p.edge_loop)
-            return run_rows<1>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
-        return run_rows<0>(p, z, g, y0, y1, slot, sdn, sown, team_edge);
-    }
-
-    template <int EDGE>
-    CA_MDEV bool run_rows(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
-                          const int *sdn, int *sown, bool team_edge)
+    CA_MDEV bool run_rows(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot, const TileWire *tw)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
@@ -695,39 +538,29 @@ struct Sweep3 {
 
         /* ---- sources ---- */
         const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
-        st.dn_mode = !pl.dn_rows ? SRC_NONE : ((pl.ghost_mask & 1u) ? SRC_GHOST : SRC_LOCAL);
-        st.up_mode = !pl.up_rows ? SRC_NONE : ((pl.ghost_mask & 2u) ? SRC_GHOST : SRC_LOCAL);
-        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * pl.dn_stride + lane * (st.dn_mode == SRC_GHOST ? 4 : WPL)
-                           : nullptr;
-        st.up = pl.up_rows ? pl.up_rows + (size_t)first * pl.up_stride + lane * (st.up_mode == SRC_GHOST ? 4 : WPL)
-                           : nullptr;
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * RECW + lane * WPL : nullptr;
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * RECW + lane * WPL : nullptr;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
         st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
               ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
-        st.push_dn = pl.push_dn_rows ? pl.push_dn_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
-        st.push_up = pl.push_up_rows ? pl.push_up_rows + (size_t)y0 * GHW + lane * 4 : nullptr;
-        st.tag_dn = (p.epoch << 16) | (uint32_t)(g + 1);    /* plane below: already generation g */
-        st.tag_up = (p.epoch << 16) | (uint32_t)g;          /* plane above: still generation g-1 */
-        st.tag_out = (p.epoch << 16) | (uint32_t)(g + 1);
 
-        /* ---- producers (ghost sources are synchronised by their row tags, not by counters) ---- */
+        /* ---- producers: tile-mates through shared memory, everybody else through gpu-scope counters ---- */
         {
-            /* team mode: the plane below is followed through shared memory, not through its gpu-scope counter */
-            const int *fdn = (st.dn_mode == SRC_LOCAL && !sdn) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
+            const int *sdn = tw ? tw->dn : nullptr, *sup = tw ? tw->up : nullptr, *sow = tw ? tw->own : nullptr;
+            const int *fdn = (pl.dn_rows && !sdn) ? pl.dn_flag + (size_t)g * pl.dn_gstride : nullptr;
             /* layout items: "generation -1" is the pack item of a plane, counted in row -1 of the table */
             const bool prev = g > 0 || p.layout_items;
-            const int *fup = (prev && st.up_mode == SRC_LOCAL) ? pl.up_flag + ((long long)g - 1) * (long long)pl.up_gstride : nullptr;
-            const int *fown = prev ? p.prog + ((long long)g - 1) * Z + z : nullptr;
+            const int *fup = (prev && pl.up_rows && !sup) ? pl.up_flag + ((long long)g - 1) * (long long)pl.up_gstride : nullptr;
+            const int *fown = (prev && !sow) ? p.prog + ((long long)g - 1) * Z + z : nullptr;
             st.flagp = lane == 0 ? fdn : (lane == 1 ? fup : (lane == 2 ? fown : nullptr));
+            st.flag_sys = (lane == 0 && (pl.ghost_mask & 1u)) || (lane == 1 && (pl.ghost_mask & 2u));
             st.have = (fdn || fup || fown) ? 0 : 0x7fffffff;
+            st.sprod = lane == 0 ? sdn : (lane == 1 ? sup : (lane == 2 ? sow : nullptr));
+            st.have_s = (sdn || sup || sow) ? 0 : 0x7fffffff;
         }
-        st.sdn = sdn;
-        st.sown = sown;
-        st.have_s = 0;
-        st.flag_period = (team_edge && p.edge_flag_rows > 0) ? p.edge_flag_rows : p.flag_rows;
-        st.next_raise = (y0 / st.flag_period + 1) * st.flag_period;
-        st.waited_flag = st.waited_tag = st.waited_team = 0;
-        st.bad_dn = st.bad_up = 0u;
+        st.sown = tw ? tw->done : nullptr;
+        st.next_raise = (y0 / p.flag_rows + 1) * p.flag_rows;
+        st.waited_flag = st.waited_team = 0;
         const long long t_item = dp_clock();
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.vmask[j] = bp_valid_mask(lane * WPL + j, p.W);
@@ -769,18 +602,18 @@ struct Sweep3 {
 
         /* ---- fill the windows: rows y0-1 (slot 2), y0 (slot 0), y0+1 (slot 1) ---- */
         if (y0 > 0) {
-            if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[2])) return false;
-            if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[2])) return false;
+            load_side(st.dn, st.hd[2]);
+            load_side(st.up, st.hu[2]);
             load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
         } else {
             zero2(st.hd[2]); zero2(st.hu[2]); zero2(st.hn);
         }
-        if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[0])) return false;
-        if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[0])) return false;
+        load_side(st.dn, st.hd[0]);
+        load_side(st.up, st.hu[0]);
         load_own_s<0>(st, st.so[0]);
         if (y0 + 1 < H) {
-            if (!load_side<EDGE>(p, st, st.dn, st.dn_mode, st.tag_dn, st.hd[1])) return false;
-            if (!load_side<EDGE>(p, st, st.up, st.up_mode, st.tag_up, st.hu[1])) return false;
+            load_side(st.dn, st.hd[1]);
+            load_side(st.up, st.hu[1]);
             load_own_h<1>(st, st.ho);
             load_own_s<1>(st, st.so[1]);
         } else {
@@ -791,16 +624,16 @@ struct Sweep3 {
 
         int y = y0;
         for (; y + 3 <= y1; y += 3) {
-            if (!step<0, EDGE>(p, st, y, y1, myprog)) return false;
-            if (!step<1, EDGE>(p, st, y + 1, y1, myprog)) return false;
-            if (!step<2, EDGE>(p, st, y + 2, y1, myprog)) return false;
+            if (!step<0>(p, st, y, y1, myprog)) return false;
+            if (!step<1>(p, st, y + 1, y1, myprog)) return false;
+            if (!step<2>(p, st, y + 2, y1, myprog)) return false;
         }
         if (y < y1) {
-            if (!step<0, EDGE>(p, st, y, y1, myprog)) return false;
+            if (!step<0>(p, st, y, y1, myprog)) return false;
             y++;
         }
         if (y < y1) {
-            if (!step<1, EDGE>(p, st, y, y1, myprog)) return false;
+            if (!step<1>(p, st, y, y1, myprog)) return false;
         }
         /* publisher mode: the mailbox is reused by the next item only once the last rows are out */
         if (slot) {
@@ -811,7 +644,6 @@ struct Sweep3 {
         }
         if (p.diag && lane == 0) {
             dp_atomic_add64(p.diag + 0, (unsigned long long)st.waited_flag);
-            dp_atomic_add64(p.diag + 1, (unsigned long long)st.waited_tag);
             dp_atomic_add64(p.diag + 2, (unsigned long long)(dp_clock() - t_item));
             dp_atomic_add64(p.diag + 3, (unsigned long long)st.waited_team);
         }
@@ -974,8 +806,7 @@ struct Sweep3 {
     }
 
     /* dispatch on the item kind: g == -1 pack, g == G unpack (layout items), else a sweep segment */
-    CA_MDEV bool run_item(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot,
-                          const int *sdn = nullptr, int *sown = nullptr, bool team_edge = false)
+    CA_MDEV bool run_item(const Bp3Params &p, int z, int g, int y0, int y1, PubSlot *slot)
     {
         if (p.layout_items) {
             if (g < 0)
@@ -983,7 +814,7 @@ struct Sweep3 {
             if (g >= p.G)
                 return unpack_plane(p, z);
         }
-        return run_segment(p, z, g, y0, y1, slot, sdn, sown, team_edge);
+        return run_rows(p, z, g, y0, y1, slot, nullptr);
     }
 
     /* the worker loop: claim items in dependency order until the list is exhausted */
@@ -1039,13 +870,115 @@ struct Sweep3 {
     }
 
     /*
-     * Team mode: the CTA claims one group of planes at a time (item = first local plane, generation, number of
-     * planes); warp w sweeps plane w of the group, warps beyond the group's size sit the item out.
+     * Tile mode, the service warp of one tile (nz planes from local plane l0, ng generations from g0).
+     * Lane w < nz * ng serves compute warp w: it carries the warp's shared-memory row counter to prog[g][z].
+     * Lanes 0 .. 2 ng - 1 additionally own one push stream each: lane j < ng the H rows of warp (0, j) for the ghost
+     * plane ABOVE the previous z-block (push_dn), lane ng + j those of warp (nz-1, j) for the ghost plane BELOW the
+     * next z-block (push_up) -- where the tile touches a z-block edge whose other side is another GPU.  Every pass:
+     * read the counters, fence.acq_rel.gpu, store the gpu-scope counters that moved; copy the new rows of every
+     * stream (the whole warp copies one H row = 2 * RWP words with coalesced 8-byte peer stores), fence.acq_rel.sys,
+     * store the peers' counters.  A row is copied out of the local record before anybody can overwrite it: generation
+     * g+1 of an edge row needs the neighbouring GPU's generation-g (or g+1) rows, which need this push.
      */
-    CA_MDEV void team_loop(const Bp3Params &p)
+    CA_MDEV void service_loop(const Bp3Params &p, int l0, int g0, int nz, int ng, const int *done)
     {
-        CA_SHARED(int, sm, BP3_MAX_TEAM + 1);       /* row counters of the team's warps, then the claimed ticket */
+        const int lane = dp_lane();
+        const int H = p.H, Z = p.Z;
+        const int n = nz * ng;
+        int *myflag = lane < n ? p.prog + (size_t)(g0 + lane / nz) * Z + (l0 + lane % nz) : nullptr;
+        int pub = 0, pushed = 0, pw = 0;
+        const uint32_t *psrc = nullptr;
+        uint32_t *pdst = nullptr;
+        int *pflag = nullptr;
+        if (lane < 2 * ng) {
+            const bool up = lane >= ng;
+            const int j = up ? lane - ng : lane;
+            const int zl = up ? l0 + nz - 1 : l0;
+            const Bp3Plane pl = p.planes[zl];
+            pdst = up ? pl.push_up_rows : pl.push_dn_rows;
+            pflag = (up ? pl.push_up_flag : pl.push_dn_flag);
+            if (pdst) {
+                pflag += g0 + j;
+                psrc = p.rows + (size_t)zl * H * RECW;
+                pw = (up ? nz - 1 : 0) + nz * j;
+            }
+        }
+        const bool streams = dp_any(pdst != nullptr);
+        long long t_idle = dp_clock(), t_busy = 0;
+        for (unsigned spins = 0;; spins++) {
+            const long long t_pass = dp_clock();
+            const int d = lane < n ? dp_ld_volatile(done + lane) : H;
+            dp_fence_cta();
+            bool any = false;
+            const bool moved = lane < n && d > pub;
+            if (dp_any(moved)) {
+                dp_fence_release();                     /* fence.acq_rel.gpu: rows before counters */
+                if (moved) {
+                    dp_st_flag(myflag, d);
+                    pub = d;
+                }
+                any = true;
+            }
+            if (streams) {
+                const int avail = (int)dp_shfl((uint32_t)d, pw);
+                const bool pm = pdst && avail > pushed;
+                const uint32_t mask = dp_ballot(pm);
+                if (mask) {
+                    for (uint32_t m = mask; m; m &= m - 1u) {
+                        const int s = dp_ffs(m) - 1;
+                        const uint32_t *src = (const uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)psrc, s);
+                        uint32_t *dst = (uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)pdst, s);
+                        const int r0 = (int)dp_shfl((uint32_t)pushed, s), r1 = (int)dp_shfl((uint32_t)avail, s);
+                        for (int r = r0; r < r1; r++) {
+                            const uint2 *a = reinterpret_cast<const uint2 *>(src + (size_t)r * RECW) + lane;
+                            uint2 *b = reinterpret_cast<uint2 *>(dst + (size_t)r * RECW) + lane;
+#pragma unroll
+                            for (int k = 0; k < WPL; k++)       /* H0 | H1 = 2 * RWP words = 32 * WPL uint2 */
+                                dp_st_cg(b + 32 * k, dp_ld_cg(a + 32 * k));
+                        }
+                    }
+                    dp_fence_sys();                     /* fence.acq_rel.sys: peer rows before the peer's counter */
+                    if (pm) {
+                        dp_st_flag_sys(pflag, avail);
+                        pushed = avail;
+                    }
+                    any = true;
+                }
+            }
+            const bool fin = (lane >= n || pub >= H) && (!pdst || pushed >= H);
+            if (dp_all(fin))
+                break;
+            if (any) {
+                t_busy += dp_clock() - t_pass;
+                t_idle = dp_clock();
+            } else {
+                dp_nanosleep(64);
+                if ((spins & 255u) == 255u) {
+                    /* a compute warp that bailed out never completes its rows */
+                    bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
+                    if (!dp_all(!bad)) {
+                        if (lane == 0)
+                            dp_set_error(p.err, 7);
+                        break;
+                    }
+                }
+            }
+        }
+        if (p.diag && lane == 0)
+            dp_atomic_add64(p.diag + 1, (unsigned long long)t_busy);
+    }
+
+    /*
+     * Tile mode: the CTA claims one tile at a time.  Item = (first local plane, first generation, nz | ng << 8, H);
+     * compute warp w = i + nz * j sweeps plane i of the tile at generation j, warps beyond nz * ng sit the item out,
+     * warp `team` (the last one) is the service warp.  Layout items (g == -1 / g == G): warp w < nz packs / unpacks
+     * plane w of the group and publishes its own counter.
+     */
+    CA_MDEV void tile_loop(const Bp3Params &p)
+    {
+        CA_SHARED(int, sm, BP3_MAX_TEAM + 1);       /* row counters of the compute warps, then the claimed ticket */
         const int w = dp_warp_in_block();
+        const int T = p.team;
         for (;;) {
             if (dp_thread() == 0) {
                 unsigned t = dp_atomic_inc(p.ticket);
@@ -1060,9 +993,21 @@ struct Sweep3 {
             if (t >= (unsigned)p.nsweeps)
                 break;
             const int4 it = p.order[t];
-            if (w < it.z)
-                run_item(p, it.x + w, it.y, 0, p.H, nullptr, w > 0 ? sm + (w - 1) : nullptr,
-                         w + 1 < it.z ? sm + w : nullptr, w + 1 == it.z);
+            const int nz = it.z & 0xff, ng = (it.z >> 8) & 0xff;
+            if (p.layout_items && (it.y < 0 || it.y >= p.G)) {
+                if (w < nz)
+                    run_item(p, it.x + w, it.y, 0, p.H, nullptr);
+            } else if (w < nz * ng) {
+                const int i = w % nz, j = w / nz;
+                TileWire tw;
+                tw.dn = i > 0 ? sm + (w - 1) : nullptr;
+                tw.up = (j > 0 && i + 1 < nz) ? sm + (w - nz + 1) : nullptr;
+                tw.own = j > 0 ? sm + (w - nz) : nullptr;
+                tw.done = sm + w;
+                run_rows(p, it.x + i, it.y + j, 0, p.H, nullptr, &tw);
+            } else if (w == T) {
+                service_loop(p, it.x, it.y, nz, ng, sm);
+            }
             dp_syncblock();                         /* the counters are cleared for the next item */
         }
     }
@@ -1105,19 +1050,19 @@ struct Bp3Bounds {
 };
 
 /*
- * Team mode is a kernel of its own (one CTA per SM): 512 threads leave every thread 128 registers -- the row
- * loop of the common variants then needs no spills -- and the widest variants run 256-thread teams.
+ * Tile mode is a kernel of its own (one CTA per SM): 16 compute warps + the service warp = 544 threads leave every
+ * thread 120 registers; the widest variants (8 state planes, 4 words per lane) run 7 compute warps + the service warp.
  */
 template <int P, int WPL>
 struct Bp3TeamBounds {
-    static constexpr int kMaxThreads = (P <= 4 && WPL <= 2) ? 512 : 256;
+    static constexpr int kTeam = (P <= 4 && WPL <= 2) ? 16 : 7;
+    static constexpr int kMaxThreads = 32 * (kTeam + 1);
 };
 
-/* largest team (warps per CTA) of a variant */
+/* largest team (compute warps per CTA) of a variant */
 inline int bp3_team_cap(int P, int WPL)
 {
-    const int t = ((P <= 4 && WPL <= 2) ? 512 : 256) / 32;
-    return t < BP3_MAX_TEAM ? t : (int)BP3_MAX_TEAM;
+    return (P <= 4 && WPL <= 2) ? 16 : 7;
 }
 
 template <int P, int WPL, class Rule>
@@ -1129,7 +1074,7 @@ CA_GLOBAL void __launch_bounds__(Bp3Bounds<P, WPL>::kMaxThreads, 1) ca3d_sweep_k
 template <int P, int WPL, class Rule>
 CA_GLOBAL void __launch_bounds__(Bp3TeamBounds<P, WPL>::kMaxThreads, 1) ca3d_team_kernel(Bp3Params p)
 {
-    Sweep3<P, WPL, Rule>::team_loop(p);
+    Sweep3<P, WPL, Rule>::tile_loop(p);
 }
 
 } // namespace clapca

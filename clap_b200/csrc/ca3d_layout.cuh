@@ -152,22 +152,16 @@ CA_GLOBAL void ca3d_unpack_kernel(Bp3Layout L)
 }
 
 /*
- * Seed a neighbour's ghost plane with the H rows of one local plane: {word, tag} pairs, lane-major
- * (bp3_types.h).  src = first row record of the plane, dst = ghost plane (possibly peer memory).
+ * Seed a neighbour's ghost plane with the H rows of one local plane (the "old plane above" of generation 0):
+ * src = first row record of the plane, dst = ghost plane (peer memory), both with the record stride NP * RWP.
  */
-CA_GLOBAL void halo_seed_kernel(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, int WPL, uint32_t tag)
+CA_GLOBAL void halo_seed_kernel(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP)
 {
     const size_t n = (size_t)H * 2 * RWP;
     const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
     for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < n; i += stride) {
-        const int y = (int)(i / (2 * RWP));
-        const int q = (int)(i % (2 * RWP));             /* pair index within the row */
-        const int lane = q / (2 * WPL), k = q % (2 * WPL);
-        const int plane = k / WPL, j = k % WPL;
-        const uint32_t v = src[(size_t)y * NP * RWP + (size_t)plane * RWP + lane * WPL + j];
-        /* pair k of the lane lives in 16-byte vector k / 2 of that lane: vector u of all lanes is contiguous */
-        uint32_t *d = dst + (size_t)y * 4 * RWP + ((size_t)(k / 2) * 32 + lane) * 4 + (size_t)(k & 1) * 2;
-        dp_st_cg(reinterpret_cast<uint2 *>(d), make_uint2(v, tag));
+        const size_t y = i / (2 * RWP), q = i % (2 * RWP);
+        dst[y * NP * RWP + q] = src[y * NP * RWP + q];
     }
 }
 

@@ -168,6 +168,45 @@ __global__ void __launch_bounds__(256) count_nonzero_kernel(const uint8_t *a, si
         atomicAdd(out, c);
 }
 
+/*
+ * Plane fingerprint: h = sum over the plane's 8-byte little-endian words w_k (zero-padded tail) of
+ * splitmix64(w_k ^ (k + 1) * 0x9E3779B97F4A7C15) mod 2^64.  Order-independent, so it reduces in parallel; the
+ * position enters every term, so permuted or shifted cells change it.  tests/oracle_lib.py holds the numpy twin.
+ */
+__device__ __forceinline__ unsigned long long plane_hash_mix(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) plane_hash_kernel(const uint8_t *a, size_t plane_bytes, size_t nplanes,
+                                                         unsigned long long *out)
+{
+    const size_t words = (plane_bytes + 7) / 8, full = plane_bytes / 8;
+    for (size_t pl = blockIdx.y; pl < nplanes; pl += gridDim.y) {
+        const uint8_t *base = a + pl * plane_bytes;
+        const bool aligned = ((uintptr_t)base & 7) == 0;
+        unsigned long long h = 0;
+        for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < words; k += (size_t)gridDim.x * blockDim.x) {
+            unsigned long long w = 0;
+            if (k < full && aligned) {
+                w = *reinterpret_cast<const unsigned long long *>(base + 8 * k);
+            } else {
+                for (int i = 0; i < 8; i++)
+                    if (8 * k + i < plane_bytes)
+                        w |= (unsigned long long)base[8 * k + i] << (8 * i);
+            }
+            h += plane_hash_mix(w ^ ((unsigned long long)(k + 1) * 0x9E3779B97F4A7C15ull));
+        }
+        for (int o = 16; o; o >>= 1)
+            h += __shfl_down_sync(0xffffffffu, h, o);
+        if ((threadIdx.x & 31) == 0 && h)
+            atomicAdd(out + pl, h);
+    }
+}
+
 /* largest cell value (chooses the number of bit planes) */
 __global__ void __launch_bounds__(256) max_u8_kernel(const uint8_t *a, size_t n, unsigned *out)
 {

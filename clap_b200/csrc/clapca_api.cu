@@ -103,11 +103,13 @@ cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cu
         return cudaErrorInvalidValue;
     return tab[rule](P, WPL, p, sms, stream, info);
 }
-int bp3_max_workers(int rule, int P, int WPL, int sms)
+int bp3_max_workers(int rule, int P, int WPL, int sms, int team, int max_ctas)
 {
     Bp3Params p;
     memset(&p, 0, sizeof(p));
     p.nsweeps = -1;                     /* query only: the launcher returns before launching */
+    p.team = team;
+    p.max_ctas = max_ctas;
     Bp3LaunchInfo info = { 0, 0, 0, 0 };
     if (bp3_launch(rule, P, WPL, p, sms, nullptr, &info) != cudaSuccess)
         return sms * 8;
@@ -313,6 +315,32 @@ static int count_on_stream(const uint8_t *cells, size_t n, cudaStream_t s, int64
     return CLAPCA_OK;
 }
 
+/*
+ * Fingerprint of every plane of a uint8 volume in device memory (see clapca.h): the planes of a sharded run are
+ * compared with those of a single-GPU run -- and with the oracle's -- without moving the cells.
+ */
+int clapca_hash_planes(const void *d_cells, size_t plane_bytes, size_t nplanes, uint64_t *hashes)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_cells || !hashes || plane_bytes == 0) return fail(CLAPCA_ERR_ARG, "hash_planes: bad arguments");
+    if (nplanes == 0) return CLAPCA_OK;
+    unsigned long long *d_h = nullptr;
+    CU(cudaMalloc(&d_h, nplanes * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_h, 0, nplanes * sizeof(unsigned long long), g_ctx.stream);
+    if (e == cudaSuccess) {
+        const size_t words = (plane_bytes + 7) / 8;
+        const unsigned bx = (unsigned)std::min<size_t>((words + 255) / 256, 64);
+        dim3 grid(bx, (unsigned)std::min<size_t>(nplanes, 65535));
+        plane_hash_kernel<<<grid, 256, 0, g_ctx.stream>>>((const uint8_t *)d_cells, plane_bytes, nplanes, d_h);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hashes, d_h, nplanes * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+    cudaFree(d_h);
+    if (e != cudaSuccess) return fail(CLAPCA_ERR_CUDA, "hash_planes: %s", cudaGetErrorString(e));
+    return CLAPCA_OK;
+}
+
 int clapca_grid_count(clapca_grid *g, int64_t *population)
 {
     if (!g || !population) return fail(CLAPCA_ERR_ARG, "grid_count: NULL argument");
@@ -381,10 +409,15 @@ cudaError_t clapca::api::launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t str
     return cudaGetLastError();
 }
 
-cudaError_t clapca::api::launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, int WPL, uint32_t tag,
-                                          cudaStream_t stream)
+cudaError_t clapca::api::launch_max_u8(const uint8_t *cells, size_t n, unsigned *d_max, cudaStream_t stream)
 {
-    halo_seed_kernel<<<grid_blocks_for((size_t)H * 2 * RWP, 256, 4), 256, 0, stream>>>(dst, src, H, RWP, NP, WPL, tag);
+    max_u8_kernel<<<grid_blocks_for((n + 15) / 16, 256), 256, 0, stream>>>(cells, n, d_max);
+    return cudaGetLastError();
+}
+
+cudaError_t clapca::api::launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, cudaStream_t stream)
+{
+    halo_seed_kernel<<<grid_blocks_for((size_t)H * 2 * RWP, 256, 4), 256, 0, stream>>>(dst, src, H, RWP, NP);
     return cudaGetLastError();
 }
 
@@ -393,10 +426,10 @@ static const int kFlagRows = 8;
 
 
 /*
- * Team mode (ca3d_bitplane.cuh): warps per CTA = planes per work item; 0 = one warp per sweep.  Default: teams
- * of 16 for the variants whose register budget allows 512-thread CTAs.  Measured on B200 at 2048^3, coral
- * (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms, and in the low-parallelism regime that
- * a rank of an 8-GPU run sees (6 generations' worth of sweeps per dependency level) 35.2 -> 16.4 ms.
+ * Tile mode (ca3d_bitplane.cuh): compute warps per CTA = planes x generations of a work item; 0 = one warp per sweep.
+ * Default: 16 compute warps (+ the service warp) for the variants whose register budget allows it.  Round 1 measured
+ * plane groups of 16 x 1 on B200 at 2048^3, coral (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms
+ * against one warp per sweep, and 35.2 -> 16.4 ms in the low-parallelism regime a rank of an 8-GPU run sees.
  */
 int clapca::api::team_config(int P, int WPL)
 {
@@ -406,24 +439,38 @@ int clapca::api::team_config(int P, int WPL)
     return std::min(t, bp3_team_cap(P, WPL));
 }
 
+/*
+ * Generations per tile.  4 x 4 tiles keep four generations of a row within ~20 row steps of each other: generation
+ * g+1 reads generation g from L2 and overwrites it there, HBM sees a quarter of the per-generation streaming of
+ * plane groups.  The planner lowers it when the launch has too few CTAs for the forward dependency (bp_plan.h).
+ */
+int clapca::api::tile_gens_config(int team)
+{
+    int tg = team >= 16 ? 4 : 1;
+    if (const char *e = getenv("CLAPCA_TILE_GENS")) { int v = atoi(e); if (v > 0) tg = v; }
+    return tg;
+}
+
 void clapca::api::sweep_knobs(Bp3Params &p, int team)
 {
     p.flag_rows = kFlagRows;
     if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
     if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
     if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
+    if (const char *e = getenv("CLAPCA_MAX_CTAS")) p.max_ctas = std::max(0, atoi(e));
     if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
     p.team = team;
-    if (const char *e = getenv("CLAPCA_EDGE_FLAG_ROWS")) p.edge_flag_rows = std::max(0, atoi(e));
 }
 
 static const int kGenBatch = 16;
 
 OrderCfg clapca::api::order_config(int Z, int H, int G, int max_workers, int team)
 {
-    OrderCfg oc = { 0, 0, kGenBatch, team };
+    OrderCfg oc = { 0, 0, kGenBatch, team, team, 1, 0 };
     if (team > 0) {
         oc.mode = 3;
+        oc.tile_g = tile_gens_config(team);     /* wanted; make_items() settles the shape for the plane list at hand */
+        oc.ctas = std::max(1, max_workers / team);
         return oc;
     }
     if (const char *e = getenv("CLAPCA_ORDER")) { int v = atoi(e); if (v >= 0 && v <= 2) oc.mode = v; }
@@ -440,7 +487,7 @@ OrderCfg clapca::api::order_config(int Z, int H, int G, int max_workers, int tea
 void clapca::api::make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                        std::vector<WorkItem> &items, bool layout_items)
 {
-    if (oc.mode == 3) bp3_make_items_team(planes, H, G, oc.team, items, layout_items);
+    if (oc.mode == 3) bp3_make_items_tile(planes, H, G, oc.tile_z, oc.tile_g, items, layout_items);
     else if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
     else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
     else bp3_make_items_timekey(planes, H, G, items, layout_items);
@@ -574,7 +621,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         {
             SlabGeom geo = { Z, 1, 0, Z };
             SlabPtrs ptr = { g->rows, prog, nullptr, nullptr, nullptr };
-            HaloLayout hl = slab_halo_layout(geo, H, RWP);
+            HaloLayout hl = slab_halo_layout(geo, H, RWP, NP, 1);
             bp3_build_planes(geo, ptr, hl, H, RWP, NP, planes);
         }
         if (g->planes_rows != g->rows || g->planes_prog != prog || g->planes_NP != NP || g->planes_RWP != RWP ||
@@ -597,11 +644,16 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
          * for smaller batches and for smaller volumes) -- the kernel is bound by the ALU pipe (LOP3), not by HBM.
          * CLAPCA_ORDER=1 selects the skewed row segments; CLAPCA_GEN_BATCH / CLAPCA_SEG_ROWS tune them.
          */
-        OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms), team);
+        Bp3Params knobs;
+        memset(&knobs, 0, sizeof(knobs));
+        sweep_knobs(knobs, team);
+        OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms, team, knobs.max_ctas), team);
         if (fused && oc.mode != 0 && oc.mode != 3) {
             if (io) oc.mode = 0;                    /* layout items exist for whole-plane orders only */
-            else return fail(CLAPCA_ERR_UNSUPPORTED, "CLAPCA_FUSED_LAYOUT needs the time-key or the team order");
+            else return fail(CLAPCA_ERR_UNSUPPORTED, "CLAPCA_FUSED_LAYOUT needs the time-key or the tile order");
         }
+        if (oc.mode == 3)
+            oc.tile_g = bp3_tile_shape(planes, H, G, team, oc.tile_g, oc.ctas, fused, &oc.tile_z);
         const int okey = oc.key() + (fused ? 50000000 : 0);
         if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != okey) {
             std::vector<WorkItem> items;

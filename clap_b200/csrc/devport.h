@@ -76,6 +76,19 @@ CA_DEV void dp_st_release(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 CA_DEV int dp_reduce_min(int v)                   { return __reduce_min_sync(CA_FULL, v); }
+/* counters written by ANOTHER GPU (peer stores over NVLink): acquire at system scope */
+CA_DEV int dp_ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+CA_DEV unsigned long long dp_shfl64(unsigned long long v, int src)
+{
+    const uint32_t lo = __shfl_sync(CA_FULL, (uint32_t)v, src), hi = __shfl_sync(CA_FULL, (uint32_t)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+CA_DEV int dp_ffs(uint32_t v)                     { return __ffs((int)v); }
 CA_DEV int dp_ld_flag_sys(const int *p)
 {
     int v;
@@ -204,6 +217,13 @@ CA_DEV int  dp_reduce_min(int v)
     }
     return v;
 }
+CA_DEV int  dp_ld_acquire_sys(const int *p)       { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CA_DEV unsigned long long dp_shfl64(unsigned long long v, int src)
+{
+    const uint32_t lo = emu_exchange((uint32_t)v, src), hi = emu_exchange((uint32_t)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+CA_DEV int  dp_ffs(uint32_t v)                    { return __builtin_ffs((int)v); }
 CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV void dp_fence_cta()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV int  dp_ld_volatile(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }

@@ -189,6 +189,13 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born_mask, uint32_t
                       uint32_t nr_states, int decay, int neigh, int steps, int engine);
 /* xyzarray_count(): core/xyarray.c:68-78 */
 int clapca_grid_count(clapca_grid *g, int64_t *population);
+/*
+ * 64-bit fingerprint of every plane of a uint8 volume in DEVICE memory (nplanes planes of plane_bytes bytes each;
+ * clapca_grid_device_ptr / clapca_slab_device_ptr): the sum over the plane's 8-byte little-endian words w_k of
+ * splitmix64(w_k ^ (k + 1) * 0x9E3779B97F4A7C15), mod 2^64.  Lets a sharded run be compared plane by plane with a
+ * single-GPU run (xyzarray contents, not just xyzarray_count()) without moving 8 GiB through the host.
+ */
+int clapca_hash_planes(const void *d_cells, size_t plane_bytes, size_t nplanes, uint64_t *hashes);
 /* the seeding loop of ca2d_generate() (core/ca2d.c:86-90) into a device-resident 2D grid; see clapca_ca2d_generate */
 int clapca_grid_seed2d(clapca_grid *g, int64_t side, uint32_t nr_states, uint64_t rand48_state,
                        uint64_t *rand48_state_after);
@@ -237,9 +244,12 @@ int clapca_grid_last_stats(clapca_grid *g, clapca_run_stats *st);
  * straight into the neighbour GPU's ghost plane over NVLink (CUDA IPC peer mapping) and raise its
  * progress counter; there is no separate halo kernel and no host round trip per generation.
  *
- * Call order on every rank: create -> ipc_handle -> (exchange handles) -> connect -> upload ->
- * prepare -> (barrier across ranks) -> run -> download.  `max_value` must be the largest cell value
- * over ALL ranks (it fixes the number of state planes), `max_generations` bounds `steps`.
+ * Call order on every rank: create -> ipc_handle -> (exchange handles) -> connect -> { upload ->
+ * prepare -> (barrier across ranks) -> run -> download } repeated.  The barrier after prepare is the only one:
+ * the ghost-plane counters alternate between two banks, so a rank may upload / prepare run k+1 while a slower
+ * neighbour is still finishing run k.  `max_value` must be the largest cell value over ALL ranks (it fixes the
+ * number of state planes; prepare verifies the uploaded cells against it and fails with CLAPCA_ERR_ARG),
+ * `max_generations` bounds `steps`.  Every rank must call prepare the same number of times.
  */
 typedef struct clapca_slab clapca_slab;
 
@@ -254,6 +264,13 @@ void *clapca_slab_device_ptr(clapca_slab *s);
 /* 64-byte CUDA IPC handle of this rank's halo region; connect() maps the two neighbours' regions */
 int clapca_slab_ipc_handle(clapca_slab *s, void *handle64);
 int clapca_slab_connect(clapca_slab *s, const void *handle_next_rank, const void *handle_prev_rank);
+/*
+ * Several slabs of ONE process on one device (tests, single-GPU boxes): instead of IPC handles the slabs exchange
+ * their halo pointers directly.  The sweep launches of all ranks must be co-resident, so each keeps to
+ * `max_ctas` CTAs (0 = no limit); every rank runs prepare / run on its own thread -- a slab owns its stream.
+ */
+void *clapca_slab_halo_ptr(clapca_slab *s);
+int clapca_slab_connect_local(clapca_slab *s, void *halo_next_rank, void *halo_prev_rank, int max_ctas);
 /* local planes from/to host or device memory, local order */
 int clapca_slab_upload(clapca_slab *s, const uint8_t *src);
 int clapca_slab_download(clapca_slab *s, uint8_t *dst);

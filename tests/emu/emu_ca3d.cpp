@@ -4,7 +4,11 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [edgeflagrows [layout [chunk [ghostdefer]]]]]]]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [tilegens [layout [chunk]]]]]]]]]]]
+ *   team     > 0: tile mode, compute warps per CTA (every CTA gets one more warp, the service warp); `warps` / team
+ *            CTAs are launched per rank.  tilegens = wanted generations per tile (the planner lowers it when the
+ *            launch has too few CTAs for the forward dependency).  Several ranks need tile mode: the service warp
+ *            carries the halo rows.
  *   layout   1 = layout items (pack / unpack run as work items of the sweep launch, cells resident),
  *            2 = layout items fed by a "copy engine" thread that delivers the cells chunk by chunk and raises
  *                in_ready, while a second thread drains finished chunks as their planes' out_done words show the epoch
@@ -21,7 +25,6 @@
 #include <chrono>
 #include <algorithm>
 #include "emu_runtime.h"
-#define CLAPCA_EDGE_DEFER 1
 #include "../../clap_b200/csrc/ca3d_bitplane.cuh"
 #include "../../clap_b200/csrc/ca3d_layout.cuh"
 #include "../../clap_b200/csrc/bp_plan.h"
@@ -49,9 +52,9 @@ template <int P, int WPL, class Rule>
 static void launch_sweep(const Bp3Params &p, int warps)
 {
     if (p.team > 0) {
-        /* team mode: CTAs of `team` warps, each CTA sweeps a group of consecutive planes */
+        /* tile mode: CTAs of `team` compute warps + the service warp, each CTA sweeps a tile of planes x generations */
         const int blocks = (warps + p.team - 1) / p.team;
-        emu_launch(blocks, p.team * 32, [&]() { Sweep3<P, WPL, Rule>::team_loop(p); });
+        emu_launch(blocks, (p.team + 1) * 32, [&]() { Sweep3<P, WPL, Rule>::tile_loop(p); });
         return;
     }
     if (p.pub_workers > 0) {
@@ -117,10 +120,13 @@ int main(int argc, char **argv)
     int genBatch = argc > 15 ? atoi(argv[15]) : 0;   /* > 0: generation-batched diagonal order, -1: time-key order */
     int pubWorkers = argc > 16 ? atoi(argv[16]) : 0; /* > 0: publisher mode, worker warps per CTA */
     int team = argc > 17 ? atoi(argv[17]) : 0;       /* > 0: team mode, warps (= planes of a group) per CTA */
-    int edgeFlagRows = argc > 18 ? atoi(argv[18]) : 0;
+    int tileGens = argc > 18 ? atoi(argv[18]) : 1;   /* tile mode: wanted generations per tile */
     int layout = argc > 19 ? atoi(argv[19]) : 0;
     int chunk = argc > 20 ? atoi(argv[20]) : 2;
-    int ghostDefer = argc > 21 ? atoi(argv[21]) : 0;    /* != 0: multi-rank runs use the deferred-tag-check row loop */
+    if (ranks > 1 && team <= 0) {
+        fprintf(stderr, "several ranks need tile mode (team > 0)\n");
+        return 2;
+    }
     if (layout && (ranks != 1 || (team <= 0 && genBatch >= 0))) {
         fprintf(stderr, "layout items: single rank, time-key (genbatch -1) or team order\n");
         return 2;
@@ -187,7 +193,7 @@ int main(int argc, char **argv)
     for (int r = 0; r < ranks; r++) {
         Rank &k = rk[r];
         k.geo = SlabGeom{ Z, ranks, r, blockB > 0 ? blockB : (Z + ranks - 1) / ranks };
-        k.hl = slab_halo_layout(k.geo, H, RWP);
+        k.hl = slab_halo_layout(k.geo, H, RWP, NP, Gcap);
         const int Zl = k.geo.local_planes();
         k.cells.resize((size_t)W * H * (Zl ? Zl : 1));
         for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
@@ -206,8 +212,14 @@ int main(int argc, char **argv)
                          rk[(r + ranks - 1) % ranks].halo.data() };
         bp3_build_planes(k.geo, ptr, k.hl, H, RWP, NP, k.planes);
         std::vector<WorkItem> items;
-        if (team > 0)
-            bp3_make_items_team(k.planes, H, G, team, items, layout != 0);
+        if (team > 0) {
+            const int ctas = (warps + team - 1) / team;
+            int Tz = team, Tg = 1;
+            if (ranks > 1) Tg = bp3_tile_shape_all_ranks(k.geo, H, G, team, tileGens, ctas, &Tz);
+            else Tg = bp3_tile_shape(k.planes, H, G, team, tileGens, ctas, layout != 0, &Tz);
+            if (r == 0) fprintf(stderr, "tile shape %d planes x %d generations\n", Tz, Tg);
+            bp3_make_items_tile(k.planes, H, G, Tz, Tg, items, layout != 0);
+        }
         else if (genBatch > 0)
             bp3_make_items_batched(k.planes, Z, H, G, genBatch, items);
         else if (genBatch < 0)
@@ -230,13 +242,10 @@ int main(int argc, char **argv)
         k.p.flag_rows = flagRows;
         k.p.pub_workers = pubWorkers;
         k.p.team = team;
-        k.p.edge_flag_rows = edgeFlagRows;
         k.p.ticket = &k.ticket;
         k.p.err = &err;
         k.p.surv = surv; k.p.born = born; k.p.bornval = bornval;
         k.p.spin_limit = 20LL * 1000 * 1000 * 1000;      /* 20 s of emulator wall clock */
-        for (const Bp3Plane &pl : k.planes)
-            if (pl.ghost_mask || pl.push_dn_rows || pl.push_up_rows) k.p.edge_loop = ghostDefer ? 2 : 1;
         if (layout) {
             k.out_done.assign(Zl + 1, 0);
             k.p.layout_items = 1;
@@ -249,15 +258,13 @@ int main(int argc, char **argv)
         }
     }
     /* halo init: the first plane of every block but the first seeds the ghost plane above the previous block */
-    const uint32_t epoch = 7;
     for (int r = 0; r < ranks; r++) {
-        rk[r].p.epoch = epoch;
         for (size_t l = 0; l < rk[r].planes.size(); l++) {
             const Bp3Plane &pl = rk[r].planes[l];
             if (!pl.push_dn_rows) continue;
             const uint32_t *src = rk[r].rows.data() + (size_t)l * H * NP * RWP;
             uint32_t *dst = pl.push_dn_rows;
-            emu_launch(1, 64, [&]() { halo_seed_kernel(dst, src, H, RWP, NP, WPL, epoch << 16); });
+            emu_launch(1, 64, [&]() { halo_seed_kernel(dst, src, H, RWP, NP); });
         }
     }
     std::vector<uint8_t> host_in, host_out;

@@ -67,16 +67,18 @@ def test_ca3d_row_segments(emu_bin, args):
 
 
 @pytest.mark.parametrize("args", [
-    (45, 7, 12, 4, 7, 3, 1, 1, 3, 3, 2, 0, 0, 2),        # 2 emulated GPUs, contiguous slabs
-    (45, 37, 12, 6, 7, 3, 1, 1, 3, 5, 2, 2, 5, 2),       # 2 GPUs, z-blocks of 2 planes, segments of 5 rows
-    (45, 50, 13, 5, 3, 3, 1, 1, 3, 3, 3, 2, 16, 4),      # 3 GPUs, ragged last block
-    (33, 30, 16, 5, 10, 8, 1, 1, 4, 2, 4, 1, 7, 2),      # 4 GPUs, single-plane blocks (every plane is an edge)
-    (33, 64, 9, 6, 0, 3, 1, 0, 4, 2, 4, 5, 32, 2),       # more ranks than blocks need
-    (20, 5, 3, 4, 7, 3, 1, 1, 4, 2, 4, 1, 1, 1),         # ranks without any plane
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team tilegens
+    (45, 7, 12, 4, 7, 3, 1, 1, 3, 3, 2, 0, 0, 2, 0, 0, 1, 1),        # 2 emulated GPUs, contiguous slabs, one plane per CTA
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 6, 2, 2, 0, 2, 0, 0, 2, 1),       # 2 GPUs, z-blocks of 2 planes
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 9, 3, 2, 0, 4, 0, 0, 3, 1),       # 3 GPUs, ragged last block
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 4, 4, 1, 0, 2, 0, 0, 2, 1),      # 4 GPUs, single-plane blocks (every plane is an edge)
+    (33, 64, 9, 6, 0, 3, 1, 0, 4, 8, 4, 5, 0, 2, 0, 0, 4, 1),        # more ranks than blocks need
+    (20, 5, 3, 4, 7, 3, 1, 1, 4, 4, 4, 1, 0, 1, 0, 0, 2, 1),         # ranks without any plane
 ])
 def test_ca3d_slab_decomposition_peer_ghost_planes(emu_bin, args):
-    """The multi-GPU path: ranks run concurrently, edge planes push their H rows into the neighbour's ghost
-    planes and raise its counters, exactly as the peer stores over NVLink do on the real machine."""
+    """The multi-GPU path: ranks run concurrently, the service warp of every tile that touches a z-block edge
+    copies finished H rows into the neighbour's ghost plane and raises its counters, exactly as the peer stores
+    over NVLink do on the real machine."""
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
@@ -85,8 +87,7 @@ def test_ca3d_slab_decomposition_peer_ghost_planes(emu_bin, args):
     (45, 20, 12, 7, 7, 3, 1, 1, 3, 5, 1, 0, 0, 2, 3),        # batches of 3,2,2 generations, diagonal order
     (45, 20, 12, 7, 7, 3, 1, 1, 3, 1, 1, 0, 0, 4, 2),        # a single worker: the order alone must be executable
     (64, 16, 9, 10, 10, 4, 2, 1, 9, 9, 1, 0, 0, 3, 4),
-    (33, 24, 10, 9, 0, 3, 1, 0, 4, 4, 3, 2, 0, 2, 4),        # 3 ranks, z-blocks of 2 planes
-    (33, 24, 10, 6, 8, 3, 1, 2, 4, 3, 2, 0, 0, 2, 50),       # batch larger than G == plain diagonal order
+    (33, 24, 10, 6, 8, 3, 1, 2, 4, 3, 1, 0, 0, 2, 50),       # batch larger than G == plain diagonal order
     (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1),       # time-key order
 ])
 def test_ca3d_generation_batched_diagonal_order(emu_bin, args):
@@ -100,10 +101,6 @@ def test_ca3d_generation_batched_diagonal_order(emu_bin, args):
     (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 1, -1, 1),       # one worker and its publisher
     (64, 33, 6, 9, 10, 4, 2, 1, 9, 7, 1, 0, 4, 5, 0, 3),         # row segments: mailbox handed over mid-sweep
     (45, 20, 12, 7, 7, 3, 1, 1, 3, 5, 1, 0, 0, 2, 3, 5),         # generation-batched diagonals
-    (45, 37, 12, 6, 7, 3, 1, 1, 3, 5, 2, 2, 5, 2, 0, 3),         # 2 ranks, ghost rows + publisher
-    (45, 50, 13, 5, 3, 3, 1, 1, 3, 3, 3, 2, 16, 1, 0, 2),        # 3 ranks, ragged last block
-    (33, 30, 16, 5, 10, 8, 1, 1, 4, 2, 4, 1, 7, 1, 0, 1),        # 4 ranks, every plane is an edge
-    (20, 5, 3, 4, 7, 3, 1, 1, 4, 2, 4, 1, 1, 1, 0, 2),           # ranks without any plane
 ])
 def test_ca3d_publisher_warps(emu_bin, args):
     """Publisher mode: workers bump a shared-memory mailbox after every row, one extra warp per CTA does the
@@ -112,10 +109,10 @@ def test_ca3d_publisher_warps(emu_bin, args):
 
 
 @pytest.mark.parametrize("args", [
-    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team tilegens
     (45, 20, 12, 5, 7, 3, 1, 1, 3, 8, 1, 0, 0, 2, 0, 0, 4),              # 2 CTAs of 4 warps, groups of 4 planes
-    (45, 20, 12, 5, 7, 3, 1, 1, 3, 3, 1, 0, 0, 8, 0, 0, 3, 2),           # a single CTA: the claim order alone
-    (64, 33, 7, 9, 10, 4, 2, 1, 9, 12, 1, 0, 0, 4, 0, 0, 5, 1),          # ragged last group, edge plane raised every row
+    (45, 20, 12, 5, 7, 3, 1, 1, 3, 3, 1, 0, 0, 8, 0, 0, 3, 1),           # a single CTA: the claim order alone
+    (64, 33, 7, 9, 10, 4, 2, 1, 9, 12, 1, 0, 0, 4, 0, 0, 5, 1),          # ragged last group
     (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 3, 0, 0, 1),             # teams of one warp
     (45, 20, 12, 5, 7, 3, 1, 1, 3, 24, 1, 0, 0, 8, 0, 0, 24),            # team larger than the volume
     (45, 37, 12, 6, 7, 3, 1, 1, 3, 6, 2, 2, 0, 2, 0, 0, 3),              # 2 ranks, z-blocks of 2 planes < team
@@ -125,13 +122,35 @@ def test_ca3d_publisher_warps(emu_bin, args):
     (33, 5, 9, 4, 8, 8, 1, 2, 3, 6, 2, 4, 0, 2, 0, 0, 3),                # ca3d_make seed (255s), 2 ranks
 ])
 def test_ca3d_plane_teams(emu_bin, args):
-    """Team mode: a CTA sweeps a group of consecutive planes, warp w follows warp w-1 through a shared-memory
-    row counter raised after every row; only group edges use gpu-scope counters / ghost tags."""
+    """Tile mode with one generation per tile (plane groups): a CTA sweeps a group of consecutive planes, warp w
+    follows warp w-1 through a shared-memory row counter raised after every row; the service warp publishes the
+    gpu-scope counters and pushes the z-block edges' rows to the neighbouring ranks."""
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
 @pytest.mark.parametrize("args", [
-    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows layout chunk
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team tilegens
+    (45, 20, 12, 8, 7, 3, 1, 1, 3, 40, 1, 0, 0, 2, 0, 0, 4, 2),          # 10 CTAs, tiles of 2 planes x 2 generations
+    (45, 20, 12, 9, 7, 3, 1, 1, 3, 256, 1, 0, 0, 2, 0, 0, 16, 4),        # 4 x 4 tiles, ragged last generation group
+    (45, 20, 13, 7, 10, 4, 1, 1, 3, 128, 1, 0, 0, 2, 0, 0, 8, 2),        # 4 planes x 2 generations, ragged last plane group
+    (64, 33, 7, 9, 10, 4, 2, 1, 9, 96, 1, 0, 0, 4, 0, 0, 6, 3),          # 2 x 3 is refused (Tg <= Tz): falls to 3 x 2
+    (45, 20, 12, 8, 7, 3, 1, 1, 3, 8, 1, 0, 0, 2, 0, 0, 4, 2),           # too few CTAs for the forward dependency: 4 x 1
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 48, 2, 2, 0, 2, 0, 0, 4, 2),          # 2 ranks, blocks of 2 planes: every tile has two edges
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 64, 3, 5, 0, 4, 0, 0, 4, 2),          # 3 ranks, blocks of 5 = tiles of 2 + 2 + 1 planes
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 64, 4, 1, 0, 2, 0, 0, 4, 2),         # 4 ranks, single-plane blocks: 1-plane tiles, 2 generations each
+    (33, 30, 16, 9, 7, 3, 1, 1, 4, 256, 4, 4, 0, 2, 0, 0, 16, 4),        # 4 ranks, 4 x 4 tiles = one z-block each
+    (33, 5, 9, 6, 8, 8, 1, 2, 3, 60, 2, 4, 0, 2, 0, 0, 4, 2),            # ca3d_make seed (255s), 2 ranks
+    (2048, 6, 8, 4, 7, 3, 2, 0, 9, 64, 2, 4, 0, 2, 0, 0, 16, 4),         # BASELINE config-4 row width, 2 ranks
+])
+def test_ca3d_tiles_of_planes_and_generations(emu_bin, args):
+    """Tile mode proper: a CTA sweeps nz planes x ng generations; generation g+1 of a plane follows generation g a
+    few rows behind through shared-memory counters, and tiles depend on their NEXT neighbour in z (co-residency,
+    bp_plan.h).  Multi-rank cases push several generations of an edge plane through one ghost plane in place."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team tilegens layout chunk
     (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1, 0, 0, 0, 1, 2),        # time-key order, cells resident
     (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 1, 0, 0, 8, -1, 0, 0, 0, 2, 3),        # ... fed / drained chunk by chunk
     (24, 12, 10, 9, 10, 3, 1, 1, 5, 1, 1, 0, 0, 3, -1, 0, 0, 0, 2, 16),      # one worker: the claim order alone
@@ -143,25 +162,13 @@ def test_ca3d_plane_teams(emu_bin, args):
     (1030, 2, 3, 2, 0, 3, 2, 1, 8, 3, 1, 0, 0, 2, -1, 0, 0, 0, 2, 1),        # ragged row end inside a word
     (96, 4, 5, 5, 7, 3, 4, 1, 7, 4, 1, 0, 0, 2, 0, 0, 3, 0, 2, 2),           # 4 words per lane
     (1, 1, 1, 3, 7, 3, 1, 1, 5, 2, 1, 0, 0, 2, -1, 0, 0, 0, 2, 1),
+    (45, 20, 13, 6, 7, 3, 1, 1, 3, 80, 1, 0, 0, 2, 0, 0, 4, 2, 2, 4),        # 2 x 2 tiles with pack / unpack groups around them
+    (45, 20, 12, 9, 7, 3, 1, 1, 3, 320, 1, 0, 0, 2, 0, 0, 16, 4, 1, 2),      # 4 x 4 tiles, cells resident
 ])
 def test_ca3d_layout_items_streamed(emu_bin, args):
     """Layout items: pack ("generation -1") and unpack ("generation G") run as work items of the sweep launch; a
     feeder thread plays the H2D copy stream (cells arrive chunk by chunk, then the in_ready word moves) and a
     drainer thread plays the host side of the D2H (copies a chunk out once its planes carry the epoch)."""
-    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
-
-
-@pytest.mark.parametrize("args", [
-    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team edgeflagrows layout chunk ghostdefer
-    (45, 37, 12, 6, 7, 3, 1, 1, 3, 6, 2, 2, 0, 2, 0, 0, 3, 0, 0, 2, 1),          # 2 ranks, z-blocks of 2 planes < team
-    (45, 50, 13, 5, 3, 3, 1, 1, 3, 8, 3, 5, 0, 4, 0, 0, 4, 1, 0, 2, 1),          # 3 ranks, blocks of 5 = groups of 4 + 1
-    (33, 30, 16, 5, 10, 8, 1, 1, 4, 4, 4, 1, 0, 2, 0, 0, 2, 0, 0, 2, 1),         # 4 ranks, every plane is an edge
-    (64, 37, 12, 6, 7, 3, 2, 1, 9, 5, 2, 2, 5, 2, 0, 0, 0, 0, 0, 2, 1),          # one warp per sweep, row segments, 2 words per lane
-    (45, 20, 12, 5, 7, 3, 1, 1, 3, 4, 2, 0, 0, 1, -1, 2, 0, 0, 0, 2, 1),         # publisher warps, time-key order
-])
-def test_ca3d_deferred_ghost_tag_check_loop(emu_bin, args):
-    """The opt-in third instantiation of the row loop (-DCLAPCA_EDGE_DEFER=1, edge_loop == 2): ghost rows are
-    fetched one row step before their tags are looked at, a stale row is re-read by the out-of-line cold path."""
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
