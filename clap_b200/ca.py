@@ -110,6 +110,16 @@ def ca2d_generate(ca, side, steps, rng, engine=ENGINE_AUTO):
     return arr
 
 
+def hash_planes(device_ptr, plane_bytes, nplanes):
+    """clapca_hash_planes(): one 64-bit fingerprint per plane of a uint8 volume in device memory (numpy uint64)."""
+    lib = _lib.lib()
+    out = np.zeros(max(1, int(nplanes)), np.uint64)
+    if nplanes:
+        check(lib, lib.clapca_hash_planes(c_void_p(int(device_ptr)), int(plane_bytes), int(nplanes),
+                                          out.ctypes.data_as(c_void_p)))
+    return out[:int(nplanes)]
+
+
 class Grid:
     """A uint8 grid resident in device memory (clapca_grid_*): upload once, run many times."""
 

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) count_nonzero_kernel(const uint8_t *a, si
 /*
  * Plane fingerprint: h = sum over the plane's 8-byte little-endian words w_k (zero-padded tail) of
  * splitmix64(w_k ^ (k + 1) * 0x9E3779B97F4A7C15) mod 2^64.  Order-independent, so it reduces in parallel; the
- * position enters every term, so permuted or shifted cells change it.  tests/oracle_lib.py holds the numpy twin.
+ * position enters every term, so permuted or shifted cells change it.  clap_b200/synth.py holds the numpy twin.
  */
 __device__ __forceinline__ unsigned long long plane_hash_mix(unsigned long long x)
 {

@@ -29,6 +29,96 @@ def test_single_rank_slab_equals_oracle(gpu, oracle):
     assert np.array_equal(got, want)
 
 
+# ---- the sharded path on ONE device: several ranks of one process, each launch on its share of the SMs ------------
+# (ghost planes, peer pushes by the tiles' service warps, banked counters -- everything but the NVLink hop itself)
+
+@pytest.mark.parametrize("case", [
+    # d0   d1   d2  gens rule ranks block
+    (70, 24, 20, 6, 7, 2, 2),           # z-blocks smaller than a tile: every tile has two edges
+    (70, 24, 20, 6, 7, 2, 10),          # contiguous slabs
+    (256, 64, 48, 8, 0, 4, 4),          # 4 ranks, one tile row per block
+    (256, 64, 50, 9, 7, 3, 16),         # ragged last block, ragged last generation group
+    (2048, 96, 64, 8, 7, 4, 16),        # BASELINE config-4 row width, the bench's block size
+    (1000, 40, 33, 5, 2, 2, 4),         # 4 state planes (pyroclastic), ragged rows
+    (300, 30, 12, 4, 7, 4, 1),          # single-plane blocks: every plane is an edge on both sides
+])
+def test_local_ranks_equal_single_gpu_and_oracle(gpu, oracle, case):
+    from clap_b200.slab import LocalRanks
+    d0, d1, d2, gens, rule, ranks, block = case
+    rng = np.random.default_rng(d0 * 7 + d2)
+    full = (rng.integers(1, 6, (d2, d1, d0)) * (rng.random((d2, d1, d0)) < 0.3)).astype(np.uint8)
+    want = full.copy()
+    wpop = gpu.ca3d_run(want, rule, gens)
+    if full.size <= 1 << 22:
+        chk = full.copy()
+        s, b, n = oracle.ca3d_rule(rule)
+        assert oracle.ca3d_run(chk, s, b, n, gens) == wpop and np.array_equal(chk, want)
+    lr = LocalRanks(d0, d1, d2, ranks, gens, int(full.max()), block)
+    try:
+        for rep in range(3):                # odd and even runs use the two banks of ghost counters
+            lr.upload(full)
+            assert lr.run(rule, gens) == wpop, f"rep {rep}: population"
+            got = lr.download()
+            assert np.array_equal(got, want), f"rep {rep}: {int((got != want).sum())} cells differ"
+        from clap_b200 import synth
+        assert np.array_equal(lr.plane_hashes(), synth.plane_hashes_numpy(np, want))
+    finally:
+        lr.close()
+
+
+def test_local_ranks_ca3d_make_volume_with_255s(gpu, oracle):
+    """the reference's own seed (ca3d_make leaves 255s) through the sharded path: 8 state planes"""
+    from clap_b200.slab import LocalRanks
+    full = oracle.ca3d_make(48, 24, 20, 42)
+    assert full.max() == 255
+    want = full.copy()
+    s, b, n = oracle.ca3d_rule(7)
+    wpop = oracle.ca3d_run(want, s, b, n, 6)
+    lr = LocalRanks(48, 24, 20, 2, 6, 255, 4)
+    try:
+        lr.upload(full)
+        assert lr.run(7, 6) == wpop
+        assert np.array_equal(lr.download(), want)
+    finally:
+        lr.close()
+
+
+def test_slab_prepare_rejects_cells_above_max_value(gpu):
+    """the slab path must verify the caller's max_value (the pack kernel would drop the upper bits)"""
+    from clap_b200 import ClapcaError
+    from clap_b200.slab import ShardedVolume
+    vol = np.zeros((4, 8, 40), np.uint8)
+    vol[1, 2, 3] = 9
+    sv = ShardedVolume(40, 8, 4, 0, 1, 3, 5)
+    try:
+        sv.upload(vol)
+        with pytest.raises(ClapcaError):
+            sv.prepare(7, 3)
+    finally:
+        sv.close()
+
+
+@pytest.mark.slow
+def test_local_ranks_on_a_slab_of_the_benched_volume(gpu):
+    """2048 x 2048 rows of the benched seed volume (clap_b200/synth.py), 64 planes, 4 ranks in blocks of 16 planes
+    against the single-GPU run: the configuration SCALE runs, at a depth one device holds four times over."""
+    import torch
+    from clap_b200 import synth
+    from clap_b200.slab import LocalRanks
+    d0 = d1 = 2048
+    d2, gens = 64, 10
+    full = synth.synth_torch(torch, d0, d1, 0, d2, "cuda:0").cpu().numpy()
+    want = full.copy()
+    wpop = gpu.ca3d_run(want, 7, gens)
+    lr = LocalRanks(d0, d1, d2, 4, gens, 5, 16)
+    try:
+        lr.upload(full)
+        assert lr.run(7, gens) == wpop
+        assert np.array_equal(lr.plane_hashes(), synth.plane_hashes_numpy(np, want))
+    finally:
+        lr.close()
+
+
 def _ngpus():
     import torch
     return torch.cuda.device_count()

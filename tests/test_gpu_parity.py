@@ -226,11 +226,13 @@ def test_ca3d_engines_agree_256cube(gpu):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("team", [1, 3, 16])
-def test_ca3d_team_mode_vs_oracle(gpu, oracle, monkeypatch, team):
-    """Team mode (CLAPCA_TEAM: one CTA sweeps a group of consecutive planes, warps follow each other through
-    shared-memory row counters) against the oracle on ragged shapes, 255-valued cells and every plane count."""
+@pytest.mark.parametrize("team,tile_gens", [(1, 1), (3, 1), (16, 1), (16, 2), (16, 4), (6, 2), (4, 2)])
+def test_ca3d_tile_mode_vs_oracle(gpu, oracle, monkeypatch, team, tile_gens):
+    """Tile mode (CLAPCA_TEAM compute warps per CTA, CLAPCA_TILE_GENS generations per tile: one CTA sweeps nz planes
+    x ng generations, warps follow each other through shared-memory row counters, the service warp publishes the
+    gpu-scope counters) against the oracle on ragged shapes, 255-valued cells and every plane count."""
     monkeypatch.setenv("CLAPCA_TEAM", str(team))
+    monkeypatch.setenv("CLAPCA_TILE_GENS", str(tile_gens))
     rng = np.random.default_rng(400 + team)
     for shape, nca in (((1, 1, 1), 7), ((33, 6, 5), 0), ((100, 17, 11), 3), ((130, 9, 40), 7), ((70, 40, 37), 6),
                        ((1500, 24, 9), 7), ((2048, 30, 20), 8), ((4096, 12, 5), 7), ((64, 20, 35), 2)):
@@ -251,10 +253,15 @@ def test_ca3d_team_mode_agrees_with_sweep_mode_512(gpu, monkeypatch):
     monkeypatch.setenv("CLAPCA_TEAM", "0")
     pa = gpu.ca3d_run(a, 7, 12, engine=BITPLANE)
     monkeypatch.setenv("CLAPCA_TEAM", "16")
-    monkeypatch.setenv("CLAPCA_EDGE_FLAG_ROWS", "2")
+    monkeypatch.setenv("CLAPCA_TILE_GENS", "1")
     pb = gpu.ca3d_run(b, 7, 12, engine=BITPLANE)
     assert pa == pb == int(np.count_nonzero(a))
     assert np.array_equal(a, b)
+    for tg in ("2", "4"):                  # 8 x 2 and 4 x 4 tiles: generations of a row a few rows apart
+        c = vol.copy()
+        monkeypatch.setenv("CLAPCA_TILE_GENS", tg)
+        assert gpu.ca3d_run(c, 7, 12, engine=BITPLANE) == pa
+        assert np.array_equal(a, c), tg
 
 
 def test_ca3d_generations_compose_large(gpu):

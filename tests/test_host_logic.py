@@ -72,10 +72,10 @@ def test_python_rand48_block_matches_scalar_stream():
 def test_default_block_planes(d2, nranks):
     b = default_block_planes(d2, nranks)
     per_rank = -(-d2 // nranks)
-    assert 1 <= b <= max(1, per_rank) and b <= 128
+    assert 1 <= b <= max(1, per_rank) and b <= 16
     blocks = plan_blocks(d2, nranks, b)
     assert sum(z1 - z0 for _, z0, z1 in blocks) == d2
     if d2 >= nranks:                                   # nobody is left without planes
         assert all(local_planes(d2, nranks, b, r) for r in range(nranks))
-    if per_rank >= 64 and nranks > 1:                  # at least two blocks per rank keep the pipeline fill short
+    if per_rank >= 8 and nranks > 1:                   # at least two blocks per rank keep the pipeline fill short
         assert min(sum(1 for r, _, _ in blocks if r == k) for k in range(nranks)) >= 2

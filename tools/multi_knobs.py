@@ -60,9 +60,17 @@ def main():
             best_k, best_t = min(best_k, float(t[0])), min(best_t, float(t[1]))
         tp = torch.tensor([pop], dtype=torch.int64, device=dev)
         dist.all_reduce(tp)
+        # the cells, not just their count: per-plane fingerprints against the committed single-GPU run's
+        import numpy as np
+        hz = torch.zeros(side, dtype=torch.int64, device=dev)
+        if vol.n_local:
+            hz[torch.tensor(vol.zglobal, device=dev)] = torch.from_numpy(vol.plane_hashes().view(np.int64)).to(dev)
+        dist.all_reduce(hz)
         if rank == 0:
+            ev = bench.parity_evidence("ca3d_%d" % side, hz.cpu().numpy().view(np.uint64)) if gens == 50 and "ca3d_%d" % side in bench.WORKLOADS else {}
             print(f"N={world} side {side} gens {gens} block {block} {' '.join(parts[1:])}: sweep {best_k:8.3f} ms  step {best_t:8.3f} ms  "
-                  f"{side ** 3 * gens / (best_t * 1e-3) / 1e9:7.1f} GCUPS  pop {int(tp[0])}", flush=True)
+                  f"{side ** 3 * gens / (best_t * 1e-3) / 1e9:7.1f} GCUPS  pop {int(tp[0])}  bit_equal_to_n1 {ev.get('bit_equal_to_n1')} "
+                  f"reference_planes {ev.get('equal_to_unmodified_reference')}", flush=True)
         vol.close()
         del seed
         torch.cuda.empty_cache()
