@@ -221,9 +221,8 @@ size_t clapca_device_mem_bytes(void) { return g_ctx.mem; }
 
 int clapca_ca3d_rule(int nca, uint32_t *surv, uint32_t *born, uint32_t *nr_states)
 {
-    int i = nca % 9;            /* core/ca3d.c:126 */
-    if (i < 0)
-        return fail(CLAPCA_ERR_ARG, "negative rule index %d", nca);
+    /* core/ca3d.c:126 computes nca % array_size(cas) in size_t: a negative index wraps through 2^64 (-1 -> rule 6) */
+    const int i = (int)((size_t)(long)nca % 9u);
     if (surv) *surv = kCas[i][0];
     if (born) *born = kCas[i][1];
     if (nr_states) *nr_states = kCas[i][2];
@@ -887,31 +886,33 @@ int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3], uint32_t surv, uint32_t 
 /* ---- ca2d ------------------------------------------------------------------- */
 
 /* rows are cut into at most 16 warps x 32 lanes x 4 words: 65536 cells (32768 with 8 state planes) */
-static bool bp2_supported(const clapca_grid *g, int64_t side, int decay, int neigh)
+static bool bp2_supported(const clapca_grid *g, int64_t side, int decay, int neigh, int P)
 {
     if (side < g->d0 || side < g->d1)
         return false;                       /* partial sweeps: cell-wavefront engine */
     if ((neigh == CLAPCA_NEIGH_VNV || neigh == CLAPCA_NEIGH_MV) && decay)
         return false;                       /* value-comparing counts that matter: cell-wavefront engine */
     int wpl, warps;
-    return g->d0 < (1 << 30) && bp2_shape_for(g->d1, 3, &wpl, &warps);
+    return g->d0 < (1 << 30) && bp2_shape_for(g->d1, P, &wpl, &warps);
+}
+
+/* largest cell value of the grid (device reduction) */
+static int grid_max_value(clapca_grid *g, unsigned *maxv)
+{
+    CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+    CU(launch_max_u8(g->cells, g->n, g_ctx.d_max, g->stream));
+    CU(cudaMemcpyAsync(maxv, g_ctx.d_max, sizeof(*maxv), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return CLAPCA_OK;
 }
 
 static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh,
-                          int steps)
+                          int steps, int P)
 {
     const int W = (int)g->d0, H = (int)g->d1;       /* x extent = engine rows, y extent = cells per row */
     const uint32_t nrval = nr_states & 0xffu;
     const bool moore = (neigh == CLAPCA_NEIGH_M1 || neigh == CLAPCA_NEIGH_MV);
 
-    unsigned maxv = 0;
-    CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
-    max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&maxv, g_ctx.d_max, sizeof(maxv), cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
-    if (born && nrval > maxv) maxv = nrval;
-    const int P = bp2_planes_for(maxv);
     int WPL = 0, warps = 0;
     if (!bp2_shape_for(H, P, &WPL, &warps))
         return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: rows of %d cells with %d state planes are too wide", H, P);
@@ -1005,14 +1006,26 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv
     memset(&g->stats, 0, sizeof(g->stats));
     if (steps == 0 || side <= 0)
         return CLAPCA_OK;
-    const bool bp_ok = bp2_supported(g, side, decay, neigh);
+    /*
+     * The number of state planes -- and with it the widest row the bit-plane engine takes (32768 cells with 8 planes,
+     * 65536 below) -- depends on the largest value that can occur: scan the data BEFORE choosing the engine, so that
+     * AUTO falls back to the cell-wavefront engine instead of failing (the reference handles any size).
+     */
+    int P = 3;
+    if (engine != CLAPCA_ENGINE_WAVEFRONT) {
+        unsigned maxv = 0;
+        if (int rc = grid_max_value(g, &maxv)) return rc;
+        if (born && (nr_states & 0xffu) > maxv) maxv = nr_states & 0xffu;
+        P = bp2_planes_for(maxv);
+    }
+    const bool bp_ok = engine != CLAPCA_ENGINE_WAVEFRONT && bp2_supported(g, side, decay, neigh, P);
     if (engine == CLAPCA_ENGINE_AUTO)
         engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
     if (engine == CLAPCA_ENGINE_BITPLANE) {
         if (!bp_ok)
             return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: needs a full sweep (side >= extent), rows of at "
-                        "most 65536 cells and an alive-bit neighbourhood (vnv/mv only without decay)");
-        return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps);
+                        "most 65536 cells (32768 with values >= 16) and an alive-bit neighbourhood (vnv/mv only without decay)");
+        return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps, P);
     }
     if (engine != CLAPCA_ENGINE_WAVEFRONT)
         return fail(CLAPCA_ERR_ARG, "grid_run2d: unknown engine %d", engine);

@@ -45,8 +45,9 @@ CA3D_RULES = (
 
 
 def ca3d_rule(nca):
-    """Rule selected by ca3d_run(xyz, nca, ...): index nca % 9 (core/ca3d.c:126)."""
-    return CA3D_RULES[nca % len(CA3D_RULES)]
+    """Rule selected by ca3d_run(xyz, nca, ...): index nca % 9 computed in size_t (core/ca3d.c:126), so a negative
+    index wraps through 2^64 first (-1 selects rule 6, as in the reference)."""
+    return CA3D_RULES[(int(nca) & ((1 << 64) - 1)) % len(CA3D_RULES)]
 
 
 # core/terrain.c:391-398 and :400-415

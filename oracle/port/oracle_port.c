@@ -161,7 +161,7 @@ int ora_ca3d_rule(int nca, unsigned *surv, unsigned *born, unsigned *nr_states)
         /* coral        */ { RANGE(5, 8), RANGE(6, 7) | B(9) | B(12), 4 },
         /* crystal_1    */ { RANGE(0, 6), B(1) | B(3), 2 },
     };
-    int i = nca % 9;                                    /* ca3d.c:126 */
+    int i = (int)((size_t)(long)nca % 9u);              /* ca3d.c:126: the modulo is taken in size_t */
     *surv = tab[i][0];
     *born = tab[i][1];
     *nr_states = tab[i][2];

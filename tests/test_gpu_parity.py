@@ -60,6 +60,105 @@ def test_ca3d_cfg2_128cube_10gen(gpu, oracle, engine):
     assert oracle.fnv(vol) == int(g["cfg2_final_hash"])
 
 
+def _seed_b(oracle, vol, seed):
+    """SURVEY 8(d) cfg 2 'seed B' (denser): every zero cell, in memory order, becomes 1 + lrand48() % 5 with
+    probability 1/4 -- two draws of one lrand48 stream per hit, one per miss"""
+    from clap_b200.ca import Rand48
+    out = vol.copy().reshape(-1)
+    zero = np.flatnonzero(out == 0)
+    # draw k decides zero cell k; a hit consumes one more draw: resolve the data-dependent stream in blocks
+    rng = Rand48(seed)
+    draws = rng.lrand48_block(2 * len(zero) + 2)
+    i = k = 0
+    while k < len(zero):
+        if draws[i] % 4 == 0:
+            out[zero[k]] = 1 + draws[i + 1] % 5
+            i += 2
+        else:
+            i += 1
+        k += 1
+    return out.reshape(vol.shape)
+
+
+_CFG2_SEEDS = {}
+
+
+def _cfg2_seed(oracle, variant):
+    if not _CFG2_SEEDS:
+        a = oracle.ca3d_make(128, 128, 128, 42)
+        _CFG2_SEEDS["A255"] = a.copy()
+        _CFG2_SEEDS["A255"][np.random.default_rng(255).random(a.shape) < 0.002] = 255
+        _CFG2_SEEDS["A"] = np.minimum(a, 5)     # seed A without ca3d_prune's 255 marks (those are the A255 case)
+        _CFG2_SEEDS["B"] = _seed_b(oracle, _CFG2_SEEDS["A"], 43)
+    return _CFG2_SEEDS[variant].copy()
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "A255"])
+@pytest.mark.parametrize("nca", range(9))
+def test_ca3d_cfg2_128cube_10gen_every_rule_and_seed(gpu, oracle, nca, variant):
+    """SURVEY 7.2 exit criterion / BASELINE config 2 in full: 128^3 x 10 generations for ALL nine rules, on seed A
+    (srand48(42); ca3d_make), the denser seed B, and seed A with 255s injected -- against the oracle port."""
+    vol = _cfg2_seed(oracle, variant)
+    want = vol.copy()
+    s, b, n = oracle.ca3d_rule(nca)
+    wpop = oracle.ca3d_run(want, s, b, n, 10)
+    pop = gpu.ca3d_run(vol, nca, 10, engine=BITPLANE)
+    assert pop == wpop and np.array_equal(vol, want), (nca, variant)
+
+
+def test_ca3d_test0_loop_over_all_nine_rules(gpu, oracle):
+    """core/test.c:625-637 loops CA3D_MAX times over ca3d_make(16, 8, 4) + ca3d_run(4 steps) and asks for a non-empty
+    result; here every nca of that loop (and the wrap-around indices ca3d.c:126 allows) against the oracle"""
+    for nca in list(range(9)) + [9, 16, -1]:
+        vol = oracle.ca3d_make(16, 8, 4, 7 + (nca % 9))
+        want = vol.copy()
+        s, b, n = oracle.ca3d_rule(nca)
+        wpop = oracle.ca3d_run(want, s, b, n, 4)
+        for engine in (WAVEFRONT, BITPLANE):
+            got = vol.copy()
+            assert gpu.ca3d_run(got, nca, 4, engine=engine) == wpop
+            assert np.array_equal(got, want), (nca, engine)
+    assert gpu.ca3d_rule(-1).name == "ca_spiky_growth"        # (size_t)-1 % 9 == 6, as in the reference
+
+
+@pytest.mark.slow
+def test_ca3d_cfg4_chain_1024cube_2_generations_vs_port(gpu, oracle):
+    """Link (i) of the config-4 parity chain at its upper end: 1024^3 = 2^30 cells -- the largest cube the
+    reference's 32-bit index can address -- for 2 generations against the oracle port (~40 s of CPU)."""
+    import torch
+    from clap_b200 import synth as seedgen
+    side = 1024
+    vol = seedgen.synth_torch(torch, side, side, 0, side, "cuda:0").cpu().numpy()
+    want = vol.copy()
+    s, b, n = oracle.ca3d_rule(7)
+    wpop = oracle.ca3d_run(want, s, b, n, 2)
+    pop = gpu.ca3d_run(vol, 7, 2, engine=BITPLANE)
+    assert pop == wpop
+    assert np.array_equal(vol, want)
+
+
+def test_ca3d_benched_volume_bottom_planes_equal_the_unmodified_reference(gpu):
+    """Links (ii)/(iii) anchor: planes 0..7 of the BENCHED 2048^3 volume after 50 generations are determined by its
+    bottom 58 planes (plane z of generation g sees z+1 of g-1 and nothing above).  The unmodified reference computed
+    them once (tests/golden/make_golden_cfg4_planes.py); the GPU runs the same 58-plane slab here, bench.py checks the
+    same fingerprints on the full volume at every N."""
+    import json
+    import torch
+    from clap_b200 import synth as seedgen
+    from clap_b200.ca import hash_planes
+    with open(os.path.join(G, "cfg4_planes_2048.json")) as f:
+        a = json.load(f)
+    side, k, gens = a["side"], a["planes"], a["generations"]
+    seed = seedgen.synth_torch(torch, side, side, 0, k + gens, "cuda:0")
+    grid = gpu.Grid(side, side, k + gens)
+    assert ["%016x" % int(h) for h in hash_planes(seed.data_ptr(), side * side, k)] == a["seed_plane_hashes"]
+    grid.upload(seed.data_ptr())
+    grid.run3d(a["nca"], gens)
+    got = ["%016x" % int(h) for h in hash_planes(grid.device_ptr(), side * side, k)]
+    grid.close()
+    assert got == a["plane_hashes"]
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 7, 3), (5, 1, 9), (9, 5, 1), (31, 6, 5), (32, 6, 5), (33, 6, 5),
                                    (100, 17, 11), (130, 9, 40)])
@@ -531,9 +630,12 @@ def test_terrain_cfg5_rows_vs_oracle(gpu, oracle):
     got = gpu.terrain_heightmap(12345, nr_v, 0.0, maze)
     map0 = oracle.terrain_map0(12345, nr_v)
     assert np.array_equal(gpu.terrain_map0(12345, nr_v).view(np.uint32), map0.view(np.uint32))
-    for i0 in (0, 4093, 8188):
-        want = oracle.terrain_heightmap(map0, 0.0, maze, i0=i0, i1=i0 + 4)
-        _field_close(got[i0:i0 + 4], want[i0:i0 + 4])
+    # 256 rows spread over the map: both edges, maze-cell boundaries (multiples of 8) and everything in between
+    rows = sorted(set([0, 1, 2, 3, 8188, 8189, 8190, 8191] + list(range(5, nr_v, 33))))
+    assert len(rows) >= 256
+    for i0 in rows:
+        want = oracle.terrain_heightmap(map0, 0.0, maze, i0=i0, i1=i0 + 1)
+        _field_close(got[i0:i0 + 1], want[i0:i0 + 1])
 
 
 # ---- terrain mesh stage: core/terrain.c:93-110 (calc_normal), :479-516 (vertex / normal / uv / index buffers) ----
