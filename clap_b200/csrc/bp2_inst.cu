@@ -1,16 +1,28 @@
 /*
- * bp2_inst.cu -- instantiates ca2d_sweep_kernel for every (P, WPL, neighbourhood) variant and provides
- * the cooperative launcher.
+ * bp2_inst.cu -- instantiates ca2d_sweep_kernel for ONE rule (-DBP2_RULE=0..2: run-time masks, cave smoothing,
+ * ca_test) and every (P, WPL, neighbourhood) variant, and provides its cooperative launcher.
  */
 #include "bp2_launch.h"
 
+#ifndef BP2_RULE
+#error "compile with -DBP2_RULE=<0..2>"
+#endif
+
 namespace clapca {
+
+#if BP2_RULE == 1
+typedef Rule2Cave TheRule2;
+#elif BP2_RULE == 2
+typedef Rule2Test TheRule2;
+#else
+typedef Rule2Dyn TheRule2;
+#endif
 
 template <int P, int WPL, bool MOORE>
 static cudaError_t launch_one(int warps, const Bp2Params &p, int sms, cudaStream_t stream, Bp2LaunchInfo *info)
 {
-    auto kern = ca2d_sweep_kernel<P, WPL, MOORE>;
-    const int threads = warps * 32;
+    auto kern = ca2d_sweep_kernel<P, WPL, MOORE, TheRule2>;
+    const int threads = (warps + 1) * 32;       /* the compute warps + the publisher warp */
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
     if (e != cudaSuccess) return e;
@@ -34,10 +46,13 @@ static cudaError_t launch_one(int warps, const Bp2Params &p, int sms, cudaStream
     return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(threads), args, 0, stream);
 }
 
-cudaError_t bp2_launch(int P, int WPL, bool moore, int warps, const Bp2Params &p, int sms, cudaStream_t stream,
-                       Bp2LaunchInfo *info)
+#define BP2_CONCAT2(a, b) a##b
+#define BP2_CONCAT(a, b) BP2_CONCAT2(a, b)
+
+cudaError_t BP2_CONCAT(bp2_launch_rule, BP2_RULE)(int P, int WPL, bool moore, int warps, const Bp2Params &p, int sms,
+                                                  cudaStream_t stream, Bp2LaunchInfo *info)
 {
-    if (warps < 1 || warps > 16)
+    if (warps < 1 || warps > BP2_MAX_WARPS)
         return cudaErrorInvalidValue;
 #define BP2_CASE(PP, WW) \
     if (P == PP && WPL == WW) \

@@ -14,11 +14,18 @@ struct Bp2LaunchInfo {
 };
 
 /*
- * Cooperative launch with `warps` warps per CTA (the row is split across them) and at most p.G CTAs.
- * p.G < 0: occupancy query only (info->blocks = CTAs the device can keep resident).
+ * Cooperative launch with `warps` compute warps per CTA (the row is split across them; one more warp publishes the
+ * progress counters) and at most p.G CTAs.  The rule instantiation follows from p.born / p.surv / p.nrval
+ * (bp2_rule_for).  p.G < 0: occupancy query only (info->blocks = CTAs the device can keep resident).
  */
 cudaError_t bp2_launch(int P, int WPL, bool moore, int warps, const Bp2Params &p, int sms, cudaStream_t stream,
                        Bp2LaunchInfo *info);
+
+/* one translation unit per rule (bp2_inst.cu with -DBP2_RULE=n): the builds run in parallel */
+#define BP2_DECLARE_RULE(n) \
+    cudaError_t bp2_launch_rule##n(int P, int WPL, bool moore, int warps, const Bp2Params &p, int sms, \
+                                   cudaStream_t stream, Bp2LaunchInfo *info);
+BP2_DECLARE_RULE(0) BP2_DECLARE_RULE(1) BP2_DECLARE_RULE(2)
 
 /* state planes for values up to maxval: {1,3,4,8} */
 inline int bp2_planes_for(unsigned maxval)

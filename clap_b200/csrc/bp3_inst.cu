@@ -86,6 +86,16 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     pp.pub_workers = (p.pub_workers > 0 && p.team <= 0) ? wpc : 0;
     pp.team = p.team > 0 ? wpc : 0;
     void *args[] = { &pp };
+    /*
+     * Several ranks sharing one device (p.max_ctas > 0: LocalRanks, tests): the ranks' kernels feed each other, so
+     * they must run CONCURRENTLY -- cooperative launches of different streams are not guaranteed to (the driver may
+     * hold a cooperative grid back until the device is free of others).  Every rank keeps to its share of the SMs
+     * (the sum of all ranks' CTAs does not exceed the SM count), so plain launches are co-resident as well.
+     */
+    if (p.max_ctas > 0) {
+        kern<<<dim3(blocks), dim3(threads), 0, stream>>>(pp);
+        return cudaGetLastError();
+    }
     /* cooperative launch: fails instead of silently running a non-co-resident grid */
     return cudaLaunchCooperativeKernel((void *)kern, dim3(blocks), dim3(threads), args, 0, stream);
 }

@@ -18,13 +18,28 @@
  * Layout: row record x = [S0 .. S(P-1)] plane-rows of RWS 32-bit words, bit i of word w = cell y = 32w+i,
  * padding bits always 0.  P = 1 for binary rules (BASELINE config 3: 16384^2 cells = 32 MiB).
  *
- * Parallelism.  One CTA sweeps one generation: warp w / lane l owns WPL consecutive words of the row; the
- * scan is resolved word -> warp (ballots) -> CTA (one packed word per warp in shared memory, one
- * __syncthreads per row).  Generation g follows generation g-1 two rows behind (row x needs rows <= x+1
- * of the previous generation), so all G generations are in flight in ONE launch, each publishing a
- * progress counter prog[g] = rows completed (st.release after the CTA barrier) that the next generation
- * polls (ld.acquire).  Storage is single-buffered, like the reference's: a row is overwritten only after
- * its last reader has passed.  The whole working set (a few rows per generation) lives in L2.
+ * Parallelism.  One CTA sweeps one generation; warp w / lane l owns WPL consecutive words of every row.  The
+ * row-to-row chain (row x+1 needs the new row x) is the critical path of the whole run -- side + 2 G row steps --
+ * so a row step is built for LATENCY, not throughput (round 1 paid a CTA barrier, a shared-memory round trip and a
+ * three-level scan per row: 0.79 us):
+ *
+ *   - no CTA barrier.  The warps of a CTA run SKEWED, coupled only to their two neighbours through one-word
+ *     mailboxes in shared memory (value = row tag | bit): warp w computes its carry map for row x from data it
+ *     already has, receives the carry into its span from warp w-1, hands the carry out to warp w+1 and the new
+ *     alive bit of its first cell back to warp w-1 (Moore: the H3 sum of the cell left of the span boundary needs
+ *     it).  The dependency cycle of a row step is (w,x) -> (w+1,x) -> (w,x+1): two mailbox hops and one warp-local
+ *     scan, independent of the number of warps;
+ *   - rows are prefetched three rows ahead into a 4-slot register window: the L2 latency of the previous
+ *     generation's rows is off the chain;
+ *   - no gpu-scope fence in the compute warps.  They raise per-warp row counters in shared memory; ONE extra
+ *     publisher warp per CTA carries them to the global table prog[g][w] (one fence.acq_rel.gpu per pass), which
+ *     warp w of generation g+1 polls for its own span and its two neighbours' (it reads one word beyond either end).
+ *
+ * Generation g follows generation g-1 a few rows behind (row x needs rows <= x+1 of the previous generation, the
+ * prefetch asks for x+3), so all G generations are in flight in ONE launch.  Storage is single-buffered, like the
+ * reference's: a row is overwritten only after its last reader has passed -- inside a generation the mailbox
+ * protocol guarantees it (a warp hands out the bit that lets a neighbour overwrite a row only after it has consumed
+ * that row's outside word).  The whole working set (a few rows per generation) lives in L2.
  */
 #ifndef CLAPCA_CA2D_BITPLANE_CUH
 #define CLAPCA_CA2D_BITPLANE_CUH
@@ -37,37 +52,106 @@ namespace clapca {
 struct Bp2Params {
     uint32_t *rows;         /* [M][P][RWS] */
     int N, M, G;            /* cells per row (reference y extent), rows (reference x extent), generations */
-    int RWS;                /* words per plane-row = warps per CTA * 32 * WPL */
-    int *prog;              /* [G] rows completed by generation g */
+    int RWS;                /* words per plane-row = compute warps per CTA * 32 * WPL */
+    int *prog;              /* [G][warps] rows completed by warp w of generation g */
     unsigned *ticket;       /* next generation to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
     uint32_t born, surv;    /* 9-bit masks; surv is all ones when the rule does not decay */
     uint32_t nrval;         /* (uint8_t)nr_states: the value a born cell takes (core/ca2d.c:71) */
-    int flag_rows;          /* the progress counter is raised every flag_rows rows */
+    int flag_rows;          /* unused since round 2 (the publisher warp raises the counters as fast as it can) */
     long long spin_limit;
 };
 
-enum { BP2_SMEM_WORDS = 2 * 32 + 2 };
+enum { BP2_MAX_WARPS = 16 };
+/* shared memory of a CTA (words): carry mailboxes, first-bit mailboxes, row counters, the claimed generation */
+enum { BP2_SM_CIN = 0, BP2_SM_FN = BP2_MAX_WARPS, BP2_SM_DONE = 2 * BP2_MAX_WARPS, BP2_SM_TICKET = 3 * BP2_MAX_WARPS,
+       BP2_SMEM_WORDS = 3 * BP2_MAX_WARPS + 2 };
 
-template <int P, int WPL, bool MOORE>
+/*
+ * Rules.  K has 3 bits (0..7), the tables are needed at n = K and n = K + 1.  A compile-time rule costs ONE LOP3 per
+ * table; the run-time rule walks a mux tree over mask bits that are broadcast to words once per sweep (Tabs).
+ * kMono: both masks are upward closed in n (a cell that is alive with n neighbours is alive with n+1) -- then the
+ * new alive bit of the in-row predecessor can only turn a dead cell alive, the chain a'(y) = f0 | (f1 & a'(y-1)) is
+ * a CARRY chain, and one integer add resolves a whole word (see step()).  The cave-smoothing rules are of that kind.
+ */
+constexpr bool bp2_upward_closed(uint32_t mask)
+{
+    for (int n = 0; n < 8; n++)
+        if (((mask >> n) & 1u) && !((mask >> (n + 1)) & 1u))
+            return false;
+    return true;
+}
+
+template <uint32_t BORN, uint32_t SURV>
+struct Rule2Const {
+    static constexpr bool kMono = bp2_upward_closed(BORN) && bp2_upward_closed(SURV);
+    struct Tabs { };
+    CA_MDEV void setup(const Bp2Params &, Tabs &) { }
+    CA_MDEV void eval(const Bp2Params &, const Tabs &, const uint32_t k[3], int,
+                      uint32_t &s0, uint32_t &s1, uint32_t &b0, uint32_t &b1)
+    {
+        s0 = bs_tab3<SURV & 0xFFu>(k[0], k[1], k[2]);
+        s1 = bs_tab3<(SURV >> 1) & 0xFFu>(k[0], k[1], k[2]);
+        b0 = bs_tab3<BORN & 0xFFu>(k[0], k[1], k[2]);
+        b1 = bs_tab3<(BORN >> 1) & 0xFFu>(k[0], k[1], k[2]);
+    }
+};
+
+struct Rule2Dyn {
+    static constexpr bool kMono = false;
+    struct Tabs { uint32_t t[4][8]; };
+    CA_MDEV void setup(const Bp2Params &p, Tabs &tb)
+    {
+        const uint32_t m[4] = { p.surv, p.surv >> 1, p.nrval ? p.born : 0u, p.nrval ? p.born >> 1 : 0u };
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int n = 0; n < 8; n++) tb.t[i][n] = bs_bit(m[i], n);
+    }
+    CA_MDEV uint32_t tab(const uint32_t t[8], const uint32_t k[3], int nb)
+    {
+        uint32_t a = bs_mux(k[0], t[1], t[0]), b = bs_mux(k[0], t[3], t[2]);
+        uint32_t lo = bs_mux(k[1], b, a);
+        if (nb < 3)
+            return lo;
+        uint32_t c = bs_mux(k[0], t[5], t[4]), d = bs_mux(k[0], t[7], t[6]);
+        return bs_mux(k[2], bs_mux(k[1], d, c), lo);
+    }
+    CA_MDEV void eval(const Bp2Params &, const Tabs &tb, const uint32_t k[3], int nb,
+                      uint32_t &s0, uint32_t &s1, uint32_t &b0, uint32_t &b1)
+    {
+        s0 = tab(tb.t[0], k, nb);
+        s1 = tab(tb.t[1], k, nb);
+        b0 = tab(tb.t[2], k, nb);       /* nr_states == 0: a "born" cell takes the value 0 -- the tables are all zero */
+        b1 = tab(tb.t[3], k, nb);
+    }
+};
+
+template <int P, int WPL, bool MOORE, class Rule>
 struct Sweep2 {
+    /* register window of state rows x .. x+AHEAD; row x+AHEAD is loaded during step x.  The wide variants keep the
+       three-row window of round 1 (the fourth row would spill) */
+    enum { SLOTS = (P * WPL >= 12) ? 3 : 4, AHEAD = SLOTS - 1 };
+
     struct St {
-        uint32_t so[3][P][WPL];     /* state rows x, x+1, x+2; slot = row % 3 */
-        uint32_t xo[3];             /* alive word beyond this warp's span (lane 0: left word, lane 31: right word) */
+        uint32_t so[SLOTS][P][WPL]; /* state rows, slot = row % 4 */
+        uint32_t xo[SLOTS];         /* alive word beyond this warp's span (lane 0: left word, lane 31: right word) */
         uint32_t hn[2][WPL];        /* Moore: H3 of the new row x-1; von Neumann: hn[0] = its alive bits */
         uint32_t vmask[WPL];
         uint32_t *rec;              /* lane-adjusted record of the current row */
         const uint32_t *xrec;       /* lane 0 / 31: the word just outside the warp's span (row x), else null */
+        const int *flagp;           /* lanes 0..2: counter of warp w-1 / w / w+1 of the previous generation, else null */
         int have;
+        typename Rule::Tabs tabs;   /* run-time rule: the mask bits, broadcast to words once per sweep */
     };
 
-    CA_MDEV bool wait_rows(const Bp2Params &p, St &st, const int *flag, int need)
+    CA_MDEV bool wait_rows(const Bp2Params &p, St &st, int need)
     {
         if (st.have >= need)
             return true;
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
-            int v = dp_lane() == 0 ? dp_ld_acquire(flag) : 0x7fffffff;
+            int v = st.flagp ? dp_ld_acquire(st.flagp) : 0x7fffffff;
             st.have = dp_reduce_min(v);
             if (st.have >= need)
                 break;
@@ -78,13 +162,54 @@ struct Sweep2 {
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
                         dp_atomic_max(p.err, 1);
-                    /* keep going: every warp of the CTA must reach the barriers; the claim loop exits on err */
-                    st.have = 0x7fffffff;
-                    break;
+                    return false;
                 }
             }
         }
         dp_syncwarp();
+        return true;
+    }
+
+    /* mailbox: one shared-memory word = (row + 1) << 1 | bit, polled by ONE lane; -1 = watchdog / abort */
+    CA_MDEV int recv_bit(const Bp2Params &p, const uint32_t *box, int x)
+    {
+        const uint32_t want = (uint32_t)(x + 1);
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            const uint32_t v = (uint32_t)dp_ld_volatile((const int *)box);
+            if ((v >> 1) == want)
+                return (int)(v & 1u);
+            if (spins == 0) t0 = dp_clock();
+            if ((spins & 1023u) == 1023u && (dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit)) {
+                dp_atomic_max(p.err, 2);
+                return -1;
+            }
+            dp_team_pause();
+        }
+    }
+    CA_MDEV void send_bit(uint32_t *box, int x, uint32_t bit)
+    {
+        dp_st_volatile((int *)box, (int)(((uint32_t)(x + 1) << 1) | (bit & 1u)));
+    }
+
+    /*
+     * One-word mailboxes: before the carry of row x goes to warp `to`, that of row x-1 must have been consumed.
+     * Moore: it has -- this warp could not have started row x without warp `to`'s first bit of row x-1, which it
+     * computes from that carry.  von Neumann: nothing comes back, so look at warp `to`'s row counter instead (it
+     * trails by one mailbox hop; this never waits in steady state).  false = watchdog / abort (err is set).
+     */
+    CA_MDEV bool wait_consumed(const Bp2Params &p, const uint32_t *smem, int to, int x)
+    {
+        if (MOORE)
+            return true;
+        long long t0 = dp_clock();
+        for (unsigned spins = 1; dp_ld_volatile((const int *)smem + BP2_SM_DONE + to) < x; spins++) {
+            if ((spins & 1023u) == 0u && (dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit)) {
+                dp_atomic_max(p.err, 2);
+                return false;
+            }
+            dp_team_pause();
+        }
         return true;
     }
 
@@ -136,13 +261,12 @@ struct Sweep2 {
         if (lane == 31) next = xo;
     }
 
-    /* M = x % 3 (slot of the current row) */
+    /* M = x % SLOTS (slot of the current row); false = aborted */
     template <int M>
-    CA_MDEV void step(const Bp2Params &p, St &st, int x, const int *flag_prev, int *myprog, uint32_t *smem,
-                      int &next_raise)
+    CA_MDEV bool step(const Bp2Params &p, St &st, int x, uint32_t *smem)
     {
-        constexpr int B = M, C = (M + 1) % 3, A = (M + 2) % 3;
-        const int lane = dp_lane(), warp = dp_warp_in_block(), nw = dp_block_threads() >> 5;
+        constexpr int B = M, C = (M + 1) % SLOTS, A = (M + AHEAD) % SLOTS;
+        const int lane = dp_lane(), warp = dp_warp_in_block(), nw = (dp_block_threads() >> 5) - 1;
         const int RWS = p.RWS;
 
         /* ---- neighbour count K (everything but the in-row predecessor) ---- */
@@ -179,76 +303,116 @@ struct Sweep2 {
             }
         }
 
-        /* ---- prefetch row x+2 into the slot row x-1 used to occupy ---- */
-        if (x + 2 < p.M) {
-            if (flag_prev)
-                wait_rows(p, st, flag_prev, x + 3 < p.M ? x + 3 : p.M);
-            load_row<2, A>(st, RWS);
+        /* ---- prefetch row x+3 into the slot row x-1 used to occupy ---- */
+        if (x + AHEAD < p.M) {
+            if (!wait_rows(p, st, x + AHEAD + 1 < p.M ? x + AHEAD + 1 : p.M))
+                return false;
+            load_row<AHEAD, A>(st, RWS);
         } else {
             zero_row<A>(st);
         }
 
-        /* ---- rule tables, word scan ---- */
-        uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], D[WPL], Cc[WPL];
-        uint32_t dl = 1u, cl = 0u;
+        /* ---- rule tables; the map from the carry INTO this warp's span to every cell ---- */
+        uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], f0[WPL], f1[WPL];
         const int nb = MOORE ? 3 : 2;
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
-            s0[j] = bs_tab_dyn(p.surv, k[j], nb);
-            s1[j] = bs_tab_dyn(p.surv >> 1, k[j], nb);
-            if (p.nrval) {
-                b0[j] = bs_tab_dyn(p.born, k[j], nb);
-                b1[j] = bs_tab_dyn(p.born >> 1, k[j], nb);
-            } else {
-                b0[j] = b1[j] = 0u;     /* a "born" cell takes the value 0: nothing happens */
+            Rule::eval(p, st.tabs, k[j], nb, s0[j], s1[j], b0[j], b1[j]);
+            /* new alive bit if the predecessor's new alive bit is 0 / 1 */
+            f0[j] = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & st.vmask[j];
+            f1[j] = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & st.vmask[j];
+        }
+        uint32_t an[WPL], pred[WPL];    /* new alive bits of y and of y-1 */
+        uint32_t cin_lane;
+        int got = 0;
+        if constexpr (Rule::kMono) {
+            /*
+             * Monotone rule: f0 is a subset of f1, a'(y) = f0 | (f1 & a'(y-1)) -- generate / propagate, exactly the
+             * carry chain of f0 + f1.  Lane level: carry out of the lane's words for carry-in 0 (g) and whether
+             * every cell propagates (pr); warp level: the same add on the ballots.
+             */
+            uint32_t c = 0u, pr = ~0u;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                const unsigned long long t = (unsigned long long)f0[j] + f1[j] + c;
+                c = (uint32_t)(t >> 32);
+                pr &= f0[j] ^ f1[j];
             }
-            uint32_t f0 = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & st.vmask[j];
-            uint32_t f1 = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & st.vmask[j];
-            D[j] = f0 ^ f1;
-            Cc[j] = f0;
-            bs_scan_word(D[j], Cc[j]);
-            uint32_t d = D[j] >> 31, c = Cc[j] >> 31;
-            cl = c ^ (d & cl);
-            dl = d & dl;
+            const uint32_t BG = dp_ballot(c != 0u), BP = dp_ballot(pr == ~0u);
+            const unsigned long long tw = (unsigned long long)BG + (BG | BP);
+            if (lane == 0) {
+                if (warp > 0)
+                    got = recv_bit(p, smem + BP2_SM_CIN + warp, x);
+                if (got >= 0) {
+                    const uint32_t cw = (uint32_t)got;
+                    if (warp + 1 < nw && wait_consumed(p, smem, warp + 1, x))
+                        send_bit(smem + BP2_SM_CIN + warp + 1, x, (uint32_t)(tw >> 32) | ((BP == ~0u) & cw));
+                    if (MOORE && warp > 0)
+                        send_bit(smem + BP2_SM_FN + warp - 1, x, (f0[0] | (f1[0] & cw)) & 1u);
+                }
+            }
+            got = (int)dp_shfl((uint32_t)got, 0);
+            if (got < 0)
+                return false;
+            const uint32_t cb = (uint32_t)(tw + (uint32_t)got) ^ BG ^ (BG | BP);   /* bit l = carry into lane l */
+            c = cin_lane = (cb >> lane) & 1u;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                const unsigned long long t = (unsigned long long)f0[j] + f1[j] + c;
+                pred[j] = (uint32_t)t ^ f0[j] ^ f1[j];          /* bit i = carry into bit i = a'(y-1) */
+                c = (uint32_t)(t >> 32);
+                an[j] = (pred[j] >> 1) | (c << 31);
+            }
+        } else {
+            /* general rule: GF(2) affine maps, Kogge-Stone inside a word, then on the warp's ballots */
+            uint32_t D[WPL], Cc[WPL];
+            uint32_t dl = 1u, cl = 0u;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                D[j] = f0[j] ^ f1[j];
+                Cc[j] = f0[j];
+                bs_scan_word(D[j], Cc[j]);
+                uint32_t d = D[j] >> 31, c = Cc[j] >> 31;
+                cl = c ^ (d & cl);
+                dl = d & dl;
+            }
+            uint32_t BD = dp_ballot(dl != 0), BC = dp_ballot(cl != 0);
+            bs_scan_word(BD, BC);
+            /* this lane's carry-in is c_in0 ^ (p_in & warp carry-in) */
+            const uint32_t c_in0 = lane ? (BC >> (lane - 1)) & 1u : 0u;
+            const uint32_t p_in = lane ? (BD >> (lane - 1)) & 1u : 1u;
+            /* the carry into this warp's span arrives from warp w-1; hand ours to warp w+1 and the new alive bit of
+               our first cell back to warp w-1 (lane 0 holds the first cell's map) */
+            if (lane == 0) {
+                if (warp > 0)
+                    got = recv_bit(p, smem + BP2_SM_CIN + warp, x);
+                if (got >= 0) {
+                    const uint32_t cw = (uint32_t)got;
+                    if (warp + 1 < nw && wait_consumed(p, smem, warp + 1, x))
+                        send_bit(smem + BP2_SM_CIN + warp + 1, x, (BC >> 31) ^ ((BD >> 31) & cw));
+                    if (MOORE && warp > 0)
+                        send_bit(smem + BP2_SM_FN + warp - 1, x, (Cc[0] ^ (D[0] & cw)) & 1u);
+                }
+            }
+            got = (int)dp_shfl((uint32_t)got, 0);
+            if (got < 0)
+                return false;
+            uint32_t cin = c_in0 ^ (p_in & (uint32_t)got);
+            cin_lane = cin;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                uint32_t cm = 0u - cin;
+                an[j] = Cc[j] ^ (D[j] & cm);
+                pred[j] = (an[j] << 1) | cin;
+                cin = an[j] >> 31;
+            }
         }
 
-        /* ---- warp scan, then the CTA scan through shared memory ---- */
-        uint32_t BD = dp_ballot(dl != 0), BC = dp_ballot(cl != 0);
-        bs_scan_word(BD, BC);
-        /* this lane's carry-in is c_in0 ^ (p_in & warp carry-in) */
-        const uint32_t c_in0 = lane ? (BC >> (lane - 1)) & 1u : 0u;
-        const uint32_t p_in = lane ? (BD >> (lane - 1)) & 1u : 1u;
-        uint32_t *slot = smem + (x & 1) * 32;
-        if (lane == 0)      /* bit 0/1: the warp's map, bit 2/3: the map of its first cell */
-            slot[warp] = (BD >> 31) | ((BC >> 31) << 1) | ((D[0] & 1u) << 2) | ((Cc[0] & 1u) << 3);
-        dp_syncblock();
-        /* every warp's stores of row x-1 precede this barrier: the counter may now say x rows are done */
-        if (x == next_raise) {
-            next_raise += p.flag_rows;
-            if (dp_thread() == 0)
-                dp_st_release(myprog, x);
-        }
-        const uint32_t mine = lane < nw ? slot[lane] : 1u;      /* identity map beyond the last warp */
-        uint32_t WD = dp_ballot((mine & 1u) != 0), WC = dp_ballot((mine & 2u) != 0);
-        bs_scan_word(WD, WC);
-        const uint32_t cin_w = warp ? (WC >> (warp - 1)) & 1u : 0u;
-        const uint32_t cout_w = (WC >> warp) & 1u;
-        /* new alive bit of the first cell of the next warp (0 beyond the row) */
-        const uint32_t nxt = dp_shfl(mine, warp + 1 < 32 ? warp + 1 : 31);
-        const uint32_t first_next = (warp + 1 < nw) ? (((nxt >> 3) ^ ((nxt >> 2) & cout_w)) & 1u) : 0u;
-        uint32_t cin = c_in0 ^ (p_in & cin_w);
-        const uint32_t cin_lane = cin;
-
-        /* ---- apply: new alive bits, state planes ---- */
-        uint32_t an[WPL];
+        /* ---- apply: state planes ---- */
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
-            uint32_t cm = 0u - cin;
-            an[j] = Cc[j] ^ (D[j] & cm);
-            uint32_t pred = (an[j] << 1) | cin;              /* new alive bit of y-1 */
-            cin = an[j] >> 31;
-            uint32_t sv = bs_mux(pred, s1[j], s0[j]);
-            uint32_t bn = bs_mux(pred, b1[j], b0[j]);
+            uint32_t sv = bs_mux(pred[j], s1[j], s0[j]);
+            uint32_t bn = bs_mux(pred[j], b1[j], b0[j]);
             uint32_t dec = ao[j] & ~sv;                      /* alive, neither surviving nor exempt: value - 1 */
             uint32_t brn = ~ao[j] & bn & st.vmask[j];        /* dead, born: value = nr_states */
             uint32_t borrow = dec;
@@ -261,10 +425,31 @@ struct Sweep2 {
             }
         }
 
+        /* ---- store row x, raise this warp's row counter (the publisher warp takes it to gpu scope) ---- */
+#pragma unroll
+        for (int q = 0; q < P; q++)
+            LaneVec<WPL>::st(st.rec + (size_t)q * RWS, st.so[B][q]);
+        st.rec += (size_t)P * RWS;
+        if (st.xrec) st.xrec += (size_t)P * RWS;
+        dp_syncwarp();
+        if (lane == 0) {
+            dp_fence_cta();
+            dp_st_volatile((int *)smem + BP2_SM_DONE + warp, x + 1);
+        }
+
         /* ---- what the next row needs from this one ---- */
         if (MOORE) {
             uint32_t nx = dp_shfl_down(an[0], 1);
-            if (lane == 31) nx = first_next;
+            if (lane == 31) {
+                /* new alive bit of the first cell of the next warp (0 beyond the row) */
+                int fb = 0;
+                if (warp + 1 < nw)
+                    fb = recv_bit(p, smem + BP2_SM_FN + warp, x);
+                nx = fb > 0 ? 1u : 0u;
+                got = fb;
+            }
+            if (!dp_all(got >= 0))
+                return false;
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
                 /* bit i of l = a'(y-1): the predecessor chain again, word by word */
@@ -279,78 +464,138 @@ struct Sweep2 {
 #pragma unroll
             for (int j = 0; j < WPL; j++) st.hn[0][j] = an[j];
         }
-
-        /* ---- store row x ---- */
-#pragma unroll
-        for (int q = 0; q < P; q++)
-            LaneVec<WPL>::st(st.rec + (size_t)q * RWS, st.so[B][q]);
-        st.rec += (size_t)P * RWS;
-        if (st.xrec) st.xrec += (size_t)P * RWS;
+        return true;
     }
 
-    /* all rows of generation g */
+    /* all rows of generation g, this warp's span */
     CA_MDEV void sweep(const Bp2Params &p, int g, uint32_t *smem)
     {
-        const int lane = dp_lane(), warp = dp_warp_in_block(), nw = dp_block_threads() >> 5;
+        const int lane = dp_lane(), warp = dp_warp_in_block(), nw = (dp_block_threads() >> 5) - 1;
         const int RWS = p.RWS, M = p.M;
         const int word0 = (warp * 32 + lane) * WPL;
-        int *myprog = p.prog + g;
-        const int *flag_prev = g > 0 ? p.prog + g - 1 : nullptr;
         St st;
         st.rec = p.rows + word0;
         st.xrec = (lane == 0 && warp > 0) ? p.rows + word0 - 1
                 : ((lane == 31 && warp + 1 < nw) ? p.rows + word0 + WPL : nullptr);
-        st.have = flag_prev ? 0 : 0x7fffffff;
+        {
+            const int *prev = g > 0 ? p.prog + (size_t)(g - 1) * nw : nullptr;
+            const int src = warp - 1 + lane;    /* lanes 0..2 -> warps w-1, w, w+1 */
+            st.flagp = (prev && lane < 3 && src >= 0 && src < nw) ? prev + src : nullptr;
+            st.have = prev ? 0 : 0x7fffffff;
+        }
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
             st.vmask[j] = bp_valid_mask(word0 + j, p.N);
             st.hn[0][j] = st.hn[1][j] = 0u;
         }
-        if (flag_prev)
-            wait_rows(p, st, flag_prev, 2 < M ? 2 : M);
+        Rule::setup(p, st.tabs);
+        if (!wait_rows(p, st, AHEAD < M ? AHEAD : M))
+            return;
         load_row<0, 0>(st, RWS);
-        if (M > 1) load_row<1, 1>(st, RWS);
-        else zero_row<1>(st);
-        zero_row<2>(st);
-
-        int next_raise = p.flag_rows;
+        if (M > 1) load_row<1, 1>(st, RWS); else zero_row<1>(st);
         int x = 0;
-        for (; x + 3 <= M; x += 3) {
-            step<0>(p, st, x, flag_prev, myprog, smem, next_raise);
-            step<1>(p, st, x + 1, flag_prev, myprog, smem, next_raise);
-            step<2>(p, st, x + 2, flag_prev, myprog, smem, next_raise);
+        if constexpr (SLOTS == 4) {
+            if (M > 2) load_row<2, 2>(st, RWS); else zero_row<2>(st);
+            zero_row<3>(st);
+            for (; x + 4 <= M; x += 4) {
+                if (!step<0>(p, st, x, smem)) return;
+                if (!step<1>(p, st, x + 1, smem)) return;
+                if (!step<2>(p, st, x + 2, smem)) return;
+                if (!step<3>(p, st, x + 3, smem)) return;
+            }
+            if (x < M) { if (!step<0>(p, st, x, smem)) return; x++; }
+            if (x < M) { if (!step<1>(p, st, x, smem)) return; x++; }
+            if (x < M) { if (!step<2>(p, st, x, smem)) return; x++; }
+        } else {
+            zero_row<2>(st);
+            for (; x + 3 <= M; x += 3) {
+                if (!step<0>(p, st, x, smem)) return;
+                if (!step<1>(p, st, x + 1, smem)) return;
+                if (!step<2>(p, st, x + 2, smem)) return;
+            }
+            if (x < M) { if (!step<0>(p, st, x, smem)) return; x++; }
+            if (x < M) { if (!step<1>(p, st, x, smem)) return; x++; }
         }
-        if (x < M) { step<0>(p, st, x, flag_prev, myprog, smem, next_raise); x++; }
-        if (x < M) { step<1>(p, st, x, flag_prev, myprog, smem, next_raise); x++; }
-        dp_syncblock();             /* the last row's stores of every warp */
-        if (dp_thread() == 0)
-            dp_st_release(myprog, M);
+    }
+
+    /* the publisher warp: lane w carries compute warp w's row counter to prog[g][w]; one gpu-scope fence per pass */
+    CA_MDEV void publish(const Bp2Params &p, int g, const uint32_t *smem)
+    {
+        const int lane = dp_lane(), nw = (dp_block_threads() >> 5) - 1;
+        int *flag = lane < nw ? p.prog + (size_t)g * nw + lane : nullptr;
+        int pub = 0;
+        long long t_idle = dp_clock();
+        for (unsigned spins = 0;; spins++) {
+            const int d = flag ? dp_ld_volatile((const int *)smem + BP2_SM_DONE + lane) : p.M;
+            dp_fence_cta();
+            const bool moved = flag && d > pub;
+            if (dp_any(moved)) {
+                dp_fence_release();
+                if (moved) {
+                    dp_st_flag(flag, d);
+                    pub = d;
+                }
+                t_idle = dp_clock();
+            } else {
+                dp_nanosleep(40);
+            }
+            if (dp_all(!flag || pub >= p.M))
+                break;
+            if ((spins & 255u) == 255u) {
+                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
+                if (!dp_all(!bad)) {
+                    if (lane == 0)
+                        dp_atomic_max(p.err, 3);
+                    break;
+                }
+            }
+        }
     }
 
     CA_MDEV void kernel_body(const Bp2Params &p, uint32_t *smem)
     {
+        const int warp = dp_warp_in_block(), nw = (dp_block_threads() >> 5) - 1;
         for (;;) {
             if (dp_thread() == 0) {
                 unsigned t = dp_atomic_inc(p.ticket);
                 if (dp_ld_flag(p.err) != 0)
                     t = 0xffffffffu;
-                smem[64] = t;
+                smem[BP2_SM_TICKET] = t;
             }
+            if (dp_thread() < BP2_SM_TICKET)
+                smem[dp_thread()] = 0u;             /* mailboxes and row counters: tags restart with every generation */
             dp_syncblock();
-            const unsigned g = smem[64];
-            dp_syncblock();         /* smem[64] may be rewritten by the next claim */
+            const unsigned g = smem[BP2_SM_TICKET];
             if (g >= (unsigned)p.G)
                 break;
-            sweep(p, (int)g, smem);
+            if (warp < nw)
+                sweep(p, (int)g, smem);
+            else
+                publish(p, (int)g, smem);
+            dp_syncblock();         /* everything of this generation is out before the shared words are reused */
         }
     }
 };
 
-template <int P, int WPL, bool MOORE>
-CA_GLOBAL void __launch_bounds__(512) ca2d_sweep_kernel(Bp2Params p)
+/* the compile-time rules: BASELINE config 3's cave smoothing (born 5..8, survive 4..8) and ca_test (terrain.c:391-398) */
+typedef Rule2Const<0x1E0u, 0x1F0u> Rule2Cave;
+typedef Rule2Const<0x00Cu, 0x180u> Rule2Test;
+enum { BP2_RULE_DYN = 0, BP2_RULE_CAVE = 1, BP2_RULE_TEST = 2, BP2_NRULES = 3 };
+
+/* which instantiation serves (born, surv, nrval) -- surv is already all ones for a rule that does not decay */
+inline int bp2_rule_for(uint32_t born, uint32_t surv, uint32_t nrval)
+{
+    if (!nrval) return BP2_RULE_DYN;            /* births are no-ops: only the run-time tables model that */
+    if ((born & 0x1ffu) == 0x1E0u && (surv & 0x1ffu) == 0x1F0u) return BP2_RULE_CAVE;
+    if ((born & 0x1ffu) == 0x00Cu && (surv & 0x1ffu) == 0x180u) return BP2_RULE_TEST;
+    return BP2_RULE_DYN;
+}
+
+template <int P, int WPL, bool MOORE, class Rule>
+CA_GLOBAL void __launch_bounds__(32 * (BP2_MAX_WARPS + 1), 1) ca2d_sweep_kernel(Bp2Params p)
 {
     CA_SHARED(uint32_t, smem, BP2_SMEM_WORDS);
-    Sweep2<P, WPL, MOORE>::kernel_body(p, smem);
+    Sweep2<P, WPL, MOORE, Rule>::kernel_body(p, smem);
 }
 
 } // namespace clapca

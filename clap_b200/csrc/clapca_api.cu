@@ -103,6 +103,15 @@ cudaError_t bp3_launch(int rule, int P, int WPL, const Bp3Params &p, int sms, cu
         return cudaErrorInvalidValue;
     return tab[rule](P, WPL, p, sms, stream, info);
 }
+cudaError_t bp2_launch(int P, int WPL, bool moore, int warps, const Bp2Params &p, int sms, cudaStream_t stream,
+                       Bp2LaunchInfo *info)
+{
+    switch (bp2_rule_for(p.born, p.surv, p.nrval)) {
+    case BP2_RULE_CAVE: return bp2_launch_rule1(P, WPL, moore, warps, p, sms, stream, info);
+    case BP2_RULE_TEST: return bp2_launch_rule2(P, WPL, moore, warps, p, sms, stream, info);
+    default: return bp2_launch_rule0(P, WPL, moore, warps, p, sms, stream, info);
+    }
+}
 int bp3_max_workers(int rule, int P, int WPL, int sms, int team, int max_ctas)
 {
     Bp3Params p;
@@ -945,12 +954,12 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
         {
             size_t have = g->prog_count * sizeof(int);
             void *p = g->prog;
-            if (int rc = ensure_bytes(&p, &have, (size_t)G * sizeof(int))) { g->prog = nullptr; return rc; }
+            if (int rc = ensure_bytes(&p, &have, (size_t)G * warps * sizeof(int))) { g->prog = nullptr; return rc; }
             g->prog = (int *)p;
             g->prog_count = have / sizeof(int);
             g->planes_prog = nullptr;       /* the 3D plane descriptors cached on this grid are stale now */
         }
-        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * warps * sizeof(int), g->stream));
         CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
         Bp2Params p;
         memset(&p, 0, sizeof(p));

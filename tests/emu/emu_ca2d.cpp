@@ -3,7 +3,7 @@
  * on the host warp emulator and compares the final grid and population with the oracle restatement of
  * ca2d_step().  TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca2d W H G born surv nr_states decay moore P WPL warps seedkind rngseed [ctas [flagrows]]
+ * usage: emu_ca2d W H G born surv nr_states decay moore P WPL warps seedkind rngseed [ctas [flagrows [forcedyn]]]
  *   W, H     grid extent in x / y (index y*W + x); the whole grid is swept (side >= max(W,H))
  *   seedkind 0 = reference seeding density (cells are 0 or nr_states), 1 = dense random 0..2^P-1
  */
@@ -28,13 +28,28 @@ static uint32_t rnd()
     return (uint32_t)((rng_state * 0x2545F4914F6CDD1DULL) >> 32);
 }
 
+static int force_dyn = 0;       /* argv[16]: 1 = run the run-time-mask instantiation even for a rule that has its own */
+
+template <int P, int WPL, bool MOORE>
+static void dispatch_rule(const Bp2Params &p, int ctas, int warps)
+{
+    const int rule = force_dyn ? BP2_RULE_DYN : bp2_rule_for(p.born, p.surv, p.nrval);
+    fprintf(stderr, "rule instantiation %d\n", rule);
+    if (rule == BP2_RULE_CAVE)
+        emu_launch(ctas, (warps + 1) * 32, [&]() { ca2d_sweep_kernel<P, WPL, MOORE, Rule2Cave>(p); });
+    else if (rule == BP2_RULE_TEST)
+        emu_launch(ctas, (warps + 1) * 32, [&]() { ca2d_sweep_kernel<P, WPL, MOORE, Rule2Test>(p); });
+    else
+        emu_launch(ctas, (warps + 1) * 32, [&]() { ca2d_sweep_kernel<P, WPL, MOORE, Rule2Dyn>(p); });
+}
+
 template <int P, int WPL>
 static void dispatch(bool moore, const Bp2Params &p, int ctas, int warps)
 {
     if (moore)
-        emu_launch(ctas, warps * 32, [&]() { ca2d_sweep_kernel<P, WPL, true>(p); });
+        dispatch_rule<P, WPL, true>(p, ctas, warps);
     else
-        emu_launch(ctas, warps * 32, [&]() { ca2d_sweep_kernel<P, WPL, false>(p); });
+        dispatch_rule<P, WPL, false>(p, ctas, warps);
 }
 
 template <int P>
@@ -62,6 +77,7 @@ int main(int argc, char **argv)
     rng_state ^= (uint64_t)atoll(argv[13]) * 0x9E3779B97F4A7C15ULL;
     int ctas = argc > 14 ? atoi(argv[14]) : 3;
     int flagRows = argc > 15 ? atoi(argv[15]) : 2;
+    force_dyn = argc > 16 ? atoi(argv[16]) : 0;
 
     const unsigned nrval = nr & 0xffu;
     const unsigned vmax = P >= 8 ? 255u : (1u << P) - 1u;
@@ -82,7 +98,7 @@ int main(int argc, char **argv)
     int64_t want_pop = ora_count(want.data(), (int64_t)n);
 
     std::vector<uint32_t> rows((size_t)W * P * RWS, 0u);
-    std::vector<int> prog(G > 0 ? G : 1, 0);
+    std::vector<int> prog((size_t)(G > 0 ? G : 1) * warps, 0);
     unsigned ticket = 0;
     int err = 0;
     unsigned long long pop = 0;

@@ -194,6 +194,22 @@ def test_ca2d_bitplane_rules_and_shapes(emu_bin, args):
 
 
 @pytest.mark.parametrize("args", [
+    #  W    H   G  born   surv  nr decay moore P WPL warps kind seed ctas flagrows forcedyn
+    (40, 70, 5, 0x1e0, 0x1f0, 1, 1, 1, 1, 1, 1, 0, 2, 3, 2, 1),       # cave rule through the run-time tables + Kogge-Stone scan
+    (33, 2100, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 2, 0, 2, 3, 1, 1),
+    (40, 40, 3, 0xc, 0x180, 4, 1, 1, 3, 1, 1, 0, 1, 2, 2, 1),         # ca_test through the run-time tables
+    (33, 300, 6, 0x1e0, 0x1f0, 5, 1, 1, 3, 4, 1, 1, 3, 2, 2, 0),      # cave masks, multi-state, dense values: carry-chain path with decay
+    (21, 5000, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 3, 0, 9, 4, 2, 0),     # carry chain across three warps, long runs of propagating cells
+    (9, 700, 5, 0x1e0, 0x1f0, 1, 1, 0, 1, 1, 1, 0, 5, 2, 2, 0),       # cave masks with the von Neumann count
+    (19, 3000, 3, 0xc, 0x180, 4, 1, 1, 3, 2, 2, 1, 4, 3, 2, 0),       # ca_test compile-time tables across two warps
+])
+def test_ca2d_rule_instantiations_agree(emu_bin, args):
+    """The compile-time rules (one LOP3 per table; the monotone cave rule resolves the in-row chain with an integer
+    add) and the run-time rule (mux trees, Kogge-Stone scan) are different code: each against the oracle."""
+    _run(os.path.join(emu_bin, "emu_ca2d"), *args)
+
+
+@pytest.mark.parametrize("args", [
     (5, 2100, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 2, 0, 2, 3, 1),         # rows span two warps, 2 words per lane
     (4, 3000, 3, 0x6, 0x1c, 2, 1, 0, 3, 1, 3, 1, 3, 2, 2),            # three warps, von Neumann
     (7, 2050, 3, 0xc, 0x180, 4, 1, 1, 3, 1, 3, 0, 4, 1, 3),           # a single CTA runs every generation in turn

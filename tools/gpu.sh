@@ -32,14 +32,16 @@ knobs)
     timeout 1500 python tools/tune_lowpar.py "${1:-2048}" "${2:-50}" "0" "8" "${3:-}" 2>&1 | tee -a gpurun_out/knobs_$TAG.txt
     ;;
 launches)
+    # only the library's own kernels (namespace clapca): the seed generator alone launches thousands of torch kernels
     timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 \
+        --kernel-name-base demangled -k regex:clapca \
         --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-secondary "$@" \
         > gpurun_out/launches_$TAG.log 2>&1
     tail -2 gpurun_out/launches_$TAG.log; wc -l gpurun_out/launches_$TAG.csv
     ;;
 ncufull)
     k=$1; shift
-    timeout 1800 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 1 -f -o gpurun_out/prof_$TAG \
+    timeout 1800 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$k" -c 1 -f -o gpurun_out/prof_$TAG \
         python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-secondary "$@" > gpurun_out/ncufull_$TAG.log 2>&1
     tail -2 gpurun_out/ncufull_$TAG.log
     ncu -i gpurun_out/prof_$TAG.ncu-rep --page details > gpurun_out/prof_$TAG.details.txt 2>&1
