@@ -18,28 +18,28 @@
  * Layout: row record x = [S0 .. S(P-1)] plane-rows of RWS 32-bit words, bit i of word w = cell y = 32w+i,
  * padding bits always 0.  P = 1 for binary rules (BASELINE config 3: 16384^2 cells = 32 MiB).
  *
- * Parallelism.  One CTA sweeps one generation; warp w / lane l owns WPL consecutive words of every row.  The
- * row-to-row chain (row x+1 needs the new row x) is the critical path of the whole run -- side + 2 G row steps --
- * so a row step is built for LATENCY, not throughput (round 1 paid a CTA barrier, a shared-memory round trip and a
- * three-level scan per row: 0.79 us):
+ * Parallelism.  One CTA sweeps one generation; warp w / lane l owns WPL consecutive words of every row, and the
+ * in-row chain is resolved word -> warp (ballots) -> CTA (one packed word per warp in shared memory, ONE barrier
+ * per row over the compute warps).  The row-to-row chain (row x+1 needs the new row x) is the critical path of the
+ * whole run -- side + 2 G row steps -- so a row step is built for a short DEPENDENT instruction stream (round 1:
+ * 326 instructions per warp and row, 0.79 us per row, ncu: stalled on fixed-latency dependencies, not on memory):
  *
- *   - no CTA barrier.  The warps of a CTA run SKEWED, coupled only to their two neighbours through one-word
- *     mailboxes in shared memory (value = row tag | bit): warp w computes its carry map for row x from data it
- *     already has, receives the carry into its span from warp w-1, hands the carry out to warp w+1 and the new
- *     alive bit of its first cell back to warp w-1 (Moore: the H3 sum of the cell left of the span boundary needs
- *     it).  The dependency cycle of a row step is (w,x) -> (w+1,x) -> (w,x+1): two mailbox hops and one warp-local
- *     scan, independent of the number of warps;
+ *   - the rule is a template parameter where it matters (one LOP3 per table instead of a 7-deep mux tree over
+ *     run-time mask bits; the run-time rule broadcasts its mask bits to words once per sweep);
+ *   - monotone rules (cave smoothing) resolve the in-row chain with integer adds -- the carry chain of f0 + f1 --
+ *     at every level (word, warp ballots, CTA) instead of three 5-step Kogge-Stone scans;
  *   - rows are prefetched three rows ahead into a 4-slot register window: the L2 latency of the previous
  *     generation's rows is off the chain;
- *   - no gpu-scope fence in the compute warps.  They raise per-warp row counters in shared memory; ONE extra
- *     publisher warp per CTA carries them to the global table prog[g][w] (one fence.acq_rel.gpu per pass), which
- *     warp w of generation g+1 polls for its own span and its two neighbours' (it reads one word beyond either end).
+ *   - no gpu-scope fence in the compute warps: thread 0 raises a row counter in shared memory every few rows and ONE
+ *     extra publisher warp per CTA (it does not take part in the row barrier) carries it to the global counter
+ *     prog[g] that generation g+1 polls.
+ *   (A barrier-free variant -- warps skewed, coupled to their neighbours by shared-memory mailboxes -- was measured
+ *   on B200 and lost 3x: two polling hops per row cost more than one barrier; profiles/r02_ca2d_variants.txt.)
  *
  * Generation g follows generation g-1 a few rows behind (row x needs rows <= x+1 of the previous generation, the
  * prefetch asks for x+3), so all G generations are in flight in ONE launch.  Storage is single-buffered, like the
- * reference's: a row is overwritten only after its last reader has passed -- inside a generation the mailbox
- * protocol guarantees it (a warp hands out the bit that lets a neighbour overwrite a row only after it has consumed
- * that row's outside word).  The whole working set (a few rows per generation) lives in L2.
+ * reference's: a row is overwritten only after its last reader has passed.  The whole working set (a few rows per
+ * generation) lives in L2.
  */
 #ifndef CLAPCA_CA2D_BITPLANE_CUH
 #define CLAPCA_CA2D_BITPLANE_CUH
@@ -53,19 +53,18 @@ struct Bp2Params {
     uint32_t *rows;         /* [M][P][RWS] */
     int N, M, G;            /* cells per row (reference y extent), rows (reference x extent), generations */
     int RWS;                /* words per plane-row = compute warps per CTA * 32 * WPL */
-    int *prog;              /* [G][warps] rows completed by warp w of generation g */
+    int *prog;              /* [G] rows completed by generation g */
     unsigned *ticket;       /* next generation to claim */
     int *err;               /* != 0: watchdog fired, everybody bails out */
     uint32_t born, surv;    /* 9-bit masks; surv is all ones when the rule does not decay */
     uint32_t nrval;         /* (uint8_t)nr_states: the value a born cell takes (core/ca2d.c:71) */
-    int flag_rows;          /* unused since round 2 (the publisher warp raises the counters as fast as it can) */
+    int flag_rows;          /* the shared-memory row counter is raised every flag_rows rows (the publisher warp takes it from there) */
     long long spin_limit;
 };
 
 enum { BP2_MAX_WARPS = 16 };
-/* shared memory of a CTA (words): carry mailboxes, first-bit mailboxes, row counters, the claimed generation */
-enum { BP2_SM_CIN = 0, BP2_SM_FN = BP2_MAX_WARPS, BP2_SM_DONE = 2 * BP2_MAX_WARPS, BP2_SM_TICKET = 3 * BP2_MAX_WARPS,
-       BP2_SMEM_WORDS = 3 * BP2_MAX_WARPS + 2 };
+/* shared memory of a CTA (words): the warps' carry maps (two rows in flight), the row counter, the claimed generation */
+enum { BP2_SM_SLOT = 0, BP2_SM_DONE = 2 * 32, BP2_SM_TICKET = 2 * 32 + 1, BP2_SMEM_WORDS = 2 * 32 + 2 };
 
 /*
  * Rules.  K has 3 bits (0..7), the tables are needed at n = K and n = K + 1.  A compile-time rule costs ONE LOP3 per
@@ -140,15 +139,15 @@ struct Sweep2 {
         uint32_t vmask[WPL];
         uint32_t *rec;              /* lane-adjusted record of the current row */
         const uint32_t *xrec;       /* lane 0 / 31: the word just outside the warp's span (row x), else null */
-        const int *flagp;           /* lanes 0..2: counter of warp w-1 / w / w+1 of the previous generation, else null */
+        const int *flagp;           /* lane 0: counter of the previous generation, else null */
         int have;
         typename Rule::Tabs tabs;   /* run-time rule: the mask bits, broadcast to words once per sweep */
     };
 
-    CA_MDEV bool wait_rows(const Bp2Params &p, St &st, int need)
+    CA_MDEV void wait_rows(const Bp2Params &p, St &st, int need)
     {
         if (st.have >= need)
-            return true;
+            return;
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
             int v = st.flagp ? dp_ld_acquire(st.flagp) : 0x7fffffff;
@@ -162,55 +161,13 @@ struct Sweep2 {
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
                         dp_atomic_max(p.err, 1);
-                    return false;
+                    /* keep going: every warp of the CTA must reach the row barriers; the claim loop exits on err */
+                    st.have = 0x7fffffff;
+                    break;
                 }
             }
         }
         dp_syncwarp();
-        return true;
-    }
-
-    /* mailbox: one shared-memory word = (row + 1) << 1 | bit, polled by ONE lane; -1 = watchdog / abort */
-    CA_MDEV int recv_bit(const Bp2Params &p, const uint32_t *box, int x)
-    {
-        const uint32_t want = (uint32_t)(x + 1);
-        long long t0 = 0;
-        for (unsigned spins = 0;; spins++) {
-            const uint32_t v = (uint32_t)dp_ld_volatile((const int *)box);
-            if ((v >> 1) == want)
-                return (int)(v & 1u);
-            if (spins == 0) t0 = dp_clock();
-            if ((spins & 1023u) == 1023u && (dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit)) {
-                dp_atomic_max(p.err, 2);
-                return -1;
-            }
-            dp_team_pause();
-        }
-    }
-    CA_MDEV void send_bit(uint32_t *box, int x, uint32_t bit)
-    {
-        dp_st_volatile((int *)box, (int)(((uint32_t)(x + 1) << 1) | (bit & 1u)));
-    }
-
-    /*
-     * One-word mailboxes: before the carry of row x goes to warp `to`, that of row x-1 must have been consumed.
-     * Moore: it has -- this warp could not have started row x without warp `to`'s first bit of row x-1, which it
-     * computes from that carry.  von Neumann: nothing comes back, so look at warp `to`'s row counter instead (it
-     * trails by one mailbox hop; this never waits in steady state).  false = watchdog / abort (err is set).
-     */
-    CA_MDEV bool wait_consumed(const Bp2Params &p, const uint32_t *smem, int to, int x)
-    {
-        if (MOORE)
-            return true;
-        long long t0 = dp_clock();
-        for (unsigned spins = 1; dp_ld_volatile((const int *)smem + BP2_SM_DONE + to) < x; spins++) {
-            if ((spins & 1023u) == 0u && (dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit)) {
-                dp_atomic_max(p.err, 2);
-                return false;
-            }
-            dp_team_pause();
-        }
-        return true;
     }
 
     /* state planes (and the outside word) of the row D rows after the current one into slot S */
@@ -261,9 +218,9 @@ struct Sweep2 {
         if (lane == 31) next = xo;
     }
 
-    /* M = x % SLOTS (slot of the current row); false = aborted */
+    /* M = x % SLOTS (slot of the current row) */
     template <int M>
-    CA_MDEV bool step(const Bp2Params &p, St &st, int x, uint32_t *smem)
+    CA_MDEV void step(const Bp2Params &p, St &st, int x, uint32_t *smem)
     {
         constexpr int B = M, C = (M + 1) % SLOTS, A = (M + AHEAD) % SLOTS;
         const int lane = dp_lane(), warp = dp_warp_in_block(), nw = (dp_block_threads() >> 5) - 1;
@@ -305,8 +262,7 @@ struct Sweep2 {
 
         /* ---- prefetch row x+3 into the slot row x-1 used to occupy ---- */
         if (x + AHEAD < p.M) {
-            if (!wait_rows(p, st, x + AHEAD + 1 < p.M ? x + AHEAD + 1 : p.M))
-                return false;
+            wait_rows(p, st, x + AHEAD + 1 < p.M ? x + AHEAD + 1 : p.M);
             load_row<AHEAD, A>(st, RWS);
         } else {
             zero_row<A>(st);
@@ -323,13 +279,14 @@ struct Sweep2 {
             f1[j] = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & st.vmask[j];
         }
         uint32_t an[WPL], pred[WPL];    /* new alive bits of y and of y-1 */
-        uint32_t cin_lane;
-        int got = 0;
+        uint32_t cin_lane, first_next;
+        uint32_t *slot = smem + BP2_SM_SLOT + (x & 1) * 32;
         if constexpr (Rule::kMono) {
             /*
              * Monotone rule: f0 is a subset of f1, a'(y) = f0 | (f1 & a'(y-1)) -- generate / propagate, exactly the
              * carry chain of f0 + f1.  Lane level: carry out of the lane's words for carry-in 0 (g) and whether
-             * every cell propagates (pr); warp level: the same add on the ballots.
+             * every cell propagates (pr); warp level: the same add on the ballots; CTA level: once more on the
+             * warps' (generate, propagate) bits.
              */
             uint32_t c = 0u, pr = ~0u;
 #pragma unroll
@@ -340,21 +297,17 @@ struct Sweep2 {
             }
             const uint32_t BG = dp_ballot(c != 0u), BP = dp_ballot(pr == ~0u);
             const unsigned long long tw = (unsigned long long)BG + (BG | BP);
-            if (lane == 0) {
-                if (warp > 0)
-                    got = recv_bit(p, smem + BP2_SM_CIN + warp, x);
-                if (got >= 0) {
-                    const uint32_t cw = (uint32_t)got;
-                    if (warp + 1 < nw && wait_consumed(p, smem, warp + 1, x))
-                        send_bit(smem + BP2_SM_CIN + warp + 1, x, (uint32_t)(tw >> 32) | ((BP == ~0u) & cw));
-                    if (MOORE && warp > 0)
-                        send_bit(smem + BP2_SM_FN + warp - 1, x, (f0[0] | (f1[0] & cw)) & 1u);
-                }
-            }
-            got = (int)dp_shfl((uint32_t)got, 0);
-            if (got < 0)
-                return false;
-            const uint32_t cb = (uint32_t)(tw + (uint32_t)got) ^ BG ^ (BG | BP);   /* bit l = carry into lane l */
+            if (lane == 0)      /* bit 0/1: the warp generates / propagates, bit 2/3: f0 / f1 of its first cell */
+                slot[warp] = (uint32_t)(tw >> 32) | ((uint32_t)(BP == ~0u) << 1) | ((f0[0] & 1u) << 2) | ((f1[0] & 1u) << 3);
+            dp_syncblock_named(1, nw * 32);
+            raise_counter(p, x, smem);
+            const uint32_t mine = lane < nw ? slot[lane] : 0u;      /* beyond the last warp: kill */
+            const uint32_t WG = dp_ballot((mine & 1u) != 0), WP = dp_ballot((mine & 2u) != 0);
+            const uint32_t cw = (WG + (WG | WP)) ^ WG ^ (WG | WP);  /* bit w = carry into warp w (nw <= 16: no overflow) */
+            const uint32_t cin_w = (cw >> warp) & 1u, cout_w = (cw >> (warp + 1)) & 1u;
+            const uint32_t nxt = dp_shfl(mine, warp + 1 < 32 ? warp + 1 : 31);
+            first_next = (warp + 1 < nw) ? (((nxt >> 2) | ((nxt >> 3) & cout_w)) & 1u) : 0u;
+            const uint32_t cb = (uint32_t)(tw + cin_w) ^ BG ^ (BG | BP);   /* bit l = carry into lane l */
             c = cin_lane = (cb >> lane) & 1u;
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
@@ -364,7 +317,7 @@ struct Sweep2 {
                 an[j] = (pred[j] >> 1) | (c << 31);
             }
         } else {
-            /* general rule: GF(2) affine maps, Kogge-Stone inside a word, then on the warp's ballots */
+            /* general rule: GF(2) affine maps, Kogge-Stone inside a word, on the warp's ballots, on the warps' maps */
             uint32_t D[WPL], Cc[WPL];
             uint32_t dl = 1u, cl = 0u;
 #pragma unroll
@@ -381,23 +334,19 @@ struct Sweep2 {
             /* this lane's carry-in is c_in0 ^ (p_in & warp carry-in) */
             const uint32_t c_in0 = lane ? (BC >> (lane - 1)) & 1u : 0u;
             const uint32_t p_in = lane ? (BD >> (lane - 1)) & 1u : 1u;
-            /* the carry into this warp's span arrives from warp w-1; hand ours to warp w+1 and the new alive bit of
-               our first cell back to warp w-1 (lane 0 holds the first cell's map) */
-            if (lane == 0) {
-                if (warp > 0)
-                    got = recv_bit(p, smem + BP2_SM_CIN + warp, x);
-                if (got >= 0) {
-                    const uint32_t cw = (uint32_t)got;
-                    if (warp + 1 < nw && wait_consumed(p, smem, warp + 1, x))
-                        send_bit(smem + BP2_SM_CIN + warp + 1, x, (BC >> 31) ^ ((BD >> 31) & cw));
-                    if (MOORE && warp > 0)
-                        send_bit(smem + BP2_SM_FN + warp - 1, x, (Cc[0] ^ (D[0] & cw)) & 1u);
-                }
-            }
-            got = (int)dp_shfl((uint32_t)got, 0);
-            if (got < 0)
-                return false;
-            uint32_t cin = c_in0 ^ (p_in & (uint32_t)got);
+            if (lane == 0)      /* bit 0/1: the warp's map, bit 2/3: the map of its first cell */
+                slot[warp] = (BD >> 31) | ((BC >> 31) << 1) | ((D[0] & 1u) << 2) | ((Cc[0] & 1u) << 3);
+            dp_syncblock_named(1, nw * 32);
+            raise_counter(p, x, smem);
+            const uint32_t mine = lane < nw ? slot[lane] : 1u;      /* identity map beyond the last warp */
+            uint32_t WD = dp_ballot((mine & 1u) != 0), WC = dp_ballot((mine & 2u) != 0);
+            bs_scan_word(WD, WC);
+            const uint32_t cin_w = warp ? (WC >> (warp - 1)) & 1u : 0u;
+            const uint32_t cout_w = (WC >> warp) & 1u;
+            /* new alive bit of the first cell of the next warp (0 beyond the row) */
+            const uint32_t nxt = dp_shfl(mine, warp + 1 < 32 ? warp + 1 : 31);
+            first_next = (warp + 1 < nw) ? (((nxt >> 3) ^ ((nxt >> 2) & cout_w)) & 1u) : 0u;
+            uint32_t cin = c_in0 ^ (p_in & cin_w);
             cin_lane = cin;
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
@@ -425,31 +374,17 @@ struct Sweep2 {
             }
         }
 
-        /* ---- store row x, raise this warp's row counter (the publisher warp takes it to gpu scope) ---- */
+        /* ---- store row x ---- */
 #pragma unroll
         for (int q = 0; q < P; q++)
             LaneVec<WPL>::st(st.rec + (size_t)q * RWS, st.so[B][q]);
         st.rec += (size_t)P * RWS;
         if (st.xrec) st.xrec += (size_t)P * RWS;
-        dp_syncwarp();
-        if (lane == 0) {
-            dp_fence_cta();
-            dp_st_volatile((int *)smem + BP2_SM_DONE + warp, x + 1);
-        }
 
         /* ---- what the next row needs from this one ---- */
         if (MOORE) {
             uint32_t nx = dp_shfl_down(an[0], 1);
-            if (lane == 31) {
-                /* new alive bit of the first cell of the next warp (0 beyond the row) */
-                int fb = 0;
-                if (warp + 1 < nw)
-                    fb = recv_bit(p, smem + BP2_SM_FN + warp, x);
-                nx = fb > 0 ? 1u : 0u;
-                got = fb;
-            }
-            if (!dp_all(got >= 0))
-                return false;
+            if (lane == 31) nx = first_next;
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
                 /* bit i of l = a'(y-1): the predecessor chain again, word by word */
@@ -464,7 +399,18 @@ struct Sweep2 {
 #pragma unroll
             for (int j = 0; j < WPL; j++) st.hn[0][j] = an[j];
         }
-        return true;
+    }
+
+    /*
+     * Right after the row barrier of row x: every warp's stores of rows < x precede it.  Every flag_rows rows thread 0
+     * says so in shared memory (CTA-scope release) for the publisher warp.
+     */
+    CA_MDEV void raise_counter(const Bp2Params &p, int x, uint32_t *smem)
+    {
+        if (dp_thread() == 0 && x > 0 && (x % p.flag_rows) == 0) {
+            dp_fence_cta();
+            dp_st_volatile((int *)smem + BP2_SM_DONE, x);
+        }
     }
 
     /* all rows of generation g, this warp's span */
@@ -477,20 +423,15 @@ struct Sweep2 {
         st.rec = p.rows + word0;
         st.xrec = (lane == 0 && warp > 0) ? p.rows + word0 - 1
                 : ((lane == 31 && warp + 1 < nw) ? p.rows + word0 + WPL : nullptr);
-        {
-            const int *prev = g > 0 ? p.prog + (size_t)(g - 1) * nw : nullptr;
-            const int src = warp - 1 + lane;    /* lanes 0..2 -> warps w-1, w, w+1 */
-            st.flagp = (prev && lane < 3 && src >= 0 && src < nw) ? prev + src : nullptr;
-            st.have = prev ? 0 : 0x7fffffff;
-        }
+        st.flagp = (g > 0 && lane == 0) ? p.prog + (g - 1) : nullptr;
+        st.have = g > 0 ? 0 : 0x7fffffff;
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
             st.vmask[j] = bp_valid_mask(word0 + j, p.N);
             st.hn[0][j] = st.hn[1][j] = 0u;
         }
         Rule::setup(p, st.tabs);
-        if (!wait_rows(p, st, AHEAD < M ? AHEAD : M))
-            return;
+        wait_rows(p, st, AHEAD < M ? AHEAD : M);
         load_row<0, 0>(st, RWS);
         if (M > 1) load_row<1, 1>(st, RWS); else zero_row<1>(st);
         int x = 0;
@@ -498,55 +439,56 @@ struct Sweep2 {
             if (M > 2) load_row<2, 2>(st, RWS); else zero_row<2>(st);
             zero_row<3>(st);
             for (; x + 4 <= M; x += 4) {
-                if (!step<0>(p, st, x, smem)) return;
-                if (!step<1>(p, st, x + 1, smem)) return;
-                if (!step<2>(p, st, x + 2, smem)) return;
-                if (!step<3>(p, st, x + 3, smem)) return;
+                step<0>(p, st, x, smem);
+                step<1>(p, st, x + 1, smem);
+                step<2>(p, st, x + 2, smem);
+                step<3>(p, st, x + 3, smem);
             }
-            if (x < M) { if (!step<0>(p, st, x, smem)) return; x++; }
-            if (x < M) { if (!step<1>(p, st, x, smem)) return; x++; }
-            if (x < M) { if (!step<2>(p, st, x, smem)) return; x++; }
+            if (x < M) { step<0>(p, st, x, smem); x++; }
+            if (x < M) { step<1>(p, st, x, smem); x++; }
+            if (x < M) { step<2>(p, st, x, smem); x++; }
         } else {
             zero_row<2>(st);
             for (; x + 3 <= M; x += 3) {
-                if (!step<0>(p, st, x, smem)) return;
-                if (!step<1>(p, st, x + 1, smem)) return;
-                if (!step<2>(p, st, x + 2, smem)) return;
+                step<0>(p, st, x, smem);
+                step<1>(p, st, x + 1, smem);
+                step<2>(p, st, x + 2, smem);
             }
-            if (x < M) { if (!step<0>(p, st, x, smem)) return; x++; }
-            if (x < M) { if (!step<1>(p, st, x, smem)) return; x++; }
+            if (x < M) { step<0>(p, st, x, smem); x++; }
+            if (x < M) { step<1>(p, st, x, smem); x++; }
+        }
+        dp_syncblock_named(1, nw * 32);     /* the last row's stores of every warp */
+        if (dp_thread() == 0) {
+            dp_fence_cta();
+            dp_st_volatile((int *)smem + BP2_SM_DONE, M);
         }
     }
 
-    /* the publisher warp: lane w carries compute warp w's row counter to prog[g][w]; one gpu-scope fence per pass */
+    /* the publisher warp: carries the CTA's row counter to prog[g]; the only gpu-scope fences of the CTA */
     CA_MDEV void publish(const Bp2Params &p, int g, const uint32_t *smem)
     {
-        const int lane = dp_lane(), nw = (dp_block_threads() >> 5) - 1;
-        int *flag = lane < nw ? p.prog + (size_t)g * nw + lane : nullptr;
+        const int lane = dp_lane();
         int pub = 0;
         long long t_idle = dp_clock();
-        for (unsigned spins = 0;; spins++) {
-            const int d = flag ? dp_ld_volatile((const int *)smem + BP2_SM_DONE + lane) : p.M;
-            dp_fence_cta();
-            const bool moved = flag && d > pub;
-            if (dp_any(moved)) {
-                dp_fence_release();
-                if (moved) {
-                    dp_st_flag(flag, d);
-                    pub = d;
-                }
+        for (unsigned spins = 0; pub < p.M; spins++) {
+            /* one lane looks, everybody follows: the lanes must agree on when the loop ends */
+            const int d = (int)dp_shfl(lane == 0 ? (uint32_t)dp_ld_volatile((const int *)smem + BP2_SM_DONE) : 0u, 0);
+            if (d > pub) {
+                dp_fence_cta();
+                dp_fence_release();         /* fence.acq_rel.gpu: rows before the counter (cumulative over the CTA-scope release) */
+                if (lane == 0)
+                    dp_st_flag(p.prog + g, d);
+                pub = d;
                 t_idle = dp_clock();
             } else {
                 dp_nanosleep(40);
-            }
-            if (dp_all(!flag || pub >= p.M))
-                break;
-            if ((spins & 255u) == 255u) {
-                bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
-                if (!dp_all(!bad)) {
-                    if (lane == 0)
-                        dp_atomic_max(p.err, 3);
-                    break;
+                if ((spins & 255u) == 255u) {
+                    bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
+                    if (!dp_all(!bad)) {
+                        if (lane == 0)
+                            dp_atomic_max(p.err, 3);
+                        break;
+                    }
                 }
             }
         }
@@ -562,8 +504,8 @@ struct Sweep2 {
                     t = 0xffffffffu;
                 smem[BP2_SM_TICKET] = t;
             }
-            if (dp_thread() < BP2_SM_TICKET)
-                smem[dp_thread()] = 0u;             /* mailboxes and row counters: tags restart with every generation */
+            for (int i = dp_thread(); i < BP2_SM_TICKET; i += dp_block_threads())
+                smem[i] = 0u;                       /* carry maps and the row counter restart with every generation */
             dp_syncblock();
             const unsigned g = smem[BP2_SM_TICKET];
             if (g >= (unsigned)p.G)

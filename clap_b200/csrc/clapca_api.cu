@@ -954,12 +954,12 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
         {
             size_t have = g->prog_count * sizeof(int);
             void *p = g->prog;
-            if (int rc = ensure_bytes(&p, &have, (size_t)G * warps * sizeof(int))) { g->prog = nullptr; return rc; }
+            if (int rc = ensure_bytes(&p, &have, (size_t)G * sizeof(int))) { g->prog = nullptr; return rc; }
             g->prog = (int *)p;
             g->prog_count = have / sizeof(int);
             g->planes_prog = nullptr;       /* the 3D plane descriptors cached on this grid are stale now */
         }
-        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * warps * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * sizeof(int), g->stream));
         CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
         Bp2Params p;
         memset(&p, 0, sizeof(p));
@@ -972,7 +972,7 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
         /* a cell that neither survives nor decays keeps its value: same as surviving (core/ca2d.c:72-75) */
         p.surv = decay ? (surv & 0x1ffu) : 0x1ffu;
         p.nrval = nrval;
-        p.flag_rows = 8;
+        p.flag_rows = 4;
         if (const char *e = getenv("CLAPCA_2D_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
         p.spin_limit = 4000000000LL;
         Bp2LaunchInfo info;

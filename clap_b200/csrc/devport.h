@@ -43,6 +43,11 @@ CA_DEV uint32_t dp_ballot(bool p)                 { return __ballot_sync(CA_FULL
 CA_DEV bool     dp_all(bool p)                    { return __all_sync(CA_FULL, p); }
 CA_DEV void     dp_syncwarp()                     { __syncwarp(); }
 CA_DEV void     dp_syncblock()                    { __syncthreads(); }
+/* named barrier over the first `nthreads` threads' worth of warps that use it (bar.sync id, nthreads) */
+CA_DEV void     dp_syncblock_named(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 
 /* data written by other SMs inside the same launch: bypass the (incoherent) L1 */
 CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return __ldcg(p); }
@@ -173,6 +178,7 @@ uint32_t emu_ballot(bool p);
 void     emu_yield();
 long long emu_clock();
 void     emu_syncblock();                            /* all warps of the block */
+void     emu_syncblock_named(int id, int nthreads);  /* nthreads / 32 warps of the block */
 void    *emu_block_shared(size_t bytes);             /* the block's shared memory (same buffer for every thread) */
 
 CA_DEV int  dp_lane()            { return emu_lane(); }
@@ -189,6 +195,7 @@ CA_DEV uint32_t dp_ballot(bool p)                 { return emu_ballot(p); }
 CA_DEV bool     dp_all(bool p)                    { return emu_ballot(p) == CA_FULL; }
 CA_DEV void     dp_syncwarp()                     { (void)emu_ballot(true); }
 CA_DEV void     dp_syncblock()                    { emu_syncblock(); }
+CA_DEV void     dp_syncblock_named(int id, int nthreads) { emu_syncblock_named(id, nthreads); }
 
 template <typename T> CA_DEV T dp_ld_cg_any(const T *p)
 {

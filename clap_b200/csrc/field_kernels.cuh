@@ -69,8 +69,19 @@ __device__ __forceinline__ float fk_hash31(int x, int y, int z, uint32_t seed)
     return (float)(h ^ (h >> 16)) * (1.0f / 4294967296.0f);
 }
 
+/*
+ * ((v % period) + period) % period of the reference (core/noise.c:177-185) without the two signed divisions: lattice
+ * coordinates of a periodic field lie within one period of [0, period) (the bake samples [-eps, period_units + eps]),
+ * where one conditional add / subtract gives the same number; anything further out takes the division.
+ */
 __device__ __forceinline__ int fk_wrap(int v, int period)
 {
+    if (v >= 0 && v < period)
+        return v;
+    if (v < 0 && v >= -period)
+        return v + period;
+    if (v >= period && v - period < period)
+        return v - period;
     return (v % period + period) % period;
 }
 
@@ -79,10 +90,11 @@ __device__ __forceinline__ float fk_value_noise3d(float x, float y, float z, int
 {
     int x0 = (int)floorf(x), y0 = (int)floorf(y), z0 = (int)floorf(z);
     float xf = x - (float)x0, yf = y - (float)y0, zf = z - (float)z0;
-    int x1 = fk_wrap(x0 + 1, period), y1 = fk_wrap(y0 + 1, period), z1 = fk_wrap(z0 + 1, period);
+    /* wrap(v + 1) == wrap(wrap(v) + 1): the upper corner follows from the wrapped lower one */
     x0 = fk_wrap(x0, period);
     y0 = fk_wrap(y0, period);
     z0 = fk_wrap(z0, period);
+    const int x1 = x0 + 1 == period ? 0 : x0 + 1, y1 = y0 + 1 == period ? 0 : y0 + 1, z1 = z0 + 1 == period ? 0 : z0 + 1;
 
     float ux = fk_smoothf(xf), uy = fk_smoothf(yf), uz = fk_smoothf(zf);
     float lo0 = fk_linf(fk_hash31(x0, y0, z0, seed), fk_hash31(x1, y0, z0, seed), ux);

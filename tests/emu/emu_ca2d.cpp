@@ -98,7 +98,7 @@ int main(int argc, char **argv)
     int64_t want_pop = ora_count(want.data(), (int64_t)n);
 
     std::vector<uint32_t> rows((size_t)W * P * RWS, 0u);
-    std::vector<int> prog((size_t)(G > 0 ? G : 1) * warps, 0);
+    std::vector<int> prog(G > 0 ? G : 1, 0);
     unsigned ticket = 0;
     int err = 0;
     unsigned long long pop = 0;

@@ -17,9 +17,15 @@ namespace {
 constexpr int kLanes = 32;
 constexpr size_t kStack = 256 * 1024;
 
+struct NamedBarrier {
+    std::atomic<int> arrived{0};
+    std::atomic<unsigned> generation{0};
+};
+
 struct Block {
     std::atomic<int> arrived{0};
     std::atomic<unsigned> generation{0};
+    NamedBarrier named[16];
     int warps = 0;
     std::vector<char> smem;
 };
@@ -174,6 +180,26 @@ void emu_syncblock()
         }
     }
     (void)emu_ballot(true);                 /* lane 0 is through: release the other lanes */
+}
+
+/* bar.sync id, nthreads: the first nthreads / 32 arriving warps of the block form the barrier */
+void emu_syncblock_named(int id, int nthreads)
+{
+    Warp *w = tw;
+    (void)emu_ballot(true);
+    if (w->cur == 0) {
+        NamedBarrier *b = &w->blk->named[id & 15];
+        const int nwarps = nthreads / kLanes;
+        unsigned g = b->generation.load(std::memory_order_acquire);
+        if (b->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nwarps) {
+            b->arrived.store(0, std::memory_order_relaxed);
+            b->generation.fetch_add(1, std::memory_order_acq_rel);
+        } else {
+            while (b->generation.load(std::memory_order_acquire) == g)
+                sched_yield();
+        }
+    }
+    (void)emu_ballot(true);
 }
 
 void *emu_block_shared(size_t bytes)

@@ -53,7 +53,8 @@ def test_local_ranks_equal_single_gpu_and_oracle(gpu, oracle, case):
         chk = full.copy()
         s, b, n = oracle.ca3d_rule(rule)
         assert oracle.ca3d_run(chk, s, b, n, gens) == wpop and np.array_equal(chk, want)
-    lr = LocalRanks(d0, d1, d2, ranks, gens, int(full.max()), block)
+    # max_value covers the cells AND the value a born cell takes (pyroclastic: 9 -> 4 state planes)
+    lr = LocalRanks(d0, d1, d2, ranks, gens, max(int(full.max()), gpu.ca3d_rule(rule).nr_states - 1), block)
     try:
         for rep in range(3):                # odd and even runs use the two banks of ghost counters
             lr.upload(full)
