@@ -72,6 +72,10 @@ SIGNATURES = {
     "clapca_slab_connect": (c_int, [c_void_p, c_void_p, c_void_p]),
     "clapca_slab_halo_ptr": (c_void_p, [c_void_p]),
     "clapca_slab_connect_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "clapca_noise_bake_array": (c_int, [POINTER(c_void_p), c_size_t, c_int, c_float, c_float, c_float, c_uint32, POINTER(c_float)]),
+    "clapca_tex3d_array": (c_void_p, [c_void_p]),
+    "clapca_tex3d_download": (c_int, [c_void_p, c_void_p]),
+    "clapca_tex3d_destroy": (c_int, [c_void_p]),
     "clapca_hash_planes": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "clapca_slab_upload": (c_int, [c_void_p, c_void_p]),
     "clapca_slab_download": (c_int, [c_void_p, c_void_p]),

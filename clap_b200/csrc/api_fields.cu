@@ -19,7 +19,7 @@ int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacuna
     if (!d_out || size < 1 || size > 4096 || octaves < 0 || (int)period_units < 1)
         return fail(CLAPCA_ERR_ARG, "noise bake: bad arguments (size %zu, octaves %d, period %g)", size, octaves,
                     (double)period_units);
-    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed };
+    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed, 0 };
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
@@ -46,6 +46,83 @@ int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float
     if (!rc) rc = clapca_memcpy_d2h(out, d, bytes);
     cudaFree(d);
     return rc;
+}
+
+/* ---- the bake as a device-resident 3D texture object ---------------------------------------- */
+
+struct clapca_tex3d {
+    cudaArray_t array = nullptr;
+    cudaSurfaceObject_t surf = 0;
+    size_t size = 0;
+};
+
+int clapca_tex3d_destroy(clapca_tex3d *t)
+{
+    if (!t) return CLAPCA_OK;
+    if (t->surf) cudaDestroySurfaceObject(t->surf);
+    if (t->array) cudaFreeArray(t->array);
+    delete t;
+    return CLAPCA_OK;
+}
+
+int clapca_noise_bake_array(clapca_tex3d **out, size_t size, int octaves, float lacunarity, float gain,
+                            float period_units, uint32_t seed, float *kernel_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!out || size < 1 || size > 2048 || octaves < 0 || (int)period_units < 1)
+        return fail(CLAPCA_ERR_ARG, "noise bake (array): bad arguments (size %zu, octaves %d, period %g)", size, octaves,
+                    (double)period_units);
+    clapca_tex3d *t = new (std::nothrow) clapca_tex3d();
+    if (!t) return fail(CLAPCA_ERR_NOMEM, "noise bake (array): host allocation failed");
+    t->size = size;
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();     /* TEX_FMT_RGBA8 */
+    cudaError_t e = cudaMalloc3DArray(&t->array, &desc, make_cudaExtent(size, size, size), cudaArraySurfaceLoadStore);
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = t->array;
+        e = cudaCreateSurfaceObject(&t->surf, &rd);
+    }
+    if (e != cudaSuccess) {
+        clapca_tex3d_destroy(t);
+        return fail(e == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA, "noise bake (array): %s",
+                    cudaGetErrorString(e));
+    }
+    NoiseBakeParams p = { nullptr, (unsigned)size, octaves, lacunarity, gain, period_units, seed, t->surf };
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, g_ctx.stream));
+    noise_bake_surface_kernel<<<grid_blocks_for(size * size * size, 256, 8), 256, 0, g_ctx.stream>>>(p);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(b, g_ctx.stream);
+    int rc = e == cudaSuccess ? timed_sync(a, b, kernel_ms) : fail(CLAPCA_ERR_CUDA, "noise bake (array): %s", cudaGetErrorString(e));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (rc) {
+        clapca_tex3d_destroy(t);
+        return rc;
+    }
+    *out = t;
+    return CLAPCA_OK;
+}
+
+void *clapca_tex3d_array(clapca_tex3d *t) { return t ? (void *)t->array : nullptr; }
+
+int clapca_tex3d_download(clapca_tex3d *t, uint8_t *host_rgba8)
+{
+    if (int rc = need_init()) return rc;
+    if (!t || !host_rgba8) return fail(CLAPCA_ERR_ARG, "tex3d_download: NULL argument");
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.srcArray = t->array;
+    cp.dstPtr = make_cudaPitchedPtr(host_rgba8, t->size * 4, t->size, t->size);
+    cp.extent = make_cudaExtent(t->size, t->size, t->size);
+    cp.kind = cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&cp, g_ctx.stream));
+    CU(cudaStreamSynchronize(g_ctx.stream));
+    return CLAPCA_OK;
 }
 
 int clapca_noise_fbm3(float *out, const float *xyz, size_t n, int octaves, float lacunarity, float gain,

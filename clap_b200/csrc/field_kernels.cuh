@@ -126,38 +126,62 @@ __device__ __forceinline__ uint32_t fk_unorm8(float g)
 }
 
 struct NoiseBakeParams {
-    uint32_t *out;          /* RGBA8 texels, x fastest */
+    uint32_t *out;          /* RGBA8 texels, x fastest (linear bake); unused by the array bake */
     unsigned size;
     int octaves;
     float lacunarity, gain, period_units;
     uint32_t seed;
+    cudaSurfaceObject_t surf;   /* array bake: a 3D CUDA array of uchar4 bound as a surface */
 };
 
-/* noise_grad3d_bake_rgba8(): core/noise.c:222-270, one thread per voxel */
-__global__ void __launch_bounds__(256) noise_bake_kernel(NoiseBakeParams p)
+/* one voxel of noise_grad3d_bake_rgba8(): core/noise.c:236-264 -- central differences of the fBm, normalised, packed */
+__device__ __forceinline__ uint32_t fk_bake_voxel(const NoiseBakeParams &p, unsigned x, unsigned y, unsigned z)
 {
-    const size_t voxels = (size_t)p.size * p.size * p.size;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
     const float step = p.period_units / (float)p.size;
     const float eps = step;
     const int period = (int)p.period_units;
     const float scale = 0.5f / eps;
+    const float px = (float)x * step, py = (float)y * step, pz = (float)z * step;
 
+    float gx = (fk_fbm3(px + eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                fk_fbm3(px - eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+    float gy = (fk_fbm3(px, py + eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                fk_fbm3(px, py - eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+    float gz = (fk_fbm3(px, py, pz + eps, p.octaves, p.lacunarity, p.gain, period, p.seed) -
+                fk_fbm3(px, py, pz - eps, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
+    float len2 = gx * gx + gy * gy + gz * gz;
+    float inv = 1.0f / sqrtf(len2 > FLT_MIN ? len2 : FLT_MIN);
+
+    return fk_unorm8(gx * inv) | (fk_unorm8(gy * inv) << 8) | (fk_unorm8(gz * inv) << 16);
+}
+
+/* noise_grad3d_bake_rgba8(): core/noise.c:222-270, one thread per voxel, into a linear buffer */
+__global__ void __launch_bounds__(256) noise_bake_kernel(NoiseBakeParams p)
+{
+    const size_t voxels = (size_t)p.size * p.size * p.size;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += stride) {
         const unsigned x = (unsigned)(i % p.size), y = (unsigned)((i / p.size) % p.size);
         const unsigned z = (unsigned)(i / ((size_t)p.size * p.size));
-        const float px = (float)x * step, py = (float)y * step, pz = (float)z * step;
+        p.out[i] = fk_bake_voxel(p, x, y, z);
+    }
+}
 
-        float gx = (fk_fbm3(px + eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
-                    fk_fbm3(px - eps, py, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
-        float gy = (fk_fbm3(px, py + eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed) -
-                    fk_fbm3(px, py - eps, pz, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
-        float gz = (fk_fbm3(px, py, pz + eps, p.octaves, p.lacunarity, p.gain, period, p.seed) -
-                    fk_fbm3(px, py, pz - eps, p.octaves, p.lacunarity, p.gain, period, p.seed)) * scale;
-        float len2 = gx * gx + gy * gy + gz * gz;
-        float inv = 1.0f / sqrtf(len2 > FLT_MIN ? len2 : FLT_MIN);
-
-        p.out[i] = fk_unorm8(gx * inv) | (fk_unorm8(gy * inv) << 8) | (fk_unorm8(gz * inv) << 16);
+/*
+ * The same bake straight into a 3D CUDA array through a surface: the array is what the renderer's 3D
+ * texture maps under CUDA / GL or Vulkan interop (noise_grad3d_bake_rgba8_tex, core/noise.c:272-294, uploads the host
+ * copy with texture_load) -- the texels never visit the host.
+ */
+__global__ void __launch_bounds__(256) noise_bake_surface_kernel(NoiseBakeParams p)
+{
+    const size_t voxels = (size_t)p.size * p.size * p.size;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += stride) {
+        const unsigned x = (unsigned)(i % p.size), y = (unsigned)((i / p.size) % p.size);
+        const unsigned z = (unsigned)(i / ((size_t)p.size * p.size));
+        const uint32_t t = fk_bake_voxel(p, x, y, z);
+        surf3Dwrite(make_uchar4((unsigned char)t, (unsigned char)(t >> 8), (unsigned char)(t >> 16), 0), p.surf,
+                    (int)(x * sizeof(uchar4)), (int)y, (int)z);
     }
 }
 

@@ -17,6 +17,41 @@ def noise_grad3d_bake_rgba8(size, octaves=4, lacunarity=2.0, gain=0.5, period_un
     return out
 
 
+class NoiseTexture3D:
+    """The bake as a device-resident 3D RGBA8 texture (clapca_noise_bake_array): a CUDA array written
+    through a surface -- what noise_grad3d_bake_rgba8_tex() (core/noise.c:272-294) hands the renderer, minus the
+    host round trip.  `array` is the cudaArray_t to register with the graphics API; download() reads it back."""
+
+    def __init__(self, size, octaves=4, lacunarity=2.0, gain=0.5, period_units=64.0, seed=0xC14D):
+        from ctypes import c_float
+        self._lib = _lib.lib()
+        self.size = int(size)
+        h, ms = c_void_p(), c_float()
+        check(self._lib, self._lib.clapca_noise_bake_array(byref(h), size, octaves, lacunarity, gain, period_units, seed,
+                                                           byref(ms)))
+        self._h, self.kernel_ms = h, ms.value
+
+    @property
+    def array(self):
+        return self._lib.clapca_tex3d_array(self._h)
+
+    def download(self):
+        out = np.empty((self.size, self.size, self.size, 4), dtype=np.uint8)
+        check(self._lib, self._lib.clapca_tex3d_download(self._h, out.ctypes.data_as(c_void_p)))
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.clapca_tex3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def noise_fbm3(xyz, octaves, lacunarity, gain, period, seed):
     """fbm3_periodic(): core/noise.c:204-220 at the points xyz[n, 3] (float32)."""
     lib = _lib.lib()

@@ -278,6 +278,20 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv_mask, uint32_t born_mask, 
 int clapca_slab_run(clapca_slab *s, int64_t *local_population);
 int clapca_slab_last_stats(clapca_slab *s, clapca_run_stats *st);
 
+/*
+ * SURVEY 8(f).3 -- the gradient-noise bake as a device-resident 3D texture: noise_grad3d_bake_rgba8_tex()
+ * (core/noise.c:272-294) bakes on the host and uploads with texture_load(); here the kernel writes the RGBA8 texels
+ * straight into a 3D CUDA array through a surface.  clapca_tex3d_array() returns the cudaArray_t -- the object a
+ * renderer's TEX_3D / TEX_FMT_RGBA8 texture is mapped to under CUDA / GL or Vulkan interop, so the texels never visit
+ * the host; clapca_tex3d_download() reads it back (size^3 * 4 bytes, x fastest) for whoever wants the host copy.
+ */
+typedef struct clapca_tex3d clapca_tex3d;
+int clapca_noise_bake_array(clapca_tex3d **out, size_t size, int octaves, float lacunarity, float gain,
+                            float period_units, uint32_t seed, float *kernel_ms);
+void *clapca_tex3d_array(clapca_tex3d *t);
+int clapca_tex3d_download(clapca_tex3d *t, uint8_t *host_rgba8);
+int clapca_tex3d_destroy(clapca_tex3d *t);
+
 /* device-resident field evaluation for benchmarks: results stay in device memory */
 int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
                              float period_units, uint32_t seed, float *kernel_ms);

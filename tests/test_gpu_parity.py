@@ -573,6 +573,38 @@ def test_noise_bake_256_against_oracle_slices(gpu, oracle):
     assert not got[..., 3].any()
 
 
+def test_noise_bake_into_cuda_array_equals_linear_bake_and_golden(gpu, oracle):
+    """the bake written straight into a 3D CUDA array through a surface (the object a renderer's
+    TEX_3D / RGBA8 texture maps under interop) reads back identical to the linear bake and to the golden vectors;
+    odd sizes exercise the array's pitched layout."""
+    g = np.load(os.path.join(G, "noise.npz"))
+    for size, args, key in ((16, (4, 2.0, 0.5, 5.0, 0xC14D), "bake_16_p5"), (24, (3, 2.3, 0.45, 37.0, 99), "bake_24_p37_o3")):
+        tex = gpu.NoiseTexture3D(size, *args)
+        assert tex.array
+        got = tex.download()
+        tex.close()
+        assert np.array_equal(got, g[key]), key
+    for size in (1, 7, 33, 64):
+        tex = gpu.NoiseTexture3D(size, 4, 2.0, 0.5, 9.0, 7)
+        got = tex.download()
+        tex.close()
+        assert np.array_equal(got, gpu.noise_grad3d_bake_rgba8(size, 4, 2.0, 0.5, 9.0, 7)), size
+    tex = gpu.NoiseTexture3D(64)                # engine defaults (noise.c:309-317)
+    assert oracle.fnv(tex.download()) == int(g["bake_64_default_hash"])
+    tex.close()
+
+
+def test_noise_lattice_wrap_far_outside_the_period(gpu, oracle):
+    """fk_wrap() takes a conditional add / subtract within one period of [0, period) and the reference's double
+    modulo beyond: points many periods away (both signs) must still match the oracle bit for bit"""
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([rng.uniform(-1e4, 1e4, (4000, 3)), rng.uniform(-40, 80, (4000, 3)),
+                          np.array([[-37.0, 37.0, 74.0], [-0.5, 36.999, 37.0], [-74.0001, 73.9999, 0.0]])]).astype(np.float32)
+    got = gpu.noise_fbm3(pts, 4, 2.0, 0.5, 37, 0xC14D)
+    want = oracle.fbm3(pts, 4, 2.0, 0.5, 37, 0xC14D)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 # ---- terrain --------------------------------------------------------------------------------------
 
 def _field_close(got, want):
