@@ -905,8 +905,9 @@ struct Sweep3 {
         }
         const bool streams = dp_any(pdst != nullptr);
         long long t_idle = dp_clock(), t_busy = 0;
+        unsigned idle_since = 0;
         for (unsigned spins = 0;; spins++) {
-            const long long t_pass = dp_clock();
+            const long long t_pass = p.diag ? dp_clock() : 0;
             const int d = lane < n ? dp_ld_volatile(done + lane) : H;
             dp_fence_cta();
             bool any = false;
@@ -949,12 +950,13 @@ struct Sweep3 {
             if (dp_all(fin))
                 break;
             if (any) {
-                t_busy += dp_clock() - t_pass;
-                t_idle = dp_clock();
+                if (p.diag) t_busy += dp_clock() - t_pass;
+                idle_since = spins;
             } else {
                 dp_nanosleep(64);
                 if ((spins & 255u) == 255u) {
                     /* a compute warp that bailed out never completes its rows */
+                    if (spins - idle_since < 512u) t_idle = dp_clock();
                     bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
                     if (!dp_all(!bad)) {
                         if (lane == 0)
