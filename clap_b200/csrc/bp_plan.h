@@ -72,14 +72,15 @@ struct SlabGeom {
 struct HaloLayout {
     size_t gp;                      /* words per ghost plane */
     size_t ghost_dn, ghost_up;      /* first ghost plane below / above; local block lb at + gp * lb */
-    size_t flags;                   /* counters: bank b at + b * 2 * nlb_max * Gcap ints */
+    size_t flags;                   /* counters: bank b at + b * bank_words() ints; Gcap + 1 per ghost plane, the first one
+                                       is "generation -1" (layout items: the neighbour's pack item) */
     size_t total_words;
     int nlb_max, Gcap;
     size_t flag_index(int bank, int up, int lb) const
     {
-        return flags + (((size_t)bank * 2 + (size_t)up) * nlb_max + (size_t)lb) * Gcap;
+        return flags + (((size_t)bank * 2 + (size_t)up) * nlb_max + (size_t)lb) * (Gcap + 1) + 1;    /* generation 0 */
     }
-    size_t bank_words() const { return (size_t)2 * nlb_max * Gcap; }
+    size_t bank_words() const { return (size_t)2 * nlb_max * (Gcap + 1); }
 };
 
 inline HaloLayout slab_halo_layout(const SlabGeom &geo, int H, int RWP, int NP, int Gcap)
@@ -387,7 +388,8 @@ inline int bp3_tile_shape(const std::vector<Bp3Plane> &planes, int H, int G, int
 }
 
 /* the same for a sharded volume: every rank must run the same shape, so take the smallest Tg over the ranks' plane lists */
-inline int bp3_tile_shape_all_ranks(const SlabGeom &geo, int H, int G, int team, int want, int ctas, int *Tz_out)
+inline int bp3_tile_shape_all_ranks(const SlabGeom &geo, int H, int G, int team, int want, int ctas, int *Tz_out,
+                                    bool layout_items = false)
 {
     int Tg = std::max(1, want), Tz = team;
     std::vector<Bp3Plane> planes;
@@ -395,7 +397,7 @@ inline int bp3_tile_shape_all_ranks(const SlabGeom &geo, int H, int G, int team,
         SlabGeom g = geo;
         g.rank = r;
         bp3_topology_planes(g, planes);
-        Tg = std::min(Tg, bp3_tile_shape(planes, H, G, team, Tg, ctas, false, &Tz));
+        Tg = std::min(Tg, bp3_tile_shape(planes, H, G, team, Tg, ctas, layout_items, &Tz));
     }
     /* Tg only ever shrinks along the loop and a shape that passed for a larger Tg was not necessarily re-checked
        for this one on the earlier ranks: confirm, falling back to plane groups */
@@ -405,7 +407,7 @@ inline int bp3_tile_shape_all_ranks(const SlabGeom &geo, int H, int G, int team,
             g.rank = r;
             bp3_topology_planes(g, planes);
             int tz = team;
-            if (bp3_tile_shape(planes, H, G, team, Tg, ctas, false, &tz) != Tg) { Tg = 1; break; }
+            if (bp3_tile_shape(planes, H, G, team, Tg, ctas, layout_items, &tz) != Tg) { Tg = 1; break; }
         }
     }
     *Tz_out = Tg > 1 ? team / Tg : team;

@@ -870,6 +870,45 @@ struct Sweep3 {
     }
 
     /*
+     * H rows [r0, r1) of one plane from the local row records to a peer's ghost plane (both with the record stride):
+     * H0 | H1 of a row are 2 * RWP contiguous words = 32 * WPL uint2, so the warp moves a row with WPL coalesced 8-byte
+     * accesses per lane.  The loads of a batch of rows are ALL issued before the first store: a row-by-row copy pays
+     * one L2 round trip per row (~0.5 us) and cannot follow eight streams that each finish a row every ~1.3 us
+     * (measured on 2 x B200: 4 x 4 tiles with 16-plane blocks ran 2x slower than one GPU until the copies were batched).
+     */
+    CA_MDEV void copy_h_rows(uint32_t *dst, const uint32_t *src, int r0, int r1)
+    {
+        constexpr int BATCH = 16 / WPL;
+        constexpr int RS = RECW / 2;                /* record stride in uint2 */
+        const int lane = dp_lane();
+        const uint2 *a = reinterpret_cast<const uint2 *>(src + (size_t)r0 * RECW) + lane;
+        uint2 *b = reinterpret_cast<uint2 *>(dst + (size_t)r0 * RECW) + lane;
+        int n = r1 - r0;
+        for (; n >= BATCH; n -= BATCH, a += BATCH * RS, b += BATCH * RS) {
+            uint2 v[BATCH][WPL];
+#pragma unroll
+            for (int i = 0; i < BATCH; i++)
+#pragma unroll
+                for (int k = 0; k < WPL; k++)
+                    v[i][k] = dp_ld_cg(a + i * RS + 32 * k);
+#pragma unroll
+            for (int i = 0; i < BATCH; i++)
+#pragma unroll
+                for (int k = 0; k < WPL; k++)
+                    dp_st_cg(b + i * RS + 32 * k, v[i][k]);
+        }
+        for (; n > 0; n--, a += RS, b += RS) {      /* the tail of a pass, row by row */
+            uint2 v[WPL];
+#pragma unroll
+            for (int k = 0; k < WPL; k++)
+                v[k] = dp_ld_cg(a + 32 * k);
+#pragma unroll
+            for (int k = 0; k < WPL; k++)
+                dp_st_cg(b + 32 * k, v[k]);
+        }
+    }
+
+    /*
      * Tile mode, the service warp of one tile (nz planes from local plane l0, ng generations from g0).
      * Lane w < nz * ng serves compute warp w: it carries the warp's shared-memory row counter to prog[g][z].
      * Lanes 0 .. 2 ng - 1 additionally own one push stream each: lane j < ng the H rows of warp (0, j) for the ghost
@@ -930,13 +969,7 @@ struct Sweep3 {
                         const uint32_t *src = (const uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)psrc, s);
                         uint32_t *dst = (uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)pdst, s);
                         const int r0 = (int)dp_shfl((uint32_t)pushed, s), r1 = (int)dp_shfl((uint32_t)avail, s);
-                        for (int r = r0; r < r1; r++) {
-                            const uint2 *a = reinterpret_cast<const uint2 *>(src + (size_t)r * RECW) + lane;
-                            uint2 *b = reinterpret_cast<uint2 *>(dst + (size_t)r * RECW) + lane;
-#pragma unroll
-                            for (int k = 0; k < WPL; k++)       /* H0 | H1 = 2 * RWP words = 32 * WPL uint2 */
-                                dp_st_cg(b + 32 * k, dp_ld_cg(a + 32 * k));
-                        }
+                        copy_h_rows(dst, src, r0, r1);
                     }
                     dp_fence_sys();                     /* fence.acq_rel.sys: peer rows before the peer's counter */
                     if (pm) {
@@ -971,6 +1004,34 @@ struct Sweep3 {
     }
 
     /*
+     * Layout items of a sharded volume: the first plane of a z-block is the "old plane above" of generation 0 for the
+     * last plane of the previous block -- on another GPU.  While a compute warp packs that plane (and raises
+     * prog[-1][z] every 32 rows) the service warp copies the finished H rows into the neighbour's ghost plane and raises
+     * its "generation -1" counter: the halo seed of a resident run (api_slab.cu) moved into the launch.
+     */
+    CA_MDEV void seed_push(const Bp3Params &p, int zl)
+    {
+        const int lane = dp_lane();
+        const int H = p.H;
+        const Bp3Plane pl = p.planes[zl];
+        if (!pl.push_dn_rows)
+            return;
+        const int *myprog = p.prog - p.Z + zl;
+        const uint32_t *src = p.rows + (size_t)zl * H * RECW;
+        int pushed = 0;
+        while (pushed < H) {
+            if (!wait_word(p, myprog, pushed + 1, false, 8))
+                return;
+            const int avail = (int)dp_shfl((uint32_t)(lane == 0 ? dp_ld_acquire(myprog) : 0), 0);
+            copy_h_rows(pl.push_dn_rows, src, pushed, avail);
+            dp_fence_sys();
+            if (lane == 0)
+                dp_st_flag_sys(pl.push_dn_flag - 1, avail);
+            pushed = avail;
+        }
+    }
+
+    /*
      * Tile mode: the CTA claims one tile at a time.  Item = (first local plane, first generation, nz | ng << 8, H);
      * compute warp w = i + nz * j sweeps plane i of the tile at generation j, warps beyond nz * ng sit the item out,
      * warp `team` (the last one) is the service warp.  Layout items (g == -1 / g == G): warp w < nz packs / unpacks
@@ -999,6 +1060,8 @@ struct Sweep3 {
             if (p.layout_items && (it.y < 0 || it.y >= p.G)) {
                 if (w < nz)
                     run_item(p, it.x + w, it.y, 0, p.H, nullptr);
+                else if (w == T && it.y < 0)
+                    seed_push(p, it.x);             /* a packed z-block edge is the neighbour's "old plane above" of generation 0 */
             } else if (w < nz * ng) {
                 const int i = w % nz, j = w / nz;
                 TileWire tw;
@@ -1052,19 +1115,25 @@ struct Bp3Bounds {
 };
 
 /*
- * Tile mode is a kernel of its own (one CTA per SM): 16 compute warps + the service warp = 544 threads leave every
- * thread 120 registers; the widest variants (8 state planes, 4 words per lane) run 7 compute warps + the service warp.
+ * Tile mode is a kernel of its own (one CTA per SM).  The register file is split over the SM's four sub-partitions, so
+ * what a thread may use follows from the warps per SUB-PARTITION: 16 warps (15 compute + the service warp) are 4 per
+ * sub-partition = 128 registers per thread; a 17th warp would put 5 on one of them and cap every thread at 96 (ptxas
+ * then spills in the row loop as soon as the service path grows).  15 compute warps = tiles of 5 planes x 3 generations.
+ * The widest variants (8 state planes, 4 words per lane) run 7 compute warps + the service warp.
  */
+#ifndef CLAPCA_TEAM_WARPS
+#define CLAPCA_TEAM_WARPS 15
+#endif
 template <int P, int WPL>
 struct Bp3TeamBounds {
-    static constexpr int kTeam = (P <= 4 && WPL <= 2) ? 16 : 7;
+    static constexpr int kTeam = (P <= 4 && WPL <= 2) ? CLAPCA_TEAM_WARPS : 7;
     static constexpr int kMaxThreads = 32 * (kTeam + 1);
 };
 
 /* largest team (compute warps per CTA) of a variant */
 inline int bp3_team_cap(int P, int WPL)
 {
-    return (P <= 4 && WPL <= 2) ? 16 : 7;
+    return (P <= 4 && WPL <= 2) ? CLAPCA_TEAM_WARPS : 7;
 }
 
 template <int P, int WPL, class Rule>

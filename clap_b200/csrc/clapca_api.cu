@@ -435,26 +435,31 @@ static const int kFlagRows = 8;
 
 /*
  * Tile mode (ca3d_bitplane.cuh): compute warps per CTA = planes x generations of a work item; 0 = one warp per sweep.
- * Default: 16 compute warps (+ the service warp) for the variants whose register budget allows it.  Round 1 measured
- * plane groups of 16 x 1 on B200 at 2048^3, coral (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms
- * against one warp per sweep, and 35.2 -> 16.4 ms in the low-parallelism regime a rank of an 8-GPU run sees.
+ * Default: 15 compute warps + the service warp (16 warps = 4 per SM sub-partition = 128 registers per thread) for the
+ * variants whose register budget allows it.  Round 1 measured plane groups of 16 x 1 on B200 at 2048^3, coral
+ * (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms against one warp per sweep, and 35.2 -> 16.4 ms
+ * in the low-parallelism regime a rank of an 8-GPU run sees.
  */
 int clapca::api::team_config(int P, int WPL)
 {
-    int t = bp3_team_cap(P, WPL) >= 16 ? 16 : 0;
+    int t = bp3_team_cap(P, WPL) >= 12 ? bp3_team_cap(P, WPL) : 0;
     if (const char *e = getenv("CLAPCA_TEAM")) t = atoi(e);
     if (t <= 0) return 0;
     return std::min(t, bp3_team_cap(P, WPL));
 }
 
 /*
- * Generations per tile.  4 x 4 tiles keep four generations of a row within ~20 row steps of each other: generation
- * g+1 reads generation g from L2 and overwrites it there, HBM sees a quarter of the per-generation streaming of
- * plane groups.  The planner lowers it when the launch has too few CTAs for the forward dependency (bp_plan.h).
+ * Generations per tile.  Tiles of several generations keep those generations of a row within ~20 row steps of each
+ * other: generation g+1 reads generation g from L2 and overwrites it there, and HBM sees 1 / ng of the per-generation
+ * streaming of plane groups (measured with 4 x 4 tiles: 540 -> 138 GB per 2048^3 x 50 run).  The planner lowers it when the launch has too few CTAs for the forward dependency (bp_plan.h).
  */
 int clapca::api::tile_gens_config(int team)
 {
-    int tg = team >= 16 ? 4 : 1;
+    /* the largest divisor g of the team with g <= team / g: 15 -> 3 (5 x 3), 16 -> 4 (4 x 4), 12 -> 3 (4 x 3) */
+    int tg = 1;
+    for (int g = 2; g * g <= team; g++)
+        if (team % g == 0) tg = g;
+    if (team < 12) tg = 1;
     if (const char *e = getenv("CLAPCA_TILE_GENS")) { int v = atoi(e); if (v > 0) tg = v; }
     return tg;
 }

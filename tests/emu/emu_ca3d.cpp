@@ -127,8 +127,12 @@ int main(int argc, char **argv)
         fprintf(stderr, "several ranks need tile mode (team > 0)\n");
         return 2;
     }
-    if (layout && (ranks != 1 || (team <= 0 && genBatch >= 0))) {
-        fprintf(stderr, "layout items: single rank, time-key (genbatch -1) or team order\n");
+    if (layout && (team <= 0 && genBatch >= 0)) {
+        fprintf(stderr, "layout items: time-key (genbatch -1) or tile order\n");
+        return 2;
+    }
+    if (layout == 2 && ranks != 1) {
+        fprintf(stderr, "layout 2 (copy-engine threads): single rank\n");
         return 2;
     }
 
@@ -215,7 +219,7 @@ int main(int argc, char **argv)
         if (team > 0) {
             const int ctas = (warps + team - 1) / team;
             int Tz = team, Tg = 1;
-            if (ranks > 1) Tg = bp3_tile_shape_all_ranks(k.geo, H, G, team, tileGens, ctas, &Tz);
+            if (ranks > 1) Tg = bp3_tile_shape_all_ranks(k.geo, H, G, team, tileGens, ctas, &Tz, layout != 0);
             else Tg = bp3_tile_shape(k.planes, H, G, team, tileGens, ctas, layout != 0, &Tz);
             if (r == 0) fprintf(stderr, "tile shape %d planes x %d generations\n", Tz, Tg);
             bp3_make_items_tile(k.planes, H, G, Tz, Tg, items, layout != 0);
@@ -258,7 +262,7 @@ int main(int argc, char **argv)
         }
     }
     /* halo init: the first plane of every block but the first seeds the ghost plane above the previous block */
-    for (int r = 0; r < ranks; r++) {
+    for (int r = 0; r < ranks && !layout; r++) {    /* layout items: the pack items' service warps seed the ghost planes */
         for (size_t l = 0; l < rk[r].planes.size(); l++) {
             const Bp3Plane &pl = rk[r].planes[l];
             if (!pl.push_dn_rows) continue;
@@ -318,14 +322,25 @@ int main(int argc, char **argv)
     std::vector<uint8_t> got(n, 0xEE);
     unsigned long long pop = 0;
     if (layout) {
-        Rank &k = rk[0];
-        for (int z = 0; z < Z; z++)
-            if (k.out_done[z] != 3) {
-                printf("FAIL out_done[%d]=%d\n", z, k.out_done[z]);
-                return 1;
+        for (int r = 0; r < ranks; r++) {
+            Rank &k = rk[r];
+            const int Zl = k.geo.local_planes();
+            for (int z = 0; z < Zl; z++)
+                if (k.out_done[z] != 3) {
+                    printf("FAIL rank %d out_done[%d]=%d\n", r, z, k.out_done[z]);
+                    return 1;
+                }
+            pop += k.pop;
+            if (layout == 2) {
+                got = host_out;
+                continue;
             }
-        got = layout == 2 ? host_out : k.cells;
-        pop = k.pop;
+            for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
+                int jb = k.geo.global_block(lb);
+                memcpy(got.data() + (size_t)k.geo.block_z0(jb) * W * H, k.cells.data() + (size_t)k.geo.local_z0(lb) * W * H,
+                       (size_t)k.geo.block_len(jb) * W * H);
+            }
+        }
     }
     for (int r = 0; r < ranks && !layout; r++) {
         Rank &k = rk[r];
