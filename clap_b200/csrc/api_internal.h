@@ -95,6 +95,22 @@ OrderCfg order_config(int Z, int H, int G, int max_workers, int team);
 void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                 std::vector<WorkItem> &items, bool layout_items);
 
+/* host side of a streamed run: see stream_volume() in clapca_api.cu */
+struct StreamPlan {
+    uint8_t *d_cells;           /* device cells of the (local) planes, reference layout */
+    const uint8_t *host_in;     /* pinned */
+    uint8_t *host_out;          /* pinned */
+    size_t plane_bytes;
+    int Z, chunk;               /* planes, planes per H2D chunk */
+    int *d_in_ready;            /* device word: chunks landed */
+    int *h_io;                  /* pinned + mapped: [0, Z) per-plane done flags, then the chunk ordinals 1, 2, ... */
+    int epoch;                  /* value the unpack items store into the done flags */
+    cudaStream_t s_kernel, s_in, s_out;
+};
+int stream_volume(const StreamPlan &sp, bool *stuck);
+/* planes per H2D chunk of a streamed run */
+int io_chunk_planes(size_t plane_bytes, int Z);
+
 /* the layout kernels live in ONE translation unit (clapca_api.cu); these launch them */
 cudaError_t launch_ca3d_pack(const Bp3Layout &L, cudaStream_t stream);
 cudaError_t launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t stream);

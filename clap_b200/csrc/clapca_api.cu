@@ -506,18 +506,8 @@ void clapca::api::make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &pl
     else bp3_make_items_timekey(planes, H, G, items, layout_items);
 }
 
-extern "C" {
-#pragma GCC visibility push(default)
-
-/* CLAPCA_FUSED_LAYOUT=1: device-resident runs also convert the layout inside the sweep launch (layout items) */
-static bool fused_layout_default()
-{
-    const char *e = getenv("CLAPCA_FUSED_LAYOUT");
-    return e && atoi(e) != 0;
-}
-
 /* planes per H2D chunk of a streamed run: ~32 MiB; CLAPCA_IO_CHUNK_MB / CLAPCA_IO_CHUNK_PLANES override */
-static int io_chunk_planes(size_t plane_bytes, int Z)
+int clapca::api::io_chunk_planes(size_t plane_bytes, int Z)
 {
     size_t mb = 32;
     if (const char *e = getenv("CLAPCA_IO_CHUNK_MB")) { int v = atoi(e); if (v > 0) mb = (size_t)v; }
@@ -529,12 +519,72 @@ static int io_chunk_planes(size_t plane_bytes, int Z)
     return (int)c;
 }
 
+extern "C" {
+#pragma GCC visibility push(default)
+
+/* CLAPCA_FUSED_LAYOUT=1: device-resident runs also convert the layout inside the sweep launch (layout items) */
+static bool fused_layout_default()
+{
+    const char *e = getenv("CLAPCA_FUSED_LAYOUT");
+    return e && atoi(e) != 0;
+}
+
 static inline void cpu_relax()
 {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
 #endif
 }
+
+#pragma GCC visibility pop
+} /* extern "C" */
+
+/*
+ * Host side of a streamed run (the sweep launch with layout items is already in flight on sp.s_kernel).  H2D: every
+ * chunk of planes, then its ordinal into the device word the pack items poll (stream order = arrival order).  D2H:
+ * this thread follows the unpack items' per-plane flags in host-mapped memory and releases a chunk's copy as soon as
+ * all its planes carry the run's epoch.  *stuck = the launch ended without finishing a chunk.
+ */
+int clapca::api::stream_volume(const StreamPlan &sp, bool *stuck)
+{
+    const int nchunks = (sp.Z + sp.chunk - 1) / sp.chunk;
+    for (int c = 0; c < nchunks; c++) {
+        const size_t off = (size_t)c * sp.chunk * sp.plane_bytes;
+        const size_t len = (size_t)std::min(sp.chunk, sp.Z - c * sp.chunk) * sp.plane_bytes;
+        CU(cudaMemcpyAsync(sp.d_cells + off, sp.host_in + off, len, cudaMemcpyHostToDevice, sp.s_in));
+        CU(cudaMemcpyAsync(sp.d_in_ready, sp.h_io + sp.Z + c, sizeof(int), cudaMemcpyHostToDevice, sp.s_in));
+    }
+    volatile const int *flag = sp.h_io;
+    bool kernel_done = false;
+    unsigned spins = 0;
+    *stuck = false;
+    for (int c = 0; c < nchunks && !*stuck;) {
+        const int z0 = c * sp.chunk, z1 = std::min(sp.Z, z0 + sp.chunk);
+        bool ready = true;
+        for (int z = z0; z < z1; z++)
+            if (flag[z] != sp.epoch) { ready = false; break; }
+        if (ready) {
+            const size_t off = (size_t)z0 * sp.plane_bytes;
+            CU(cudaMemcpyAsync(sp.host_out + off, sp.d_cells + off, (size_t)(z1 - z0) * sp.plane_bytes,
+                               cudaMemcpyDeviceToHost, sp.s_out));
+            c++;
+            continue;
+        }
+        if (kernel_done) { *stuck = true; break; }      /* the launch ended without finishing this chunk */
+        if ((++spins & 255u) == 0u) {
+            cudaError_t e = cudaStreamQuery(sp.s_kernel);
+            if (e == cudaSuccess) kernel_done = true;   /* one more look at the flags, then give up */
+            else if (e != cudaErrorNotReady) return fail(CLAPCA_ERR_CUDA, "streamed run: %s", cudaGetErrorString(e));
+        }
+        cpu_relax();
+    }
+    CU(cudaStreamSynchronize(sp.s_in));
+    CU(cudaStreamSynchronize(sp.s_out));
+    return CLAPCA_OK;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
 
 /*
  * The bit-plane engine on a device-resident grid.  io == nullptr: the cells are in g->cells and the result
@@ -724,40 +774,10 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     CU(cudaEventRecord(g->ev[2], g->stream));
 
     if (io) {
-        /* H2D: every chunk, then its ordinal into the word the pack items poll (stream order = arrival order) */
-        for (int c = 0; c < nchunks; c++) {
-            const size_t off = (size_t)c * chunk * plane_bytes;
-            const size_t len = (size_t)std::min(chunk, Z - c * chunk) * plane_bytes;
-            CU(cudaMemcpyAsync(g->cells + off, io->host_in + off, len, cudaMemcpyHostToDevice, g_ctx.stream_in));
-            CU(cudaMemcpyAsync(g->d_in_ready, g->h_io + Z + c, sizeof(int), cudaMemcpyHostToDevice, g_ctx.stream_in));
-        }
-        /* D2H: this thread follows the unpack items plane by plane and releases a chunk's copy when it is whole */
-        volatile const int *flag = g->h_io;
-        const int epoch = g->io_epoch;
-        bool kernel_done = false, stuck = false;
-        unsigned spins = 0;
-        for (int c = 0; c < nchunks && !stuck;) {
-            const int z0 = c * chunk, z1 = std::min(Z, z0 + chunk);
-            bool ready = true;
-            for (int z = z0; z < z1; z++)
-                if (flag[z] != epoch) { ready = false; break; }
-            if (ready) {
-                const size_t off = (size_t)z0 * plane_bytes;
-                CU(cudaMemcpyAsync(io->host_out + off, g->cells + off, (size_t)(z1 - z0) * plane_bytes,
-                                   cudaMemcpyDeviceToHost, g_ctx.stream_out));
-                c++;
-                continue;
-            }
-            if (kernel_done) { stuck = true; break; }     /* the launch ended without finishing this chunk */
-            if ((++spins & 255u) == 0u) {
-                cudaError_t e = cudaStreamQuery(g->stream);
-                if (e == cudaSuccess) kernel_done = true;   /* one more look at the flags, then give up */
-                else if (e != cudaErrorNotReady) return fail(CLAPCA_ERR_CUDA, "streamed run: %s", cudaGetErrorString(e));
-            }
-            cpu_relax();
-        }
-        CU(cudaStreamSynchronize(g_ctx.stream_in));
-        CU(cudaStreamSynchronize(g_ctx.stream_out));
+        bool stuck = false;
+        StreamPlan sp = { g->cells, io->host_in, io->host_out, plane_bytes, Z, chunk, g->d_in_ready, g->h_io, g->io_epoch,
+                          g->stream, g_ctx.stream_in, g_ctx.stream_out };
+        if (int rc = stream_volume(sp, &stuck)) return rc;
         CU(cudaEventRecord(g->ev[3], g->stream));
         unsigned long long pop = 0;
         int err = 0;

@@ -23,14 +23,32 @@ from .rules import CellAutomaton, ca3d_rule
 DEFAULT_BLOCK_PLANES = 16
 
 
-def default_block_planes(d2, nranks):
-    """z-block size of the scaling bench.  Small blocks keep the ranks' pipeline short: rank r can start 3 r B row
-    steps after rank 0 and the last rank idles as long at the end, which at 2048^3 x 50 on 8 GPUs cost more than the
-    per-edge overhead ever did (SCALE_r01: 0.57 efficiency with blocks of 128 planes).  With the halo rows carried
-    by the tiles' service warps an edge costs the compute warps nothing, so the block is as small as one tile row of
-    16 planes -- but every rank keeps at least two blocks."""
-    per_rank = max(1, -(-int(d2) // max(1, int(nranks))))
-    return max(1, min(16, max(4, per_rank // 2), per_rank))
+TILE_PLANES = 5     # planes per tile of the default kernel variant (15 compute warps = 5 planes x 3 generations)
+
+
+def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=60):
+    """z-block size of the scaling bench: a multiple of the tile height (a ragged tile leaves most of a CTA idle), at
+    most `largest` planes: the largest one for which the most loaded rank stays within 1.5 % of the best balance any
+    candidate reaches (fewer z-block edges).  Measured on 2 x B200 at 2048^3 x 50 (profiles/r02_knobs_multi_n2.txt): blocks of 15 /
+    30 / 60 / 120 planes sweep in 60.3 / 57.3 / 56.7 / 71.0 ms -- small blocks pay for their edges, large ones for the
+    pipeline fill (rank r starts 3 r B row steps after rank 0 and the last rank idles as long at the end)."""
+    d2, nranks = int(d2), max(1, int(nranks))
+    if nranks == 1:
+        return d2
+    per_rank = -(-d2 // nranks)
+    cands = {}
+    b = tile_planes
+    while b <= max(tile_planes, min(largest, per_rank // 2 if per_rank >= 2 * tile_planes else per_rank)):
+        loads = [0] * nranks
+        for j, z0 in enumerate(range(0, d2, b)):
+            loads[j % nranks] += min(b, d2 - z0)
+        cands[b] = max(loads)
+        b += tile_planes
+    if not cands:
+        return max(1, min(per_rank, d2))
+    fair = min(cands.values())
+    best = max(b for b, load in cands.items() if load <= 1.015 * fair)      # the largest block within 1.5 % of the best balance
+    return max(1, min(best, d2))
 
 
 # ---- pure host-side planning (mirrors SlabGeom in csrc/bp_plan.h; unit-tested on CPU) -----------------

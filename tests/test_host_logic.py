@@ -72,10 +72,21 @@ def test_python_rand48_block_matches_scalar_stream():
 def test_default_block_planes(d2, nranks):
     b = default_block_planes(d2, nranks)
     per_rank = -(-d2 // nranks)
-    assert 1 <= b <= max(1, per_rank) and b <= 16
+    assert 1 <= b <= d2
     blocks = plan_blocks(d2, nranks, b)
     assert sum(z1 - z0 for _, z0, z1 in blocks) == d2
-    if d2 >= nranks:                                   # nobody is left without planes
-        assert all(local_planes(d2, nranks, b, r) for r in range(nranks))
-    if per_rank >= 8 and nranks > 1:                   # at least two blocks per rank keep the pipeline fill short
+    if nranks == 1:
+        assert b == d2
+        return
+    assert b <= 60 or b <= per_rank
+    loads = [sum(z1 - z0 for r, z0, z1 in blocks if r == k) for k in range(nranks)]
+    if d2 >= 40 * nranks:               # the most loaded rank stays within a few percent of its fair share
+        assert max(loads) <= 1.04 * d2 / nranks + 5, (b, loads)
+        assert b % 5 == 0               # whole tiles
         assert min(sum(1 for r, _, _ in blocks if r == k) for k in range(nranks)) >= 2
+
+
+def test_default_block_planes_of_the_scaling_bench():
+    assert default_block_planes(2048, 2) == 60
+    assert default_block_planes(2048, 8) == 20
+    assert max(sum(z1 - z0 for r, z0, z1 in plan_blocks(2048, 8, 20) if r == k) for k in range(8)) == 260
