@@ -436,33 +436,48 @@ def run_ca3d_sharded(args, torch, dist, dev, local, workload):
     dist.all_reduce(hz)                                   # every plane has exactly one owner: sum = gather
     hashes = hz.cpu().numpy().view(np.uint64)
 
-    # end to end: pinned host slabs in, pinned host slabs out
+    # end to end: pinned host slabs in, pinned host slabs out, one pipeline per rank (clapca_slab_run_streamed)
     e2e = None
     if not args.no_e2e:
         nbytes = vol.n_local * d0 * d1
         host_in = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
         host_out = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
         host_in[:nbytes].copy_(seed_dev.reshape(-1)[:nbytes])
+        local_hashes = vol.plane_hashes() if vol.n_local else None
         torch.cuda.synchronize()
         n_e2e = max(1, min(args.steps, 3))
+        streamed = os.environ.get("CLAPCA_STREAMED", "1") != "0"
         dts = []
         for i in range(1 + n_e2e):
             dist.barrier()
             t0 = time.perf_counter()
-            vol.upload(host_in.data_ptr())
-            vol.prepare(rule, gens)
-            dist.barrier()
-            vol.run()
-            vol.download(host_out.data_ptr())
+            if streamed:
+                vol.prepare_streamed(rule, gens)
+                dist.barrier()
+                vol.run_streamed(host_in.data_ptr(), host_out.data_ptr())
+            else:
+                vol.upload(host_in.data_ptr())
+                vol.prepare(rule, gens)
+                dist.barrier()
+                vol.run()
+                vol.download(host_out.data_ptr())
             dist.barrier()
             if i:
                 dts.append(time.perf_counter() - t0)
-        t = torch.tensor([sum(dts) / len(dts)], dtype=torch.float64, device=dev)
+        # the host result must be the device-resident run's, cell for cell
+        same = 1
+        if vol.n_local:
+            vol.upload(host_out.data_ptr())
+            same = int(np.array_equal(vol.plane_hashes(), local_hashes))
+        t = torch.tensor([sum(dts) / len(dts), -float(same)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert float(t[1]) == -1.0, "end-to-end result differs from the device-resident run on some rank"
         e2e = {"value": d0 * d1 * d2 * gens / float(t[0]) / 1e9, "unit": "GCUPS",
                "h2d_bytes_per_step": d0 * d1 * d2, "d2h_bytes_per_step": d0 * d1 * d2 + 8 * world,
                "ms_per_step": float(t[0]) * 1e3, "steps": n_e2e,
-               "pipeline": "per rank: upload, prepare, (barrier), run, download"}
+               "pipeline": "per rank, streamed: H2D chunks | pack+sweep+unpack in one launch (halo rows over NVLink) | D2H chunks"
+                           if streamed else "per rank: upload, prepare, (barrier), run, download",
+               "verified_equal_to_resident_run": True}
 
     line = None
     if rank == 0:

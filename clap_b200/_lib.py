@@ -70,6 +70,8 @@ SIGNATURES = {
     "clapca_slab_device_ptr": (c_void_p, [c_void_p]),
     "clapca_slab_ipc_handle": (c_int, [c_void_p, c_void_p]),
     "clapca_slab_connect": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "clapca_slab_prepare_streamed": (c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_int]),
+    "clapca_slab_run_streamed": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64)]),
     "clapca_slab_halo_ptr": (c_void_p, [c_void_p]),
     "clapca_slab_connect_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "clapca_noise_bake_array": (c_int, [POINTER(c_void_p), c_size_t, c_int, c_float, c_float, c_float, c_uint32, POINTER(c_float)]),

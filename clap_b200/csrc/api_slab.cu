@@ -35,6 +35,14 @@ struct clapca_slab {
     cudaStream_t stream = nullptr;      /* the slab's own stream: slabs of one process run concurrently */
     int max_ctas = 0;                   /* > 0: CTAs of the sweep launch (ranks sharing one device) */
     unsigned max_value = 0;
+    /* streamed runs (layout items): copy streams, chunk-arrival word, per-plane done flags in host-mapped memory */
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    int *d_in_ready = nullptr;
+    int *h_io = nullptr;
+    size_t h_io_count = 0;
+    int io_epoch = 0, io_chunk = 1;
+    cudaEvent_t ev_io = nullptr;
+    bool streamed_order = false;        /* the claim order on the device holds pack / unpack items */
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     uint32_t surv = 0, born = 0, nr_states = 0;
     int G = 0, rule = BP3_RULE_DYN;
@@ -71,7 +79,7 @@ int clapca_slab_create(clapca_slab **out, int64_t d0, int64_t d1, int64_t d2_glo
     if (e == cudaSuccess) e = cudaMalloc(&s->rows, zl * s->H * s->NP * s->RWP * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&s->halo, s->hl.total_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(s->halo, 0, s->hl.total_words * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&s->prog, (size_t)s->Gcap * zl * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->prog, (size_t)(s->Gcap + 1) * zl * sizeof(int));   /* row 0: "generation -1" (pack items) */
     if (e == cudaSuccess) e = cudaMalloc(&s->planes, zl * sizeof(Bp3Plane));
     if (e == cudaSuccess) e = cudaMalloc(&s->ticket, kTicketWords * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_pop, sizeof(unsigned long long));
@@ -96,6 +104,11 @@ int clapca_slab_destroy(clapca_slab *s)
     void *bufs[] = { s->cells, s->rows, s->halo, s->prog, s->planes, s->order, s->ticket, s->d_pop, s->d_max };
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (s->d_in_ready) cudaFree(s->d_in_ready);
+    if (s->h_io) cudaFreeHost(s->h_io);
+    if (s->ev_io) cudaEventDestroy(s->ev_io);
+    if (s->stream_in) cudaStreamDestroy(s->stream_in);
+    if (s->stream_out) cudaStreamDestroy(s->stream_out);
     if (s->stream) cudaStreamDestroy(s->stream);
     for (int i = 0; i < 5; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -136,7 +149,7 @@ int clapca_slab_ipc_handle(clapca_slab *s, void *handle64)
 /* this rank's plane descriptors for the bank of ghost counters the next run uses */
 static int slab_build_planes(clapca_slab *s, int bank)
 {
-    SlabPtrs ptr = { s->rows, s->prog, s->halo, s->halo_next, s->halo_prev };
+    SlabPtrs ptr = { s->rows, s->prog + (s->Zl ? s->Zl : 1), s->halo, s->halo_next, s->halo_prev };
     bp3_build_planes(s->geo, ptr, s->hl, s->H, s->RWP, s->NP, s->h_planes, bank);
     if (s->Zl)
         CU(cudaMemcpyAsync(s->planes, s->h_planes.data(), s->h_planes.size() * sizeof(Bp3Plane), cudaMemcpyHostToDevice,
@@ -205,11 +218,12 @@ int clapca_slab_download(clapca_slab *s, uint8_t *dst)
 }
 
 /*
- * Step 1 of a sharded run (all ranks, then a barrier): lay the local planes out as bit-plane row
- * records, seed the neighbour's ghost planes with the H rows of every block's first plane (the
- * "old plane above" of generation 0) and clear the progress counters.
+ * Step 1 of a sharded run (all ranks, then a barrier).  Resident runs: lay the local planes out as bit-plane row
+ * records, seed the neighbour's ghost planes with the H rows of every block's first plane (the "old plane above" of
+ * generation 0).  Streamed runs: nothing is on the device yet -- the pack items of the launch do both.  Either way:
+ * the claim order for `steps` generations, this run's bank of ghost counters cleared, the progress table cleared.
  */
-int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t nr_states, int steps)
+static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t nr_states, int steps, bool streamed)
 {
     if (int rc = need_init()) return rc;
     if (!s) return fail(CLAPCA_ERR_ARG, "slab_prepare: NULL slab");
@@ -223,8 +237,9 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     for (int i = 0; i < 9; i++)
         if (kCas[i][0] == surv && kCas[i][1] == born && kCas[i][2] == nr_states) { s->rule = i; break; }
 
-    /* the cells must fit the state planes chosen at create time: the pack kernel would silently drop the upper bits */
-    if (s->Zl) {
+    /* the cells must fit the state planes chosen at create time: the pack kernel would silently drop the upper bits
+       (streamed runs: the pack items check while they convert, err = 4) */
+    if (s->Zl && !streamed) {
         unsigned maxv = 0;
         CU(cudaMemsetAsync(s->d_max, 0, sizeof(unsigned), s->stream));
         CU(launch_max_u8(s->cells, (size_t)s->Zl * s->W * s->H, s->d_max, s->stream));
@@ -246,11 +261,11 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     const int max_ctas = s->max_ctas > 0 ? s->max_ctas : knobs.max_ctas;
     OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms, team, max_ctas), team);
     /* every rank must settle on the same tile shape: decide it from all ranks' plane lists */
-    oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z);
-    if (s->order_G != steps || s->team != team || s->order_key != oc.key()) {
+    oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z, streamed);
+    if (s->order_G != steps || s->team != team || s->order_key != oc.key() || s->streamed_order != streamed) {
         std::vector<WorkItem> items;
         s->team = team;
-        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items, false);
+        make_items(oc, s->h_planes, s->geo.Zg, s->H, steps, items, streamed);
         void *p = s->order;
         if (int rc = ensure_bytes(&p, &s->order_bytes, (items.size() ? items.size() : 1) * sizeof(int4))) {
             s->order = nullptr;
@@ -262,6 +277,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
         s->n_items = (int)items.size();
         s->order_G = steps;
         s->order_key = oc.key();
+        s->streamed_order = streamed;
     }
     /* ghost counters of this run's bank: cleared here, raised by the neighbours only after the barrier that follows */
     if (int rc = slab_build_planes(s, bank)) return rc;
@@ -269,7 +285,7 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
         CU(cudaMemsetAsync(s->halo + s->hl.flags + (size_t)bank * s->hl.bank_words(), 0, s->hl.bank_words() * sizeof(int),
                            s->stream));
     CU(cudaEventRecord(s->ev[0], s->stream));
-    if (s->Zl) {
+    if (s->Zl && !streamed) {
         Bp3Layout L = { s->cells, s->rows, s->W, s->H, s->Zl, s->P, s->RWP, s->d_pop };
         CU(launch_ca3d_pack(L, s->stream));
         /* halo seed: H rows of each block's first plane -> ghost plane above the previous block (generation 0's "old plane above") */
@@ -279,11 +295,83 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
             CU(launch_halo_seed(pl.push_dn_rows, s->rows + l * (size_t)s->H * s->NP * s->RWP, s->H, s->RWP, s->NP, s->stream));
         }
     }
-    CU(cudaMemsetAsync(s->prog, 0, (size_t)s->Gcap * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
+    if (streamed) {
+        /* chunk-arrival word, per-plane done flags (host-mapped), copy streams */
+        if (!s->stream_in) CU(cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
+        if (!s->stream_out) CU(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+        if (!s->d_in_ready) CU(cudaMalloc(&s->d_in_ready, 64));
+        if (!s->ev_io) CU(cudaEventCreateWithFlags(&s->ev_io, cudaEventDisableTiming));
+        const int Zl = s->Zl ? s->Zl : 1;
+        s->io_chunk = io_chunk_planes((size_t)s->W * s->H, Zl);
+        const int nchunks = (Zl + s->io_chunk - 1) / s->io_chunk;
+        const size_t want = (size_t)Zl + nchunks;
+        if (s->h_io_count < want) {
+            if (s->h_io) cudaFreeHost(s->h_io);
+            s->h_io = nullptr;
+            s->h_io_count = 0;
+            CU(cudaHostAlloc((void **)&s->h_io, want * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+            memset(s->h_io, 0, want * sizeof(int));
+            s->h_io_count = want;
+            s->io_epoch = 0;
+        }
+        for (int c = 0; c < nchunks; c++) s->h_io[Zl + c] = c + 1;
+        s->io_epoch++;
+        CU(cudaMemsetAsync(s->d_in_ready, 0, sizeof(int), s->stream));
+        CU(cudaMemsetAsync(s->d_pop, 0, sizeof(unsigned long long), s->stream));
+    }
+    CU(cudaMemsetAsync(s->prog, 0, (size_t)(s->Gcap + 1) * (s->Zl ? s->Zl : 1) * sizeof(int), s->stream));
     CU(cudaMemsetAsync(s->ticket, 0, kTicketWords * sizeof(unsigned), s->stream));
     CU(cudaEventRecord(s->ev[1], s->stream));
     CU(cudaStreamSynchronize(s->stream));
     s->prepared = true;
+    return CLAPCA_OK;
+}
+
+int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t nr_states, int steps)
+{
+    return slab_prepare(s, surv, born, nr_states, steps, false);
+}
+
+int clapca_slab_prepare_streamed(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t nr_states, int steps)
+{
+    return slab_prepare(s, surv, born, nr_states, steps, true);
+}
+
+/* the sweep launch of a prepared slab; streamed: with layout items (pack / unpack inside the launch) */
+static int slab_launch(clapca_slab *s, bool streamed, int *workers)
+{
+    *workers = 0;
+    if (!s->n_items)
+        return CLAPCA_OK;
+    Bp3Params p;
+    memset(&p, 0, sizeof(p));
+    p.rows = s->rows;
+    p.planes = s->planes;
+    p.W = s->W; p.H = s->H; p.Z = s->Zl; p.G = s->G; p.RWP = s->RWP;
+    p.prog = s->prog + (s->Zl ? s->Zl : 1);
+    p.order = s->order;
+    p.nsweeps = s->n_items;
+    sweep_knobs(p, s->team);
+    if (s->max_ctas > 0) p.max_ctas = s->max_ctas;
+    p.ticket = s->ticket;
+    p.err = (int *)(s->ticket + 1);
+    p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
+    p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
+    p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
+    if (streamed) {
+        int *h_io_dev = nullptr;
+        CU(cudaHostGetDevicePointer((void **)&h_io_dev, s->h_io, 0));
+        p.layout_items = 1;
+        p.io_cells = s->cells;
+        p.io_chunk = s->io_chunk;
+        p.population = s->d_pop;
+        p.in_ready = s->d_in_ready;
+        p.out_done = h_io_dev;
+        p.io_epoch = s->io_epoch;
+    }
+    Bp3LaunchInfo info;
+    CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
+    *workers = info.workers;
     return CLAPCA_OK;
 }
 
@@ -294,31 +382,12 @@ int clapca_slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
 int clapca_slab_run(clapca_slab *s, int64_t *local_population)
 {
     if (int rc = need_init()) return rc;
-    if (!s || !s->prepared) return fail(CLAPCA_ERR_STATE, "slab_run: slab is not prepared");
+    if (!s || !s->prepared || s->streamed_order) return fail(CLAPCA_ERR_STATE, "slab_run: slab is not prepared (for a resident run)");
     s->prepared = false;
     memset(&s->stats, 0, sizeof(s->stats));
     CU(cudaEventRecord(s->ev[2], s->stream));
     int workers = 0;
-    if (s->n_items) {
-        Bp3Params p;
-        memset(&p, 0, sizeof(p));
-        p.rows = s->rows;
-        p.planes = s->planes;
-        p.W = s->W; p.H = s->H; p.Z = s->Zl; p.G = s->G; p.RWP = s->RWP;
-        p.prog = s->prog;
-        p.order = s->order;
-        p.nsweeps = s->n_items;
-        sweep_knobs(p, s->team);
-        if (s->max_ctas > 0) p.max_ctas = s->max_ctas;
-        p.ticket = s->ticket;
-        p.err = (int *)(s->ticket + 1);
-        p.diag = diag_enabled() ? (unsigned long long *)(s->ticket + 4) : nullptr;
-        p.surv = s->surv; p.born = s->born; p.bornval = (s->nr_states - 1u) & 0xffu;
-        p.spin_limit = 20000000000LL;       /* ~10 s: ranks enter the kernel at slightly different times */
-        Bp3LaunchInfo info;
-        CU(bp3_launch(s->rule, s->P, s->WPL, p, g_ctx.sms, s->stream, &info));
-        workers = info.workers;
-    }
+    if (int rc = slab_launch(s, false, &workers)) return rc;
     CU(cudaEventRecord(s->ev[3], s->stream));
     diag_report("slab", s->ticket, s->stream, s->geo.rank);
     CU(cudaMemsetAsync(s->d_pop, 0, sizeof(unsigned long long), s->stream));
@@ -345,6 +414,54 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
     s->stats.engine = CLAPCA_ENGINE_BITPLANE;
     s->stats.planes = s->P;
     s->stats.workers = workers;
+    return CLAPCA_OK;
+}
+
+/*
+ * Step 2 of a streamed run (after the barrier): host -> device -> host as ONE pipeline per rank.  host_in / host_out
+ * hold this rank's planes in local order (pinned memory); the launch's pack items follow the H2D chunks, every
+ * generation follows a few planes behind, the unpack items flag finished planes and this thread releases their D2H
+ * copies -- while the z-block edges trade halo rows with the neighbouring ranks as in a resident run.
+ */
+int clapca_slab_run_streamed(clapca_slab *s, const uint8_t *host_in, uint8_t *host_out, int64_t *local_population)
+{
+    if (int rc = need_init()) return rc;
+    if (!s || !s->prepared || !s->streamed_order)
+        return fail(CLAPCA_ERR_STATE, "slab_run_streamed: call clapca_slab_prepare_streamed first");
+    if (s->Zl && (!host_in || !host_out)) return fail(CLAPCA_ERR_ARG, "slab_run_streamed: NULL buffer");
+    s->prepared = false;
+    memset(&s->stats, 0, sizeof(s->stats));
+    CU(cudaEventRecord(s->ev_io, s->stream));
+    CU(cudaStreamWaitEvent(s->stream_in, s->ev_io, 0));         /* the chunk-arrival word is cleared before the first chunk lands */
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    int workers = 0;
+    if (int rc = slab_launch(s, true, &workers)) return rc;
+    CU(cudaEventRecord(s->ev[3], s->stream));
+    bool stuck = false;
+    if (s->Zl) {
+        StreamPlan sp = { s->cells, host_in, host_out, (size_t)s->W * s->H, s->Zl, s->io_chunk, s->d_in_ready, s->h_io,
+                          s->io_epoch, s->stream, s->stream_in, s->stream_out };
+        if (int rc = stream_volume(sp, &stuck)) return rc;
+    }
+    unsigned long long pop = 0;
+    int err = 0;
+    CU(cudaMemcpyAsync(&pop, s->d_pop, sizeof(pop), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&err, s->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    diag_report("slab (streamed)", s->ticket, s->stream, s->geo.rank);
+    if (err == 4)
+        return fail(CLAPCA_ERR_ARG, "slab_run_streamed: a cell value exceeds the max_value %u given to slab_create", s->max_value);
+    if (err || stuck)
+        return fail(CLAPCA_ERR_TIMEOUT, "slab_run_streamed: dataflow watchdog fired on rank %d (err=%d)", s->geo.rank, err);
+    if (local_population) *local_population = (int64_t)pop;
+    float sweep = 0;
+    CU(cudaEventElapsedTime(&sweep, s->ev[2], s->ev[3]));
+    s->stats.total_ms = s->stats.kernel_ms = sweep;
+    s->stats.launches = s->n_items ? 1 : 0;
+    s->stats.engine = CLAPCA_ENGINE_BITPLANE;
+    s->stats.planes = s->P;
+    s->stats.workers = workers;
+    s->stats.streamed = 1;
     return CLAPCA_OK;
 }
 

@@ -168,11 +168,25 @@ class ShardedVolume:
         check(self._lib, self._lib.clapca_slab_run(self._h, byref(pop)))
         return pop.value
 
+    def prepare_streamed(self, rule, steps):
+        rule = rule if isinstance(rule, CellAutomaton) else ca3d_rule(int(rule))
+        check(self._lib, self._lib.clapca_slab_prepare_streamed(self._h, rule.surv_mask, rule.born_mask, rule.nr_states,
+                                                                int(steps)))
+
+    def run_streamed(self, host_in, host_out):
+        """host -> device -> host as one pipeline (clapca_slab_run_streamed): this rank's planes, local order, in
+        page-locked memory (numpy arrays over pinned storage or raw addresses)"""
+        pin = host_in.ctypes.data if isinstance(host_in, np.ndarray) else int(host_in)
+        pout = host_out.ctypes.data if isinstance(host_out, np.ndarray) else int(host_out)
+        pop = c_int64(0)
+        check(self._lib, self._lib.clapca_slab_run_streamed(self._h, c_void_p(pin), c_void_p(pout), byref(pop)))
+        return pop.value
+
     def stats(self):
         st = RunStats()
         check(self._lib, self._lib.clapca_slab_last_stats(self._h, byref(st)))
         return {"total_ms": st.total_ms, "kernel_ms": st.kernel_ms, "launches": st.launches, "planes": st.planes,
-                "workers": st.workers}
+                "workers": st.workers, "streamed": bool(st.streamed)}
 
 
 class LocalRanks:
@@ -234,6 +248,29 @@ class LocalRanks:
                 vol.download(buf)
                 out[vol.zglobal] = buf
         return out
+
+    def run_streamed(self, rule, steps, host_in, host_out):
+        """every rank's host -> device -> host pipeline at once.  host_in / host_out: per-rank lists of pinned uint8
+        buffers (this rank's planes in local order); returns the population of the whole volume"""
+        import threading
+        for vol in self.ranks:
+            vol.prepare_streamed(rule, steps)
+        pops, errs = [0] * self.nranks, []
+
+        def work(r):
+            try:
+                pops[r] = self.ranks[r].run_streamed(host_in[r], host_out[r])
+            except Exception as e:      # noqa: BLE001 -- re-raised below, on the caller's thread
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(r,)) for r in range(self.nranks)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return sum(pops)
 
     def plane_hashes(self):
         out = np.zeros(self.dims[2], np.uint64)

@@ -276,6 +276,15 @@ int clapca_slab_upload(clapca_slab *s, const uint8_t *src);
 int clapca_slab_download(clapca_slab *s, uint8_t *dst);
 int clapca_slab_prepare(clapca_slab *s, uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states, int steps);
 int clapca_slab_run(clapca_slab *s, int64_t *local_population);
+/*
+ * The same run from host memory to host memory as one pipeline per rank (cf. clapca_grid_run3d_streamed): no upload /
+ * download calls -- host_in / host_out hold this rank's planes in local order in page-locked memory, the launch packs
+ * the planes as their H2D chunks land, seeds the neighbours' ghost planes itself, and hands finished planes back
+ * while later ones are still being swept.  Call order: prepare_streamed -> (barrier across ranks) -> run_streamed.
+ * Cells above the max_value given to slab_create make the run fail with CLAPCA_ERR_ARG.
+ */
+int clapca_slab_prepare_streamed(clapca_slab *s, uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states, int steps);
+int clapca_slab_run_streamed(clapca_slab *s, const uint8_t *host_in, uint8_t *host_out, int64_t *local_population);
 int clapca_slab_last_stats(clapca_slab *s, clapca_run_stats *st);
 
 /*

@@ -164,6 +164,12 @@ def test_ca3d_tiles_of_planes_and_generations(emu_bin, args):
     (1, 1, 1, 3, 7, 3, 1, 1, 5, 2, 1, 0, 0, 2, -1, 0, 0, 0, 2, 1),
     (45, 20, 13, 6, 7, 3, 1, 1, 3, 80, 1, 0, 0, 2, 0, 0, 4, 2, 2, 4),        # 2 x 2 tiles with pack / unpack groups around them
     (45, 20, 12, 9, 7, 3, 1, 1, 3, 320, 1, 0, 0, 2, 0, 0, 16, 4, 1, 2),      # 4 x 4 tiles, cells resident
+    # sharded volumes: the pack items' service warps seed the neighbours' ghost planes ("generation -1" counters)
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 48, 2, 2, 0, 2, 0, 0, 4, 2, 1, 2),        # 2 ranks, z-blocks of 2 planes, 2 x 2 tiles
+    (45, 50, 13, 5, 3, 3, 1, 1, 3, 64, 3, 5, 0, 4, 0, 0, 4, 2, 1, 2),        # 3 ranks, ragged last block
+    (33, 30, 16, 5, 10, 8, 1, 1, 4, 64, 4, 1, 0, 2, 0, 0, 4, 1, 1, 2),       # 4 ranks, single-plane blocks
+    (33, 30, 16, 9, 7, 3, 1, 1, 4, 320, 4, 4, 0, 2, 0, 0, 16, 4, 1, 2),      # 4 ranks, 4 x 4 tiles
+    (33, 30, 15, 7, 7, 3, 1, 1, 4, 300, 2, 5, 0, 2, 0, 0, 15, 3, 1, 2),      # 2 ranks, the default 5 x 3 tiles
 ])
 def test_ca3d_layout_items_streamed(emu_bin, args):
     """Layout items: pack ("generation -1") and unpack ("generation G") run as work items of the sweep launch; a

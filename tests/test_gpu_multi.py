@@ -84,6 +84,59 @@ def test_local_ranks_ca3d_make_volume_with_255s(gpu, oracle):
         lr.close()
 
 
+@pytest.mark.parametrize("case", [
+    # d0   d1   d2  gens rule ranks block
+    (70, 24, 20, 6, 7, 2, 5),
+    (256, 64, 50, 9, 7, 3, 10),         # ragged last block / generation group
+    (2048, 96, 60, 8, 7, 4, 5),         # BASELINE config-4 row width, every tile has two z-block edges
+    (1000, 40, 33, 5, 2, 2, 10),        # 4 state planes
+])
+def test_local_ranks_streamed_host_to_host_equals_resident(gpu, oracle, monkeypatch, case):
+    """clapca_slab_run_streamed: per rank, upload / pack / every generation / unpack / download as one pipeline
+    (layout items + the halo seed pushed by the pack items' service warps), against the single-GPU result"""
+    import torch
+    from clap_b200 import ClapcaError
+    from clap_b200.slab import LocalRanks
+    d0, d1, d2, gens, rule, ranks, block = case
+    monkeypatch.setenv("CLAPCA_IO_CHUNK_PLANES", "3")
+    rng = np.random.default_rng(d0 + d2)
+    full = (rng.integers(1, 6, (d2, d1, d0)) * (rng.random((d2, d1, d0)) < 0.3)).astype(np.uint8)
+    want = full.copy()
+    wpop = gpu.ca3d_run(want, rule, gens)
+    maxv = max(int(full.max()), gpu.ca3d_rule(rule).nr_states - 1)
+    lr = LocalRanks(d0, d1, d2, ranks, gens, maxv, block)
+    try:
+        keep, hin, hout = [], [], []
+        for vol in lr.ranks:
+            n = max(1, vol.n_local) * d1 * d0
+            a, b = torch.empty(n, dtype=torch.uint8, pin_memory=True), torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            keep += [a, b]
+            hin.append(a.numpy())
+            hout.append(b.numpy())
+            if vol.n_local:
+                hin[-1][:vol.n_local * d1 * d0] = full[vol.zglobal].reshape(-1)
+        for rep in range(2):
+            for b in hout:
+                b[...] = 0xEE
+            assert lr.run_streamed(rule, gens, hin, hout) == wpop, rep
+            got = np.zeros_like(full)
+            for vol, b in zip(lr.ranks, hout):
+                if vol.n_local:
+                    got[vol.zglobal] = b[:vol.n_local * d1 * d0].reshape(vol.n_local, d1, d0)
+            assert np.array_equal(got, want), (rep, int((got != want).sum()))
+        # a resident run on the same slabs afterwards (the claim order is rebuilt without layout items)
+        lr.upload(full)
+        assert lr.run(rule, gens) == wpop
+        assert np.array_equal(lr.download(), want)
+        # the bound given at create time is enforced by the pack items
+        if maxv < 255 and d0 == 70:        # (the other ranks only notice through their watchdogs: once is enough)
+            hin[0][0] = 200
+            with pytest.raises(ClapcaError):
+                lr.run_streamed(rule, gens, hin, hout)
+    finally:
+        lr.close()
+
+
 def test_slab_prepare_rejects_cells_above_max_value(gpu):
     """the slab path must verify the caller's max_value (the pack kernel would drop the upper bits)"""
     from clap_b200 import ClapcaError
