@@ -997,7 +997,7 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
         /* a cell that neither survives nor decays keeps its value: same as surviving (core/ca2d.c:72-75) */
         p.surv = decay ? (surv & 0x1ffu) : 0x1ffu;
         p.nrval = nrval;
-        p.flag_rows = 4;
+        p.flag_rows = 8;        /* measured on B200, 16384^2 x 100: 10.3 / 9.8 / 9.3 ms with 2 / 4 / 8 rows per counter update */
         if (const char *e = getenv("CLAPCA_2D_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
         p.spin_limit = 4000000000LL;
         Bp2LaunchInfo info;
