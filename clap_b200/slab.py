@@ -27,18 +27,21 @@ TILE_PLANES = 5     # planes per tile of the default kernel variant (15 compute 
 
 
 def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=60):
-    """z-block size of the scaling bench: a multiple of the tile height (a ragged tile leaves most of a CTA idle), at
-    most `largest` planes: the largest one for which the most loaded rank stays within 1.5 % of the best balance any
-    candidate reaches (fewer z-block edges).  Measured on 2 x B200 at 2048^3 x 50 (profiles/r02_knobs_multi_n2.txt): blocks of 15 /
-    30 / 60 / 120 planes sweep in 60.3 / 57.3 / 56.7 / 71.0 ms -- small blocks pay for their edges, large ones for the
-    pipeline fill (rank r starts 3 r B row steps after rank 0 and the last rank idles as long at the end)."""
+    """z-block size of the scaling bench: a multiple of the tile height (a ragged tile leaves most of a CTA idle), the
+    largest one up to `largest` planes that still gives every rank about six blocks and keeps the most loaded rank
+    within 10 % of its fair share.  Measured at 2048^3 x 50 (profiles/r02_knobs_multi_n2.txt, r02_knobs_multi_n8*.txt):
+    2 GPUs, blocks of 15 / 30 / 60 / 120 planes: sweep 60.3 / 57.3 / 56.7 / 71.0 ms; 8 GPUs, blocks of 20 / 30 / 40 / 45 /
+    50 planes: 20.3 / 19.8 / 18.6 / 18.9 / 19.9 ms -- z-block edges cost more than a few percent of imbalance (every edge
+    adds the NVLink hop to the wave that carries generation 0 up the volume), and blocks that are too large leave the
+    last ranks waiting for that wave (rank r starts ~3.7 r B row steps after rank 0)."""
     d2, nranks = int(d2), max(1, int(nranks))
     if nranks == 1:
         return d2
     per_rank = -(-d2 // nranks)
+    top = max(tile_planes, min(largest, per_rank // 6 if per_rank >= 6 * tile_planes else per_rank // 2))
     cands = {}
     b = tile_planes
-    while b <= max(tile_planes, min(largest, per_rank // 2 if per_rank >= 2 * tile_planes else per_rank)):
+    while b <= top:
         loads = [0] * nranks
         for j, z0 in enumerate(range(0, d2, b)):
             loads[j % nranks] += min(b, d2 - z0)
@@ -46,8 +49,9 @@ def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=60):
         b += tile_planes
     if not cands:
         return max(1, min(per_rank, d2))
-    fair = min(cands.values())
-    best = max(b for b, load in cands.items() if load <= 1.015 * fair)      # the largest block within 1.5 % of the best balance
+    fair = d2 / nranks
+    ok = [b for b, load in cands.items() if load <= 1.10 * fair]
+    best = max(ok) if ok else min(cands, key=lambda k: (cands[k], -k))
     return max(1, min(best, d2))
 
 

@@ -80,13 +80,13 @@ def test_default_block_planes(d2, nranks):
         return
     assert b <= 60 or b <= per_rank
     loads = [sum(z1 - z0 for r, z0, z1 in blocks if r == k) for k in range(nranks)]
-    if d2 >= 40 * nranks:               # the most loaded rank stays within a few percent of its fair share
-        assert max(loads) <= 1.04 * d2 / nranks + 5, (b, loads)
+    if d2 >= 40 * nranks:               # the most loaded rank stays within 10 % of its fair share
+        assert max(loads) <= 1.10 * d2 / nranks + 5, (b, loads)
         assert b % 5 == 0               # whole tiles
         assert min(sum(1 for r, _, _ in blocks if r == k) for k in range(nranks)) >= 2
 
 
 def test_default_block_planes_of_the_scaling_bench():
     assert default_block_planes(2048, 2) == 60
-    assert default_block_planes(2048, 8) == 20
-    assert max(sum(z1 - z0 for r, z0, z1 in plan_blocks(2048, 8, 20) if r == k) for k in range(8)) == 260
+    assert default_block_planes(2048, 4) == 60
+    assert default_block_planes(2048, 8) == 40         # the measured optimum (profiles/r02_knobs_multi_n8*.txt)
