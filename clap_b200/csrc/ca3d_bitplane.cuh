@@ -69,6 +69,7 @@ struct Bp3Params {
     int max_ctas;           /* host side only: > 0 caps the CTAs of the launch (several ranks sharing one device) */
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: tile mode -- a CTA of `team` compute warps + ONE service warp sweeps a tile (see below) */
+    int halo_ldst;          /* != 0: the service warp moves halo rows with ld / st instead of TMA bulk copies */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -869,6 +870,48 @@ struct Sweep3 {
         }
     }
 
+    /* shared memory of a tile's CTA */
+    struct alignas(16) TileShared {
+        uint32_t stage[16][2 * RWP];        /* staging slots of the halo rows on their way to a peer (H0 | H1 of one row each) */
+        unsigned long long bar;             /* mbarrier: bytes of the bulk loads into the slots */
+        int cnt[BP3_MAX_TEAM + 1];          /* row counters of the compute warps, then the claimed ticket */
+    };
+
+    /*
+     * The same copy by the TMA engine: 1-D bulk copies local row record -> staging slot (completion counted on an
+     * mbarrier) and staging slot -> peer ghost plane over NVLink (bulk group), 16 rows per batch, issued by ONE lane:
+     * the service warp spends a handful of instructions per row and holds no row data in registers.  `phase` is the
+     * mbarrier phase parity, carried by the caller.  The copies are complete (bulk_done) before the peer's counter moves.
+     */
+    CA_MDEV void bulk_copy_h_rows(TileShared &ts, uint32_t *dst, const uint32_t *src, int r0, int r1, uint32_t &phase,
+                                  const Bp3Params &p)
+    {
+        constexpr uint32_t ROWB = 2 * RWP * 4;
+        const int lane = dp_lane();
+        for (int r = r0; r < r1; r += 16) {
+            const int n = r1 - r < 16 ? r1 - r : 16;
+            if (lane == 0) {
+                dp_bulk_wait_read();                /* the previous batch has left the slots */
+                dp_mbar_expect_tx(&ts.bar, (uint32_t)n * ROWB);
+                for (int i = 0; i < n; i++)
+                    dp_bulk_g2s(ts.stage[i], src + (size_t)(r + i) * RECW, ROWB, &ts.bar);
+                long long t0 = 0;
+                for (unsigned spins = 1; !dp_mbar_try_wait(&ts.bar, phase); spins++) {
+                    if (spins == 1) t0 = dp_clock();
+                    if ((spins & 4095u) == 0u && (dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit)) {
+                        dp_set_error(p.err, 9);
+                        break;
+                    }
+                }
+                for (int i = 0; i < n; i++)
+                    dp_bulk_s2g(dst + (size_t)(r + i) * RECW, ts.stage[i], ROWB);
+                dp_bulk_commit();
+            }
+            phase ^= 1u;
+        }
+        dp_syncwarp();
+    }
+
     /*
      * H rows [r0, r1) of one plane from the local row records to a peer's ghost plane (both with the record stride):
      * H0 | H1 of a row are 2 * RWP contiguous words = 32 * WPL uint2, so the warp moves a row with WPL coalesced 8-byte
@@ -919,7 +962,7 @@ struct Sweep3 {
      * store the peers' counters.  A row is copied out of the local record before anybody can overwrite it: generation
      * g+1 of an edge row needs the neighbouring GPU's generation-g (or g+1) rows, which need this push.
      */
-    CA_MDEV void service_loop(const Bp3Params &p, int l0, int g0, int nz, int ng, const int *done)
+    CA_MDEV void service_loop(const Bp3Params &p, int l0, int g0, int nz, int ng, TileShared &ts, uint32_t &phase)
     {
         const int lane = dp_lane();
         const int H = p.H, Z = p.Z;
@@ -943,6 +986,7 @@ struct Sweep3 {
             }
         }
         const bool streams = dp_any(pdst != nullptr);
+        const int *done = ts.cnt;
         long long t_idle = dp_clock(), t_busy = 0;
         unsigned idle_since = 0;
         for (unsigned spins = 0;; spins++) {
@@ -964,12 +1008,21 @@ struct Sweep3 {
                 const bool pm = pdst && avail > pushed;
                 const uint32_t mask = dp_ballot(pm);
                 if (mask) {
+                    if (!p.halo_ldst)
+                        dp_fence_proxy_async();         /* the rows were written through the generic proxy; the bulk loads read them through the async proxy */
                     for (uint32_t m = mask; m; m &= m - 1u) {
                         const int s = dp_ffs(m) - 1;
                         const uint32_t *src = (const uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)psrc, s);
                         uint32_t *dst = (uint32_t *)(size_t)dp_shfl64((unsigned long long)(size_t)pdst, s);
                         const int r0 = (int)dp_shfl((uint32_t)pushed, s), r1 = (int)dp_shfl((uint32_t)avail, s);
-                        copy_h_rows(dst, src, r0, r1);
+                        if (p.halo_ldst)
+                            copy_h_rows(dst, src, r0, r1);
+                        else
+                            bulk_copy_h_rows(ts, dst, src, r0, r1, phase, p);
+                    }
+                    if (!p.halo_ldst && lane == 0) {
+                        dp_bulk_wait();                 /* every bulk store of this pass is complete ... */
+                        dp_fence_proxy_async();         /* ... and ordered before the generic-proxy counter store */
                     }
                     dp_fence_sys();                     /* fence.acq_rel.sys: peer rows before the peer's counter */
                     if (pm) {
@@ -1009,7 +1062,7 @@ struct Sweep3 {
      * prog[-1][z] every 32 rows) the service warp copies the finished H rows into the neighbour's ghost plane and raises
      * its "generation -1" counter: the halo seed of a resident run (api_slab.cu) moved into the launch.
      */
-    CA_MDEV void seed_push(const Bp3Params &p, int zl)
+    CA_MDEV void seed_push(const Bp3Params &p, int zl, TileShared &ts, uint32_t &phase)
     {
         const int lane = dp_lane();
         const int H = p.H;
@@ -1023,7 +1076,16 @@ struct Sweep3 {
             if (!wait_word(p, myprog, pushed + 1, false, 8))
                 return;
             const int avail = (int)dp_shfl((uint32_t)(lane == 0 ? dp_ld_acquire(myprog) : 0), 0);
-            copy_h_rows(pl.push_dn_rows, src, pushed, avail);
+            if (p.halo_ldst) {
+                copy_h_rows(pl.push_dn_rows, src, pushed, avail);
+            } else {
+                dp_fence_proxy_async();
+                bulk_copy_h_rows(ts, pl.push_dn_rows, src, pushed, avail, phase, p);
+                if (lane == 0) {
+                    dp_bulk_wait();
+                    dp_fence_proxy_async();
+                }
+            }
             dp_fence_sys();
             if (lane == 0)
                 dp_st_flag_sys(pl.push_dn_flag - 1, avail);
@@ -1039,9 +1101,14 @@ struct Sweep3 {
      */
     CA_MDEV void tile_loop(const Bp3Params &p)
     {
-        CA_SHARED(int, sm, BP3_MAX_TEAM + 1);       /* row counters of the compute warps, then the claimed ticket */
+        CA_SHARED(TileShared, tsp, 1);
+        TileShared &ts = tsp[0];
+        int *sm = ts.cnt;                           /* row counters of the compute warps, then the claimed ticket */
         const int w = dp_warp_in_block();
         const int T = p.team;
+        uint32_t phase = 0u;                        /* service warp: parity of the staging mbarrier's current phase */
+        if (dp_thread() == 0)
+            dp_mbar_init(&ts.bar, 1);
         for (;;) {
             if (dp_thread() == 0) {
                 unsigned t = dp_atomic_inc(p.ticket);
@@ -1061,7 +1128,7 @@ struct Sweep3 {
                 if (w < nz)
                     run_item(p, it.x + w, it.y, 0, p.H, nullptr);
                 else if (w == T && it.y < 0)
-                    seed_push(p, it.x);             /* a packed z-block edge is the neighbour's "old plane above" of generation 0 */
+                    seed_push(p, it.x, ts, phase);  /* a packed z-block edge is the neighbour's "old plane above" of generation 0 */
             } else if (w < nz * ng) {
                 const int i = w % nz, j = w / nz;
                 TileWire tw;
@@ -1071,7 +1138,7 @@ struct Sweep3 {
                 tw.done = sm + w;
                 run_rows(p, it.x + i, it.y + j, 0, p.H, nullptr, &tw);
             } else if (w == T) {
-                service_loop(p, it.x, it.y, nz, ng, sm);
+                service_loop(p, it.x, it.y, nz, ng, ts, phase);
             }
             dp_syncblock();                         /* the counters are cleared for the next item */
         }

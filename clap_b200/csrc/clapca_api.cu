@@ -473,6 +473,8 @@ void clapca::api::sweep_knobs(Bp3Params &p, int team)
     if (const char *e = getenv("CLAPCA_MAX_CTAS")) p.max_ctas = std::max(0, atoi(e));
     if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
     p.team = team;
+    /* CLAPCA_HALO_LDST=1: halo rows by ld / st of the service warp instead of TMA bulk copies (A/B measurements) */
+    if (const char *e = getenv("CLAPCA_HALO_LDST")) p.halo_ldst = atoi(e) != 0;
 }
 
 static const int kGenBatch = 16;

@@ -130,6 +130,47 @@ CA_DEV int  dp_popc(uint32_t v)                   { return __popc(v); }
 CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s) { return __funnelshift_l(lo, hi, s); }
 CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, s); }
 
+/*
+ * 1-D bulk copies of the TMA engine (cp.async.bulk) and the mbarrier that counts their bytes.  Issued by ONE thread;
+ * the copy itself runs in the async proxy, off the issuing warp.  Addresses and sizes are multiples of 16 bytes.
+ */
+CA_DEV uint32_t dp_smem_addr(const void *p)       { return (uint32_t)__cvta_generic_to_shared(p); }
+CA_DEV void dp_mbar_init(unsigned long long *bar, int arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dp_smem_addr(bar)), "r"(arrivals) : "memory");
+}
+/* this thread arrives and announces `bytes` of bulk-copy traffic for the current phase */
+CA_DEV void dp_mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(dp_smem_addr(bar)), "r"(bytes) : "memory");
+}
+/* has the phase with this parity completed? */
+CA_DEV bool dp_mbar_try_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(dp_smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* global -> shared, completion counted on `bar` */
+CA_DEV void dp_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dp_smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(dp_smem_addr(bar)) : "memory");
+}
+/* shared -> global (any global address: local HBM or a peer's over NVLink), completion through bulk groups */
+CA_DEV void dp_bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(dp_smem_addr(smem_src)), "r"(bytes) : "memory");
+}
+CA_DEV void dp_bulk_commit()                      { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* all committed shared -> global copies have READ their source (the staging slots may be reused) / are complete */
+CA_DEV void dp_bulk_wait_read()                   { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CA_DEV void dp_bulk_wait()                        { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+/* order this thread's generic-proxy accesses against its async-proxy (bulk copy) accesses */
+CA_DEV void dp_fence_proxy_async()                { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 /* one LOP3 with a compile-time truth table: bit (a<<2|b<<1|c) of LUT */
 template <unsigned LUT>
 CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
@@ -269,6 +310,38 @@ CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s)
 {
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
 }
+
+/*
+ * bulk copies on the emulator: synchronous memcpy; the "mbarrier" word holds the phase (bit 0 of the low half) and the
+ * bytes still expected (high half) -- one issuing thread, so no atomics are needed for the bookkeeping itself
+ */
+CA_DEV void dp_mbar_init(unsigned long long *bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+CA_DEV void dp_mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    __atomic_store_n(bar, (__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1ull) | ((unsigned long long)bytes << 32), __ATOMIC_SEQ_CST);
+}
+CA_DEV bool dp_mbar_try_wait(unsigned long long *bar, uint32_t parity)
+{
+    return (uint32_t)(__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1ull) != (parity & 1u);
+}
+CA_DEV void dp_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    memcpy(smem_dst, gsrc, bytes);
+    unsigned long long v = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+    unsigned long long left = (v >> 32) - bytes;
+    v = left ? ((v & 1ull) | (left << 32)) : ((v & 1ull) ^ 1ull);
+    __atomic_store_n(bar, v, __ATOMIC_SEQ_CST);
+}
+CA_DEV void dp_bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    memcpy(gdst, smem_src, bytes);
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+CA_DEV void dp_bulk_commit()                      { }
+CA_DEV void dp_bulk_wait_read()                   { }
+CA_DEV void dp_bulk_wait()                        { }
+CA_DEV void dp_fence_proxy_async()                { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <unsigned LUT>
 CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)

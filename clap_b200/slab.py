@@ -26,12 +26,12 @@ DEFAULT_BLOCK_PLANES = 16
 TILE_PLANES = 5     # planes per tile of the default kernel variant (15 compute warps = 5 planes x 3 generations)
 
 
-def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=60):
+def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=40):
     """z-block size of the scaling bench: a multiple of the tile height (a ragged tile leaves most of a CTA idle), the
     largest one up to `largest` planes that still gives every rank about six blocks and keeps the most loaded rank
     within 10 % of its fair share.  Measured at 2048^3 x 50 (profiles/r02_knobs_multi_n2.txt, r02_knobs_multi_n8*.txt):
     2 GPUs, blocks of 15 / 30 / 60 / 120 planes: sweep 60.3 / 57.3 / 56.7 / 71.0 ms; 8 GPUs, blocks of 20 / 30 / 40 / 45 /
-    50 planes: 20.3 / 19.8 / 18.6 / 18.9 / 19.9 ms -- z-block edges cost more than a few percent of imbalance (every edge
+    50 planes: 20.3 / 19.8 / 18.6 / 18.9 / 19.9 ms; 4 GPUs, 30 / 40 / 60 planes: 34.5 / 32.3 / 33.8 ms -- z-block edges cost more than a few percent of imbalance (every edge
     adds the NVLink hop to the wave that carries generation 0 up the volume), and blocks that are too large leave the
     last ranks waiting for that wave (rank r starts ~3.7 r B row steps after rank 0)."""
     d2, nranks = int(d2), max(1, int(nranks))

@@ -78,7 +78,7 @@ def test_default_block_planes(d2, nranks):
     if nranks == 1:
         assert b == d2
         return
-    assert b <= 60 or b <= per_rank
+    assert b <= 40 or b <= per_rank
     loads = [sum(z1 - z0 for r, z0, z1 in blocks if r == k) for k in range(nranks)]
     if d2 >= 40 * nranks:               # the most loaded rank stays within 10 % of its fair share
         assert max(loads) <= 1.10 * d2 / nranks + 5, (b, loads)
@@ -87,6 +87,6 @@ def test_default_block_planes(d2, nranks):
 
 
 def test_default_block_planes_of_the_scaling_bench():
-    assert default_block_planes(2048, 2) == 60
-    assert default_block_planes(2048, 4) == 60
+    assert default_block_planes(2048, 2) == 40
+    assert default_block_planes(2048, 4) == 40         # measured: 32.3 ms against 33.8 (60) and 34.5 (30)
     assert default_block_planes(2048, 8) == 40         # the measured optimum (profiles/r02_knobs_multi_n8*.txt)
