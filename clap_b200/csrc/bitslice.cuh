@@ -66,6 +66,46 @@ CA_DEV void bs_count3d(const uint32_t d[4], const uint32_t u[4], const uint32_t 
     k[4] = ch | (sh & cg);
 }
 
+/* T = a + b of two 2-bit numbers (each 0..3) -> 3-bit number (0..6): 4 LOP3 */
+CA_DEV void bs_add2x2(const uint32_t a[2], const uint32_t b[2], uint32_t t[3])
+{
+    uint32_t c0 = a[0] & b[0];
+    t[0] = a[0] ^ b[0];
+    t[1] = bs_xor3(a[1], b[1], c0);
+    t[2] = bs_maj3(a[1], b[1], c0);
+}
+
+/*
+ * 3D neighbour count without the in-row predecessor, from the per-row pair sums T(r) = Hdn(r) + Hup(r) (0..6) of rows
+ * y-1, y, y+1 -- each T is formed once (bs_add2x2) and serves three consecutive rows:
+ *   K = T(y-1) + T(y) + T(y+1) + Hnew(0..3) + Hold(0..3) + r(0..1)   (max 25)
+ * as a carry-save tree of 11 full / 2 half adders: 22 LOP3 (+ 4 for the new T) against 34 for two vertical 3-sums
+ * and their sum.
+ */
+CA_DEV void bs_count3d_t(const uint32_t ta[3], const uint32_t tb[3], const uint32_t tc[3], const uint32_t n[2],
+                         const uint32_t o[2], uint32_t r, uint32_t k[5])
+{
+    /* weight 1: ta0 tb0 tc0 n0 o0 r */
+    uint32_t s1 = bs_xor3(ta[0], tb[0], tc[0]), c1 = bs_maj3(ta[0], tb[0], tc[0]);
+    uint32_t s2 = bs_xor3(n[0], o[0], r),       c2 = bs_maj3(n[0], o[0], r);
+    k[0] = s1 ^ s2;
+    uint32_t c3 = s1 & s2;
+    /* weight 2: ta1 tb1 tc1 n1 o1 c1 c2 c3 */
+    uint32_t s4 = bs_xor3(ta[1], tb[1], tc[1]), d1 = bs_maj3(ta[1], tb[1], tc[1]);
+    uint32_t s5 = bs_xor3(n[1], o[1], c1),      d2 = bs_maj3(n[1], o[1], c1);
+    uint32_t s6 = bs_xor3(s4, c2, c3),          d3 = bs_maj3(s4, c2, c3);
+    k[1] = s5 ^ s6;
+    uint32_t d4 = s5 & s6;
+    /* weight 4: ta2 tb2 tc2 d1 d2 d3 d4 */
+    uint32_t s7 = bs_xor3(ta[2], tb[2], tc[2]), e1 = bs_maj3(ta[2], tb[2], tc[2]);
+    uint32_t s8 = bs_xor3(d1, d2, d3),          e2 = bs_maj3(d1, d2, d3);
+    k[2] = bs_xor3(s7, s8, d4);
+    uint32_t e3 = bs_maj3(s7, s8, d4);
+    /* weight 8 / 16 */
+    k[3] = bs_xor3(e1, e2, e3);
+    k[4] = bs_maj3(e1, e2, e3);
+}
+
 /* ---- rule tables on a bit-sliced count ----------------------------------- */
 
 /* compile-time 8-entry table over (k2,k1,k0) */
@@ -131,6 +171,20 @@ CA_DEV void bs_scan_word(uint32_t &D, uint32_t &C)
 }
 
 /*
+ * The same scan on E = ~D ("the chain breaks here"): C ^= ~E & (C << s); E |= E << s.  Both shifts are plain left
+ * shifts (IMAD.SHL on the FMA pipe) where the D form needs (D << s) | low-ones -- an LEA on the ALU pipe, the pipe
+ * that bounds the sweep kernels: 2 instead of 3 ALU-pipe instructions per step.
+ */
+CA_DEV void bs_scan_word_e(uint32_t &E, uint32_t &C)
+{
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        C = dp_lop3<0xD2>(C, E, C << s);        /* C ^ (~E & (C << s)) */
+        E |= E << s;
+    }
+}
+
+/*
  * Warp-level stage: every lane contributes the map (dl, cl) from its carry-in
  * to its last cell; returns the lane's carry-in bit (0 or 1).  `cut_after`
  * is a lane mask of lanes after which the chain restarts with 0 (row ends).
@@ -142,6 +196,42 @@ CA_DEV uint32_t bs_scan_warp(uint32_t dl, uint32_t cl, uint32_t cut_after)
     bs_scan_word(BD, BC);           /* carry-in of lane 0 is 0: result bit i = BC bit i */
     int lane = dp_lane();
     return lane ? (BC >> (lane - 1)) & 1u : 0u;
+}
+
+/*
+ * The scan in two parts.  After the shifts by 1, 2, 4 bit i of E is clear only if cells i-7 .. i ALL pass their
+ * predecessor's bit on; unless such a run of 8 exists somewhere (bits 8..31 of ~E), the shifts by 8 and 16 change
+ * nothing and the caller skips them for the whole warp (one vote).  Exact either way -- the fast path is just the
+ * common case: a run of 8 dependent cells is rare in any rule's steady state.
+ */
+CA_DEV void bs_scan_word_e_lo(uint32_t &E, uint32_t &C)
+{
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+        C = dp_lop3<0xD2>(C, E, C << s);
+        E |= E << s;
+    }
+}
+CA_DEV void bs_scan_word_e_hi(uint32_t &E, uint32_t &C)
+{
+#pragma unroll
+    for (int s = 8; s < 32; s <<= 1) {
+        C = dp_lop3<0xD2>(C, E, C << s);
+        E |= E << s;
+    }
+}
+
+/*
+ * The warp-level stage on E = ~D; el / cl: this lane's map breaks the chain / emits 1 for carry-in 0.  When every
+ * lane breaks the chain (the common case: a lane holds 32 * WPL cells) the carry into lane i is simply cl of lane i-1.
+ */
+CA_DEV uint32_t bs_scan_warp_e(bool el, bool cl)
+{
+    uint32_t BE = dp_ballot(el);
+    uint32_t BC = dp_ballot(cl);
+    if (BE != 0xffffffffu)
+        bs_scan_word_e(BE, BC);     /* carry-in of lane 0 is 0: result bit i = BC bit i */
+    return ((BC + BC) >> dp_lane()) & 1u;
 }
 
 } // namespace clapca

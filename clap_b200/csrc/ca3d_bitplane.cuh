@@ -219,11 +219,8 @@ template <> struct LaneVec<4> {
 template <int WPL>
 CA_DEV void bp_hsum(const uint32_t a[WPL], uint32_t h0[WPL], uint32_t h1[WPL])
 {
-    const int lane = dp_lane();
-    uint32_t prev = dp_shfl_up(a[WPL - 1], 1);      /* last word of the lane on the left  */
-    uint32_t next = dp_shfl_down(a[0], 1);          /* first word of the lane on the right */
-    if (lane == 0)  prev = 0u;
-    if (lane == 31) next = 0u;
+    const uint32_t prev = dp_shfl_up0(a[WPL - 1]);      /* last word of the lane on the left (0 outside the row)  */
+    const uint32_t next = dp_shfl_down0(a[0]);          /* first word of the lane on the right */
 #pragma unroll
     for (int j = 0; j < WPL; j++) {
         uint32_t left  = j ? a[j - 1] : prev;
@@ -265,7 +262,8 @@ struct Sweep3 {
 
     struct St {
         /* slot of row r = (r - y0 + 3) % 3 */
-        uint32_t hd[3][2][WPL], hu[3][2][WPL];      /* H rows of the plane below (new) / above (old) */
+        uint32_t tt[3][3][WPL];                     /* T(r) = H(plane below, new)(r) + H(plane above, old)(r), rows y-1, y, y+1 */
+        uint32_t hd[2][WPL], hu[2][WPL];            /* the side planes' H rows loaded last (row y+1 when a step starts) */
         uint32_t so[3][P][WPL];                     /* own state rows y, y+1, y+2 */
         uint32_t ho[2][WPL];                        /* H of own old row y+1 */
         uint32_t hn[2][WPL];                        /* H of own new row y-1 */
@@ -378,6 +376,16 @@ struct Sweep3 {
         LaneVec<WPL>::ld(st.rec + D * RECW, h[0]);
         LaneVec<WPL>::ld(st.rec + D * RECW + RWP, h[1]);
     }
+    /* T = Hdn + Hup of the side rows loaded last */
+    CA_MDEV void pair_sum(const St &st, uint32_t t[3][WPL])
+    {
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            uint32_t d_[2] = { st.hd[0][j], st.hd[1][j] }, u_[2] = { st.hu[0][j], st.hu[1][j] }, t_[3];
+            bs_add2x2(d_, u_, t_);
+            t[0][j] = t_[0]; t[1][j] = t_[1]; t[2][j] = t_[2];
+        }
+    }
     CA_MDEV void zero_s(uint32_t s[P][WPL])
     {
 #pragma unroll
@@ -409,21 +417,19 @@ struct Sweep3 {
             ao[j] = a | hi;
             ge2[j] = hi;
         }
-        uint32_t nxt = dp_shfl_down(ao[0], 1);
-        if (lane == 31) nxt = 0u;
+        const uint32_t nxt = dp_shfl_down0(ao[0]);
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
-            uint32_t a_[2] = { st.hd[A][0][j], st.hd[A][1][j] }, b_[2] = { st.hd[B][0][j], st.hd[B][1][j] };
-            uint32_t c_[2] = { st.hd[C][0][j], st.hd[C][1][j] };
-            uint32_t vd[4], vu[4];
-            bs_add3x2(a_, b_, c_, vd);
-            uint32_t e_[2] = { st.hu[A][0][j], st.hu[A][1][j] }, f_[2] = { st.hu[B][0][j], st.hu[B][1][j] };
-            uint32_t g_[2] = { st.hu[C][0][j], st.hu[C][1][j] };
-            bs_add3x2(e_, f_, g_, vu);
+            /* row y+1 of the side planes arrived during the previous step: its pair sum takes the slot row y-2 left */
+            uint32_t d_[2] = { st.hd[0][j], st.hd[1][j] }, u_[2] = { st.hu[0][j], st.hu[1][j] }, t_[3];
+            bs_add2x2(d_, u_, t_);
+            st.tt[C][0][j] = t_[0]; st.tt[C][1][j] = t_[1]; st.tt[C][2][j] = t_[2];
+            uint32_t a_[3] = { st.tt[A][0][j], st.tt[A][1][j], st.tt[A][2][j] };
+            uint32_t b_[3] = { st.tt[B][0][j], st.tt[B][1][j], st.tt[B][2][j] };
             uint32_t n_[2] = { st.hn[0][j], st.hn[1][j] }, o_[2] = { st.ho[0][j], st.ho[1][j] };
             uint32_t right = (j + 1 < WPL) ? ao[j + 1] : nxt;
             uint32_t r = dp_funnel_r(ao[j], right, 1);      /* old alive bit of x+1 */
-            bs_count3d(vd, vu, n_, o_, r, k[j]);
+            bs_count3d_t(a_, b_, t_, n_, o_, r, k[j]);
         }
 
         /* ---- prefetch row y+2 while the rule / scan / update below run ---- */
@@ -438,45 +444,57 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                load_side(st.dn, st.hd[A]);
-                load_side(st.up, st.hu[A]);
+                load_side(st.dn, st.hd);
+                load_side(st.up, st.hu);
             } else {
-                zero2(st.ho); zero2(st.hd[A]); zero2(st.hu[A]);
+                zero2(st.ho); zero2(st.hd); zero2(st.hu);
                 zero_s(st.so[A]);
             }
         }
 
         /* ---- rule tables, in-row scan ---- */
-        uint32_t s0[WPL], s1[WPL], b0[WPL], b1[WPL], D[WPL], Cc[WPL];
-        uint32_t dl = 1u, cl = 0u;          /* lane map: identity so far */
+        uint32_t s0[WPL], s1[WPL], E[WPL], Cc[WPL];
+        uint32_t el = 0u, cl = 0u;          /* lane map in bit 31 (el: the chain breaks inside the lane): identity so far */
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
-            Rule::eval(p, k[j], s0[j], s1[j], b0[j], b1[j]);
-            /* new alive bit if the predecessor's new alive bit is 0 / 1 */
-            uint32_t f0 = bs_mux(ao[j], s0[j] | ge2[j], b0[j]) & st.vmask[j];
-            uint32_t f1 = bs_mux(ao[j], s1[j] | ge2[j], b1[j]) & st.vmask[j];
-            D[j] = f0 ^ f1;
+            uint32_t b0, b1;
+            Rule::eval(p, k[j], s0[j], s1[j], b0, b1);
+            /* new alive bit if the predecessor's new alive bit is 0 / 1 (padding cells are dead: only births need the mask) */
+            const uint32_t nv = ~ao[j] & st.vmask[j];
+            const uint32_t f0 = (ao[j] & (s0[j] | ge2[j])) | (b0 & nv);
+            const uint32_t f1 = (ao[j] & (s1[j] | ge2[j])) | (b1 & nv);
+            E[j] = ~(f0 ^ f1);
             Cc[j] = f0;
-            bs_scan_word(D[j], Cc[j]);
-            /* compose into the lane map: carry-out = c ^ (d & carry-in) */
-            uint32_t d = D[j] >> 31, c = Cc[j] >> 31;
-            cl = c ^ (d & cl);
-            dl = d & dl;
+            bs_scan_word_e_lo(E[j], Cc[j]);
         }
-        uint32_t cin = bs_scan_warp(dl, cl, 0u);
+        {
+            uint32_t open8 = 0u;            /* runs of 8 dependent cells: the scan needs its last two steps */
+#pragma unroll
+            for (int j = 0; j < WPL; j++) open8 |= ~E[j];
+            if (dp_any((open8 & 0xffffff00u) != 0u)) {
+#pragma unroll
+                for (int j = 0; j < WPL; j++) bs_scan_word_e_hi(E[j], Cc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < WPL; j++) {
+            /* compose into the lane map: carry-out = c ^ (d & carry-in), carried in bit 31 of whole words */
+            cl = Cc[j] ^ (~E[j] & cl);
+            el |= E[j];
+        }
+        uint32_t cin = bs_scan_warp_e((int)el < 0, (int)cl < 0);
 
         /* ---- apply: new alive bits, state planes ---- */
         uint32_t an[WPL];
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
             uint32_t cm = 0u - cin;
-            an[j] = Cc[j] ^ (D[j] & cm);
-            uint32_t pred = (an[j] << 1) | cin;              /* new alive bit of x-1 */
+            an[j] = Cc[j] ^ (~E[j] & cm);
+            uint32_t pred = an[j] * 2u + cin;                /* new alive bit of x-1 */
             cin = an[j] >> 31;
             uint32_t sv = bs_mux(pred, s1[j], s0[j]);
-            uint32_t bn = bs_mux(pred, b1[j], b0[j]);
             uint32_t dec = ao[j] & ~sv;                      /* alive, not surviving: state - 1 */
-            uint32_t brn = ~ao[j] & bn & st.vmask[j];        /* dead, born: state = nr_states - 1 */
+            uint32_t brn = an[j] & ~ao[j];                   /* dead, born: state = nr_states - 1 */
             uint32_t borrow = dec;
 #pragma unroll
             for (int q = 0; q < P; q++) {
@@ -601,27 +619,33 @@ struct Sweep3 {
         if (!wait_rows(p, st, y0 + 2 < H ? y0 + 2 : H))
             return false;
 
-        /* ---- fill the windows: rows y0-1 (slot 2), y0 (slot 0), y0+1 (slot 1) ---- */
+        /* ---- fill the windows: pair sums of rows y0-1 (slot 2) and y0 (slot 0); row y0+1 waits in hd / hu ---- */
         if (y0 > 0) {
-            load_side(st.dn, st.hd[2]);
-            load_side(st.up, st.hu[2]);
+            load_side(st.dn, st.hd);
+            load_side(st.up, st.hu);
+            pair_sum(st, st.tt[2]);
             load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
         } else {
-            zero2(st.hd[2]); zero2(st.hu[2]); zero2(st.hn);
+#pragma unroll
+            for (int j = 0; j < WPL; j++) st.tt[2][0][j] = st.tt[2][1][j] = st.tt[2][2][j] = 0u;
+            zero2(st.hn);
         }
-        load_side(st.dn, st.hd[0]);
-        load_side(st.up, st.hu[0]);
+        load_side(st.dn, st.hd);
+        load_side(st.up, st.hu);
+        pair_sum(st, st.tt[0]);
         load_own_s<0>(st, st.so[0]);
         if (y0 + 1 < H) {
-            load_side(st.dn, st.hd[1]);
-            load_side(st.up, st.hu[1]);
+            load_side(st.dn, st.hd);
+            load_side(st.up, st.hu);
             load_own_h<1>(st, st.ho);
             load_own_s<1>(st, st.so[1]);
         } else {
-            zero2(st.hd[1]); zero2(st.hu[1]); zero2(st.ho);
+            zero2(st.hd); zero2(st.hu); zero2(st.ho);
             zero_s(st.so[1]);
         }
         zero_s(st.so[2]);
+#pragma unroll
+        for (int j = 0; j < WPL; j++) st.tt[1][0][j] = st.tt[1][1][j] = st.tt[1][2][j] = 0u;
 
         int y = y0;
         for (; y + 3 <= y1; y += 3) {

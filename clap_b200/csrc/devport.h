@@ -39,6 +39,19 @@ CA_DEV int  dp_thread()          { return (int)threadIdx.x; }
 CA_DEV uint32_t dp_shfl(uint32_t v, int src)      { return __shfl_sync(CA_FULL, v, src); }
 CA_DEV uint32_t dp_shfl_up(uint32_t v, int d)     { return __shfl_up_sync(CA_FULL, v, d); }
 CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { return __shfl_down_sync(CA_FULL, v, d); }
+/* neighbour lane's value, 0 where there is no such lane (the shuffle's own range predicate: no lane compare, no select) */
+CA_DEV uint32_t dp_shfl_up0(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.up.b32 %0|p, %1, 1, 0, 0xffffffff;\n\t@!p mov.b32 %0, 0;\n\t}" : "=r"(r) : "r"(v));
+    return r;
+}
+CA_DEV uint32_t dp_shfl_down0(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.down.b32 %0|p, %1, 1, 31, 0xffffffff;\n\t@!p mov.b32 %0, 0;\n\t}" : "=r"(r) : "r"(v));
+    return r;
+}
 CA_DEV uint32_t dp_ballot(bool p)                 { return __ballot_sync(CA_FULL, p); }
 CA_DEV bool     dp_all(bool p)                    { return __all_sync(CA_FULL, p); }
 CA_DEV void     dp_syncwarp()                     { __syncwarp(); }
@@ -232,6 +245,8 @@ CA_DEV int  dp_thread()          { return emu_warp_in_block() * 32 + emu_lane();
 CA_DEV uint32_t dp_shfl(uint32_t v, int src)      { return emu_exchange(v, src); }
 CA_DEV uint32_t dp_shfl_up(uint32_t v, int d)     { int l = emu_lane(); return emu_exchange(v, l - d >= 0 ? l - d : l); }
 CA_DEV uint32_t dp_shfl_down(uint32_t v, int d)   { int l = emu_lane(); return emu_exchange(v, l + d < 32 ? l + d : l); }
+CA_DEV uint32_t dp_shfl_up0(uint32_t v)           { int l = emu_lane(); uint32_t r = emu_exchange(v, l - 1 >= 0 ? l - 1 : l); return l ? r : 0u; }
+CA_DEV uint32_t dp_shfl_down0(uint32_t v)         { int l = emu_lane(); uint32_t r = emu_exchange(v, l + 1 < 32 ? l + 1 : l); return l < 31 ? r : 0u; }
 CA_DEV uint32_t dp_ballot(bool p)                 { return emu_ballot(p); }
 CA_DEV bool     dp_all(bool p)                    { return emu_ballot(p) == CA_FULL; }
 CA_DEV void     dp_syncwarp()                     { (void)emu_ballot(true); }

@@ -14,8 +14,9 @@
  *                in_ready, while a second thread drains finished chunks as their planes' out_done words show the epoch
  *            (single rank, time-key or team order)
  *   nca      0..8 = compile-time rule of cas[], 9 = run-time rule (coral masks),
- *            10   = run-time rule with random masks
- *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s)
+ *            10   = run-time rule with random masks, 11 / 12 = run-time "chain" rules (rows are one / a few
+ *                   dependency chains: the long-run paths of the in-row scan)
+ *   seedkind 0 = sparse values 0..5, 1 = dense 0..min(2^P-1,255), 2 = ca3d_make seed (has 255s), 3 = binary (0 / 1)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -139,6 +140,14 @@ int main(int argc, char **argv)
     unsigned surv, born, nr;
     if (nca <= 9) {
         ora_ca3d_rule(nca == 9 ? 7 : nca, &surv, &born, &nr);
+    } else if (nca == 11 || nca == 12) {
+        /* "chain" rules: the table flips between every K and K + 1, so (almost) every cell depends on its in-row
+           predecessor -- rows are single dependency chains (11) or chains broken only where K is 6 or 13 (12): the
+           long-run paths of the in-row scan (bitslice.cuh: bs_scan_word_e_hi, the warp stage) */
+        surv = 0x5555555u;
+        born = 0x2aaaaaau;
+        if (nca == 12) { surv ^= 1u << 7; born ^= 1u << 14; }
+        nr = 2;
     } else {
         surv = rnd() & 0x7ffffff;
         born = rnd() & rnd() & 0x7ffffff;
@@ -161,7 +170,9 @@ int main(int argc, char **argv)
             for (auto &c : cells) if (c > vmax) c = (uint8_t)vmax;
     } else {
         for (auto &c : cells) {
-            if (seedkind == 0)
+            if (seedkind == 3)
+                c = (uint8_t)(rnd() & 1u);
+            else if (seedkind == 0)
                 c = (rnd() % 4 == 0) ? (uint8_t)(1 + rnd() % (vmax < 5 ? vmax : 5)) : 0;
             else
                 c = (rnd() % 5 < 2) ? 0 : (uint8_t)(rnd() % (vmax + 1));

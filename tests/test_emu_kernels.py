@@ -31,6 +31,19 @@ def test_ca3d_every_rule(emu_bin, nca):
     _run(exe, 64, 4, 3, 2, nca, 4, 2, 1, nca, 7)
 
 
+@pytest.mark.parametrize("nca", [11, 12])
+def test_ca3d_chain_rules_long_dependency_runs(emu_bin, nca):
+    """Rules whose table flips between every K and K+1: whole rows are one in-row dependency chain, so the scan's
+    rare paths (runs of >= 8 dependent cells inside a word, lanes that never break the chain) do all the work."""
+    exe = os.path.join(emu_bin, "emu_ca3d")
+    _run(exe, 45, 7, 6, 3, nca, 3, 1, 0, 4, 5)
+    _run(exe, 300, 5, 4, 3, nca, 3, 1, 3, 5, 3)           # binary seed: no cell ever has a state >= 2 to break the chain
+    _run(exe, 1030, 3, 3, 2, nca, 3, 2, 3, 6, 3)
+    _run(exe, 2048, 2, 2, 2, nca, 4, 2, 3, 7, 4)
+    _run(exe, 97, 4, 5, 4, nca, 3, 4, 1, 8, 4)
+    _run(exe, 500, 4, 5, 4, nca, 3, 4, 3, 8, 4)
+
+
 @pytest.mark.parametrize("shape", [
     (1, 1, 1, 3), (5, 1, 1, 3), (1, 5, 1, 3), (1, 1, 5, 3), (32, 3, 3, 2), (31, 3, 3, 2), (33, 2, 2, 5),
     (40, 6, 5, 0), (16, 8, 4, 4),

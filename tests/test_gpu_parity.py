@@ -187,6 +187,25 @@ def test_ca3d_custom_masks_run_time_rule(gpu, oracle):
         assert np.array_equal(vol, want)
 
 
+@pytest.mark.parametrize("flip", [None, (7, 14)])
+def test_ca3d_chain_rules_long_dependency_runs(gpu, oracle, flip):
+    """Rules whose table flips between every K and K+1 on a binary volume: every cell depends on its in-row
+    predecessor, so a row is one dependency chain (or a few, with two table entries flipped back) -- the scan's
+    rare paths (runs of >= 8 dependent cells in a word, lanes that never break the chain) carry the whole result."""
+    surv, born = 0x5555555, 0x2aaaaaa
+    if flip:
+        surv ^= 1 << flip[0]
+        born ^= 1 << flip[1]
+    rule = gpu.CellAutomaton("chain", born_mask=born, surv_mask=surv, nr_states=2)
+    rng = np.random.default_rng(77)
+    for shape in ((6, 9, 300), (4, 7, 1030), (3, 6, 2048), (5, 5, 45)):
+        vol = (rng.random(shape) < 0.5).astype(np.uint8)
+        want = vol.copy()
+        wpop = oracle.ca3d_run(want, surv, born, 2, 4)
+        assert gpu.ca3d_run(vol, rule, 4, engine=BITPLANE) == wpop, shape
+        assert np.array_equal(vol, want), shape
+
+
 def test_ca3d_wide_rows_thin_slab_vs_oracle(gpu, oracle):
     """Rows of the BASELINE config-4 width (2048 cells = 2 words per lane) on a thin slab the oracle finishes."""
     rng = np.random.default_rng(12)
