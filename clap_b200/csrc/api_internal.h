@@ -82,15 +82,17 @@ struct OrderCfg {
     int team;           /* mode 3: compute warps per CTA = tile_z * tile_g */
     int tile_z, tile_g; /* mode 3: planes / generations per tile */
     int ctas;           /* mode 3: CTAs the launch keeps resident (bounds tile_g, see bp_plan.h) */
+    int tile_skew;      /* mode 3: key distance between generation groups (0 = tile_z + 1, see bp3_make_items_tile) */
     int key() const
     {
-        return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? tile_z * 256 + tile_g : 0)));
+        return mode * 100000 + (mode == 1 ? seg_rows : (mode == 2 ? gen_batch : (mode == 3 ? tile_z * 256 + tile_g : 0)))
+             + (mode == 3 ? (tile_skew % 4000) * 500000 : 0);
     }
 };
 int team_config(int P, int WPL);
 /* wanted generations per tile for a team of `team` compute warps (CLAPCA_TILE_GENS overrides) */
 int tile_gens_config(int team);
-void sweep_knobs(Bp3Params &p, int team);
+void sweep_knobs(Bp3Params &p, int team, bool single_gpu = false);
 OrderCfg order_config(int Z, int H, int G, int max_workers, int team);
 void make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                 std::vector<WorkItem> &items, bool layout_items);

@@ -260,8 +260,12 @@ static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     sweep_knobs(knobs, team);
     const int max_ctas = s->max_ctas > 0 ? s->max_ctas : knobs.max_ctas;
     OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms, team, max_ctas), team);
+    /* sharded volumes keep generation group b + 1 right behind group b: the z pipeline across the ranks needs the
+       other groups to fill its bubbles (CLAPCA_SLAB_TILE_SKEW for experiments; every rank must use the same value) */
+    oc.tile_skew = 0;
+    if (const char *e = getenv("CLAPCA_SLAB_TILE_SKEW")) oc.tile_skew = std::max(0, atoi(e));
     /* every rank must settle on the same tile shape: decide it from all ranks' plane lists */
-    oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z, streamed);
+    oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z, streamed, oc.tile_skew);
     if (s->order_G != steps || s->team != team || s->order_key != oc.key() || s->streamed_order != streamed) {
         std::vector<WorkItem> items;
         s->team = team;

@@ -464,9 +464,12 @@ int clapca::api::tile_gens_config(int team)
     return tg;
 }
 
-void clapca::api::sweep_knobs(Bp3Params &p, int team)
+void clapca::api::sweep_knobs(Bp3Params &p, int team, bool single_gpu)
 {
     p.flag_rows = kFlagRows;
+    /* the generation groups of a single-GPU run are far apart in time (order_config): a tile's first generation reads
+       its rows from HBM, 6 rows ahead covers that latency (98.3 -> 94.5 ms at 2048^3 x 50; 16 rows ahead: 108 ms) */
+    p.prefetch_rows = (single_gpu && team > 0) ? 6 : 0;
     if (const char *e = getenv("CLAPCA_FLAG_ROWS")) { int v = atoi(e); if (v > 0) p.flag_rows = v; }
     if (const char *e = getenv("CLAPCA_PREFETCH_ROWS")) p.prefetch_rows = std::max(0, atoi(e));
     if (const char *e = getenv("CLAPCA_CTAS_PER_SM")) p.max_ctas_per_sm = std::max(0, atoi(e));
@@ -481,11 +484,26 @@ static const int kGenBatch = 16;
 
 OrderCfg clapca::api::order_config(int Z, int H, int G, int max_workers, int team)
 {
-    OrderCfg oc = { 0, 0, kGenBatch, team, team, 1, 0 };
+    OrderCfg oc = { 0, 0, kGenBatch, team, team, 1, 0, 0 };
     if (team > 0) {
         oc.mode = 3;
         oc.tile_g = tile_gens_config(team);     /* wanted; make_items() settles the shape for the plane list at hand */
         oc.ctas = std::max(1, max_workers / team);
+        /*
+         * Key distance between generation groups on one GPU (bp_plan.h, bp3_make_items_tile; slabs set their own).
+         * A tile follows its z-predecessor (3 tz + flag_rows) rows behind, so one generation group keeps at most
+         * H / (3 tz + flag_rows) CTAs busy; `active` groups in flight keep all of them busy, and no more groups than
+         * that should be: every active group puts one more ticket between a tile and its forward partner (the tile's
+         * late warps wait for the partner, its early warps for them at the end-of-item barrier).  Measured at
+         * 2048^3 x 50, 148 CTAs of 5 x 3 tiles (profiles/r02_knobs_tile_skew_ca3d_2048.txt): distance tz + 1 (all 17
+         * groups interleaved) 98.0 ms, Z / 4 .. Z / 2 94.4-94.9 ms, 2100 (one group at a time, 89 CTAs busy) 119 ms.
+         */
+        {
+            const int tz = std::max(1, team / std::max(1, oc.tile_g));
+            const int active = 1 + (oc.ctas * (3 * tz + kFlagRows) + H - 1) / std::max(H, 1);
+            oc.tile_skew = std::max(tz + 1, Z / active);
+        }
+        if (const char *e = getenv("CLAPCA_TILE_SKEW")) oc.tile_skew = std::max(0, atoi(e));
         return oc;
     }
     if (const char *e = getenv("CLAPCA_ORDER")) { int v = atoi(e); if (v >= 0 && v <= 2) oc.mode = v; }
@@ -502,7 +520,7 @@ OrderCfg clapca::api::order_config(int Z, int H, int G, int max_workers, int tea
 void clapca::api::make_items(const OrderCfg &oc, const std::vector<Bp3Plane> &planes, int Zg, int H, int G,
                        std::vector<WorkItem> &items, bool layout_items)
 {
-    if (oc.mode == 3) bp3_make_items_tile(planes, H, G, oc.tile_z, oc.tile_g, items, layout_items);
+    if (oc.mode == 3) bp3_make_items_tile(planes, H, G, oc.tile_z, oc.tile_g, items, layout_items, nullptr, oc.tile_skew);
     else if (oc.mode == 1) bp3_make_items(planes, Zg, H, G, oc.seg_rows, items);
     else if (oc.mode == 2) bp3_make_items_batched(planes, Zg, H, G, oc.gen_batch, items);
     else bp3_make_items_timekey(planes, H, G, items, layout_items);
@@ -711,14 +729,14 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
          */
         Bp3Params knobs;
         memset(&knobs, 0, sizeof(knobs));
-        sweep_knobs(knobs, team);
+        sweep_knobs(knobs, team, true);
         OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms, team, knobs.max_ctas), team);
         if (fused && oc.mode != 0 && oc.mode != 3) {
             if (io) oc.mode = 0;                    /* layout items exist for whole-plane orders only */
             else return fail(CLAPCA_ERR_UNSUPPORTED, "CLAPCA_FUSED_LAYOUT needs the time-key or the tile order");
         }
         if (oc.mode == 3)
-            oc.tile_g = bp3_tile_shape(planes, H, G, team, oc.tile_g, oc.ctas, fused, &oc.tile_z);
+            oc.tile_g = bp3_tile_shape(planes, H, G, team, oc.tile_g, oc.ctas, fused, &oc.tile_z, oc.tile_skew);
         const int okey = oc.key() + (fused ? 50000000 : 0);
         if (g->order_Z != Z || g->order_H != H || g->order_G != G || g->order_L != okey) {
             std::vector<WorkItem> items;
@@ -744,7 +762,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.prog = prog;
         p.order = g->order;
         p.nsweeps = g->n_items;
-        sweep_knobs(p, team);
+        sweep_knobs(p, team, true);
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;

@@ -4,7 +4,7 @@
  * volume and the population with the oracle restatement of ca3d_run().
  * TEST ONLY: built and executed by tests/test_emu_kernels.py.
  *
- * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [tilegens [layout [chunk]]]]]]]]]]]
+ * usage: emu_ca3d W H Z G nca P WPL seedkind rngseed [warps [ranks [block [seg [flagrows [genbatch [pubworkers [team [tilegens [layout [chunk [gskew]]]]]]]]]]]]
  *   team     > 0: tile mode, compute warps per CTA (every CTA gets one more warp, the service warp); `warps` / team
  *            CTAs are launched per rank.  tilegens = wanted generations per tile (the planner lowers it when the
  *            launch has too few CTAs for the forward dependency).  Several ranks need tile mode: the service warp
@@ -124,6 +124,7 @@ int main(int argc, char **argv)
     int tileGens = argc > 18 ? atoi(argv[18]) : 1;   /* tile mode: wanted generations per tile */
     int layout = argc > 19 ? atoi(argv[19]) : 0;
     int chunk = argc > 20 ? atoi(argv[20]) : 2;
+    int gskew = argc > 21 ? atoi(argv[21]) : 0;      /* tile mode: key distance between generation groups (0 = Tz + 1) */
     if (ranks > 1 && team <= 0) {
         fprintf(stderr, "several ranks need tile mode (team > 0)\n");
         return 2;
@@ -230,10 +231,10 @@ int main(int argc, char **argv)
         if (team > 0) {
             const int ctas = (warps + team - 1) / team;
             int Tz = team, Tg = 1;
-            if (ranks > 1) Tg = bp3_tile_shape_all_ranks(k.geo, H, G, team, tileGens, ctas, &Tz, layout != 0);
-            else Tg = bp3_tile_shape(k.planes, H, G, team, tileGens, ctas, layout != 0, &Tz);
+            if (ranks > 1) Tg = bp3_tile_shape_all_ranks(k.geo, H, G, team, tileGens, ctas, &Tz, layout != 0, gskew);
+            else Tg = bp3_tile_shape(k.planes, H, G, team, tileGens, ctas, layout != 0, &Tz, gskew);
             if (r == 0) fprintf(stderr, "tile shape %d planes x %d generations\n", Tz, Tg);
-            bp3_make_items_tile(k.planes, H, G, Tz, Tg, items, layout != 0);
+            bp3_make_items_tile(k.planes, H, G, Tz, Tg, items, layout != 0, nullptr, gskew);
         }
         else if (genBatch > 0)
             bp3_make_items_batched(k.planes, Z, H, G, genBatch, items);

@@ -191,6 +191,21 @@ def test_ca3d_layout_items_streamed(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
 
 
+@pytest.mark.parametrize("args", [
+    #  W   H   Z   G  rule P WPL kind seed warps ranks block seg flagrows genbatch pubworkers team tilegens layout chunk gskew
+    (45, 20, 12, 8, 7, 3, 1, 1, 3, 40, 1, 0, 0, 2, 0, 0, 4, 2, 0, 2, 1000),      # generation groups one after the other
+    (45, 20, 12, 9, 7, 3, 1, 1, 3, 256, 1, 0, 0, 2, 0, 0, 16, 4, 0, 2, 7),       # a little more skew than Tz + 1
+    (45, 20, 13, 7, 10, 4, 1, 1, 3, 12, 1, 0, 0, 2, 0, 0, 8, 2, 0, 2, 1000),     # 3 CTAs only: the window rule still holds
+    (33, 30, 15, 7, 7, 3, 1, 1, 4, 45, 1, 0, 0, 2, 0, 0, 15, 3, 0, 2, 2048),     # the default 5 x 3 tiles
+    (45, 20, 13, 6, 7, 3, 1, 1, 3, 80, 1, 0, 0, 2, 0, 0, 4, 2, 2, 4, 1000),      # with pack / unpack groups (streamed)
+    (45, 37, 12, 6, 7, 3, 1, 1, 3, 48, 2, 2, 0, 2, 0, 0, 4, 2, 0, 2, 1000),      # 2 ranks
+])
+def test_ca3d_tile_order_generation_group_skew(emu_bin, args):
+    """The key distance between the generation groups of the tile order (bp_plan.h, bp3_make_items_tile): any value
+    above Tz is a valid claim order; large values run the groups one after the other."""
+    _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+
+
 # ---- 2D bit-plane engine (ca2d_bitplane.cuh): one CTA per generation, CTA-wide scan -----------------------
 
 @pytest.mark.parametrize("args", [
