@@ -10,7 +10,8 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int64
                     c_uint, c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+# CLAPCA_LIB_DIR: another in-tree build of the same sources (A/B measurements of compile-time variants)
+LIB_DIR = os.environ.get("CLAPCA_LIB_DIR") or os.path.join(_HERE, "lib")
 CUDA_LIB = os.path.join(LIB_DIR, "libclapca_cuda.so")
 HOST_LIB = os.path.join(LIB_DIR, "libclapca_host.so")
 

@@ -116,6 +116,7 @@ int io_chunk_planes(size_t plane_bytes, int Z);
 /* the layout kernels live in ONE translation unit (clapca_api.cu); these launch them */
 cudaError_t launch_ca3d_pack(const Bp3Layout &L, cudaStream_t stream);
 cudaError_t launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t stream);
+cudaError_t preload_ca3d_layout(int P);
 cudaError_t launch_max_u8(const uint8_t *cells, size_t n, unsigned *d_max, cudaStream_t stream);
 cudaError_t launch_halo_seed(uint32_t *dst, const uint32_t *src, int H, int RWP, int NP, cudaStream_t stream);
 

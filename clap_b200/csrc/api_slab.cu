@@ -249,6 +249,15 @@ static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
             return fail(CLAPCA_ERR_ARG, "slab_prepare: a cell value of %u exceeds the max_value %u given to slab_create "
                         "(%d state planes)", maxv, s->max_value, s->P);
     }
+    /*
+     * Every kernel a rank launches while a neighbour's sweep may already be spinning on this rank's rows must be
+     * LOADED by now: with lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, loading
+     * synchronises with the running work of the context, and a rank of the same process (LocalRanks, or a caller's
+     * threads) would wait for a sweep that waits for it -- measured: the first P = 8 run of a process sat out both
+     * watchdogs in exactly that way, behind the unpack kernel its neighbour launches right after its sweep.  The sweep
+     * kernel itself is loaded by the occupancy query of order_config() below.
+     */
+    CU(preload_ca3d_layout(s->P));
     s->epoch++;                                 /* every rank prepares successfully the same number of times */
     const int bank = (int)(s->epoch & 1u);
 
@@ -341,6 +350,39 @@ int clapca_slab_prepare_streamed(clapca_slab *s, uint32_t surv, uint32_t born, u
     return slab_prepare(s, surv, born, nr_states, steps, true);
 }
 
+/* CLAPCA_DUMP=1: after a watchdog, the progress table and the ghost counters of this rank (what was everybody waiting for?) */
+static void slab_post_mortem(clapca_slab *s)
+{
+    const char *e = getenv("CLAPCA_DUMP");
+    if (!e || !atoi(e))
+        return;
+    const int Zl = s->Zl ? s->Zl : 1;
+    std::vector<int> prog((size_t)(s->G + 1) * Zl);
+    if (cudaMemcpy(prog.data(), s->prog, prog.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return;
+    fprintf(stderr, "clapca post-mortem rank %d: H %d, local planes %d, generations %d; prog[g][z] (g = -1 first):\n",
+            s->geo.rank, s->H, s->Zl, s->G);
+    for (int g = 0; g <= s->G; g++) {
+        fprintf(stderr, "  g %2d:", g - 1);
+        for (int z = 0; z < Zl; z++) fprintf(stderr, " %d", prog[(size_t)g * Zl + z]);
+        fprintf(stderr, "\n");
+    }
+    if (s->geo.R > 1) {
+        const int bank = (int)(s->epoch & 1u);
+        std::vector<int> fl(s->hl.bank_words());
+        if (cudaMemcpy(fl.data(), s->halo + s->hl.flags + (size_t)bank * s->hl.bank_words(), fl.size() * sizeof(int),
+                       cudaMemcpyDeviceToHost) != cudaSuccess)
+            return;
+        for (int up = 0; up < 2; up++)
+            for (int lb = 0; lb < s->hl.nlb_max; lb++) {
+                fprintf(stderr, "  ghost %s of local block %d, counters g = -1 ..:", up ? "above" : "below", lb);
+                for (int g = 0; g <= s->hl.Gcap; g++)
+                    fprintf(stderr, " %d", fl[((size_t)up * s->hl.nlb_max + lb) * (s->hl.Gcap + 1) + g]);
+                fprintf(stderr, "\n");
+            }
+    }
+}
+
 /* the sweep launch of a prepared slab; streamed: with layout items (pack / unpack inside the launch) */
 static int slab_launch(clapca_slab *s, bool streamed, int *workers)
 {
@@ -405,8 +447,10 @@ int clapca_slab_run(clapca_slab *s, int64_t *local_population)
     CU(cudaMemcpyAsync(&pop, s->d_pop, sizeof(pop), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(&err, s->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    if (err)
+    if (err) {
+        slab_post_mortem(s);
         return fail(CLAPCA_ERR_TIMEOUT, "slab_run: dataflow watchdog fired on rank %d (err=%d)", s->geo.rank, err);
+    }
     if (local_population) *local_population = (int64_t)pop;
     float prep = 0, sweep = 0, tail = 0;
     CU(cudaEventElapsedTime(&prep, s->ev[0], s->ev[1]));

@@ -45,6 +45,7 @@ struct Bp3Layout {
     uint32_t *rows;         /* row records */
     int W, H, Z, P, RWP;
     unsigned long long *population;     /* unpack: number of non-zero cells */
+    unsigned *over;         /* pack, optional: |= 1 when a cell value does not fit the P state planes */
 };
 
 } // namespace clapca

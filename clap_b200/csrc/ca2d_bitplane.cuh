@@ -63,7 +63,14 @@ struct Bp2Params {
 };
 
 enum { BP2_MAX_WARPS = 16 };
-/* shared memory of a CTA (words): the warps' carry maps (two rows in flight), the row counter, the claimed generation */
+/*
+ * shared memory of a CTA (words): four rotating slots of two words each for the warps' carry maps, the row counter, the
+ * claimed generation.  A slot packs one bit per warp: word 0 = [generate | propagate << 16] (general rules: the warp
+ * map's [D | C << 16]), word 1 = the same two bits of the warp's FIRST cell -- lane 0 of every warp ORs its bits in
+ * before the row barrier, everybody reads the two words after it: the CTA-level chain starts from plain masks (no
+ * ballots), and the slot of row x+2 is cleared by thread 0 right after the barrier of row x (its last readers, row
+ * x-2's, are past barrier x-1; its next writers, row x+2's, are behind barrier x+1, which thread 0 has yet to reach).
+ */
 enum { BP2_SM_SLOT = 0, BP2_SM_DONE = 2 * 32, BP2_SM_TICKET = 2 * 32 + 1, BP2_SMEM_WORDS = 2 * 32 + 2 };
 
 /*
@@ -141,6 +148,7 @@ struct Sweep2 {
         const uint32_t *xrec;       /* lane 0 / 31: the word just outside the warp's span (row x), else null */
         const int *flagp;           /* lane 0: counter of the previous generation, else null */
         int have;
+        int next_raise;             /* next row count at which thread 0 raises the shared-memory row counter */
         typename Rule::Tabs tabs;   /* run-time rule: the mask bits, broadcast to words once per sweep */
     };
 
@@ -280,13 +288,13 @@ struct Sweep2 {
         }
         uint32_t an[WPL], pred[WPL];    /* new alive bits of y and of y-1 */
         uint32_t cin_lane, first_next;
-        uint32_t *slot = smem + BP2_SM_SLOT + (x & 1) * 32;
+        uint32_t *slot = smem + BP2_SM_SLOT + (x & 3) * 2;
         if constexpr (Rule::kMono) {
             /*
              * Monotone rule: f0 is a subset of f1, a'(y) = f0 | (f1 & a'(y-1)) -- generate / propagate, exactly the
              * carry chain of f0 + f1.  Lane level: carry out of the lane's words for carry-in 0 (g) and whether
              * every cell propagates (pr); warp level: the same add on the ballots; CTA level: once more on the
-             * warps' (generate, propagate) bits.
+             * warps' (generate, propagate) masks.
              */
             uint32_t c = 0u, pr = ~0u;
 #pragma unroll
@@ -297,16 +305,18 @@ struct Sweep2 {
             }
             const uint32_t BG = dp_ballot(c != 0u), BP = dp_ballot(pr == ~0u);
             const unsigned long long tw = (unsigned long long)BG + (BG | BP);
-            if (lane == 0)      /* bit 0/1: the warp generates / propagates, bit 2/3: f0 / f1 of its first cell */
-                slot[warp] = (uint32_t)(tw >> 32) | ((uint32_t)(BP == ~0u) << 1) | ((f0[0] & 1u) << 2) | ((f1[0] & 1u) << 3);
+            if (lane == 0) {
+                dp_atomic_or_cta(slot, ((uint32_t)(tw >> 32) << warp) | ((uint32_t)(BP == ~0u) << (16 + warp)));
+                dp_atomic_or_cta(slot + 1, ((f0[0] & 1u) << warp) | ((f1[0] & 1u) << (16 + warp)));
+            }
             dp_syncblock_named(1, nw * 32);
-            raise_counter(p, x, smem);
-            const uint32_t mine = lane < nw ? slot[lane] : 0u;      /* beyond the last warp: kill */
-            const uint32_t WG = dp_ballot((mine & 1u) != 0), WP = dp_ballot((mine & 2u) != 0);
+            after_barrier(p, st, x, smem);
+            const uint32_t w0 = dp_ld_volatile_u32(slot), w1 = dp_ld_volatile_u32(slot + 1);
+            const uint32_t WG = w0 & 0xffffu, WP = w0 >> 16;        /* warps beyond the last: kill */
             const uint32_t cw = (WG + (WG | WP)) ^ WG ^ (WG | WP);  /* bit w = carry into warp w (nw <= 16: no overflow) */
             const uint32_t cin_w = (cw >> warp) & 1u, cout_w = (cw >> (warp + 1)) & 1u;
-            const uint32_t nxt = dp_shfl(mine, warp + 1 < 32 ? warp + 1 : 31);
-            first_next = (warp + 1 < nw) ? (((nxt >> 2) | ((nxt >> 3) & cout_w)) & 1u) : 0u;
+            /* new alive bit of the first cell of the next warp (its bits are 0 beyond the row) */
+            first_next = ((((w1 & 0xffffu) >> (warp + 1)) | (((w1 >> 16) >> (warp + 1)) & cout_w)) & 1u);
             const uint32_t cb = (uint32_t)(tw + cin_w) ^ BG ^ (BG | BP);   /* bit l = carry into lane l */
             c = cin_lane = (cb >> lane) & 1u;
 #pragma unroll
@@ -334,18 +344,19 @@ struct Sweep2 {
             /* this lane's carry-in is c_in0 ^ (p_in & warp carry-in) */
             const uint32_t c_in0 = lane ? (BC >> (lane - 1)) & 1u : 0u;
             const uint32_t p_in = lane ? (BD >> (lane - 1)) & 1u : 1u;
-            if (lane == 0)      /* bit 0/1: the warp's map, bit 2/3: the map of its first cell */
-                slot[warp] = (BD >> 31) | ((BC >> 31) << 1) | ((D[0] & 1u) << 2) | ((Cc[0] & 1u) << 3);
+            if (lane == 0) {    /* word 0: the warp's map, word 1: the map of its first cell */
+                dp_atomic_or_cta(slot, ((BD >> 31) << warp) | ((BC >> 31) << (16 + warp)));
+                dp_atomic_or_cta(slot + 1, ((D[0] & 1u) << warp) | ((Cc[0] & 1u) << (16 + warp)));
+            }
             dp_syncblock_named(1, nw * 32);
-            raise_counter(p, x, smem);
-            const uint32_t mine = lane < nw ? slot[lane] : 1u;      /* identity map beyond the last warp */
-            uint32_t WD = dp_ballot((mine & 1u) != 0), WC = dp_ballot((mine & 2u) != 0);
+            after_barrier(p, st, x, smem);
+            const uint32_t w0 = dp_ld_volatile_u32(slot), w1 = dp_ld_volatile_u32(slot + 1);
+            uint32_t WD = (w0 & 0xffffu) | (~0u << nw), WC = w0 >> 16;     /* identity map beyond the last warp */
             bs_scan_word(WD, WC);
             const uint32_t cin_w = warp ? (WC >> (warp - 1)) & 1u : 0u;
             const uint32_t cout_w = (WC >> warp) & 1u;
             /* new alive bit of the first cell of the next warp (0 beyond the row) */
-            const uint32_t nxt = dp_shfl(mine, warp + 1 < 32 ? warp + 1 : 31);
-            first_next = (warp + 1 < nw) ? (((nxt >> 3) ^ ((nxt >> 2) & cout_w)) & 1u) : 0u;
+            first_next = ((((w1 >> 16) >> (warp + 1)) ^ (((w1 & 0xffffu) >> (warp + 1)) & cout_w)) & 1u);
             uint32_t cin = c_in0 ^ (p_in & cin_w);
             cin_lane = cin;
 #pragma unroll
@@ -358,19 +369,26 @@ struct Sweep2 {
         }
 
         /* ---- apply: state planes ---- */
+        if constexpr (P == 1) {
+            /* one state plane: values are 0 / 1 (nr_states is 1 -- or 0 / 256, and then nothing is ever born), so the
+               new state IS the new alive bit */
 #pragma unroll
-        for (int j = 0; j < WPL; j++) {
-            uint32_t sv = bs_mux(pred[j], s1[j], s0[j]);
-            uint32_t bn = bs_mux(pred[j], b1[j], b0[j]);
-            uint32_t dec = ao[j] & ~sv;                      /* alive, neither surviving nor exempt: value - 1 */
-            uint32_t brn = ~ao[j] & bn & st.vmask[j];        /* dead, born: value = nr_states */
-            uint32_t borrow = dec;
+            for (int j = 0; j < WPL; j++) st.so[B][0][j] = an[j];
+        } else {
 #pragma unroll
-            for (int q = 0; q < P; q++) {
-                uint32_t t = st.so[B][q][j];
-                st.so[B][q][j] = t ^ borrow;
-                borrow &= ~t;
-                if ((p.nrval >> q) & 1u) st.so[B][q][j] |= brn;
+            for (int j = 0; j < WPL; j++) {
+                uint32_t sv = bs_mux(pred[j], s1[j], s0[j]);
+                uint32_t bn = bs_mux(pred[j], b1[j], b0[j]);
+                uint32_t dec = ao[j] & ~sv;                      /* alive, neither surviving nor exempt: value - 1 */
+                uint32_t brn = ~ao[j] & bn & st.vmask[j];        /* dead, born: value = nr_states */
+                uint32_t borrow = dec;
+#pragma unroll
+                for (int q = 0; q < P; q++) {
+                    uint32_t t = st.so[B][q][j];
+                    st.so[B][q][j] = t ^ borrow;
+                    borrow &= ~t;
+                    if ((p.nrval >> q) & 1u) st.so[B][q][j] |= brn;
+                }
             }
         }
 
@@ -402,14 +420,24 @@ struct Sweep2 {
     }
 
     /*
-     * Right after the row barrier of row x: every warp's stores of rows < x precede it.  Every flag_rows rows thread 0
-     * says so in shared memory (CTA-scope release) for the publisher warp.
+     * Right after the row barrier of row x: every warp's stores of rows < x precede it.  Thread 0 clears the slot of
+     * row x+2 and, every flag_rows rows, says so in shared memory (CTA-scope release) for the publisher warp.  The row
+     * marks are counted, not computed: a run-time x % flag_rows is an integer division, ~25 dependent instructions in
+     * ONE warp of the CTA, and that warp was late for every row barrier.
      */
-    CA_MDEV void raise_counter(const Bp2Params &p, int x, uint32_t *smem)
+    CA_MDEV void after_barrier(const Bp2Params &p, St &st, int x, uint32_t *smem)
     {
-        if (dp_thread() == 0 && x > 0 && (x % p.flag_rows) == 0) {
-            dp_fence_cta();
-            dp_st_volatile((int *)smem + BP2_SM_DONE, x);
+        const bool mark = x == st.next_raise;
+        if (mark)
+            st.next_raise += p.flag_rows;
+        if (dp_thread() == 0) {
+            uint32_t *clr = smem + BP2_SM_SLOT + ((x + 2) & 3) * 2;
+            dp_st_volatile((int *)clr, 0);
+            dp_st_volatile((int *)clr + 1, 0);
+            if (mark) {
+                dp_fence_cta();
+                dp_st_volatile((int *)smem + BP2_SM_DONE, x);
+            }
         }
     }
 
@@ -425,6 +453,7 @@ struct Sweep2 {
                 : ((lane == 31 && warp + 1 < nw) ? p.rows + word0 + WPL : nullptr);
         st.flagp = (g > 0 && lane == 0) ? p.prog + (g - 1) : nullptr;
         st.have = g > 0 ? 0 : 0x7fffffff;
+        st.next_raise = p.flag_rows;
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
             st.vmask[j] = bp_valid_mask(word0 + j, p.N);

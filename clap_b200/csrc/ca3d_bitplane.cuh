@@ -46,6 +46,14 @@
 #include "bitslice.cuh"
 #include "bp3_types.h"
 
+/* -DCLAPCA_DEBUG_HANG: the watchdog paths say what they were waiting for (debug builds only) */
+#if defined(CLAPCA_DEBUG_HANG) && !defined(CLAPCA_EMU)
+#include <cstdio>
+#define CLAPCA_HANG_PRINT(...) printf(__VA_ARGS__)
+#else
+#define CLAPCA_HANG_PRINT(...) ((void)0)
+#endif
+
 namespace clapca {
 
 struct Bp3Params {
@@ -302,6 +310,8 @@ struct Sweep3 {
             if ((spins & 127u) == 127u) {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
+                    CLAPCA_HANG_PRINT("wait_rows: cta %d warp %d lane %d need %d have %d have_s %d flagp %p v %d err %d\n",
+                                      dp_block(), dp_warp_in_block(), dp_lane(), need, st.have, st.have_s, (const void *)st.flagp, v, dp_ld_flag(p.err));
                     if (dp_lane() == 0)
                         dp_set_error(p.err, 1);
                     return false;
@@ -332,6 +342,8 @@ struct Sweep3 {
             if ((spins & 1023u) == 1023u) {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
+                    CLAPCA_HANG_PRINT("wait_tile: cta %d warp %d lane %d need %d m %d v %d err %d\n",
+                                      dp_block(), dp_warp_in_block(), dp_lane(), need, m, v, dp_ld_flag(p.err));
                     if (dp_lane() == 0)
                         dp_set_error(p.err, 3);
                     return false;
@@ -1069,6 +1081,8 @@ struct Sweep3 {
                     if (spins - idle_since < 512u) t_idle = dp_clock();
                     bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t_idle) > 4 * p.spin_limit;
                     if (!dp_all(!bad)) {
+                        CLAPCA_HANG_PRINT("service: cta %d lane %d l0 %d g0 %d nz %d ng %d d %d pub %d pushed %d pdst %p err %d\n",
+                                          dp_block(), lane, l0, g0, nz, ng, d, pub, pushed, (void *)pdst, dp_ld_flag(p.err));
                         if (lane == 0)
                             dp_set_error(p.err, 7);
                         break;

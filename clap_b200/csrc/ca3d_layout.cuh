@@ -40,115 +40,137 @@ CA_DEV uint32_t lay_nonzero4(uint32_t v)
 }
 
 /*
- * 32 cells held in r[8] (4 per register, x ascending) -> P state words + alive word.  P covers every value that
- * occurs (the caller derives it from the maximum of the volume), so alive = OR of the state planes: no separate
- * "byte != 0" reduction -- the kernel is bound by the integer pipe, and that reduction was 40 % of its work.
+ * uint8 volume -> row records.  One warp per 32 consecutive words of a row (a row is 32 * WPL words): lane l packs the
+ * 32 cells of word 32 * group + l with two 16-byte loads and one multiply-gather per plane and register; the alive
+ * bits of the neighbouring words come from the neighbouring lanes, so H0 | H1 cost two shuffles (the first / last
+ * lane of a group that is not at the row's end looks at one more byte).  P is a template parameter and the item ->
+ * (row, word) mapping is shifts: the first version of this kernel spent more instructions on two 64-bit divisions
+ * and a run-time plane loop than on the cells (4.7 ms at 2048^3 against 2.1 ms for its 14 GB of HBM traffic).
+ *
+ * alive = OR of the P state planes -- exact when every value fits P planes.  The caller either knows that (it scanned
+ * the volume, or a caller's bound was verified), or it passes L.over: the kernel ORs in a 1 when a cell does not fit,
+ * and the caller packs again with the number of planes a max scan asks for (volumes seeded with 255s, core/ca3d.c:41-59,
+ * take that path; a volume whose values stay below nr_states saves the scan: 1.4 ms at 2048^3).
  */
-CA_DEV void lay_pack32(const uint32_t r[8], int P, uint32_t s[8], uint32_t &alive)
+template <int P>
+CA_GLOBAL void __launch_bounds__(256) ca3d_pack_rows_kernel(Bp3Layout L)
 {
-#pragma unroll
-    for (int q = 0; q < 8; q++) s[q] = 0u;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (q < P)
-                s[q] |= lay_gather4(r[j] >> q) << (4 * j);
-    }
-    alive = 0u;
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-        if (q < P)
-            alive |= s[q];
-}
-
-/* uint8 volume -> row records (one thread per word of a plane-row) */
-CA_GLOBAL void ca3d_pack_kernel(Bp3Layout L)
-{
-    const int NP = L.P + 2;
-    const size_t nwords = (size_t)L.Z * L.H * L.RWP;
-    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
-    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < nwords; i += stride) {
-        const int w = (int)(i % L.RWP);
-        const size_t row = i / L.RWP;
-        uint32_t *rec = L.rows + row * NP * L.RWP + w;
+    constexpr int NP = P + 2;
+    constexpr uint32_t kOver = P >= 8 ? 0u : (((0xffu << P) & 0xffu) * 0x01010101u);
+    const int lane = dp_lane();
+    const int gshift = L.RWP == 32 ? 0 : (L.RWP == 64 ? 1 : 2);        /* RWP = 32 * WPL, WPL = 1, 2, 4 */
+    const size_t nitems = ((size_t)L.Z * L.H) << gshift;
+    const size_t wstride = (size_t)dp_grid_blocks() * (dp_block_threads() >> 5);
+    const bool vec = (L.W & 15) == 0;
+    uint32_t over = 0u;
+    for (size_t it = (size_t)dp_block() * (dp_block_threads() >> 5) + dp_warp_in_block(); it < nitems; it += wstride) {
+        const size_t row = it >> gshift;
+        const int w = ((int)(it & ((1u << gshift) - 1u)) << 5) + lane;
         const uint8_t *src = L.cells + row * L.W;
+        uint32_t *rec = L.rows + row * NP * L.RWP + w;
         const int x0 = 32 * w;
-        uint32_t s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-        uint32_t alive = 0u;
         int n = L.W - x0;
-        n = n > 32 ? 32 : n;
-        if (n == 32 && (L.W & 15) == 0) {
-            /* whole word, 16-byte aligned rows: two 128-bit loads, multiply-gather per plane */
+        n = n > 32 ? 32 : (n < 0 ? 0 : n);
+        uint32_t s[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) s[q] = 0u;
+        if (n == 32 && vec) {
             const uint4 lo = *reinterpret_cast<const uint4 *>(src + x0);
             const uint4 hi = *reinterpret_cast<const uint4 *>(src + x0 + 16);
             const uint32_t r[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
-            lay_pack32(r, L.P, s, alive);
-        } else {
-            for (int i2 = 0; i2 < n; i2++) {
-                uint32_t v = src[x0 + i2];
-#pragma unroll
-                for (int q = 0; q < 8; q++) s[q] |= ((v >> q) & 1u) << i2;
-                alive |= (uint32_t)(v != 0) << i2;
-            }
-        }
-        uint32_t left  = (n > 0 && x0 > 0) ? (uint32_t)(src[x0 - 1] != 0) : 0u;
-        uint32_t right = (n > 0 && x0 + 32 < L.W) ? (uint32_t)(src[x0 + 32] != 0) : 0u;
-        uint32_t l = (alive << 1) | left, r = (alive >> 1) | (right << 31);
-        rec[0] = l ^ alive ^ r;
-        rec[(size_t)L.RWP] = (l & alive) | (l & r) | (alive & r);
-        for (int q = 0; q < L.P; q++)
-            rec[(size_t)(2 + q) * L.RWP] = s[q];
-    }
-}
-
-/* row records -> uint8 volume, and the population count of the result */
-CA_GLOBAL void ca3d_unpack_kernel(Bp3Layout L)
-{
-    const int NP = L.P + 2;
-    const int RW = (L.W + 31) / 32;
-    const size_t nwords = (size_t)L.Z * L.H * RW;
-    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
-    unsigned long long pop = 0;
-    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < nwords; i += stride) {
-        const int w = (int)(i % RW);
-        const size_t row = i / RW;
-        const uint32_t *rec = L.rows + row * NP * L.RWP + w;
-        uint8_t *dst = L.cells + row * L.W;
-        const int x0 = 32 * w;
-        uint32_t s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-        uint32_t alive = 0u;
-        for (int q = 0; q < L.P; q++) {
-            s[q] = rec[(size_t)(2 + q) * L.RWP];
-            alive |= s[q];
-        }
-        pop += (unsigned)dp_popc(alive);
-        int n = L.W - x0;
-        n = n > 32 ? 32 : n;
-        if (n == 32 && (L.W & 15) == 0) {
-            uint32_t r[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                uint32_t v = 0u;
+                over |= r[j];
 #pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (q < L.P)
-                        v |= lay_spread4(s[q] >> (4 * j)) << q;
-                r[j] = v;
+                for (int q = 0; q < P; q++)
+                    s[q] += lay_gather4(r[j] >> q) << (4 * j);      /* disjoint bits: + is |, and an IMAD */
             }
-            *reinterpret_cast<uint4 *>(dst + x0) = make_uint4(r[0], r[1], r[2], r[3]);
-            *reinterpret_cast<uint4 *>(dst + x0 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
         } else {
             for (int i2 = 0; i2 < n; i2++) {
-                uint32_t v = 0;
+                const uint32_t v = src[x0 + i2];
+                over |= v;
 #pragma unroll
-                for (int q = 0; q < 8; q++) v |= ((s[q] >> i2) & 1u) << q;
-                dst[x0 + i2] = (uint8_t)v;
+                for (int q = 0; q < P; q++) s[q] |= ((v >> q) & 1u) << i2;
             }
         }
+        uint32_t alive = 0u;
+#pragma unroll
+        for (int q = 0; q < P; q++) alive |= s[q];
+        uint32_t left = dp_shfl_up0(alive) >> 31, right = dp_shfl_down0(alive) & 1u;
+        if (lane == 0 && x0 > 0 && n > 0) left = (uint32_t)(src[x0 - 1] != 0);
+        if (lane == 31 && x0 + 32 < L.W) right = (uint32_t)(src[x0 + 32] != 0);
+        const uint32_t l = (alive << 1) | left, r = (alive >> 1) | (right << 31);
+        rec[0] = l ^ alive ^ r;
+        rec[(size_t)L.RWP] = (l & alive) | (l & r) | (alive & r);
+#pragma unroll
+        for (int q = 0; q < P; q++)
+            rec[(size_t)(2 + q) * L.RWP] = s[q];
     }
-    if (pop)
-        dp_atomic_add64(L.population, pop);
+    if (L.over && dp_any((over & kOver) != 0u) && lane == 0)
+        dp_atomic_or_global(L.over, 1u);
+}
+
+/* row records -> uint8 volume, and the population count of the result; same work split as the pack kernel */
+template <int P>
+CA_GLOBAL void __launch_bounds__(256) ca3d_unpack_rows_kernel(Bp3Layout L)
+{
+    constexpr int NP = P + 2;
+    const int lane = dp_lane();
+    const int gshift = L.RWP == 32 ? 0 : (L.RWP == 64 ? 1 : 2);
+    const size_t nitems = ((size_t)L.Z * L.H) << gshift;
+    const size_t wstride = (size_t)dp_grid_blocks() * (dp_block_threads() >> 5);
+    const bool vec = (L.W & 15) == 0;
+    unsigned pop = 0u;
+    unsigned long long total = 0ull;
+    for (size_t it = (size_t)dp_block() * (dp_block_threads() >> 5) + dp_warp_in_block(); it < nitems; it += wstride) {
+        const size_t row = it >> gshift;
+        const int w = ((int)(it & ((1u << gshift) - 1u)) << 5) + lane;
+        const int x0 = 32 * w;
+        int n = L.W - x0;
+        n = n > 32 ? 32 : (n < 0 ? 0 : n);
+        if (n > 0) {
+            const uint32_t *rec = L.rows + row * NP * L.RWP + w;
+            uint8_t *dst = L.cells + row * L.W;
+            uint32_t s[P], alive = 0u;
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                s[q] = rec[(size_t)(2 + q) * L.RWP];
+                alive |= s[q];
+            }
+            pop += (unsigned)dp_popc(alive);
+            if (n == 32 && vec) {
+                uint32_t r[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t v = 0u;
+#pragma unroll
+                    for (int q = 0; q < P; q++)
+                        v += lay_spread4(s[q] >> (4 * j)) << q;
+                    r[j] = v;
+                }
+                *reinterpret_cast<uint4 *>(dst + x0) = make_uint4(r[0], r[1], r[2], r[3]);
+                *reinterpret_cast<uint4 *>(dst + x0 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+            } else {
+                for (int i2 = 0; i2 < n; i2++) {
+                    uint32_t v = 0u;
+#pragma unroll
+                    for (int q = 0; q < P; q++) v |= ((s[q] >> i2) & 1u) << q;
+                    dst[x0 + i2] = (uint8_t)v;
+                }
+            }
+        }
+        if (pop >= 0x40000000u) { total += pop; pop = 0u; }
+    }
+    total += pop;
+    /* warp sum, one atomic per warp */
+    uint32_t lo = (uint32_t)total, hi = (uint32_t)(total >> 32);
+    for (int o = 16; o; o >>= 1) {
+        const uint32_t lo2 = dp_shfl_down(lo, o), hi2 = dp_shfl_down(hi, o);
+        const unsigned long long a = ((unsigned long long)hi << 32 | lo) + ((unsigned long long)hi2 << 32 | lo2);
+        lo = (uint32_t)a; hi = (uint32_t)(a >> 32);
+    }
+    if (lane == 0 && (lo | hi))
+        dp_atomic_add64(L.population, (unsigned long long)hi << 32 | lo);
 }
 
 /*

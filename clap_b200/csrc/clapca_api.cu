@@ -407,14 +407,41 @@ int clapca::api::timed_sync(cudaEvent_t a, cudaEvent_t b, float *ms)
 
 cudaError_t clapca::api::launch_ca3d_pack(const Bp3Layout &L, cudaStream_t stream)
 {
-    ca3d_pack_kernel<<<grid_blocks_for((size_t)L.Z * L.H * L.RWP, 256, 16), 256, 0, stream>>>(L);
+    /* one warp per 32 words of a row; grid-stride over a multiple of the SM count */
+    const int blocks = grid_blocks_for((size_t)L.Z * L.H * L.RWP, 256, 8);
+    if (L.P <= 3)      ca3d_pack_rows_kernel<3><<<blocks, 256, 0, stream>>>(L);
+    else if (L.P == 4) ca3d_pack_rows_kernel<4><<<blocks, 256, 0, stream>>>(L);
+    else               ca3d_pack_rows_kernel<8><<<blocks, 256, 0, stream>>>(L);
     return cudaGetLastError();
 }
 
 cudaError_t clapca::api::launch_ca3d_unpack(const Bp3Layout &L, cudaStream_t stream)
 {
-    ca3d_unpack_kernel<<<grid_blocks_for((size_t)L.Z * L.H * ((L.W + 31) / 32), 256, 16), 256, 0, stream>>>(L);
+    const int blocks = grid_blocks_for((size_t)L.Z * L.H * L.RWP, 256, 8);
+    if (L.P <= 3)      ca3d_unpack_rows_kernel<3><<<blocks, 256, 0, stream>>>(L);
+    else if (L.P == 4) ca3d_unpack_rows_kernel<4><<<blocks, 256, 0, stream>>>(L);
+    else               ca3d_unpack_rows_kernel<8><<<blocks, 256, 0, stream>>>(L);
     return cudaGetLastError();
+}
+
+/* force the (lazy) load of the layout kernels for P state planes: see slab_prepare() */
+cudaError_t clapca::api::preload_ca3d_layout(int P)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    if (P <= 3) {
+        e = cudaFuncGetAttributes(&fa, ca3d_pack_rows_kernel<3>);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, ca3d_unpack_rows_kernel<3>);
+    } else if (P == 4) {
+        e = cudaFuncGetAttributes(&fa, ca3d_pack_rows_kernel<4>);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, ca3d_unpack_rows_kernel<4>);
+    } else {
+        e = cudaFuncGetAttributes(&fa, ca3d_pack_rows_kernel<8>);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, ca3d_unpack_rows_kernel<8>);
+    }
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, max_u8_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, halo_seed_kernel);
+    return e;
 }
 
 cudaError_t clapca::api::launch_max_u8(const uint8_t *cells, size_t n, unsigned *d_max, cudaStream_t stream)
@@ -622,11 +649,20 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     const uint32_t bornval = (nr_states - 1u) & 0xffu;
 
     CU(cudaEventRecord(g->ev[0], g->stream));
-    /* largest value that can ever occur decides the number of state planes */
+    /*
+     * The largest value that can ever occur decides the number of state planes.  Streamed runs take the caller's
+     * bound (the pack items verify it: err = 4).  Resident runs with separate layout kernels pack SPECULATIVELY with
+     * the planes the rule alone needs (a running automaton holds values below nr_states) and let the pack kernel
+     * report cells that do not fit; only then -- seeds with other values, e.g. the 255s ca3d_prune() leaves
+     * (core/ca3d.c:41-59) -- the volume is scanned for its maximum and packed again.  The scan would cost every run
+     * a pass over the volume (1.4 ms at 2048^3), the wasted pack only the rare one.
+     */
+    const bool fused_cfg = io != nullptr || fused_layout_default();
+    const bool speculate = !fused_cfg;
     unsigned maxv = 0;
     if (io) {
-        maxv = io->max_value;           /* the caller's bound; the pack items verify it (err = 4) */
-    } else {
+        maxv = io->max_value;
+    } else if (!speculate) {
         CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
         max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
         CU(cudaGetLastError());
@@ -634,7 +670,45 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         CU(cudaStreamSynchronize(g->stream));
     }
     if (born && bornval > maxv) maxv = bornval;
-    const int P = bp_planes_for(maxv);
+    if (speculate && !born && bornval > maxv) maxv = bornval;      /* the same guess for a rule that gives no birth */
+    int P = bp_planes_for(maxv);
+    int packed = 0;                     /* kernels spent on the layout before the sweep */
+    if (speculate) {
+        const int RWPs = 32 * WPL;
+        size_t bytes = (size_t)Z * H * (P + 2) * RWPs * sizeof(uint32_t);
+        void *rp = g->rows;
+        if (int rc = ensure_bytes(&rp, &g->rows_bytes, bytes)) { g->rows = nullptr; return rc; }
+        g->rows = (uint32_t *)rp;
+        unsigned over = 0;
+        if (P < 8) {
+            CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+            Bp3Layout Ls = { g->cells, g->rows, W, H, Z, P, RWPs, g_ctx.d_count, g_ctx.d_max };
+            CU(launch_ca3d_pack(Ls, g->stream));
+            CU(cudaMemcpyAsync(&over, g_ctx.d_max, sizeof(over), cudaMemcpyDeviceToHost, g->stream));
+            CU(cudaStreamSynchronize(g->stream));
+            packed = 1;
+        }
+        if (over || P >= 8) {
+            if (over) {
+                CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+                max_u8_kernel<<<grid_blocks_for((g->n + 15) / 16, 256), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_max);
+                CU(cudaGetLastError());
+                unsigned m2 = 0;
+                CU(cudaMemcpyAsync(&m2, g_ctx.d_max, sizeof(m2), cudaMemcpyDeviceToHost, g->stream));
+                CU(cudaStreamSynchronize(g->stream));
+                maxv = std::max(maxv, m2);
+                P = bp_planes_for(maxv);
+                packed++;
+            }
+            bytes = (size_t)Z * H * (P + 2) * RWPs * sizeof(uint32_t);
+            rp = g->rows;
+            if (int rc = ensure_bytes(&rp, &g->rows_bytes, bytes)) { g->rows = nullptr; return rc; }
+            g->rows = (uint32_t *)rp;
+            Bp3Layout Ls = { g->cells, g->rows, W, H, Z, P, RWPs, g_ctx.d_count, nullptr };
+            CU(launch_ca3d_pack(Ls, g->stream));
+            packed++;
+        }
+    }
     const int NP = P + 2, RWP = 32 * WPL;
 
     int rule = BP3_RULE_DYN;
@@ -653,7 +727,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     if (io)
         if (const char *e = getenv("CLAPCA_STREAM_TEAM")) team = std::max(0, std::min(atoi(e), bp3_team_cap(P, WPL)));
     /* layout items need whole-plane items and all generations in one launch */
-    bool fused = io != nullptr || fused_layout_default();
+    bool fused = fused_cfg;
     if (fused && steps > kMaxFusedGenerations) {
         if (io) return fail(CLAPCA_ERR_UNSUPPORTED, "streamed run: at most %d generations", kMaxFusedGenerations);
         fused = false;
@@ -682,8 +756,9 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         g->io_epoch++;
     }
 
-    if (!fused) {
+    if (!fused && !speculate) {
         CU(launch_ca3d_pack(L, g->stream));
+        packed = 2;                     /* max scan + pack */
     }
     CU(cudaEventRecord(g->ev[1], g->stream));
 
@@ -731,6 +806,12 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         memset(&knobs, 0, sizeof(knobs));
         sweep_knobs(knobs, team, true);
         OrderCfg oc = order_config(Z, H, G, bp3_max_workers(rule, P, WPL, g_ctx.sms, team, knobs.max_ctas), team);
+        /* layout items: the unpack items of a plane sit one group distance behind its last generation -- a streamed
+           run wants its output to follow its input closely, so the groups stay interleaved there */
+        if (fused && oc.mode == 3 && !getenv("CLAPCA_TILE_SKEW")) {
+            oc.tile_skew = 0;
+            knobs.prefetch_rows = 0;
+        }
         if (fused && oc.mode != 0 && oc.mode != 3) {
             if (io) oc.mode = 0;                    /* layout items exist for whole-plane orders only */
             else return fail(CLAPCA_ERR_UNSUPPORTED, "CLAPCA_FUSED_LAYOUT needs the time-key or the tile order");
@@ -762,7 +843,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.prog = prog;
         p.order = g->order;
         p.nsweeps = g->n_items;
-        sweep_knobs(p, team, true);
+        sweep_knobs(p, team, !fused);
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);
         p.diag = diag_enabled() ? (unsigned long long *)(g->ticket + 4) : nullptr;
@@ -832,7 +913,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
     if (err)
         return fail(CLAPCA_ERR_TIMEOUT, "ca3d bit-plane engine: dataflow watchdog fired (err=%d)", err);
     if (population) *population = (int64_t)pop;
-    g->stats.launches = launches + (fused ? 1 : 3);     /* + max scan (+ pack, unpack) */
+    g->stats.launches = launches + (fused ? 1 : packed + 1);    /* + layout kernels before the sweep (+ unpack) */
     g->stats.engine = CLAPCA_ENGINE_BITPLANE;
     g->stats.planes = P;
     g->stats.workers = workers;

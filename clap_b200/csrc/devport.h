@@ -124,9 +124,11 @@ CA_DEV void dp_fence_release()                    { asm volatile("fence.acq_rel.
 CA_DEV void dp_fence_cta()                        { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 CA_DEV int  dp_ld_volatile(const int *p)          { return *(const volatile int *)p; }
 CA_DEV void dp_st_volatile(int *p, int v)         { *(volatile int *)p = v; }
+CA_DEV uint32_t dp_ld_volatile_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 CA_DEV unsigned long long dp_ld_volatile64(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
 CA_DEV void dp_st_volatile64(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
 CA_DEV void dp_atomic_add_cta(int *p, int v)      { atomicAdd(p, v); }
+CA_DEV void dp_atomic_or_cta(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 CA_DEV bool dp_any(bool p)                        { return __any_sync(CA_FULL, p); }
 CA_DEV void dp_fence_acquire()                    { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 CA_DEV void dp_nanosleep(unsigned ns)             { __nanosleep(ns); }
@@ -137,6 +139,7 @@ CA_DEV long long dp_clock()                       { return clock64(); }
 CA_DEV unsigned dp_atomic_inc(unsigned *p)        { return atomicAdd(p, 1u); }
 CA_DEV void dp_atomic_add64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 CA_DEV void dp_atomic_max(int *p, int v)          { atomicMax(p, v); }
+CA_DEV void dp_atomic_or_global(unsigned *p, unsigned v) { atomicOr(p, v); }
 /* error words: the FIRST non-zero code sticks (later bail-outs are consequences of it) */
 CA_DEV void dp_set_error(int *p, int v)           { atomicCAS(p, 0, v); }
 CA_DEV int  dp_popc(uint32_t v)                   { return __popc(v); }
@@ -291,9 +294,11 @@ CA_DEV void dp_fence_release()                    { __atomic_thread_fence(__ATOM
 CA_DEV void dp_fence_cta()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV int  dp_ld_volatile(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV void dp_st_volatile(int *p, int v)         { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CA_DEV uint32_t dp_ld_volatile_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV unsigned long long dp_ld_volatile64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 CA_DEV void dp_st_volatile64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 CA_DEV void dp_atomic_add_cta(int *p, int v)      { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+CA_DEV void dp_atomic_or_cta(uint32_t *p, uint32_t v) { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 CA_DEV bool dp_any(bool p)                        { return emu_ballot(p) != 0u; }
 CA_DEV void dp_fence_sys()                        { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 CA_DEV int  dp_ld_flag_sys(const int *p)          { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
@@ -311,6 +316,7 @@ CA_DEV void dp_atomic_max(int *p, int v)
     while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED))
         ;
 }
+CA_DEV void dp_atomic_or_global(unsigned *p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 CA_DEV void dp_set_error(int *p, int v)
 {
     int o = 0;

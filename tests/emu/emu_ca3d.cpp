@@ -246,7 +246,9 @@ int main(int argc, char **argv)
         for (size_t i = 0; i < items.size(); i++) k.order[i] = make_int4(items[i].z, items[i].g, items[i].y0, items[i].y1);
         if (Zl && !layout) {
             Bp3Layout L = { k.cells.data(), k.rows.data(), W, H, Zl, P, RWP, &k.pop };
-            emu_launch(2, 64, [&]() { ca3d_pack_kernel(L); });
+            if (P <= 3) emu_launch(2, 64, [&]() { ca3d_pack_rows_kernel<3>(L); });
+            else if (P == 4) emu_launch(2, 64, [&]() { ca3d_pack_rows_kernel<4>(L); });
+            else emu_launch(2, 64, [&]() { ca3d_pack_rows_kernel<8>(L); });
         }
         memset(&k.p, 0, sizeof(k.p));
         k.p.rows = k.rows.data();
@@ -361,7 +363,9 @@ int main(int argc, char **argv)
         std::vector<uint8_t> out(k.cells.size(), 0xEE);
         k.pop = 0;
         Bp3Layout L = { out.data(), k.rows.data(), W, H, Zl, P, RWP, &k.pop };
-        emu_launch(2, 64, [&]() { ca3d_unpack_kernel(L); });
+        if (P <= 3) emu_launch(2, 64, [&]() { ca3d_unpack_rows_kernel<3>(L); });
+        else if (P == 4) emu_launch(2, 64, [&]() { ca3d_unpack_rows_kernel<4>(L); });
+        else emu_launch(2, 64, [&]() { ca3d_unpack_rows_kernel<8>(L); });
         pop += k.pop;
         for (int lb = 0; lb < k.geo.local_blocks(); lb++) {
             int jb = k.geo.global_block(lb);

@@ -222,6 +222,11 @@ def test_ca3d_tile_order_generation_group_skew(emu_bin, args):
     (64, 257, 9, 0xc, 0x180, 4, 1, 1, 4, 1, 9, 1, 8, 5, 2),
     (12, 40, 4, 0xc, 0x180, 0, 1, 1, 3, 1, 1, 1, 8, 2, 2),            # nr_states == 0: births are no-ops
     (12, 40, 4, 0xc, 0x180, 256 + 3, 1, 1, 3, 1, 1, 1, 8, 2, 2),      # nr_states wraps through uint8
+    (12, 40, 4, 0xc, 0x180, 256, 1, 1, 1, 1, 2, 1, 8, 2, 2),          # one state plane and nothing is ever born
+    (40, 1500, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 1, 16, 0, 8, 3, 2),       # 16 warps per row: the packed carry masks are full
+    (40, 2000, 3, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 16, 0, 9, 3, 2),
+    (30, 1000, 3, 0xaa, 0x155, 1, 1, 1, 1, 2, 16, 0, 9, 3, 2),        # non-monotone rule across 16 warps
+    (30, 1000, 3, 0xaa, 0x155, 1, 1, 1, 1, 1, 16, 0, 9, 3, 5),        # ... row marks every 5 rows
 ])
 def test_ca2d_bitplane_rules_and_shapes(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca2d"), *args)
