@@ -49,6 +49,8 @@ SIGNATURES = {
                                      c_uint64, POINTER(c_uint64)]),
     "clapca_grid_seed2d": (c_int, [c_void_p, c_int64, c_uint32, c_uint64, POINTER(c_uint64)]),
     "clapca_noise_grad3d_bake_rgba8": (c_int, [c_void_p, c_size_t, c_int, c_float, c_float, c_float, c_uint32]),
+    "clapca_noise_blue2d_rgba32f": (c_int, [c_void_p, c_int, c_uint64, POINTER(c_uint64)]),
+    "clapca_noise_blue2d_device": (c_int, [c_void_p, c_int, c_uint64, POINTER(c_uint64), POINTER(c_float)]),
     "clapca_noise_fbm3": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_float, c_int, c_uint32]),
     "clapca_terrain_map0": (c_int, [c_void_p, c_long, c_uint]),
     "clapca_terrain_heightmap": (c_int, [c_void_p, c_long, c_uint, c_float, c_void_p, c_uint, c_float, c_int]),

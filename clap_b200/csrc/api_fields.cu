@@ -48,6 +48,54 @@ int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float
     return rc;
 }
 
+/* ---- blue_noise2d_tex(): core/noise.c:96-169, the pixels it uploads ------------------------------------------ */
+
+int clapca_noise_blue2d_device(void *d_out, int size, uint64_t rand48_state, uint64_t *state_out, float *kernel_ms)
+{
+    if (int rc = need_init()) return rc;
+    if (!d_out) return fail(CLAPCA_ERR_ARG, "blue noise: NULL output");
+    if (size != FK_GRAIN)
+        return fail(CLAPCA_ERR_UNSUPPORTED, "blue noise: size must be FILM_GRAIN_SIZE = %d (the reference's spectrum "
+                    "arrays have that size whatever it is called with, core/noise.c:17-73)", (int)FK_GRAIN);
+    BlueNoiseParams p = { (float *)d_out, rand48_state & ((1ull << 48) - 1ull) };
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, g_ctx.stream));
+    blue_noise2d_kernel<<<1, 256, 0, g_ctx.stream>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b, g_ctx.stream));
+    int rc = timed_sync(a, b, kernel_ms);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    /* the stream after the 3 * size^2 draws of noise.c:106-115 */
+    if (!rc && state_out) {
+        const unsigned long long M = (1ull << 48) - 1ull;
+        unsigned long long h = 0x5DEECE66Dull, f = 0xBull, G = 1ull, C = 0ull, n = 3ull * size * size;
+        while (n) {
+            if (n & 1ull) { G = (G * h) & M; C = (C * h + f) & M; }
+            f = (f * (h + 1ull)) & M;
+            h = (h * h) & M;
+            n >>= 1;
+        }
+        *state_out = (G * p.state + C) & M;
+    }
+    return rc;
+}
+
+int clapca_noise_blue2d_rgba32f(float *out, int size, uint64_t rand48_state, uint64_t *state_out)
+{
+    if (int rc = need_init()) return rc;
+    if (!out) return fail(CLAPCA_ERR_ARG, "blue noise: NULL output");
+    const size_t bytes = (size_t)FK_GRAIN * FK_GRAIN * 4 * sizeof(float);
+    void *d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    int rc = clapca_noise_blue2d_device(d, size, rand48_state, state_out, nullptr);
+    if (!rc) rc = clapca_memcpy_d2h(out, d, bytes);
+    cudaFree(d);
+    return rc;
+}
+
 /* ---- the bake as a device-resident 3D texture object ---------------------------------------- */
 
 struct clapca_tex3d {

@@ -278,7 +278,10 @@ struct Sweep3 {
         uint32_t vmask[WPL];
         const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load; nullptr: outside the volume */
         uint32_t *rec;                              /* lane-adjusted own record of the current row */
-        const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead */
+        const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead
+                                                       (ONE cp.async.bulk.prefetch.L2 of the record by lane 0 was measured
+                                                       instead: 99.1 ms against 93.7 ms -- a one-lane branch around a
+                                                       uniform-datapath instruction in a loop that is bound by issue) */
         PubSlot *slot;                              /* publisher mode: this worker's mailbox (else nullptr) */
         const int *sprod;                           /* tile mode: lanes 0..2 = shared-memory row counter of producer dn / up / own */
         int *sown;                                  /* tile mode: own shared-memory row counter (else nullptr) */

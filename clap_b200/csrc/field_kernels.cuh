@@ -637,5 +637,137 @@ __global__ void __launch_bounds__(256) instor_emit_kernel(InstorParams p)
     }
 }
 
+/* ---- blue_noise2d_tex(): core/noise.c:17-169 (the 64 x 64 film-grain texture, up to the upload) --------------- */
+
+enum { FK_GRAIN = 64 };     /* FILM_GRAIN_SIZE, core/shader_constants.h:13: the reference's spectrum arrays have this size */
+
+struct BlueNoiseParams {
+    float *out;                     /* FK_GRAIN^2 RGBA32F pixels */
+    unsigned long long state;       /* the caller's drand48() stream: 48-bit state before the first draw */
+};
+
+/* glibc rand48 step (the same generator as ca2d_layout.cuh; repeated here: this TU is built with -fmad=false) */
+__device__ __forceinline__ unsigned long long fk_r48_step(unsigned long long x)
+{
+    return (x * 0x5DEECE66Dull + 0xBull) & ((1ull << 48) - 1ull);
+}
+__device__ inline unsigned long long fk_r48_advance(unsigned long long x, unsigned long long n)
+{
+    const unsigned long long M = (1ull << 48) - 1ull;
+    unsigned long long h = 0x5DEECE66Dull, f = 0xBull, G = 1ull, C = 0ull;
+    while (n) {
+        if (n & 1ull) { G = (G * h) & M; C = (C * h + f) & M; }
+        f = (f * (h + 1ull)) & M;
+        h = (h * h) & M;
+        n >>= 1;
+    }
+    return (G * x + C) & M;
+}
+
+/*
+ * 64 independent 64-point FFTs over the lines of X (line l, element e at X[l * ls + e * es]): bit reversal, then six
+ * radix-2 stages of 64 x 32 butterflies spread over the CTA.  sign = -1: forward (kiss_fft inverse = 0), +1: the
+ * unnormalised inverse.  tw[m] = exp(-2 pi i m / 64), m < 32.
+ */
+__device__ inline void fk_fft64_lines(float2 *X, int ls, int es, const float2 *tw, float sign)
+{
+    for (int idx = threadIdx.x; idx < FK_GRAIN * FK_GRAIN; idx += blockDim.x) {
+        const int l = idx >> 6, e = idx & 63;
+        const int r = (int)(__brev((unsigned)e) >> 26);
+        if (e < r) {
+            float2 a = X[l * ls + e * es], b = X[l * ls + r * es];
+            X[l * ls + e * es] = b;
+            X[l * ls + r * es] = a;
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < 6; s++) {
+        const int half = 1 << s;
+        for (int idx = threadIdx.x; idx < FK_GRAIN * 32; idx += blockDim.x) {
+            const int l = idx >> 5, k = idx & 31;
+            const int j = k & (half - 1);
+            const int i0 = ((k >> s) << (s + 1)) + j, i1 = i0 + half;
+            float2 w = tw[j << (5 - s)];
+            w.y *= -sign;                               /* tw holds the forward (negative-angle) twiddles */
+            const float2 a = X[l * ls + i0 * es], b = X[l * ls + i1 * es];
+            const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+            X[l * ls + i0 * es] = make_float2(a.x + t.x, a.y + t.y);
+            X[l * ls + i1 * es] = make_float2(a.x - t.x, a.y - t.y);
+        }
+        __syncthreads();
+    }
+}
+
+/*
+ * One CTA: the three colour channels one after the other through a 64 x 64 complex tile in shared memory (white noise
+ * from the caller's drand48 stream, rows + columns forward, radial gain r / r_max, rows + columns back, / 64^2), then
+ * the joint min / max of the three channels and the normalisation to [0, 1]; alpha = 1.
+ */
+__global__ void __launch_bounds__(256) blue_noise2d_kernel(BlueNoiseParams p)
+{
+    __shared__ float2 X[FK_GRAIN * FK_GRAIN];
+    __shared__ float2 tw[32];
+    __shared__ float red[2][8];
+    const int t = threadIdx.x, nt = blockDim.x;
+    if (t < 32) {
+        float sn, cs;
+        sincospif((float)t / 32.0f, &sn, &cs);
+        tw[t] = make_float2(cs, -sn);
+    }
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int c = 0; c < 3; c++) {
+        __syncthreads();
+        /* noise.c:106-115: pixel q = x + y * size takes draws 3 q, 3 q + 1, 3 q + 2 of the stream */
+        const int per = (FK_GRAIN * FK_GRAIN + nt - 1) / nt;
+        const int q0 = t * per, q1 = min(FK_GRAIN * FK_GRAIN, q0 + per);
+        if (q0 < q1) {
+            unsigned long long st = fk_r48_advance(p.state, 3ull * (unsigned long long)q0 + (unsigned long long)c);
+            for (int q = q0; q < q1; q++) {
+                st = fk_r48_step(st);
+                const double d = (double)st * (1.0 / 281474976710656.0);        /* drand48(): X / 2^48 */
+                const double wgt = c == 0 ? 0.299 : (c == 1 ? 0.587 : 0.114);
+                X[q] = make_float2((float)(((d * 4.0 - 1.0) / 3.0) * wgt), 0.0f);
+                st = fk_r48_step(fk_r48_step(st));
+            }
+        }
+        __syncthreads();
+        fk_fft64_lines(X, FK_GRAIN, 1, tw, -1.0f);      /* rows */
+        fk_fft64_lines(X, 1, FK_GRAIN, tw, -1.0f);      /* columns */
+        /* blue_noise2d_gain(): noise.c:75-92 */
+        const float maxr = sqrtf((float)((FK_GRAIN / 2) * (FK_GRAIN / 2) + (FK_GRAIN / 2) * (FK_GRAIN / 2)));
+        for (int idx = t; idx < FK_GRAIN * FK_GRAIN; idx += nt) {
+            const int y = idx >> 6, x = idx & 63;
+            const int fy = (y <= FK_GRAIN / 2) ? y : y - FK_GRAIN, fx = (x <= FK_GRAIN / 2) ? x : x - FK_GRAIN;
+            const float r = (float)sqrt((double)(fx * fx + fy * fy));
+            const float gain = r / maxr;
+            X[idx].x *= gain;
+            X[idx].y *= gain;
+        }
+        __syncthreads();
+        fk_fft64_lines(X, FK_GRAIN, 1, tw, 1.0f);
+        fk_fft64_lines(X, 1, FK_GRAIN, tw, 1.0f);
+        for (int idx = t; idx < FK_GRAIN * FK_GRAIN; idx += nt) {
+            const float v = X[idx].x / (float)(FK_GRAIN * FK_GRAIN);
+            p.out[idx * 4 + c] = v;
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+    }
+    /* noise.c:141-152: joint range of the three channels */
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((t & 31) == 0) { red[0][t >> 5] = mn; red[1][t >> 5] = mx; }
+    __syncthreads();
+    mn = red[0][0]; mx = red[1][0];
+    for (int w = 1; w < (nt >> 5); w++) { mn = fminf(mn, red[0][w]); mx = fmaxf(mx, red[1][w]); }
+    for (int idx = t; idx < FK_GRAIN * FK_GRAIN; idx += nt) {
+        for (int c = 0; c < 3; c++)
+            p.out[idx * 4 + c] = (p.out[idx * 4 + c] - mn) / (mx - mn);
+        p.out[idx * 4 + 3] = 1.0f;
+    }
+}
+
 } // namespace clapca
 #endif

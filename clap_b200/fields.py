@@ -52,6 +52,18 @@ class NoiseTexture3D:
             pass
 
 
+def blue_noise2d(rng, size=64):
+    """blue_noise2d_tex(): core/noise.c:96-169 up to the upload -- the (size, size, 4) float32 pixels of the film-grain
+    texture.  `rng` is the caller's rand48 stream (clap_b200.ca.Rand48); it is advanced by the 3 * size^2 draws."""
+    from ctypes import c_uint64
+    lib = _lib.lib()
+    out = np.empty((size, size, 4), np.float32)
+    after = c_uint64(0)
+    check(lib, lib.clapca_noise_blue2d_rgba32f(out.ctypes.data_as(c_void_p), size, rng.x, byref(after)))
+    rng.x = int(after.value)
+    return out
+
+
 def noise_fbm3(xyz, octaves, lacunarity, gain, period, seed):
     """fbm3_periodic(): core/noise.c:204-220 at the points xyz[n, 3] (float32)."""
     lib = _lib.lib()

@@ -63,27 +63,6 @@ void ca2d_step(const struct cell_automaton *ca, unsigned char *arr, int side)
     run_steps(ca, arr, side, 1);
 }
 
-/*
- * The process-wide lrand48() stream: seed48() hands back the 48-bit state it replaces, so reading it is
- * "swap in anything, copy the old value, swap it back".  (seed48() also restores the default multiplier;
- * the reference never calls lcong48().)
- */
-static uint64_t rand48_peek(void)
-{
-    unsigned short probe[3] = { 0, 0, 0 }, cur[3];
-
-    memcpy(cur, seed48(probe), sizeof(cur));
-    seed48(cur);
-    return (uint64_t)cur[0] | (uint64_t)cur[1] << 16 | (uint64_t)cur[2] << 32;
-}
-
-static void rand48_poke(uint64_t x)
-{
-    unsigned short v[3] = { (unsigned short)x, (unsigned short)(x >> 16), (unsigned short)(x >> 32) };
-
-    seed48(v);
-}
-
 unsigned char *ca2d_generate(const struct cell_automaton *ca, int side, int steps)
 {
     unsigned char *arr = xyarray_new(side);
@@ -100,9 +79,9 @@ unsigned char *ca2d_generate(const struct cell_automaton *ca, int side, int step
         return arr;
     shim_require_gpu();
     rc = clapca_ca2d_generate(arr, side, ca->born_mask, ca->surv_mask, ca->nr_states, ca->decay,
-                              neighbourhood_id(ca), steps > 0 ? steps : 0, CLAPCA_ENGINE_AUTO, rand48_peek(), &after);
+                              neighbourhood_id(ca), steps > 0 ? steps : 0, CLAPCA_ENGINE_AUTO, shim_rand48_peek(), &after);
     if (rc != CLAPCA_OK)
         shim_fatal("clapca_ca2d_generate", rc);
-    rand48_poke(after);
+    shim_rand48_poke(after);
     return arr;
 }

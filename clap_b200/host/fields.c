@@ -27,6 +27,23 @@ unsigned char *clap_noise_grad3d_bake_rgba8(size_t size, int octaves, float lacu
     return out;
 }
 
+float *clap_blue_noise2d_rgba32f(int size)
+{
+    float *out = malloc((size_t)(size > 0 ? size : 1) * (size_t)(size > 0 ? size : 1) * 4 * sizeof(float));
+    uint64_t after = 0;
+    int rc;
+
+    if (!out)
+        return NULL;                    /* the reference reports CERR_NOMEM here (noise.c:101-103) */
+    shim_require_gpu();
+    /* the three drand48() draws per pixel come out of the process-wide stream, exactly like noise.c:106-115 */
+    rc = clapca_noise_blue2d_rgba32f(out, size, shim_rand48_peek(), &after);
+    if (rc != CLAPCA_OK)
+        shim_fatal("clapca_noise_blue2d_rgba32f", rc);
+    shim_rand48_poke(after);
+    return out;
+}
+
 float *clap_terrain_map0(long seed, unsigned int nr_v)
 {
     float *map0 = shim_alloc_zeroed((size_t)nr_v * nr_v * sizeof(float));

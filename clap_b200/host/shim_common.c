@@ -1,6 +1,7 @@
 /* shim_common.c -- see shim_common.h */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "clapca.h"
 #include "shim_common.h"
 
@@ -34,4 +35,20 @@ void *shim_alloc_zeroed(size_t bytes)
         abort();
     }
     return p;
+}
+
+uint64_t shim_rand48_peek(void)
+{
+    unsigned short probe[3] = { 0, 0, 0 }, cur[3];
+
+    memcpy(cur, seed48(probe), sizeof(cur));
+    seed48(cur);
+    return (uint64_t)cur[0] | (uint64_t)cur[1] << 16 | (uint64_t)cur[2] << 32;
+}
+
+void shim_rand48_poke(uint64_t x)
+{
+    unsigned short v[3] = { (unsigned short)x, (unsigned short)(x >> 16), (unsigned short)(x >> 32) };
+
+    seed48(v);
 }

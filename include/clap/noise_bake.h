@@ -16,4 +16,11 @@
 unsigned char *clap_noise_grad3d_bake_rgba8(size_t size, int octaves, float lacunarity, float gain,
                                             float period_units, uint32_t seed);
 
+/*
+ * The pixels blue_noise2d_tex() (core/noise.c:96-169) uploads as the film-grain texture: size x size RGBA32F, drawn
+ * from the process-wide drand48() stream (3 draws per pixel) like the reference; size must be FILM_GRAIN_SIZE (64).
+ * Caller frees with free().
+ */
+float *clap_blue_noise2d_rgba32f(int size);
+
 #endif

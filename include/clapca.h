@@ -118,6 +118,19 @@ int clapca_ca2d_generate(uint8_t *arr, int64_t side, uint32_t born_mask, uint32_
 int clapca_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, int octaves, float lacunarity,
                                    float gain, float period_units, uint32_t seed);
 
+/*
+ * blue_noise2d_tex() (core/noise.c:96-169) up to the texture upload: the size x size RGBA32F pixels of the film-grain
+ * texture -- white noise from the caller's drand48() stream (3 draws per pixel, r g b, pixel x + y * size), forward
+ * 2-D FFT per channel, radial gain r / r_max, inverse FFT, joint min / max normalisation, alpha = 1.  `size` must be
+ * FILM_GRAIN_SIZE = 64 (core/shader_constants.h:13): the reference's spectrum arrays have that size whatever it is
+ * called with.  rand48_state = the stream's 48-bit state before the first draw (what seed48() hands back);
+ * *state_out = the state after the 3 * size^2 draws.  The reference transforms with kissfft (un-vendored, float
+ * radix-4 butterflies), so its pixels are matched to float rounding (tests: 2e-5 of the [0, 1] range), not bit for bit.
+ */
+int clapca_noise_blue2d_rgba32f(float *out, int size, uint64_t rand48_state, uint64_t *state_out);
+/* the same into device memory (size^2 * 4 floats) */
+int clapca_noise_blue2d_device(void *d_out, int size, uint64_t rand48_state, uint64_t *state_out, float *kernel_ms);
+
 /* fbm3_periodic() at n sample points (xyz interleaved), for parity tests of the float field. */
 int clapca_noise_fbm3(float *out, const float *xyz, size_t n, int octaves, float lacunarity,
                       float gain, int period, uint32_t seed);

@@ -640,6 +640,95 @@ size_t ora_terrain_instantiators(const uint8_t *maze, unsigned mside, const unsi
 }
 
 /* FNV-1a 64 over a byte buffer (fixture fingerprints) */
+/* ------------------------------------------------------------------------- *
+ * blue_noise2d_tex(): core/noise.c:17-169.  kissfft is not in the tree (see the
+ * header): the two transforms are plain O(N^2) DFTs per line in double precision,
+ * rounded to float where the reference stores floats (kiss_fft_scalar = float).
+ * ------------------------------------------------------------------------- */
+enum { ORA_GRAIN = 64 };        /* FILM_GRAIN_SIZE, core/shader_constants.h:13 */
+
+static void ora_dft64_lines(float (*re)[ORA_GRAIN], float (*im)[ORA_GRAIN], int columns, int inverse)
+{
+    static double cs[ORA_GRAIN], sn[ORA_GRAIN];
+    static int have;
+    if (!have) {
+        for (int m = 0; m < ORA_GRAIN; m++) {
+            cs[m] = cos(2.0 * M_PI * m / ORA_GRAIN);
+            sn[m] = sin(2.0 * M_PI * m / ORA_GRAIN);
+        }
+        have = 1;
+    }
+    for (int l = 0; l < ORA_GRAIN; l++) {
+        double xr[ORA_GRAIN], xi[ORA_GRAIN];
+        for (int e = 0; e < ORA_GRAIN; e++) {
+            xr[e] = columns ? re[e][l] : re[l][e];
+            xi[e] = columns ? im[e][l] : im[l][e];
+        }
+        for (int k = 0; k < ORA_GRAIN; k++) {
+            double ar = 0.0, ai = 0.0;
+            for (int n = 0; n < ORA_GRAIN; n++) {
+                const int m = (k * n) % ORA_GRAIN;
+                const double c = cs[m], s = inverse ? sn[m] : -sn[m];
+                ar += xr[n] * c - xi[n] * s;
+                ai += xr[n] * s + xi[n] * c;
+            }
+            if (columns) { re[k][l] = (float)ar; im[k][l] = (float)ai; }
+            else         { re[l][k] = (float)ar; im[l][k] = (float)ai; }
+        }
+    }
+}
+
+void ora_blue_noise2d(float *rgba, uint64_t *rng)
+{
+    const int size = ORA_GRAIN;
+    /* noise.c:106-115 */
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            float r = ((ora_drand48(rng) * 4.0 - 1.0) / 3.0) * 0.299;
+            float g = ((ora_drand48(rng) * 4.0 - 1.0) / 3.0) * 0.587;
+            float b = ((ora_drand48(rng) * 4.0 - 1.0) / 3.0) * 0.114;
+            rgba[(x + y * size) * 4 + 0] = r;
+            rgba[(x + y * size) * 4 + 1] = g;
+            rgba[(x + y * size) * 4 + 2] = b;
+            rgba[(x + y * size) * 4 + 3] = 1.0;
+        }
+    static float re[ORA_GRAIN][ORA_GRAIN], im[ORA_GRAIN][ORA_GRAIN];
+    for (int c = 0; c < 3; c++) {
+        for (int i = 0; i < size * size; i++) {
+            re[i / size][i % size] = rgba[i * 4 + c];
+            im[i / size][i % size] = 0.0f;
+        }
+        ora_dft64_lines(re, im, 0, 0);              /* fft2d_fwd, noise.c:17-45: rows, then columns */
+        ora_dft64_lines(re, im, 1, 0);
+        /* blue_noise2d_gain, noise.c:75-92 */
+        float maxr = sqrtf((ORA_GRAIN / 2) * (ORA_GRAIN / 2) + (ORA_GRAIN / 2) * (ORA_GRAIN / 2));
+        for (int y = 0; y < ORA_GRAIN; y++) {
+            int fy = (y <= ORA_GRAIN / 2) ? y : y - ORA_GRAIN;
+            for (int x = 0; x < ORA_GRAIN; x++) {
+                int fx = (x <= ORA_GRAIN / 2) ? x : x - ORA_GRAIN;
+                float r = sqrt(fx * fx + fy * fy);
+                float gain = r / maxr;
+                re[y][x] *= gain;
+                im[y][x] *= gain;
+            }
+        }
+        ora_dft64_lines(re, im, 0, 1);              /* fft2d_inv, noise.c:47-73 */
+        ora_dft64_lines(re, im, 1, 1);
+        for (int i = 0; i < size * size; i++)
+            rgba[i * 4 + c] = re[i / size][i % size] / (ORA_GRAIN * ORA_GRAIN);
+    }
+    /* noise.c:141-152 */
+    float minv = INFINITY, maxv = -INFINITY;
+    for (int i = 0; i < size * size * 4; i++) {
+        if ((i & 3) == 3) continue;
+        if (rgba[i] < minv) minv = rgba[i];
+        if (rgba[i] > maxv) maxv = rgba[i];
+    }
+    for (int i = 0; i < size * size * 4; i++)
+        if ((i & 3) != 3)
+            rgba[i] = (rgba[i] - minv) / (maxv - minv);
+}
+
 uint64_t ora_fnv1a64(const void *buf, size_t n)
 {
     const uint8_t *p = buf;

@@ -49,6 +49,15 @@ float ora_fbm3_periodic(float x, float y, float z, int octaves, float lacunarity
 void  ora_noise_grad3d_bake_rgba8(uint8_t *out, size_t size, size_t z0, size_t z1, int octaves,
                                   float lacunarity, float gain, float period_units, uint32_t seed);
 
+/*
+ * blue_noise2d_tex(), core/noise.c:96-169, up to the upload: 64 x 64 RGBA32F pixels from the drand48 stream *rng.
+ * PARITY UNPINNED for the transform: the reference calls kissfft (deps/bootstrap.json: mborgerding/kissfft@7bce4153,
+ * not vendored, absent here), so this restates its documented contract -- forward DFT sum x[n] exp(-2 pi i k n / N),
+ * unnormalised inverse -- as a plain double-precision DFT; everything around it (draw order, weights, gain,
+ * normalisation) follows the reference line by line.
+ */
+void  ora_blue_noise2d(float *rgba, uint64_t *rng);
+
 /* core/terrain.c */
 float ora_get_rand_height(long seed, int x, int z);
 void  ora_terrain_map0(long seed, unsigned nr_v, float *map0);

@@ -37,6 +37,7 @@ class Port:
         lib.ora_get_rand_height.argtypes = [c_long, c_int, c_int]
         lib.ora_noise_grad3d_bake_rgba8.argtypes = [c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_float, c_float,
                                                     c_float, c_uint32]
+        lib.ora_blue_noise2d.argtypes = [c_void_p, c_void_p]
         lib.ora_terrain_map0.argtypes = [c_long, c_uint, c_void_p]
         lib.ora_terrain_field.argtypes = [c_uint, c_void_p, c_float, c_float, c_int, c_uint, c_uint, c_void_p]
         lib.ora_terrain_heightmap.argtypes = [c_uint, c_void_p, c_float, c_void_p, c_uint, c_uint, c_uint, c_void_p]
@@ -101,6 +102,13 @@ class Port:
         self.lib.ora_noise_grad3d_bake_rgba8(_vp(out), size, z0, size if z1 is None else z1, octaves, lac, gain,
                                              period_units, seed)
         return out
+
+    def blue_noise2d(self, state):
+        """(pixels float32[64, 64, 4], rand48 state after the draws) from the 48-bit state `state`"""
+        out = np.zeros((64, 64, 4), np.float32)
+        st = np.array([state], np.uint64)
+        self.lib.ora_blue_noise2d(_vp(out), _vp(st))
+        return out, int(st[0])
 
     def terrain_map0(self, seed, nr_v):
         out = np.zeros((nr_v, nr_v), np.float32)

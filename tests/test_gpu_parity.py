@@ -613,6 +613,24 @@ def test_noise_bake_into_cuda_array_equals_linear_bake_and_golden(gpu, oracle):
     tex.close()
 
 
+@pytest.mark.parametrize("seed", [1, 20260101])
+def test_blue_noise2d_pixels_vs_port(gpu, oracle, seed):
+    """blue_noise2d_tex (core/noise.c:96-169): the RGBA32F pixels, against the port (double-precision DFT; the
+    reference's kissfft is not vendored, so float rounding of the transform is the agreed tolerance: 2e-5 of the
+    [0, 1] range), and the drand48 stream is left exactly where the reference leaves it."""
+    from clap_b200.ca import Rand48
+    rng = Rand48(seed)
+    st0 = rng.x
+    got = gpu.blue_noise2d(rng)
+    want, st1 = oracle.blue_noise2d(st0)
+    assert rng.x == st1
+    assert got.shape == (64, 64, 4) and np.all(got[:, :, 3] == 1.0)
+    assert np.abs(got - want).max() < 2e-5
+    assert got[:, :, :3].min() == 0.0 and got[:, :, :3].max() == 1.0
+    with pytest.raises(gpu.ClapcaError):
+        gpu.blue_noise2d(Rand48(1), size=32)        # the reference's arrays are 64 x 64 whatever size it is given
+
+
 def test_noise_lattice_wrap_far_outside_the_period(gpu, oracle):
     """fk_wrap() takes a conditional add / subtract within one period of [0, period) and the reference's double
     modulo beyond: points many periods away (both signs) must still match the oracle bit for bit"""

@@ -233,3 +233,32 @@ def test_cfg4_chain_256cube_full_run_port_vs_reference_fingerprint(oracle):
     s, b, n = oracle.ca3d_rule(c["nca"])
     assert oracle.ca3d_run(vol, s, b, n, c["generations"]) == c["population"]
     assert "%016x" % oracle.fnv(vol) == c["fnv1a64"]
+
+
+def test_blue_noise_port_against_numpy_fft():
+    """blue_noise2d_tex (core/noise.c:96-169).  kissfft is not vendored, so the port's transform is pinned to the DFT
+    contract kissfft documents (forward exp(-2 pi i kn/N), unnormalised inverse) through numpy.fft -- an independent
+    implementation -- with everything else (draw order, weights, gain, joint normalisation) restated line by line."""
+    ora = oracle_lib.port()
+    seed = 20260101
+    st0 = ((seed & 0xFFFFFFFF) << 16) | 0x330E              # srand48(seed)
+    got, st1 = ora.blue_noise2d(st0)
+    # the same in numpy, double precision
+    a, c, m = 0x5DEECE66D, 0xB, (1 << 48) - 1
+    x = st0
+    d = np.empty(3 * 64 * 64)
+    for i in range(d.size):
+        x = (a * x + c) & m
+        d[i] = x / float(1 << 48)
+    assert x == st1
+    w = np.array([0.299, 0.587, 0.114])
+    white = (((d * 4.0 - 1.0) / 3.0).reshape(64, 64, 3) * w).astype(np.float32).astype(np.float64)
+    f = np.arange(64)
+    f = np.where(f <= 32, f, f - 64)
+    gain = (np.sqrt(f[:, None] ** 2 + f[None, :] ** 2).astype(np.float32) / np.float32(np.sqrt(np.float32(2048.0)))).astype(np.float64)
+    chans = [np.real(np.fft.ifft2(np.fft.fft2(white[:, :, k]) * gain)) for k in range(3)]
+    rgb = np.stack(chans, axis=-1)
+    want = (rgb - rgb.min()) / (rgb.max() - rgb.min())
+    assert np.all(got[:, :, 3] == 1.0)
+    assert np.abs(got[:, :, :3] - want).max() < 2e-5
+    assert got[:, :, :3].min() == 0.0 and got[:, :, :3].max() == 1.0

@@ -76,6 +76,15 @@ int main(void)
            (unsigned long long)fnv((unsigned char *)idx, 63 * 63 * 12));
     free(vx); free(norm); free(tx); free(idx);
     free(m0);
+    /* the film-grain pixels of blue_noise2d_tex (noise.c:96-169) out of the process-wide drand48 stream */
+    srand48(77);
+    float *grain = clap_blue_noise2d_rgba32f(64);
+    if (!grain) return 4;
+    double gsum = 0.0;
+    for (int i = 0; i < 64 * 64 * 4; i++) gsum += grain[i];
+    printf("grain %.6f %.8f %.8f\n", gsum, (double)grain[4 * 1000], (double)grain[4 * 4095 + 2]);
+    printf("gnext %ld\n", lrand48());         /* ... which continues 3 * 64 * 64 draws later */
+    free(grain);
     return 0;
 }
 '''
@@ -114,3 +123,9 @@ def test_reference_style_c_program(oracle):
     assert out["map0"] == "%016x" % oracle.fnv(t["map0_64_seed12345"])
     want = oracle.terrain_mesh(t["map0_64_seed12345"], 1.0, 2.0, 3.0, 50.0)
     assert out["mesh"].split() == ["%016x" % oracle.fnv(a) for a in want]
+    gpix, gst = oracle.blue_noise2d(((77 & 0xFFFFFFFF) << 16) | 0x330E)
+    gsum, g1, g2 = (float(v) for v in out["grain"].split())
+    assert abs(gsum - float(gpix.astype(np.float64).sum())) < 0.05
+    assert abs(g1 - float(gpix.reshape(-1, 4)[1000, 0])) < 2e-5 and abs(g2 - float(gpix.reshape(-1, 4)[4095, 2])) < 2e-5
+    from ctypes import c_uint64
+    assert int(out["gnext"]) == oracle.lrand48(c_uint64(gst))
