@@ -503,7 +503,14 @@ void clapca::api::sweep_knobs(Bp3Params &p, int team, bool single_gpu)
     if (const char *e = getenv("CLAPCA_MAX_CTAS")) p.max_ctas = std::max(0, atoi(e));
     if (const char *e = getenv("CLAPCA_PUB_WORKERS")) p.pub_workers = std::max(0, atoi(e));
     p.team = team;
-    /* CLAPCA_HALO_LDST=1: halo rows by ld / st of the service warp instead of TMA bulk copies (A/B measurements) */
+    /*
+     * Halo rows: batched ld / st of the service warp by default.  The TMA variant (1-D bulk copies record -> shared
+     * staging -> peer ghost plane, CLAPCA_HALO_LDST=0) was measured on 2 and 8 x B200 with the final kernel and loses:
+     * 61.5 vs 58.1 ms at N = 2, 20.3 vs 17.8 ms at N = 8 (profiles/r02_knobs_multi_n8_final.txt) -- a batch of bulk
+     * copies is a load round trip, an mbarrier wait, a store round trip and a wait_group in series before the peer's
+     * counter may move, where 32 lanes keep 16 rows of loads in flight and the stores drain behind one fence.
+     */
+    p.halo_ldst = 1;
     if (const char *e = getenv("CLAPCA_HALO_LDST")) p.halo_ldst = atoi(e) != 0;
 }
 

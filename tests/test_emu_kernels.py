@@ -15,8 +15,9 @@ def emu_bin():
     return os.path.join(EMU, "build")
 
 
-def _run(exe, *args):
-    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+def _run(exe, *args, env=None):
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **env) if env else None)
     assert r.returncode == 0, f"{args}: {r.stdout} {r.stderr}"
     assert r.stdout.startswith("OK")
 
@@ -158,8 +159,11 @@ def test_ca3d_plane_teams(emu_bin, args):
 def test_ca3d_tiles_of_planes_and_generations(emu_bin, args):
     """Tile mode proper: a CTA sweeps nz planes x ng generations; generation g+1 of a plane follows generation g a
     few rows behind through shared-memory counters, and tiles depend on their NEXT neighbour in z (co-residency,
-    bp_plan.h).  Multi-rank cases push several generations of an edge plane through one ghost plane in place."""
+    bp_plan.h).  Multi-rank cases push several generations of an edge plane through one ghost plane in place --
+    with both halo-row paths of the service warp: ld / st batches (the default) and 1-D bulk copies."""
     _run(os.path.join(emu_bin, "emu_ca3d"), *args)
+    if args[10] > 1:
+        _run(os.path.join(emu_bin, "emu_ca3d"), *args, env={"CLAPCA_HALO_LDST": "0"})
 
 
 @pytest.mark.parametrize("args", [

@@ -42,9 +42,13 @@ def test_single_rank_slab_equals_oracle(gpu, oracle):
     (1000, 40, 33, 5, 2, 2, 4),         # 4 state planes (pyroclastic), ragged rows
     (300, 30, 12, 4, 7, 4, 1),          # single-plane blocks: every plane is an edge on both sides
 ])
-def test_local_ranks_equal_single_gpu_and_oracle(gpu, oracle, case):
+@pytest.mark.parametrize("halo", ["ldst", "tma"])
+def test_local_ranks_equal_single_gpu_and_oracle(gpu, oracle, monkeypatch, case, halo):
+    """both halo-row paths of the service warp: ld / st batches (default) and TMA bulk copies (CLAPCA_HALO_LDST=0)"""
     from clap_b200.slab import LocalRanks
     d0, d1, d2, gens, rule, ranks, block = case
+    if halo == "tma":
+        monkeypatch.setenv("CLAPCA_HALO_LDST", "0")
     rng = np.random.default_rng(d0 * 7 + d2)
     full = (rng.integers(1, 6, (d2, d1, d0)) * (rng.random((d2, d1, d0)) < 0.3)).astype(np.uint8)
     want = full.copy()
