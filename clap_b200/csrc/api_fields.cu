@@ -12,6 +12,44 @@ using namespace clapca::api;
 extern "C" {
 #pragma GCC visibility push(default)
 
+/*
+ * Can the bake take the lattice path (field_kernels.cuh, noise_field_kernel)?  Yes when the +- eps samples of every
+ * voxel are bit for bit the coordinates of its neighbours' centres, in the float arithmetic the reference uses
+ * (core/noise.c:236-254: step = period_units / size, p = (float)x * step, samples p + eps and p - eps with eps = step),
+ * and the lattice fits a bounded scratch buffer.  CLAPCA_NOISE_DIRECT=1 forces the six-samples-per-voxel kernel.
+ */
+static bool noise_lattice_ok(size_t size, float period_units)
+{
+    if (const char *e = getenv("CLAPCA_NOISE_DIRECT"))
+        if (atoi(e)) return false;
+    if ((size + 2) * (size + 2) * (size + 2) * sizeof(float) > ((size_t)2 << 30))
+        return false;
+    volatile float step = period_units / (float)size;
+    for (size_t x = 0; x < size; x++) {
+        volatile float p = (float)x * step;
+        volatile float plus = p + step, minus = p - step;
+        volatile float next = (float)(x + 1) * step, prev = (float)((double)x - 1.0) * step;
+        if (plus != next || minus != prev)
+            return false;
+    }
+    return true;
+}
+
+/* fills p.field (lattice path) when the precondition holds; the caller launches its voxel kernel afterwards */
+static int noise_prepare_lattice(NoiseBakeParams &p)
+{
+    p.field = nullptr;
+    if (!noise_lattice_ok(p.size, p.period_units))
+        return CLAPCA_OK;
+    const size_t S2 = (size_t)p.size + 2, points = S2 * S2 * S2;
+    if (int rc = ensure_bytes(&g_ctx.scratch[0], &g_ctx.scratch_bytes[0], points * sizeof(float))) return rc;
+    float *field = (float *)g_ctx.scratch[0];
+    noise_field_kernel<<<grid_blocks_for(points, 256, 8), 256, 0, g_ctx.stream>>>(p, field);
+    CU(cudaGetLastError());
+    p.field = field;
+    return CLAPCA_OK;
+}
+
 int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacunarity, float gain,
                              float period_units, uint32_t seed, float *kernel_ms)
 {
@@ -19,12 +57,13 @@ int clapca_noise_bake_device(void *d_out, size_t size, int octaves, float lacuna
     if (!d_out || size < 1 || size > 4096 || octaves < 0 || (int)period_units < 1)
         return fail(CLAPCA_ERR_ARG, "noise bake: bad arguments (size %zu, octaves %d, period %g)", size, octaves,
                     (double)period_units);
-    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed, 0 };
+    NoiseBakeParams p = { (uint32_t *)d_out, (unsigned)size, octaves, lacunarity, gain, period_units, seed, 0, nullptr };
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     size_t voxels = size * size * size;
     CU(cudaEventRecord(a, g_ctx.stream));
+    if (int rc = noise_prepare_lattice(p)) return rc;
     noise_bake_kernel<<<grid_blocks_for(voxels, 256, 8), 256, 0, g_ctx.stream>>>(p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(b, g_ctx.stream));
@@ -137,11 +176,12 @@ int clapca_noise_bake_array(clapca_tex3d **out, size_t size, int octaves, float 
         return fail(e == cudaErrorMemoryAllocation ? CLAPCA_ERR_NOMEM : CLAPCA_ERR_CUDA, "noise bake (array): %s",
                     cudaGetErrorString(e));
     }
-    NoiseBakeParams p = { nullptr, (unsigned)size, octaves, lacunarity, gain, period_units, seed, t->surf };
+    NoiseBakeParams p = { nullptr, (unsigned)size, octaves, lacunarity, gain, period_units, seed, t->surf, nullptr };
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, g_ctx.stream));
+    if (int rc = noise_prepare_lattice(p)) { clapca_tex3d_destroy(t); return rc; }
     noise_bake_surface_kernel<<<grid_blocks_for(size * size * size, 256, 8), 256, 0, g_ctx.stream>>>(p);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaEventRecord(b, g_ctx.stream);

@@ -132,6 +132,7 @@ struct NoiseBakeParams {
     float lacunarity, gain, period_units;
     uint32_t seed;
     cudaSurfaceObject_t surf;   /* array bake: a 3D CUDA array of uchar4 bound as a surface */
+    const float *field;     /* lattice bake: fBm at the (size + 2)^3 lattice points -1 .. size, x fastest (else nullptr) */
 };
 
 /* one voxel of noise_grad3d_bake_rgba8(): core/noise.c:236-264 -- central differences of the fBm, normalised, packed */
@@ -155,6 +156,49 @@ __device__ __forceinline__ uint32_t fk_bake_voxel(const NoiseBakeParams &p, unsi
     return fk_unorm8(gx * inv) | (fk_unorm8(gy * inv) << 8) | (fk_unorm8(gz * inv) << 16);
 }
 
+/*
+ * The lattice bake.  A voxel's six fBm samples sit at p +- eps along one axis with eps = step -- the positions of its
+ * NEIGHBOURS' centres whenever float arithmetic makes fl(fl(x step) + step) == fl((x + 1) step) and
+ * fl(fl(x step) - step) == fl((x - 1) step) for every x (true for the engine's own bake: 37 / 256 is a dyadic
+ * rational; the host checks all `size` values before choosing this path).  Then every sample point is a lattice point
+ * k in [-1, size]^3, the fBm is evaluated ONCE per lattice point instead of six times per voxel, and the voxel is the
+ * central difference of stored neighbours: bit-identical output, a sixth of the work (the bake is bound by the
+ * float <-> double conversions of interp.h's promoted arithmetic: ncu, mio_throttle 7 per issue).
+ */
+__global__ void __launch_bounds__(256) noise_field_kernel(NoiseBakeParams p, float *field)
+{
+    const unsigned S2 = p.size + 2u;
+    const size_t points = (size_t)S2 * S2 * S2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float step = p.period_units / (float)p.size;
+    const int period = (int)p.period_units;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < points; i += stride) {
+        const int kx = (int)(i % S2) - 1, ky = (int)((i / S2) % S2) - 1, kz = (int)(i / ((size_t)S2 * S2)) - 1;
+        /* only the axis neighbours of voxels are ever read: skip lattice points outside [0, size) in two axes */
+        const int out = (kx < 0 || kx >= (int)p.size) + (ky < 0 || ky >= (int)p.size) + (kz < 0 || kz >= (int)p.size);
+        if (out > 1)
+            continue;
+        field[i] = fk_fbm3((float)kx * step, (float)ky * step, (float)kz * step, p.octaves, p.lacunarity, p.gain, period,
+                           p.seed);
+    }
+}
+
+/* one voxel from the stored lattice: core/noise.c:246-264 */
+__device__ __forceinline__ uint32_t fk_bake_voxel_lattice(const NoiseBakeParams &p, unsigned x, unsigned y, unsigned z)
+{
+    const size_t S2 = p.size + 2u;
+    const float step = p.period_units / (float)p.size;
+    const float scale = 0.5f / step;
+    const float *c = p.field + ((size_t)(z + 1u) * S2 + (y + 1u)) * S2 + (x + 1u);
+    float gx = (c[1] - c[-1]) * scale;
+    float gy = (c[S2] - c[-(ptrdiff_t)S2]) * scale;
+    float gz = (c[S2 * S2] - c[-(ptrdiff_t)(S2 * S2)]) * scale;
+    float len2 = gx * gx + gy * gy + gz * gz;
+    float inv = 1.0f / sqrtf(len2 > FLT_MIN ? len2 : FLT_MIN);
+
+    return fk_unorm8(gx * inv) | (fk_unorm8(gy * inv) << 8) | (fk_unorm8(gz * inv) << 16);
+}
+
 /* noise_grad3d_bake_rgba8(): core/noise.c:222-270, one thread per voxel, into a linear buffer */
 __global__ void __launch_bounds__(256) noise_bake_kernel(NoiseBakeParams p)
 {
@@ -163,7 +207,7 @@ __global__ void __launch_bounds__(256) noise_bake_kernel(NoiseBakeParams p)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += stride) {
         const unsigned x = (unsigned)(i % p.size), y = (unsigned)((i / p.size) % p.size);
         const unsigned z = (unsigned)(i / ((size_t)p.size * p.size));
-        p.out[i] = fk_bake_voxel(p, x, y, z);
+        p.out[i] = p.field ? fk_bake_voxel_lattice(p, x, y, z) : fk_bake_voxel(p, x, y, z);
     }
 }
 
@@ -179,7 +223,7 @@ __global__ void __launch_bounds__(256) noise_bake_surface_kernel(NoiseBakeParams
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += stride) {
         const unsigned x = (unsigned)(i % p.size), y = (unsigned)((i / p.size) % p.size);
         const unsigned z = (unsigned)(i / ((size_t)p.size * p.size));
-        const uint32_t t = fk_bake_voxel(p, x, y, z);
+        const uint32_t t = p.field ? fk_bake_voxel_lattice(p, x, y, z) : fk_bake_voxel(p, x, y, z);
         surf3Dwrite(make_uchar4((unsigned char)t, (unsigned char)(t >> 8), (unsigned char)(t >> 16), 0), p.surf,
                     (int)(x * sizeof(uchar4)), (int)y, (int)z);
     }

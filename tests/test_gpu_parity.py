@@ -573,6 +573,26 @@ def test_noise_bake_golden_exact(gpu, oracle):
     assert d.reshape(-1)[:4].tolist() == [122, 5, 93, 0]
 
 
+@pytest.mark.parametrize("case", [
+    # size octaves lacunarity gain period seed
+    (16, 4, 2.0, 0.5, 5.0, 0xC14D),        # dyadic step: the lattice path (fBm once per lattice point)
+    (24, 3, 2.3, 0.45, 37.0, 99),          # 37 / 24 is not a float-exact lattice: the six-samples-per-voxel kernel
+    (48, 4, 2.0, 0.5, 7.0, 5),             # 7 / 48: not exact either
+    (40, 2, 2.0, 0.5, 10.0, 1),            # 10 / 40 = 0.25
+    (33, 4, 2.0, 0.5, 33.0, 7),            # step 1: every sample sits on a lattice corner of octave 0
+])
+def test_noise_bake_lattice_path_equals_direct_path_and_oracle(gpu, oracle, monkeypatch, case):
+    """The bake evaluates the fBm once per lattice point when the +- eps samples are bit for bit the neighbours'
+    centres (checked on the host in the reference's float arithmetic) and six times per voxel otherwise; both must
+    give the reference's bytes."""
+    size, octv, lac, gain, period, seed = case
+    a = gpu.noise_grad3d_bake_rgba8(size, octv, lac, gain, period, seed)
+    monkeypatch.setenv("CLAPCA_NOISE_DIRECT", "1")
+    b = gpu.noise_grad3d_bake_rgba8(size, octv, lac, gain, period, seed)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, oracle.noise_bake(size, octv, lac, gain, period, seed))
+
+
 def test_noise_fbm_float_field(gpu):
     """north_star tolerance: 1e-5 relative; the kernel mirrors the reference's double promotions and is
     expected (and checked) to be exact to the last bit."""
