@@ -397,6 +397,7 @@ static int slab_launch(clapca_slab *s, bool streamed, int *workers)
     p.prog = s->prog + (s->Zl ? s->Zl : 1);
     p.order = s->order;
     p.nsweeps = s->n_items;
+    p.zeros = g_ctx.d_zeros;
     sweep_knobs(p, s->team);
     if (s->max_ctas > 0) p.max_ctas = s->max_ctas;
     p.ticket = s->ticket;

@@ -78,6 +78,7 @@ struct Bp3Params {
     int pub_workers;        /* > 0: every CTA = pub_workers worker warps + ONE publisher warp (see PubSlot) */
     int team;               /* > 0: tile mode -- a CTA of `team` compute warps + ONE service warp sweeps a tile (see below) */
     int halo_ldst;          /* != 0: the service warp moves halo rows with ld / st instead of TMA bulk copies */
+    const uint32_t *zeros;  /* >= 2 * RWP zero words: the "row" every plane outside the volume consists of */
     /*
      * Layout items (optional, see "Layout items" below): the conversion between the reference's uint8 cells and
      * the row records runs INSIDE the sweep launch, so a volume can stream host -> device -> host through it.
@@ -276,7 +277,8 @@ struct Sweep3 {
         uint32_t ho[2][WPL];                        /* H of own old row y+1 */
         uint32_t hn[2][WPL];                        /* H of own new row y-1 */
         uint32_t vmask[WPL];
-        const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load; nullptr: outside the volume */
+        const uint32_t *dn, *up;                    /* lane-adjusted, at the next row to load (a plane outside the volume: the zero row) */
+        int dn_step, up_step;                       /* words from row to row: RECW, or 0 on the zero row -- no null checks in the loop */
         uint32_t *rec;                              /* lane-adjusted own record of the current row */
         const uint32_t *pf;                         /* lanes < NP*WPL: one 128-byte line of the record prefetch_rows ahead
                                                        (ONE cp.async.bulk.prefetch.L2 of the record by lane 0 was measured
@@ -366,15 +368,11 @@ struct Sweep3 {
     }
 
     /* next H row of the plane below / above into h; advances the running pointer */
-    CA_MDEV void load_side(const uint32_t *&src, uint32_t h[2][WPL])
+    CA_MDEV void load_side(const uint32_t *&src, int step, uint32_t h[2][WPL])
     {
-        if (src) {
-            LaneVec<WPL>::ld(src, h[0]);
-            LaneVec<WPL>::ld(src + RWP, h[1]);
-            src += RECW;
-        } else {
-            zero2(h);
-        }
+        LaneVec<WPL>::ld(src, h[0]);
+        LaneVec<WPL>::ld(src + RWP, h[1]);
+        src += step;
     }
 
     /* own record at st.rec + D rows: state planes, and optionally the H planes */
@@ -459,8 +457,8 @@ struct Sweep3 {
                     return false;
                 load_own_h<2>(st, st.ho);
                 load_own_s<2>(st, st.so[A]);
-                load_side(st.dn, st.hd);
-                load_side(st.up, st.hu);
+                load_side(st.dn, st.dn_step, st.hd);
+                load_side(st.up, st.up_step, st.hu);
             } else {
                 zero2(st.ho); zero2(st.hd); zero2(st.hu);
                 zero_s(st.so[A]);
@@ -572,8 +570,10 @@ struct Sweep3 {
 
         /* ---- sources ---- */
         const int first = y0 > 0 ? y0 - 1 : 0;      /* first row loaded from the side planes */
-        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * RECW + lane * WPL : nullptr;
-        st.up = pl.up_rows ? pl.up_rows + (size_t)first * RECW + lane * WPL : nullptr;
+        st.dn = pl.dn_rows ? pl.dn_rows + (size_t)first * RECW + lane * WPL : p.zeros + lane * WPL;
+        st.up = pl.up_rows ? pl.up_rows + (size_t)first * RECW + lane * WPL : p.zeros + lane * WPL;
+        st.dn_step = pl.dn_rows ? RECW : 0;
+        st.up_step = pl.up_rows ? RECW : 0;
         st.rec = p.rows + ((size_t)z * H + y0) * RECW + lane * WPL;
         st.pf = (p.prefetch_rows > 0 && lane < NP * WPL)
               ? p.rows + ((size_t)z * H + y0 + p.prefetch_rows) * RECW + lane * 32 : nullptr;
@@ -636,8 +636,8 @@ struct Sweep3 {
 
         /* ---- fill the windows: pair sums of rows y0-1 (slot 2) and y0 (slot 0); row y0+1 waits in hd / hu ---- */
         if (y0 > 0) {
-            load_side(st.dn, st.hd);
-            load_side(st.up, st.hu);
+            load_side(st.dn, st.dn_step, st.hd);
+            load_side(st.up, st.up_step, st.hu);
             pair_sum(st, st.tt[2]);
             load_own_h<-1>(st, st.hn);              /* row y0-1 of this plane is already generation g */
         } else {
@@ -645,13 +645,13 @@ struct Sweep3 {
             for (int j = 0; j < WPL; j++) st.tt[2][0][j] = st.tt[2][1][j] = st.tt[2][2][j] = 0u;
             zero2(st.hn);
         }
-        load_side(st.dn, st.hd);
-        load_side(st.up, st.hu);
+        load_side(st.dn, st.dn_step, st.hd);
+        load_side(st.up, st.up_step, st.hu);
         pair_sum(st, st.tt[0]);
         load_own_s<0>(st, st.so[0]);
         if (y0 + 1 < H) {
-            load_side(st.dn, st.hd);
-            load_side(st.up, st.hu);
+            load_side(st.dn, st.dn_step, st.hd);
+            load_side(st.up, st.up_step, st.hu);
             load_own_h<1>(st, st.ho);
             load_own_s<1>(st, st.so[1]);
         } else {

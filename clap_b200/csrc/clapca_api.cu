@@ -204,6 +204,8 @@ int clapca_init(int device)
     CU(cudaStreamCreateWithFlags(&g_ctx.stream_out, cudaStreamNonBlocking));
     CU(cudaMalloc(&g_ctx.d_count, sizeof(unsigned long long)));
     CU(cudaMalloc(&g_ctx.d_max, sizeof(unsigned)));
+    CU(cudaMalloc(&g_ctx.d_zeros, 1024));
+    CU(cudaMemset(g_ctx.d_zeros, 0, 1024));
     g_ctx.device = device;
     return CLAPCA_OK;
 }
@@ -216,6 +218,7 @@ void clapca_shutdown(void)
     cudaDeviceSynchronize();
     if (g_ctx.d_count) cudaFree(g_ctx.d_count);
     if (g_ctx.d_max) cudaFree(g_ctx.d_max);
+    if (g_ctx.d_zeros) cudaFree(g_ctx.d_zeros);
     if (g_ctx.d_smooth) cudaFree(g_ctx.d_smooth);
     for (int i = 0; i < 5; i++)
         if (g_ctx.scratch[i]) cudaFree(g_ctx.scratch[i]);
@@ -850,6 +853,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         p.prog = prog;
         p.order = g->order;
         p.nsweeps = g->n_items;
+        p.zeros = g_ctx.d_zeros;
         sweep_knobs(p, team, !fused);
         p.ticket = g->ticket;
         p.err = (int *)(g->ticket + 1);

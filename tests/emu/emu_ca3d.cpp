@@ -260,6 +260,8 @@ int main(int argc, char **argv)
         k.p.flag_rows = flagRows;
         k.p.pub_workers = pubWorkers;
         k.p.team = team;
+        static const uint32_t zero_row[1024] = { 0 };
+        k.p.zeros = zero_row;
         /* halo rows: the product's default (ld / st batches) unless CLAPCA_HALO_LDST=0 asks for the bulk-copy path */
         k.p.halo_ldst = getenv("CLAPCA_HALO_LDST") ? atoi(getenv("CLAPCA_HALO_LDST")) != 0 : 1;
         k.p.ticket = &k.ticket;
