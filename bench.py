@@ -880,6 +880,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1 and os.environ.get("CLAPCA_NUMA_BIND", "1") != "0":
+        # a rank's pinned slabs belong next to its GPU's PCIe root (the streamed e2e moves 2 x volume / N per rank)
+        from clap_b200.slab import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -888,6 +893,8 @@ def main():
 
     if world > 1 and args.workload in WORKLOADS:
         line = run_ca3d_sharded(args, torch, dist, dev, local, args.workload)
+        if rank == 0 and line.get("e2e"):
+            line["e2e"]["numa_bound_cpus_rank0"] = len(numa_cpus) if numa_cpus else None
         if rank == 0:
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()

@@ -193,6 +193,35 @@ class ShardedVolume:
                 "workers": st.workers, "streamed": bool(st.streamed)}
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs NVML reports as closest to `device_index` (its NUMA node), so that the pinned
+    host slabs a rank allocates afterwards are first-touched next to its GPU's PCIe root.  On a two-socket 8-GPU host the
+    streamed host -> host pipelines of all ranks otherwise share whatever node the launcher happened to run on.
+    Returns the CPU set chosen, or None when NVML / the topology is not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:       # noqa: BLE001 -- older torch: fall back to the NVML index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:           # noqa: BLE001 -- advisory: never fail a run over an affinity hint
+        return None
+
+
 class LocalRanks:
     """`nranks` slabs of one process on ONE device: every rank owns its z-blocks, its halo region and its stream;
     prepare runs rank by rank (it also seeds the neighbours' ghost planes), the sweeps run concurrently from one
