@@ -60,6 +60,7 @@ SIGNATURES = {
     "clapca_grid_download": (c_int, [c_void_p, c_void_p]),
     "clapca_grid_device_ptr": (c_void_p, [c_void_p]),
     "clapca_grid_stream": (c_void_p, [c_void_p]),
+    "clapca_grid_make3d": (c_int, [c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_int64)]),
     "clapca_grid_run3d": (c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_int, c_int, POINTER(c_int64)]),
     "clapca_grid_run3d_streamed": (c_int, [c_void_p, c_void_p, c_void_p, c_uint, c_uint32, c_uint32, c_uint32, c_int,
                                            POINTER(c_int64)]),

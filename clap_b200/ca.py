@@ -167,6 +167,16 @@ class Grid:
                                                      int(steps), engine, byref(pop)))
         return pop.value
 
+    def make3d(self, rng):
+        """clapca_grid_make3d(): ca3d_make() (core/ca3d.c:144-169) into this device-resident grid -- faces, the random
+        walk (host, on a sparse picture of the volume) and the prune (255 marks included).  `rng`: the caller's Rand48
+        stream, advanced by the walk's draws.  Returns the population."""
+        from ctypes import c_uint64
+        pop, after = c_int64(0), c_uint64(0)
+        check(self._lib, self._lib.clapca_grid_make3d(self._h, rng.x, byref(after), byref(pop)))
+        rng.x = int(after.value)
+        return pop.value
+
     def run3d_streamed(self, rule, steps, host_in, host_out, max_value=255):
         """clapca_grid_run3d_streamed(): host -> device -> host as one pipeline (upload, all generations and download
         overlap inside one sweep launch when the buffers are page-locked).  host_in / host_out: numpy uint8 arrays

@@ -173,6 +173,85 @@ CA_GLOBAL void __launch_bounds__(256) ca3d_unpack_rows_kernel(Bp3Layout L)
         dp_atomic_add64(L.population, (unsigned long long)hi << 32 | lo);
 }
 
+/* ---- ca3d_make() on a device-resident volume: core/ca3d.c:41-59, 144-169 ------------------------------------- */
+
+/* the six faces of the (zeroed) volume get the value 5: one thread per row (y, z) */
+CA_GLOBAL void make3d_faces_kernel(uint8_t *cells, int d0, int d1, int d2)
+{
+    const size_t rows = (size_t)d1 * d2;
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    for (size_t r = (size_t)dp_block() * dp_block_threads() + dp_thread(); r < rows; r += stride) {
+        const int y = (int)(r % d1), z = (int)(r / d1);
+        uint8_t *row = cells + r * d0;
+        if (y == 0 || y == d1 - 1 || z == 0 || z == d2 - 1) {
+            for (int x = 0; x < d0; x++) row[x] = 5;
+        } else {
+            row[0] = 5;
+            row[d0 - 1] = 5;
+        }
+    }
+}
+
+/* the cells the random walk visited */
+CA_GLOBAL void make3d_scatter_kernel(uint8_t *cells, const unsigned long long *idx, size_t n)
+{
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < n; i += stride)
+        cells[idx[i]] = 5;
+}
+
+/*
+ * ca3d_prune(), first loop (core/ca3d.c:45-49): in sweep order, a cell whose six von Neumann neighbours are all
+ * occupied becomes (unsigned char)-1 = 255 -- an EMPTY enclosed cell too, and from then on it counts as occupied for
+ * the cells after it (+x, +y, +z), not for the cells before it.  The second loop never finds an int equal to -1
+ * (SURVEY F5), so the marks stay.  In parallel: a cell sees the NEW state of its three predecessors and the OLD state
+ * of its three successors; the system is triangular, so iterating "mark what has six" to a fixed point gives the
+ * sweep's result.  An empty cell that turns occupied is held as 254 until the fixed point (occupied for the cells
+ * after it, still empty for the cells before it); occupied cells go to 255 directly (nobody's count depends on it).
+ * *changed counts the empty cells newly marked in this pass.
+ */
+CA_GLOBAL void make3d_prune_kernel(uint8_t *cells, int d0, int d1, int d2, unsigned *changed)
+{
+    const size_t n = (size_t)d0 * d1 * d2, plane = (size_t)d0 * d1;
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < n; i += stride) {
+        const int x = (int)(i % d0), y = (int)((i / d0) % d1), z = (int)(i / plane);
+        if (x == 0 || y == 0 || z == 0 || x == d0 - 1 || y == d1 - 1 || z == d2 - 1)
+            continue;                                   /* a neighbour outside the volume reads 0: never six */
+        const volatile uint8_t *c = cells + i;
+        const uint8_t v = c[0];
+        if (v == 255 || v == 254)
+            continue;
+        /* predecessors: new state (254 counts); successors: old state (254 is still empty) */
+        const uint8_t sx = c[1], sy = c[d0], sz = c[plane];
+        const int cnt = (c[-1] != 0) + (c[-(ptrdiff_t)d0] != 0) + (c[-(ptrdiff_t)plane] != 0) +
+                        (sx != 0 && sx != 254) + (sy != 0 && sy != 254) + (sz != 0 && sz != 254);
+        if (cnt == 6) {
+            if (v == 0) {
+                cells[i] = 254;
+                dp_atomic_or_global(changed, 1u);
+            } else {
+                cells[i] = 255;
+            }
+        }
+    }
+}
+
+/* after the fixed point: the held marks become 255; counts the occupied cells (xyzarray_count, core/ca3d.c:98) */
+CA_GLOBAL void make3d_finish_kernel(uint8_t *cells, size_t n, unsigned long long *population)
+{
+    const size_t stride = (size_t)dp_grid_blocks() * dp_block_threads();
+    unsigned long long pop = 0;
+    for (size_t i = (size_t)dp_block() * dp_block_threads() + dp_thread(); i < n; i += stride) {
+        uint8_t v = cells[i];
+        if (v == 254)
+            cells[i] = v = 255;
+        pop += v != 0;
+    }
+    if (pop)
+        dp_atomic_add64(population, pop);
+}
+
 /*
  * Seed a neighbour's ghost plane with the H rows of one local plane (the "old plane above" of generation 0):
  * src = first row record of the plane, dst = ghost plane (peer memory), both with the record stride NP * RWP.

@@ -6,6 +6,7 @@
  */
 #include <cooperative_groups.h>
 
+#include <unordered_set>
 #include "api_internal.h"
 #include "bp2_launch.h"
 #include "ca2d_layout.cuh"
@@ -1241,6 +1242,105 @@ int clapca_grid_seed2d(clapca_grid *g, int64_t side, uint32_t nr_states, uint64_
     CU(cudaStreamSynchronize(g->stream));
     if (rand48_state_after)
         *rand48_state_after = r48_advance(rand48_state, (unsigned long long)side * (unsigned long long)side);
+    return CLAPCA_OK;
+}
+
+/*
+ * ca3d_make() (core/ca3d.c:144-169) into a device-resident grid.  The faces and the prune are kernels
+ * (ca3d_layout.cuh); ca3d_walk() (:63-99) is a serial chain of data-dependent lrand48() draws and runs here, on the
+ * host, against a SPARSE picture of the volume: before the prune a cell is occupied iff it lies on a face or the walk
+ * has been there, so the walk needs a hash set of its own cells, not the 8.6 GB volume.  Quirks kept: HIST_SIZE /
+ * TRIES, the history that stops growing when it is full; the undefined history[-1] read of the reference on an empty
+ * history is "stay put", as in the host shim and the oracle port.
+ */
+int clapca_grid_make3d(clapca_grid *g, uint64_t rand48_state, uint64_t *rand48_state_after, int64_t *population)
+{
+    if (int rc = need_init()) return rc;
+    if (!g) return fail(CLAPCA_ERR_ARG, "grid_make3d: NULL grid");
+    const long long d0 = g->d0, d1 = g->d1, d2 = g->d2;
+    if (d0 < 1 || d1 < 1 || d2 < 1 || d0 > 46340 || d1 > 46340 || d2 > 46340)
+        return fail(CLAPCA_ERR_ARG, "grid_make3d: bad extents");
+    unsigned long long st = rand48_state & ((1ull << 48) - 1ull);
+    auto next = [&st]() -> long {
+        st = (st * 0x5DEECE66Dull + 0xBull) & ((1ull << 48) - 1ull);
+        return (long)(st >> 17);
+    };
+    /* min3(d0 * d1, d1 * d2, d0 * d2) in the reference's int arithmetic (extents are bounded above) */
+    const long long steps = std::min(std::min(d0 * d1, d1 * d2), d0 * d2);
+    auto on_face = [&](long long x, long long y, long long z) {
+        return x == 0 || y == 0 || z == 0 || x == d0 - 1 || y == d1 - 1 || z == d2 - 1;
+    };
+    auto index = [&](long long x, long long y, long long z) { return (unsigned long long)((z * d1 + y) * d0 + x); };
+    std::unordered_set<unsigned long long> seen;
+    std::vector<unsigned long long> walked;
+    seen.reserve((size_t)std::min<long long>(steps, 1 << 24) * 2);
+    {
+        enum { HISTORY = 128, ATTEMPTS = 12 };
+        long long trail[HISTORY][3], at[3] = { d0 / 2, d1 / 2, d2 / 2 };
+        int depth = 0;
+        for (long long s = 0; s < steps; s++) {
+            long long to[3] = { 0, 0, 0 };
+            int k;
+            if (seen.insert(index(at[0], at[1], at[2])).second)
+                walked.push_back(index(at[0], at[1], at[2]));
+            for (k = 0; k < ATTEMPTS; k++) {
+                to[0] = at[0]; to[1] = at[1]; to[2] = at[2];
+                const int axis = (int)(next() % 3);
+                const int delta = (next() & 1) ? 1 : -1;
+                to[axis] += delta;
+                const bool valid = to[0] >= 0 && to[1] >= 0 && to[2] >= 0 && to[0] < d0 && to[1] < d1 && to[2] < d2;
+                if (valid && !on_face(to[0], to[1], to[2]) && !seen.count(index(to[0], to[1], to[2])))
+                    break;
+            }
+            if (k == ATTEMPTS) {
+                if (depth > 0) {
+                    depth--;
+                    at[0] = trail[depth][0]; at[1] = trail[depth][1]; at[2] = trail[depth][2];
+                }
+                continue;
+            }
+            if (depth == HISTORY)
+                continue;
+            trail[depth][0] = to[0]; trail[depth][1] = to[1]; trail[depth][2] = to[2];
+            depth++;
+            at[0] = to[0]; at[1] = to[1]; at[2] = to[2];
+        }
+    }
+    if (rand48_state_after) *rand48_state_after = st;
+
+    CU(cudaMemsetAsync(g->cells, 0, g->n, g->stream));
+    make3d_faces_kernel<<<grid_blocks_for((size_t)d1 * d2, 256, 8), 256, 0, g->stream>>>(g->cells, (int)d0, (int)d1, (int)d2);
+    CU(cudaGetLastError());
+    if (!walked.empty()) {
+        const size_t bytes = walked.size() * sizeof(unsigned long long);
+        if (int rc = ensure_bytes(&g_ctx.scratch[3], &g_ctx.scratch_bytes[3], bytes)) return rc;
+        CU(cudaMemcpyAsync(g_ctx.scratch[3], walked.data(), bytes, cudaMemcpyHostToDevice, g->stream));
+        make3d_scatter_kernel<<<grid_blocks_for(walked.size(), 256, 8), 256, 0, g->stream>>>(
+            g->cells, (const unsigned long long *)g_ctx.scratch[3], walked.size());
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(g->stream));           /* `walked` is a local */
+    }
+    /* ca3d_prune(): passes until no empty cell turns occupied any more (almost always two) */
+    for (int pass = 0;; pass++) {
+        unsigned changed = 0;
+        CU(cudaMemsetAsync(g_ctx.d_max, 0, sizeof(unsigned), g->stream));
+        make3d_prune_kernel<<<grid_blocks_for(g->n, 256, 16), 256, 0, g->stream>>>(g->cells, (int)d0, (int)d1, (int)d2,
+                                                                                  g_ctx.d_max);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&changed, g_ctx.d_max, sizeof(changed), cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        if (!changed)
+            break;
+        if (pass > 100000)
+            return fail(CLAPCA_ERR_STATE, "grid_make3d: the prune did not settle");
+    }
+    unsigned long long pop = 0;
+    CU(cudaMemsetAsync(g_ctx.d_count, 0, sizeof(unsigned long long), g->stream));
+    make3d_finish_kernel<<<grid_blocks_for(g->n, 256, 16), 256, 0, g->stream>>>(g->cells, g->n, g_ctx.d_count);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&pop, g_ctx.d_count, sizeof(pop), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (population) *population = (int64_t)pop;
     return CLAPCA_OK;
 }
 

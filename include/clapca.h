@@ -214,6 +214,14 @@ int clapca_grid_seed2d(clapca_grid *g, int64_t side, uint32_t nr_states, uint64_
                        uint64_t *rand48_state_after);
 
 /*
+ * ca3d_make() (core/ca3d.c:144-169) into a device-resident grid: faces of value 5, the random walk of ca3d_walk()
+ * (:63-99) from the centre, ca3d_prune() (:41-59, marks of 255 included).  The walk is a serial chain of lrand48() draws:
+ * it runs on the host against a sparse picture of the volume (faces + its own cells); faces, scatter and prune are
+ * kernels.  rand48_state in / out as for clapca_ca2d_generate; *population = xyzarray_count() of the result.
+ */
+int clapca_grid_make3d(clapca_grid *g, uint64_t rand48_state, uint64_t *rand48_state_after, int64_t *population);
+
+/*
  * ca3d_run() (core/ca3d.c:124-142) from host memory to host memory as ONE pipeline: the volume is copied in
  * chunk by chunk while the sweep kernel already runs, the kernel itself converts the layout plane by plane
  * (no separate pack / unpack pass), every generation follows the upload front a few planes behind, and

@@ -325,6 +325,53 @@ def test_ca3d_fused_layout_resident_vs_oracle(gpu, oracle, monkeypatch, team):
         assert np.array_equal(vol, want), shape
 
 
+@pytest.mark.parametrize("dims", [(48, 24, 20), (5, 5, 5), (4, 4, 4), (3, 3, 3), (2, 2, 2), (1, 1, 1), (3, 1, 7),
+                                  (33, 17, 9), (64, 64, 64), (9, 40, 12)])
+def test_ca3d_make_on_the_device_equals_the_reference_builder(gpu, oracle, dims):
+    """clapca_grid_make3d: faces + random walk + prune of ca3d_make() (core/ca3d.c:41-99, 144-169) with the volume on
+    the device -- the walk runs on the host against a sparse picture, the prune is a fixed-point of a parallel kernel
+    (an enclosed EMPTY cell becomes 255 and counts for the cells after it only, like in the reference's sweep)."""
+    from ctypes import c_uint64
+    from clap_b200.ca import Rand48
+    d0, d1, d2 = dims
+    for seed in (42, 7, 20260101):
+        want = oracle.ca3d_make(d0, d1, d2, seed)
+        st = oracle.srand48(seed)
+        chk = np.zeros((d2, d1, d0), np.uint8)
+        oracle.lib.ora_ca3d_make(chk.ctypes.data, d0, d1, d2, __import__("ctypes").byref(st))
+        assert np.array_equal(chk, want)
+        g = gpu.Grid(d0, d1, d2)
+        rng = Rand48(seed)
+        pop = g.make3d(rng)
+        got = np.empty((d2, d1, d0), np.uint8)
+        g.download(got)
+        g.close()
+        assert np.array_equal(got, want), (dims, seed, int((got != want).sum()))
+        assert pop == int((want != 0).sum())
+        assert rng.x == int(st.value), "the lrand48 stream continues where the reference's walk leaves it"
+
+
+def test_ca3d_make_prune_marks_enclosed_empty_cells_for_their_successors_only(gpu, oracle):
+    """the order-dependent corner of ca3d_prune(): an EMPTY cell with six occupied neighbours becomes 255 and counts as
+    occupied for the cells the sweep visits after it.  At these sizes a quarter of all seeds enclose such a cell (checked
+    against a re-run of the walk when this test was written), chain reactions included: the device prune's fixed point
+    must equal the oracle's sequential sweep for every one of them."""
+    from clap_b200.ca import Rand48
+    flips = 0
+    for dims in ((6, 6, 6), (8, 8, 8), (7, 9, 8), (10, 10, 10)):
+        g = gpu.Grid(*dims)
+        got = np.empty(dims[::-1], np.uint8)
+        for seed in range(1, 41):
+            want = oracle.ca3d_make(*dims, seed)
+            pop = g.make3d(Rand48(seed))
+            g.download(got)
+            assert np.array_equal(got, want), (dims, seed)
+            assert pop == int((want != 0).sum())
+            flips += int((want[1:-1, 1:-1, 1:-1] == 255).sum())
+        g.close()
+    assert flips > 100
+
+
 def test_ca3d_zero_steps_and_population(gpu):
     rng = np.random.default_rng(13)
     vol = synth(rng, (8, 9, 10))
