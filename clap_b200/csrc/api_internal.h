@@ -55,6 +55,7 @@ struct Ctx {
     size_t smooth_bytes = 0;
     /* grow-only device staging of the one-shot field calls (cudaMalloc / cudaFree of GBs per call costs more than the kernels) */
     void *scratch[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    void *oneshot_grid = nullptr;   /* the grid of the last one-shot call (clapca_ca3d_run & co.), kept for the next one of the same shape */
     uint32_t *d_zeros = nullptr;    /* 1 KiB of zeros: the H row of a plane outside the volume (Bp3Params::zeros) */
     size_t scratch_bytes[5] = { 0, 0, 0, 0, 0 };
 };

@@ -220,6 +220,7 @@ void clapca_shutdown(void)
     if (g_ctx.d_count) cudaFree(g_ctx.d_count);
     if (g_ctx.d_max) cudaFree(g_ctx.d_max);
     if (g_ctx.d_zeros) cudaFree(g_ctx.d_zeros);
+    if (g_ctx.oneshot_grid) clapca_grid_destroy((clapca_grid *)g_ctx.oneshot_grid);
     if (g_ctx.d_smooth) cudaFree(g_ctx.d_smooth);
     for (int i = 0; i < 5; i++)
         if (g_ctx.scratch[i]) cudaFree(g_ctx.scratch[i]);
@@ -287,6 +288,37 @@ int clapca_grid_destroy(clapca_grid *g)
         if (g->ev[i]) cudaEventDestroy(g->ev[i]);
     delete g;
     return CLAPCA_OK;
+}
+
+/*
+ * One-shot calls (host array in, host array out) run on a grid of their own.  Creating and destroying it costs several
+ * cudaMalloc / cudaFree per call -- tens of milliseconds once the context has seen large allocations, more than the
+ * 16384^2 x 100 run it serves (measured: 17 .. 107 ms for clapca_ca2d_generate from run to run) -- and a caller that
+ * steps a grid in a loop (the reference's instantiator placement: ca2d_step per generation) pays it every time.  The
+ * grid of the last one-shot call is therefore kept for the next one of the same shape, up to 1 GiB of cells.
+ */
+static int oneshot_acquire(clapca_grid **out, int64_t d0, int64_t d1, int64_t d2)
+{
+    clapca_grid *c = (clapca_grid *)g_ctx.oneshot_grid;
+    if (c && c->d0 == d0 && c->d1 == d1 && c->d2 == d2) {
+        g_ctx.oneshot_grid = nullptr;
+        *out = c;
+        return CLAPCA_OK;
+    }
+    return clapca_grid_create(out, d0, d1, d2);
+}
+
+static void oneshot_release(clapca_grid *g)
+{
+    if (!g)
+        return;
+    if (g->n > ((size_t)1 << 30)) {
+        clapca_grid_destroy(g);
+        return;
+    }
+    if (g_ctx.oneshot_grid)
+        clapca_grid_destroy((clapca_grid *)g_ctx.oneshot_grid);
+    g_ctx.oneshot_grid = g;
 }
 
 int clapca_grid_upload(clapca_grid *g, const uint8_t *host)
@@ -1021,12 +1053,12 @@ int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3], uint32_t surv, uint32_t 
     if (int rc = need_init()) return rc;
     if (!arr || !dim) return fail(CLAPCA_ERR_ARG, "ca3d_run: NULL argument");
     clapca_grid *g = nullptr;
-    int rc = clapca_grid_create(&g, dim[0], dim[1], dim[2]);
+    int rc = oneshot_acquire(&g, dim[0], dim[1], dim[2]);
     if (rc) return rc;
     rc = clapca_grid_upload(g, arr);
     if (!rc) rc = clapca_grid_run3d(g, surv, born, nr_states, steps, engine, population);
     if (!rc && steps > 0) rc = clapca_grid_download(g, arr);
-    clapca_grid_destroy(g);
+    oneshot_release(g);
     return rc;
 }
 
@@ -1209,12 +1241,12 @@ int clapca_ca2d_run(uint8_t *arr, int64_t w, int64_t h, int64_t side, uint32_t b
     if (int rc = need_init()) return rc;
     if (!arr) return fail(CLAPCA_ERR_ARG, "ca2d_run: NULL array");
     clapca_grid *g = nullptr;
-    int rc = clapca_grid_create(&g, w, h, 1);
+    int rc = oneshot_acquire(&g, w, h, 1);
     if (rc) return rc;
     rc = clapca_grid_upload(g, arr);
     if (!rc) rc = clapca_grid_run2d(g, side, born, surv, nr_states, decay, neigh, steps, engine);
     if (!rc && steps > 0) rc = clapca_grid_download(g, arr);
-    clapca_grid_destroy(g);
+    oneshot_release(g);
     return rc;
 }
 
@@ -1350,12 +1382,12 @@ int clapca_ca2d_generate(uint8_t *arr, int64_t side, uint32_t born, uint32_t sur
     if (int rc = need_init()) return rc;
     if (!arr || side < 1) return fail(CLAPCA_ERR_ARG, "ca2d_generate: bad arguments");
     clapca_grid *g = nullptr;
-    int rc = clapca_grid_create(&g, side, side, 1);
+    int rc = oneshot_acquire(&g, side, side, 1);
     if (rc) return rc;
     rc = clapca_grid_seed2d(g, side, nr_states, rand48_state, rand48_state_after);
     if (!rc && steps > 0) rc = clapca_grid_run2d(g, side, born, surv, nr_states, decay, neigh, steps, engine);
     if (!rc) rc = clapca_grid_download(g, arr);
-    clapca_grid_destroy(g);
+    oneshot_release(g);
     return rc;
 }
 
