@@ -61,6 +61,12 @@ int clapca_device_count(void);
 /*
  * Bind this process to `device` (one process per GPU), create the streams and
  * scratch the engines need.  Idempotent for the same device.
+ *
+ * Threading: the context (its stream, its population / maximum accumulators, its grow-only scratch buffers and the
+ * grid it keeps for one-shot calls) is ONE per process and not locked -- call the grid, field and one-shot entry points
+ * from one thread at a time, and do not re-initialise for another device while grids exist.  Slabs are the exception:
+ * each owns its stream and accumulators, and clapca_slab_prepare / run / run_streamed of DIFFERENT slabs may run on
+ * different threads (several ranks of one process, see clapca_slab_connect_local).  Only the error text is per thread.
  */
 int clapca_init(int device);
 void clapca_shutdown(void);
