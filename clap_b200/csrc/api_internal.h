@@ -91,7 +91,7 @@ struct OrderCfg {
              + (mode == 3 ? (tile_skew % 4000) * 500000 : 0);
     }
 };
-int team_config(int P, int WPL);
+int team_config(int P, int WPL, bool single_gpu = false);
 /* wanted generations per tile for a team of `team` compute warps (CLAPCA_TILE_GENS overrides) */
 int tile_gens_config(int team);
 void sweep_knobs(Bp3Params &p, int team, bool single_gpu = false);

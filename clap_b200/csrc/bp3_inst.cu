@@ -43,6 +43,14 @@ template <int P, int WPL>
 static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, Bp3LaunchInfo *info)
 {
     auto kern = p.team > 0 ? ca3d_team_kernel<P, WPL, TheRule> : ca3d_sweep_kernel<P, WPL, TheRule>;
+    int team_cap = bp3_team_cap(P, WPL);
+    if constexpr (P == 3 && WPL <= 2) {
+        /* teams beyond the default kernel's launch bound: the 96-register build (bp3_team_cap_wide) */
+        if (p.team > team_cap) {
+            kern = ca3d_team_wide_kernel<P, WPL, TheRule>;
+            team_cap = bp3_team_cap_wide(P, WPL);
+        }
+    }
     /* small CTAs: co-residency is bounded by registers, 128-thread granularity wastes the least of the file */
     int threads = 128, wpc = 4;             /* threads and WORKER warps per CTA */
     if (const char *e = getenv("CLAPCA_CTA_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) threads = v; }
@@ -54,7 +62,7 @@ static cudaError_t launch_one(const Bp3Params &p, int sms, cudaStream_t stream, 
     }
     if (p.team > 0) {
         /* tile mode: one CTA = `team` compute warps sweeping a tile + the service warp; an item occupies a whole CTA */
-        wpc = std::min(p.team, bp3_team_cap(P, WPL));
+        wpc = std::min(p.team, team_cap);
         threads = 32 * (wpc + 1);
     }
     int per_sm = 0;

@@ -1244,6 +1244,21 @@ inline int bp3_team_cap(int P, int WPL)
     return (P <= 4 && WPL <= 2) ? CLAPCA_TEAM_WARPS : 7;
 }
 
+/*
+ * The wide build of the tile kernel: 18 compute warps + the service warp = 19 warps, 5 on three of the four
+ * sub-partitions, which caps a thread at 96 registers (ptxas: 4 bytes of spill in the 3-plane variants).  More warps
+ * hide more of the fixed-latency stalls of an ALU-bound loop: 6 x 3 tiles sweep 2048^3 x 50 in 89.3 ms against 91.8 ms
+ * for 5 x 3 tiles at 116 registers -- but the 96-register code is slower per warp, and where the z chain bounds the run
+ * (a rank of a sharded volume; the 6-generation stand-in: 13.97 vs 13.2 ms) the 15-warp kernel wins.  So: single-GPU
+ * runs of the 3-plane variants take the wide kernel, everything else the default one
+ * (profiles/r02_knobs_18_compute_warps_96_regs.txt).
+ */
+enum { BP3_WIDE_TEAM = 18 };
+inline int bp3_team_cap_wide(int P, int WPL)
+{
+    return (P == 3 && WPL <= 2) ? (int)BP3_WIDE_TEAM : 0;
+}
+
 template <int P, int WPL, class Rule>
 CA_GLOBAL void __launch_bounds__(Bp3Bounds<P, WPL>::kMaxThreads, 1) ca3d_sweep_kernel(Bp3Params p)
 {
@@ -1252,6 +1267,12 @@ CA_GLOBAL void __launch_bounds__(Bp3Bounds<P, WPL>::kMaxThreads, 1) ca3d_sweep_k
 
 template <int P, int WPL, class Rule>
 CA_GLOBAL void __launch_bounds__(Bp3TeamBounds<P, WPL>::kMaxThreads, 1) ca3d_team_kernel(Bp3Params p)
+{
+    Sweep3<P, WPL, Rule>::tile_loop(p);
+}
+
+template <int P, int WPL, class Rule>
+CA_GLOBAL void __launch_bounds__(32 * (BP3_WIDE_TEAM + 1), 1) ca3d_team_wide_kernel(Bp3Params p)
 {
     Sweep3<P, WPL, Rule>::tile_loop(p);
 }

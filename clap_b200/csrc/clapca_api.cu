@@ -503,12 +503,19 @@ static const int kFlagRows = 8;
  * (profiles/r01_team_mode_lowpar.txt): 50 generations 123.3 -> 121.0 ms against one warp per sweep, and 35.2 -> 16.4 ms
  * in the low-parallelism regime a rank of an 8-GPU run sees.
  */
-int clapca::api::team_config(int P, int WPL)
+int clapca::api::team_config(int P, int WPL, bool single_gpu)
 {
-    int t = bp3_team_cap(P, WPL) >= 12 ? bp3_team_cap(P, WPL) : 0;
-    if (const char *e = getenv("CLAPCA_TEAM")) t = atoi(e);
+    int cap = bp3_team_cap(P, WPL);
+    int t = cap >= 12 ? cap : 0;
+    /* single-GPU runs of the 3-plane variants: the wide (19-warp, 96-register) kernel -- see bp3_team_cap_wide() */
+    if (single_gpu && bp3_team_cap_wide(P, WPL) > cap)
+        t = cap = bp3_team_cap_wide(P, WPL);
+    if (const char *e = getenv("CLAPCA_TEAM")) {
+        t = atoi(e);
+        cap = std::max(cap, bp3_team_cap_wide(P, WPL));
+    }
     if (t <= 0) return 0;
-    return std::min(t, bp3_team_cap(P, WPL));
+    return std::min(t, cap);
 }
 
 /*
@@ -765,7 +772,7 @@ static int run3d_bitplane(clapca_grid *g, uint32_t surv, uint32_t born, uint32_t
         g->rows = (uint32_t *)p;
     }
 
-    int team = team_config(P, WPL);
+    int team = team_config(P, WPL, io == nullptr);
     /* CLAPCA_STREAM_TEAM: team size of streamed runs only (the output lags the input by (team + 1) planes per generation) */
     if (io)
         if (const char *e = getenv("CLAPCA_STREAM_TEAM")) team = std::max(0, std::min(atoi(e), bp3_team_cap(P, WPL)));
