@@ -262,7 +262,9 @@ static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     const int bank = (int)(s->epoch & 1u);
 
     /* multi-GPU runs are always tiled: the service warp of a tile carries the halo rows (every variant has a team size) */
-    int team = team_config(s->P, s->WPL);
+    /* the wide kernel where it exists (3-plane variants): it wins at 2, 4 and 8 GPUs as well, with z-blocks that are a
+       multiple of its 6-plane tiles (profiles/r02_knobs_multi_wide_n{2,4,8}.txt) */
+    int team = team_config(s->P, s->WPL, true);
     if (team <= 0) team = bp3_team_cap(s->P, s->WPL);
     Bp3Params knobs;
     memset(&knobs, 0, sizeof(knobs));

@@ -23,35 +23,36 @@ from .rules import CellAutomaton, ca3d_rule
 DEFAULT_BLOCK_PLANES = 16
 
 
-TILE_PLANES = 5     # planes per tile of the default kernel variant (15 compute warps = 5 planes x 3 generations)
+TILE_PLANES = 6     # planes per tile of the kernel sharded 3-plane volumes run (18 compute warps = 6 planes x 3 generations)
 
 
-def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=40):
+def default_block_planes(d2, nranks, tile_planes=TILE_PLANES, largest=48):
     """z-block size of the scaling bench: a multiple of the tile height (a ragged tile leaves most of a CTA idle), the
-    largest one up to `largest` planes that still gives every rank about six blocks and keeps the most loaded rank
-    within 10 % of its fair share.  Measured at 2048^3 x 50 (profiles/r02_knobs_multi_n2.txt, r02_knobs_multi_n8*.txt):
-    2 GPUs, blocks of 15 / 30 / 60 / 120 planes: sweep 60.3 / 57.3 / 56.7 / 71.0 ms; 8 GPUs, blocks of 20 / 30 / 40 / 45 /
-    50 planes: 20.3 / 19.8 / 18.6 / 18.9 / 19.9 ms; 4 GPUs, 30 / 40 / 60 planes: 34.5 / 32.3 / 33.8 ms -- z-block edges cost more than a few percent of imbalance (every edge
-    adds the NVLink hop to the wave that carries generation 0 up the volume), and blocks that are too large leave the
-    last ranks waiting for that wave (rank r starts ~3.7 r B row steps after rank 0)."""
+    largest one up to `largest` planes that still gives every rank five blocks and keeps the most loaded rank within
+    15 % of its fair share.  Measured at 2048^3 x 50 with the final kernels (profiles/r02_knobs_multi_wide_n{2,4,8}.txt):
+    8 GPUs, blocks of 24 / 30 / 36 / 42 / 48 planes: sweep 18.2 / 17.8 / 17.6 / 17.2 / 16.9 ms; 4 GPUs, 36 / 42 / 48:
+    30.5 / 29.6 / 28.2 ms; 2 GPUs, 42 / 60: 49.6 / 49.0 ms -- z-block edges cost more than a few percent of imbalance
+    (every edge adds the NVLink hop to the wave that carries a generation up the volume), and blocks that are too large
+    leave the last ranks waiting for that wave (with the 15-warp kernel of earlier in the round: 50 planes 19.9 ms
+    against 18.6 ms for 40)."""
     d2, nranks = int(d2), max(1, int(nranks))
     if nranks == 1:
         return d2
     per_rank = -(-d2 // nranks)
-    top = max(tile_planes, min(largest, per_rank // 6 if per_rank >= 6 * tile_planes else per_rank // 2))
-    cands = {}
+    fair = d2 / nranks
+    best = None
     b = tile_planes
-    while b <= top:
+    while b <= min(largest, per_rank):
         loads = [0] * nranks
         for j, z0 in enumerate(range(0, d2, b)):
             loads[j % nranks] += min(b, d2 - z0)
-        cands[b] = max(loads)
+        if per_rank >= 5 * b and max(loads) <= 1.15 * fair:
+            best = b
         b += tile_planes
-    if not cands:
-        return max(1, min(per_rank, d2))
-    fair = d2 / nranks
-    ok = [b for b, load in cands.items() if load <= 1.10 * fair]
-    best = max(ok) if ok else min(cands, key=lambda k: (cands[k], -k))
+    if best is None:
+        # small volumes: the largest whole-tile block that still gives every rank two blocks, else one block per rank
+        b = (per_rank // 2) // tile_planes * tile_planes
+        best = b if b >= tile_planes else max(1, min(per_rank, d2))
     return max(1, min(best, d2))
 
 
