@@ -1248,10 +1248,9 @@ inline int bp3_team_cap(int P, int WPL)
  * The wide build of the tile kernel: 18 compute warps + the service warp = 19 warps, 5 on three of the four
  * sub-partitions, which caps a thread at 96 registers (ptxas: 4 bytes of spill in the 3-plane variants).  More warps
  * hide more of the fixed-latency stalls of an ALU-bound loop: 6 x 3 tiles sweep 2048^3 x 50 in 89.3 ms against 91.8 ms
- * for 5 x 3 tiles at 116 registers -- but the 96-register code is slower per warp, and where the z chain bounds the run
- * (a rank of a sharded volume; the 6-generation stand-in: 13.97 vs 13.2 ms) the 15-warp kernel wins.  So: single-GPU
- * runs of the 3-plane variants take the wide kernel, everything else the default one
- * (profiles/r02_knobs_18_compute_warps_96_regs.txt).
+ * for 5 x 3 tiles at 116 registers, and sharded volumes gain as well (N = 2 / 4 / 8: 53.6 -> 49.0, 31.2 -> 28.2,
+ * 17.8 -> 16.9 ms with z-blocks of 48 planes).  The 3-plane variants take the wide kernel, everything else the default
+ * one (profiles/r02_knobs_18_compute_warps_96_regs.txt, r02_knobs_multi_wide_n{2,4,8}.txt).
  */
 enum { BP3_WIDE_TEAM = 18 };
 inline int bp3_team_cap_wide(int P, int WPL)
