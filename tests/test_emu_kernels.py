@@ -153,6 +153,9 @@ def test_ca3d_plane_teams(emu_bin, args):
     (45, 50, 13, 5, 3, 3, 1, 1, 3, 64, 3, 5, 0, 4, 0, 0, 4, 2),          # 3 ranks, blocks of 5 = tiles of 2 + 2 + 1 planes
     (33, 30, 16, 5, 10, 8, 1, 1, 4, 64, 4, 1, 0, 2, 0, 0, 4, 2),         # 4 ranks, single-plane blocks: 1-plane tiles, 2 generations each
     (33, 30, 16, 9, 7, 3, 1, 1, 4, 256, 4, 4, 0, 2, 0, 0, 16, 4),        # 4 ranks, 4 x 4 tiles = one z-block each
+    (45, 20, 14, 7, 7, 3, 1, 1, 3, 360, 1, 0, 0, 2, 0, 0, 18, 3),        # the wide kernel's 6 x 3 tiles, ragged in z and g
+    (2048, 4, 7, 4, 7, 3, 2, 0, 9, 72, 1, 0, 0, 2, 0, 0, 18, 3),         # ... at the BASELINE config-4 row width
+    (33, 30, 18, 7, 7, 3, 1, 1, 4, 360, 2, 6, 0, 2, 0, 0, 18, 3),        # ... 2 ranks, z-blocks of one tile
     (33, 5, 9, 6, 8, 8, 1, 2, 3, 60, 2, 4, 0, 2, 0, 0, 4, 2),            # ca3d_make seed (255s), 2 ranks
     (2048, 6, 8, 4, 7, 3, 2, 0, 9, 64, 2, 4, 0, 2, 0, 0, 16, 4),         # BASELINE config-4 row width, 2 ranks
 ])
