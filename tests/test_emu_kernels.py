@@ -22,6 +22,13 @@ def _run(exe, *args, env=None):
     assert r.stdout.startswith("OK")
 
 
+def test_bitslice_building_blocks(emu_bin):
+    """adders, the 3D count tree (both forms), compile-time / run-time rule tables of all nine cas[] rules, and the
+    in-row scan (D form, E form, split into its common and rare part) against plain integer arithmetic, cell by cell"""
+    r = subprocess.run([os.path.join(emu_bin, "emu_bitslice")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("nca", range(11))
 def test_ca3d_every_rule(emu_bin, nca):
     exe = os.path.join(emu_bin, "emu_ca3d")
