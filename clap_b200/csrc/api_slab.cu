@@ -273,7 +273,10 @@ static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
     OrderCfg oc = order_config(s->geo.Zg, s->H, steps, bp3_max_workers(s->rule, s->P, s->WPL, g_ctx.sms, team, max_ctas), team);
     /* sharded volumes keep generation group b + 1 right behind group b: the z pipeline across the ranks needs the
        other groups to fill its bubbles (CLAPCA_SLAB_TILE_SKEW for experiments; every rank must use the same value) */
-    oc.tile_skew = 0;
+    /* ... but not glued together either: four tiles between consecutive groups of a plane group (tz + 1 = all groups
+       interleaved: N = 4 / 8 sweep 28.2 / 16.9 ms; 24 planes: 26.2 / 16.4 ms; 48: 16.5; 100: 27.7 ms at N = 4;
+       profiles/r02_knobs_multi_slab_skew.txt) */
+    oc.tile_skew = 4 * std::max(1, team / std::max(1, oc.tile_g));
     if (const char *e = getenv("CLAPCA_SLAB_TILE_SKEW")) oc.tile_skew = std::max(0, atoi(e));
     /* every rank must settle on the same tile shape: decide it from all ranks' plane lists */
     oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z, streamed, oc.tile_skew);
