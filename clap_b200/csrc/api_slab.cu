@@ -277,6 +277,8 @@ static int slab_prepare(clapca_slab *s, uint32_t surv, uint32_t born, uint32_t n
        interleaved: N = 4 / 8 sweep 28.2 / 16.9 ms; 24 planes: 26.2 / 16.4 ms; 48: 16.5; 100: 27.7 ms at N = 4;
        profiles/r02_knobs_multi_slab_skew.txt) */
     oc.tile_skew = 4 * std::max(1, team / std::max(1, oc.tile_g));
+    if (streamed) oc.tile_skew = 0;     /* layout items: the output of a plane follows its input one group distance per
+                                           generation group behind -- keep the groups glued (the measured e2e setting) */
     if (const char *e = getenv("CLAPCA_SLAB_TILE_SKEW")) oc.tile_skew = std::max(0, atoi(e));
     /* every rank must settle on the same tile shape: decide it from all ranks' plane lists */
     oc.tile_g = bp3_tile_shape_all_ranks(s->geo, s->H, steps, team, oc.tile_g, oc.ctas, &oc.tile_z, streamed, oc.tile_skew);
