@@ -90,3 +90,14 @@ def test_default_block_planes_of_the_scaling_bench():
     assert default_block_planes(2048, 2) == 48
     assert default_block_planes(2048, 4) == 48         # measured: 28.2 ms against 29.6 (42) and 30.5 (36)
     assert default_block_planes(2048, 8) == 48         # the measured optimum (profiles/r02_knobs_multi_wide_n8.txt)
+
+
+def test_numa_binding_is_advisory_without_a_gpu():
+    """bind_to_gpu_numa_node() must never fail a run: without NVML / a device it changes nothing and returns None"""
+    from clap_b200.slab import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu_numa_node(0)
+    assert got is None or got <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
