@@ -323,7 +323,7 @@ def run_ca3d(args, torch, clap_b200, dev, local, workload, headline=True):
     ms_per_step = tot_ms / nsteps
     value = updates / (ms_per_step * 1e-3) / 1e9
     kernel_ms = ker_ms / nsteps
-    roof = roofline(workload, "ca3d_team_kernel (tiles of planes x generations, all generations fused)", kernel_ms,
+    roof = roofline(workload, "ca3d_team_wide_kernel (ca3d_team_kernel for 4- and 8-plane volumes): tiles of planes x generations, all generations fused", kernel_ms,
                     updates, 2.0)
 
     e2e = None
@@ -484,7 +484,7 @@ def run_ca3d_sharded(args, torch, dist, dev, local, workload):
         updates = d0 * d1 * d2 * gens
         ms = tot / args.steps
         kms = ker / args.steps
-        roof = roofline(workload + "_n%d" % world, "ca3d_team_kernel (per GPU, tiles of planes x generations)", kms,
+        roof = roofline(workload + "_n%d" % world, "ca3d_team_wide_kernel (per GPU; ca3d_team_kernel for 4- and 8-plane volumes): tiles of planes x generations", kms,
                         updates / world, 2.0)
         nblocks = -(-d2 // block)
         line = {
