@@ -262,3 +262,21 @@ def test_blue_noise_port_against_numpy_fft():
     assert np.all(got[:, :, 3] == 1.0)
     assert np.abs(got[:, :, :3] - want).max() < 2e-5
     assert got[:, :, :3].min() == 0.0 and got[:, :, :3].max() == 1.0
+
+
+def test_ca3d_make_small_volumes_against_the_reference_fingerprints(oracle):
+    """ca3d_make() on 240 small volumes, where ca3d_prune()'s order-dependent corner is common (an empty cell with six
+    occupied neighbours turns 255 and counts for the cells after it): the port must reproduce the fingerprints the
+    UNMODIFIED reference produced (tests/golden/make_golden_ca3d_make.py), and the reference itself, where it is built."""
+    import json
+    with open(os.path.join(G, "ca3d_make_small.json")) as f:
+        g = json.load(f)
+    assert g["cells_255_inside"] > 100
+    ref = oracle_lib.ref()
+    for d0, d1, d2 in g["shapes"]:
+        want = g["fnv1a64"]["%dx%dx%d" % (d0, d1, d2)]
+        for seed, h in zip(g["seeds"], want):
+            vol = oracle.ca3d_make(d0, d1, d2, seed)
+            assert "%016x" % oracle.fnv(vol) == h, (d0, d1, d2, seed)
+            if ref is not None and seed % 8 == 0:
+                assert np.array_equal(ref.ca3d_make(d0, d1, d2, seed), vol)
