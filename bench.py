@@ -566,8 +566,14 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
     ms_per_step = tot_ms / nsteps
     kernel_ms = ker_ms / nsteps
     bytes_per_update = 0.25 if st["planes"] == 1 else 2.0
-    roof = roofline(workload, "ca2d_sweep_kernel (all generations fused)", kernel_ms, updates, bytes_per_update,
-                    note="dependency-latency bound: the in-place sweep order leaves a chain of side + 2*generations row steps")
+    if st["engine"] == "diagonal":
+        kname = "ca2d_skew_kernel (rows = diagonals 2x + y, all generations fused)"
+        note = ("issue-bound chain of 3*side + 36*generations diagonal steps (no in-row dependency, no CTA barrier); "
+                "one CTA per generation")
+    else:
+        kname = "ca2d_sweep_kernel (all generations fused)"
+        note = "dependency-latency bound: the in-place sweep order leaves a chain of side + 2*generations row steps"
+    roof = roofline(workload, kname, kernel_ms, updates, bytes_per_update, note=note)
     lib = _lib_mod.lib()
     e2e = None
     if not args.no_e2e:

@@ -17,8 +17,9 @@ HOST_LIB = os.path.join(LIB_DIR, "libclapca_host.so")
 
 OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_TIMEOUT, ERR_UNSUPPORTED, ERR_STATE = range(7)
 NEIGH_VN1, NEIGH_M1, NEIGH_VNV, NEIGH_MV = range(4)
-ENGINE_AUTO, ENGINE_WAVEFRONT, ENGINE_BITPLANE = range(3)
-ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_WAVEFRONT: "wavefront", ENGINE_BITPLANE: "bitplane"}
+ENGINE_AUTO, ENGINE_WAVEFRONT, ENGINE_BITPLANE, ENGINE_DIAGONAL = range(4)
+ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_WAVEFRONT: "wavefront", ENGINE_BITPLANE: "bitplane",
+                ENGINE_DIAGONAL: "diagonal"}
 
 
 class ClapcaError(RuntimeError):

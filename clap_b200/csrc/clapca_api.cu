@@ -9,7 +9,9 @@
 #include <unordered_set>
 #include "api_internal.h"
 #include "bp2_launch.h"
+#include "sk2_launch.h"
 #include "ca2d_layout.cuh"
+#include "ca2d_skew_layout.cuh"
 #include "ca3d_layout.cuh"
 #include "ca_wavefront.cuh"
 
@@ -111,6 +113,15 @@ cudaError_t bp2_launch(int P, int WPL, bool moore, int warps, const Bp2Params &p
     case BP2_RULE_CAVE: return bp2_launch_rule1(P, WPL, moore, warps, p, sms, stream, info);
     case BP2_RULE_TEST: return bp2_launch_rule2(P, WPL, moore, warps, p, sms, stream, info);
     default: return bp2_launch_rule0(P, WPL, moore, warps, p, sms, stream, info);
+    }
+}
+cudaError_t sk2_launch(int WPL, bool moore, int warps, const Sk2Params &p, int sms, cudaStream_t stream,
+                       Bp2LaunchInfo *info)
+{
+    switch (bp2_rule_for(p.born, p.surv, p.nrval)) {
+    case BP2_RULE_CAVE: return sk2_launch_rule1(WPL, moore, warps, p, sms, stream, info);
+    case BP2_RULE_TEST: return sk2_launch_rule2(WPL, moore, warps, p, sms, stream, info);
+    default: return sk2_launch_rule0(WPL, moore, warps, p, sms, stream, info);
     }
 }
 int bp3_max_workers(int rule, int P, int WPL, int sms, int team, int max_ctas)
@@ -1071,15 +1082,28 @@ int clapca_ca3d_run(uint8_t *arr, const int64_t dim[3], uint32_t surv, uint32_t 
 
 /* ---- ca2d ------------------------------------------------------------------- */
 
-/* rows are cut into at most 16 warps x 32 lanes x 4 words: 65536 cells (32768 with 8 state planes) */
-static bool bp2_supported(const clapca_grid *g, int64_t side, int decay, int neigh, int P)
+/* the bit engines count alive bits and sweep the whole grid */
+static bool alive_bit_full_sweep(const clapca_grid *g, int64_t side, int decay, int neigh)
 {
     if (side < g->d0 || side < g->d1)
         return false;                       /* partial sweeps: cell-wavefront engine */
     if ((neigh == CLAPCA_NEIGH_VNV || neigh == CLAPCA_NEIGH_MV) && decay)
         return false;                       /* value-comparing counts that matter: cell-wavefront engine */
+    return true;
+}
+
+/* rows are cut into at most 16 warps x 32 lanes x 4 words: 65536 cells (32768 with 8 state planes) */
+static bool bp2_supported(const clapca_grid *g, int64_t side, int decay, int neigh, int P)
+{
     int wpl, warps;
-    return g->d0 < (1 << 30) && bp2_shape_for(g->d1, P, &wpl, &warps);
+    return alive_bit_full_sweep(g, side, decay, neigh) && g->d0 < (1 << 30) && bp2_shape_for(g->d1, P, &wpl, &warps);
+}
+
+/* the diagonal engine: one state plane, at most 16384 columns (cells per diagonal), any number of rows an int holds */
+static bool sk2_supported(const clapca_grid *g, int64_t side, int decay, int neigh, int P)
+{
+    int wpl, warps;
+    return P == 1 && alive_bit_full_sweep(g, side, decay, neigh) && sk2_shape_for(g->d0, &wpl, &warps) && g->d1 <= (1LL << 28);
 }
 
 /* largest cell value of the grid (device reduction) */
@@ -1089,6 +1113,102 @@ static int grid_max_value(clapca_grid *g, unsigned *maxv)
     CU(launch_max_u8(g->cells, g->n, g_ctx.d_max, g->stream));
     CU(cudaMemcpyAsync(maxv, g_ctx.d_max, sizeof(*maxv), cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
+    return CLAPCA_OK;
+}
+
+/*
+ * One-plane grids on the diagonal engine (ca2d_skew.cuh): no in-row chain, no CTA barrier in the sweep.  Measured
+ * against the row engine on B200 (profiles/r02_ca2d_skew.txt); CLAPCA_2D_SKEW=0 / 1 forces the row / diagonal engine
+ * wherever both apply.
+ */
+static const long long kSkewMinCells = 1LL << 22;
+static bool sk2_preferred(const clapca_grid *g)
+{
+    if (const char *e = getenv("CLAPCA_2D_SKEW"))
+        return atoi(e) != 0;
+    return g->d0 * g->d1 >= kSkewMinCells;
+}
+
+static int run2d_skew(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh, int steps)
+{
+    const int W = (int)g->d0, H = (int)g->d1;
+    const uint32_t nrval = nr_states & 0xffu;
+    const bool moore = (neigh == CLAPCA_NEIGH_M1 || neigh == CLAPCA_NEIGH_MV);
+    int WPL = 0, warps = 0;
+    if (!sk2_shape_for(W, &WPL, &warps))
+        return fail(CLAPCA_ERR_UNSUPPORTED, "2D diagonal engine: %d cells per diagonal are too many", W);
+    if (const char *e = getenv("CLAPCA_2D_SKEW_WPL")) {     /* tuning: words per lane */
+        const int v = atoi(e);
+        if ((v == 1 || v == 2) && sk2_warps_for(W, v) * v <= SK2_MAX_WARPS) { WPL = v; warps = sk2_warps_for(W, v); }
+    }
+    const int T = sk2_diagonals(W, H), TR = sk2_rows_alloc(W, H);
+    const size_t rows_bytes = (size_t)TR * SK2_RS * sizeof(uint32_t);
+    {
+        void *p = g->rows;
+        if (int rc = ensure_bytes(&p, &g->rows_bytes, rows_bytes)) { g->rows = nullptr; return rc; }
+        g->rows = (uint32_t *)p;
+    }
+    unsigned long long *d_pop = g_ctx.d_count;
+    Sk2Layout L = { g->cells, g->rows, W, H, d_pop };
+    const size_t cols = (size_t)(W + 31) / 32;
+    const size_t pack_tiles = cols * ((T + SK2_TILE_T - 1) / SK2_TILE_T), unpack_tiles = cols * ((H + SK2_TILE_T - 1) / SK2_TILE_T);
+
+    CU(cudaEventRecord(g->ev[0], g->stream));
+    CU(cudaMemsetAsync(g->rows, 0, rows_bytes, g->stream));         /* everything outside the band of cells stays zero */
+    ca2d_skew_pack_kernel<<<grid_blocks_for(pack_tiles * 256, 256, 8), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[1], g->stream));
+
+    int launches = 0, ctas = 0;
+    for (int done = 0; done < steps;) {
+        const int G = std::min(steps - done, 1 << 20);
+        {
+            size_t have = g->prog_count * sizeof(int);
+            void *p = g->prog;
+            if (int rc = ensure_bytes(&p, &have, (size_t)G * sizeof(int))) { g->prog = nullptr; return rc; }
+            g->prog = (int *)p;
+            g->prog_count = have / sizeof(int);
+            g->planes_prog = nullptr;       /* the 3D plane descriptors cached on this grid are stale now */
+        }
+        CU(cudaMemsetAsync(g->prog, 0, (size_t)G * sizeof(int), g->stream));
+        CU(cudaMemsetAsync(g->ticket, 0, kTicketWords * sizeof(unsigned), g->stream));
+        Sk2Params p;
+        memset(&p, 0, sizeof(p));
+        p.rows = g->rows;
+        p.W = W; p.H = H; p.G = G; p.T = T;
+        p.prog = g->prog;
+        p.ticket = g->ticket;
+        p.err = (int *)(g->ticket + 1);
+        p.born = born & 0x1ffu;
+        /* a cell that neither survives nor decays keeps its value: same as surviving (core/ca2d.c:72-75) */
+        p.surv = decay ? (surv & 0x1ffu) : 0x1ffu;
+        p.nrval = nrval;
+        p.spin_limit = 4000000000LL;
+        Bp2LaunchInfo info;
+        CU(sk2_launch(WPL, moore, warps, p, g_ctx.sms, g->stream, &info));
+        launches++;
+        ctas = info.blocks;
+        done += G;
+    }
+    CU(cudaEventRecord(g->ev[2], g->stream));
+    CU(cudaMemsetAsync(d_pop, 0, sizeof(unsigned long long), g->stream));
+    ca2d_skew_unpack_kernel<<<grid_blocks_for(unpack_tiles * 256, 256, 8), 256, 0, g->stream>>>(L);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ev[3], g->stream));
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, g->ticket + 1, sizeof(err), cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (err)
+        return fail(CLAPCA_ERR_TIMEOUT, "ca2d diagonal engine: dataflow watchdog fired (err=%d)", err);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g->ev[0], g->ev[3]));
+    g->stats.total_ms = ms;
+    CU(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]));
+    g->stats.kernel_ms = ms;
+    g->stats.launches = launches + 2;
+    g->stats.engine = CLAPCA_ENGINE_DIAGONAL;
+    g->stats.planes = 1;
+    g->stats.workers = ctas * warps;
     return CLAPCA_OK;
 }
 
@@ -1205,12 +1325,21 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv
         P = bp2_planes_for(maxv);
     }
     const bool bp_ok = engine != CLAPCA_ENGINE_WAVEFRONT && bp2_supported(g, side, decay, neigh, P);
+    const bool sk_ok = engine != CLAPCA_ENGINE_WAVEFRONT && sk2_supported(g, side, decay, neigh, P);
     if (engine == CLAPCA_ENGINE_AUTO)
-        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
+        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : (sk_ok ? CLAPCA_ENGINE_DIAGONAL : CLAPCA_ENGINE_WAVEFRONT);
+    if (engine == CLAPCA_ENGINE_DIAGONAL) {
+        if (!sk_ok)
+            return fail(CLAPCA_ERR_UNSUPPORTED, "2D diagonal engine: needs a full sweep (side >= extent), cell values 0 / 1, at "
+                        "most 16384 columns and an alive-bit neighbourhood (vnv/mv only without decay)");
+        return run2d_skew(g, born, surv, nr_states, decay, neigh, steps);
+    }
     if (engine == CLAPCA_ENGINE_BITPLANE) {
         if (!bp_ok)
             return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: needs a full sweep (side >= extent), rows of at "
                         "most 65536 cells (32768 with values >= 16) and an alive-bit neighbourhood (vnv/mv only without decay)");
+        if (sk_ok && sk2_preferred(g))
+            return run2d_skew(g, born, surv, nr_states, decay, neigh, steps);
         return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps, P);
     }
     if (engine != CLAPCA_ENGINE_WAVEFRONT)

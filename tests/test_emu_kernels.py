@@ -271,3 +271,45 @@ def test_ca2d_rule_instantiations_agree(emu_bin, args):
 ])
 def test_ca2d_bitplane_rows_across_warps(emu_bin, args):
     _run(os.path.join(emu_bin, "emu_ca2d"), *args)
+
+
+# ---- 2D diagonal engine (ca2d_skew.cuh): rows = diagonals 2x + y, warps chained by mailboxes, no CTA barrier -----
+
+@pytest.mark.parametrize("args", [
+    #  W     H    G  born   surv  nr decay moore WPL seed ctas forcedyn density
+    (40, 70, 3, 0x1e0, 0x1f0, 1, 1, 1, 1, 1),                          # binary cave rule (alive bit folded into the count)
+    (40, 70, 5, 0x1e0, 0x1f0, 1, 1, 1, 2, 2),
+    (33, 100, 4, 0xc, 0x180, 1, 1, 1, 1, 3),                           # ca_test's masks on a binary grid
+    (20, 130, 6, 0x6, 0x1c, 1, 1, 0, 1, 4),                            # von Neumann
+    (1, 1, 3, 0x1, 0x0, 1, 1, 1, 1, 7),
+    (5, 1, 3, 0x3, 0x0, 1, 1, 1, 1, 7),
+    (1, 37, 3, 0x3, 0x2, 1, 1, 0, 1, 7),
+    (64, 257, 9, 0x8, 0xc, 1, 1, 1, 2, 8, 5, 0, 3),                    # Life, more generations than CTAs
+    (12, 40, 4, 0xc, 0x180, 256, 1, 1, 1, 8, 2),                       # nr_states wraps to 0: nothing is ever born
+    (96, 80, 4, 0x1e, 0xff, 1, 0, 1, 1, 5, 2, 0, 2),                   # no decay: survivors keep their value
+    (40, 70, 5, 0x1e0, 0x1f0, 1, 1, 1, 1, 2, 3, 1),                    # cave rule through the run-time tables
+    (33, 100, 4, 0xc, 0x180, 1, 1, 1, 2, 3, 2, 1),
+])
+def test_ca2d_diagonal_rules_and_shapes(emu_bin, args):
+    _run(os.path.join(emu_bin, "emu_ca2d_skew"), *args)
+
+
+@pytest.mark.parametrize("args", [
+    (2100, 5, 4, 0x1e0, 0x1f0, 1, 1, 1, 1, 2),                         # three warps, the band is narrower than a warp
+    (3000, 4, 3, 0x6, 0x1c, 1, 1, 0, 1, 3, 2),                         # von Neumann across warps
+    (2050, 7, 3, 0xc, 0x180, 1, 1, 1, 1, 4, 1),                        # a single CTA runs every generation in turn
+    (4200, 5, 2, 0x1e0, 0x1f0, 1, 1, 1, 2, 5, 2),
+    (1025, 9, 5, 0x1fe, 0x0, 1, 1, 1, 1, 9, 3),                        # one cell beyond a warp's span
+    (1500, 40, 4, 0xaa, 0x155, 1, 1, 1, 1, 9, 3, 0, 3),                # non-monotone rule
+    (2500, 3000, 2, 0x1e0, 0x1f0, 1, 1, 1, 1, 9, 2, 0, 4),             # groups without masks (H > 2048), posts over a long window
+    (3333, 2222, 7, 0x1e0, 0x1f0, 1, 0, 1, 1, 5, 3),
+    (5000, 2600, 5, 0x1e0, 0x1f0, 1, 1, 1, 1, 6, 5, 0, 4),             # generations queue behind each other, 5 warps
+    (7000, 1500, 4, 0xc, 0x180, 1, 1, 1, 2, 4, 4, 1, 3),               # two words per lane, run-time tables
+    (16384, 100, 2, 0x1e0, 0x1f0, 1, 1, 1, 1, 11, 2),                  # BASELINE config 3's width: 16 warps x 1 word
+    (16384, 4200, 2, 0x1e0, 0x1f0, 1, 1, 1, 2, 12, 2, 0, 4),           # ... 8 warps x 2 words, steady groups
+])
+def test_ca2d_diagonal_across_warps(emu_bin, args):
+    """The chain of warps: bit 31 of a warp's last word reaches the next warp through the tagged mailbox ring, the
+    ring's back-pressure, warps that start and finish with the band of valid cells, the publisher's minimum over the
+    warps' step counters."""
+    _run(os.path.join(emu_bin, "emu_ca2d_skew"), *args)

@@ -11,7 +11,7 @@ import oracle_lib
 pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-WAVEFRONT, BITPLANE = 1, 2
+WAVEFRONT, BITPLANE, DIAGONAL = 1, 2, 3
 ENGINES = [pytest.param(WAVEFRONT, id="wavefront"), pytest.param(BITPLANE, id="bitplane")]
 
 
@@ -582,6 +582,111 @@ def test_ca2d_cfg3_full_width_strip_vs_oracle(gpu, oracle):
     assert np.array_equal(arr, want)
     assert arr.any() and not arr.all()
 
+# ---- the diagonal 2D engine (ca2d_skew.cuh): binary grids stored along 2x + y, no in-row chain ------------------
+
+DIAG_RULES = [
+    # born, surv, nr, decay, neigh
+    (0x1E0, 0x1F0, 1, 1, oracle_lib.NEIGH_M1),          # BASELINE config 3: cave smoothing (compile-time rule, folded count)
+    (0x00C, 0x180, 1, 1, oracle_lib.NEIGH_M1),          # ca_test's masks (compile-time rule, two tables per case)
+    (0x008, 0x00C, 1, 1, oracle_lib.NEIGH_M1),          # Life (run-time tables), not monotone
+    (0x006, 0x01C, 1, 1, oracle_lib.NEIGH_VN1),         # von Neumann
+    (0x01E, 0x0FF, 1, 0, oracle_lib.NEIGH_MV),          # mv without decay reduces to the alive-bit count
+    (0x00C, 0x180, 256, 1, oracle_lib.NEIGH_M1),        # nr_states wraps to 0: nothing is ever born
+]
+
+
+@pytest.mark.parametrize("wpl", ["1", "2"])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (31, 33), (100, 37), (257, 130), (1025, 40), (40, 1025),
+                                   (2100, 24), (24, 2100), (4097, 9), (9, 4097), (3000, 2500)])
+def test_ca2d_diagonal_vs_oracle_shapes(gpu, oracle, monkeypatch, shape, wpl):
+    """Every rule family on ragged shapes: diagonals shorter than a word, crossing lane and warp spans, warps that
+    join and leave with the band of valid cells, both words-per-lane builds."""
+    monkeypatch.setenv("CLAPCA_2D_SKEW_WPL", wpl)
+    rng = np.random.default_rng(shape[0] * 977 + shape[1])
+    for born, surv, nr, decay, neigh in DIAG_RULES:
+        arr = synth(rng, shape, 0.5, 1)
+        want = oracle.ca2d_run(arr.copy(), born, surv, nr, decay, neigh, 5, side=max(shape))
+        gpu.ca2d_step(_ca(gpu, born, surv, nr, decay, neigh), arr, side=max(shape), steps=5, engine=DIAGONAL)
+        assert np.array_equal(arr, want), (shape, born, surv, nr, neigh)
+
+
+def test_ca2d_diagonal_many_generations_more_than_resident_ctas(gpu, oracle):
+    rng = np.random.default_rng(5)
+    arr = synth(rng, (96, 80), 0.5, 1)
+    want = oracle.ca2d_run(arr.copy(), 0x8, 0xC, 1, 1, oracle_lib.NEIGH_M1, 700, side=96)      # Life: B3/S23
+    gpu.ca2d_step(_ca(gpu, 0x8, 0xC, 1, 1, oracle_lib.NEIGH_M1), arr, side=96, steps=700, engine=DIAGONAL)
+    assert np.array_equal(arr, want)
+    assert arr.any()
+
+
+def test_ca2d_diagonal_rejects_what_it_cannot_run(gpu):
+    ca = _ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1)
+    with pytest.raises(gpu.ClapcaError):          # partial sweep
+        gpu.ca2d_step(ca, np.ones((64, 64), np.uint8), side=40, steps=1, engine=DIAGONAL)
+    with pytest.raises(gpu.ClapcaError):          # more than one state plane
+        gpu.ca2d_step(gpu.CA_TEST, np.full((64, 64), 3, np.uint8), steps=1, engine=DIAGONAL)
+
+
+@pytest.mark.parametrize("wpl", ["1", "2"])
+def test_ca2d_diagonal_cfg3_full_width_strips_vs_oracle(gpu, oracle, monkeypatch, wpl):
+    """BASELINE config 3's geometry one dimension at a time, 100 generations of the binary cave rule against the
+    oracle: 16384 columns (every warp of the CTA, the whole mailbox chain) x 64 rows, and 64 columns x 16384 rows
+    (one warp, 16 k steady steps)."""
+    monkeypatch.setenv("CLAPCA_2D_SKEW_WPL", wpl)
+    for k, shape in enumerate([(16384, 64), (64, 16384)]):
+        rng = np.random.default_rng(70 + k)
+        arr = synth(rng, shape, 0.45, 1)
+        want = oracle.ca2d_run(arr.copy(), 0x1E0, 0x1F0, 1, 1, oracle_lib.NEIGH_M1, 100, side=16384)
+        gpu.ca2d_step(_ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1), arr, side=16384, steps=100, engine=DIAGONAL)
+        assert np.array_equal(arr, want), shape
+        assert arr.any() and not arr.all()
+
+
+def test_ca2d_engines_agree_4096(gpu):
+    """row engine == diagonal engine == cell wavefront on a 4096^2 binary grid, 40 generations (three different orders
+    of the same in-place sweep)"""
+    rng = np.random.default_rng(61)
+    arr = synth(rng, (4096, 4096), 0.47, 1)
+    ca = _ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1)
+    outs = []
+    for engine, env in ((DIAGONAL, None), (BITPLANE, "0"), (WAVEFRONT, None)):
+        a = arr.copy()
+        if env is not None:
+            os.environ["CLAPCA_2D_SKEW"] = env
+        try:
+            gpu.ca2d_step(ca, a, steps=40, engine=engine)
+        finally:
+            os.environ.pop("CLAPCA_2D_SKEW", None)
+        outs.append(a)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert outs[0].any() and not outs[0].all()
+
+
+@pytest.mark.parametrize("wpl", ["1", "2"])
+def test_ca2d_diagonal_cfg3_full_size_reference_fingerprint(gpu, oracle, monkeypatch, wpl):
+    """BASELINE config 3 at FULL size (16384^2 x 100) on the diagonal engine against the unmodified reference's
+    fingerprints (golden/cfg3_16384.json), both words-per-lane builds; and the run stats name the engine."""
+    import json
+    from clap_b200.ca import Rand48
+    monkeypatch.setenv("CLAPCA_2D_SKEW", "1")
+    monkeypatch.setenv("CLAPCA_2D_SKEW_WPL", wpl)
+    with open(os.path.join(G, "cfg3_16384.json")) as f:
+        c = json.load(f)["cave_bin_16384_x100_seed1"]
+    r = c["rule"]
+    ca = gpu.CellAutomaton("cave", born_mask=r["born"], surv_mask=r["surv"], nr_states=r["nr"], decay=bool(r["decay"]),
+                           neigh=r["neigh"])
+    got = gpu.ca2d_generate(ca, c["side"], c["steps"], Rand48(c["srand48"]))
+    want = c["final_grid"]
+    assert int(np.count_nonzero(got)) == want["population"]
+    for row, h in want["rows"].items():
+        assert "%016x" % oracle.fnv(got[int(row)]) == h, row
+    assert "%016x" % oracle.fnv(got) == want["fnv1a64"]
+    grid = gpu.Grid(c["side"], c["side"], 1)
+    grid.upload(got)
+    grid.run2d(ca, 2)
+    assert grid.stats()["engine"] == "diagonal"
+
+
 
 def test_ca2d_cfg3_16384_generations_compose(gpu):
     """BASELINE config 3 at full size (16384^2, 100 generations), too large for the oracle in seconds: the fused
@@ -595,7 +700,7 @@ def test_ca2d_cfg3_16384_generations_compose(gpu):
     grid.upload(arr)
     grid.run2d(ca, 100)
     st = grid.stats()
-    assert st["engine"] == "bitplane" and st["planes"] == 1
+    assert st["engine"] in ("bitplane", "diagonal") and st["planes"] == 1
     a = np.empty_like(arr)
     grid.download(a)
     grid.upload(arr)

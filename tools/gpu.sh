@@ -8,6 +8,7 @@
 #   knobs "<side>" "<gens>" "<env;env;...>"     single-GPU knob sweep of the ca3d sweep (tools/tune_lowpar.py)
 #   launches [bench.py args]     ncu launch list (time + DRAM bytes per launch) of a bench command
 #   ncufull <kernel-regex> [bench.py args]      ncu --set full of one kernel -> .ncu-rep + text summary
+#   ab2d [side [gens [steps]]]   row engine vs diagonal engine on BASELINE config 3, one process (tools/ab_ca2d.py)
 #   multi N [bench.py args]      torchrun bench on N GPUs -> gpurun_out/bench_<tag>_n<N>.json
 #   multiknobs N "<env;env;...>" [steps]        N-GPU knob sweep inside one set of processes (tools/multi_knobs.py)
 set -u
@@ -27,6 +28,9 @@ golden)
     timeout 1500 python bench.py --write-plane-hashes "$@" 2> gpurun_out/bench_$TAG.err | tail -1 | tee gpurun_out/bench_$TAG.json
     tail -5 gpurun_out/bench_$TAG.err
     cp tests/golden/plane_hashes_ca3d_2048.json gpurun_out/ 2>/dev/null
+    ;;
+ab2d)
+    timeout 200 python tools/ab_ca2d.py "$@" 2>&1 | tee gpurun_out/ab_ca2d_$TAG.txt
     ;;
 knobs)
     timeout 1500 python tools/tune_lowpar.py "${1:-2048}" "${2:-50}" "0" "8" "${3:-}" 2>&1 | tee -a gpurun_out/knobs_$TAG.txt
