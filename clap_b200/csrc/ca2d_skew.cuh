@@ -40,10 +40,14 @@
 
 namespace clapca {
 
-enum { SK2_SLOTS = 12, SK2_MAX_WARPS = 16, SK2_RING = 48, SK2_PAD_WORDS = 4 };
-/* words between diagonals: fixed (16 warps x 32 lanes + pad), so that every row address of a group of steps is the
-   group's pointer + a constant */
-enum { SK2_RS = SK2_MAX_WARPS * 32 + SK2_PAD_WORDS };
+enum { SK2_SLOTS = 12, SK2_MAX_WARPS = 18, SK2_RING = 48, SK2_PAD_WORDS = 6 };
+/* lanes 0..30 of a warp own words; lane 31 only LOADS the words right of the span (they are lane 0's of the next warp)
+   and hands them to lane 30 by shuffle: one load per lane and step, no lane-31 special case in the step */
+enum { SK2_OWN_LANES = 31 };
+/* words between diagonals: fixed (18 warps x 31 lanes + pad, a multiple of 4), so that every row address of a group of
+   steps is the group's pointer + a constant */
+enum { SK2_RS = SK2_MAX_WARPS * SK2_OWN_LANES + SK2_PAD_WORDS };
+CA_HOSTDEV int sk2_warp_cells(int WPL)              { return SK2_OWN_LANES * 32 * WPL; }
 enum { SK2_SM_DONE = 0, SK2_SM_RING = SK2_MAX_WARPS, SK2_SM_TICKET = SK2_SM_RING + SK2_MAX_WARPS * SK2_RING,
        SK2_SMEM_WORDS = SK2_SM_TICKET + 1 };
 #define SK2_INF 0x7fffffff
@@ -69,8 +73,8 @@ CA_HOSTDEV int sk2_rows_alloc(int W, int H)
        ragged last word column */
     return (T + SK2_SLOTS - 1) / SK2_SLOTS * SK2_SLOTS + 2 * SK2_SLOTS + 64;
 }
-/* at most SK2_MAX_WARPS / WPL warps: 16384 cells per diagonal either way (the kernels' launch bounds) */
-CA_HOSTDEV int sk2_warps_for(int W, int WPL)        { return (W + 1024 * WPL - 1) / (1024 * WPL); }
+/* at most SK2_MAX_WARPS / WPL warps (the kernels' launch bounds): 17856 cells per diagonal either way */
+CA_HOSTDEV int sk2_warps_for(int W, int WPL)        { return (W + sk2_warp_cells(WPL) - 1) / sk2_warp_cells(WPL); }
 
 CA_DEV uint32_t sk2_ones_below(int k)               { return k <= 0 ? 0u : (k >= 32 ? ~0u : ((1u << k) - 1u)); }
 
@@ -127,13 +131,30 @@ struct Sk2RuleDyn {
 typedef Sk2RuleConst<0x1E0u, 0x1F0u> Sk2RuleCave;
 typedef Sk2RuleConst<0x00Cu, 0x180u> Sk2RuleTest;
 
+/*
+ * A window slot: the lane's words of one old row.  Two words per lane are ONE 64-bit value from the load to the use:
+ * as two 32-bit values ptxas gave a few slots unpaired home registers, loaded those rows into a scratch pair and
+ * MOVed them out five instructions later -- a full L2 latency inside the step.
+ */
+template <int WPL> struct Sk2Win;
+template <> struct Sk2Win<1> {
+    uint32_t v;
+    CA_MEMBER void load(const uint32_t *p) { v = dp_ld_cg(p); }
+    CA_MEMBER uint32_t get(int) const { return v; }
+};
+template <> struct Sk2Win<2> {
+    unsigned long long v;
+    CA_MEMBER void load(const uint32_t *p) { v = dp_ld_cg(reinterpret_cast<const unsigned long long *>(p)); }
+    CA_MEMBER uint32_t get(int j) const { return j ? (uint32_t)(v >> 32) : (uint32_t)v; }
+};
+
 template <int WPL, bool MOORE, class Rule>
 struct Skew2 {
     enum { SLOTS = SK2_SLOTS };
     static_assert(SLOTS % 3 == 0 && SK2_RING % SLOTS == 0, "the shifted rows rotate with period 3; a group never wraps the ring");
 
     struct St {
-        uint32_t win[SLOTS][WPL + 1];   /* old rows t .. t+SLOTS-1, slot = row % SLOTS; [WPL] = the word right of the span */
+        Sk2Win<WPL> win[SLOTS];         /* old rows t .. t+SLOTS-1, slot = row % SLOTS */
         uint32_t rsh[3][WPL];           /* old rows t+1 .. t+3 shifted to x+1, slot = row % 3 */
         uint32_t lsh[3][WPL];           /* new rows t-1 .. t-3 shifted to x-1, slot = row % 3 */
         uint32_t n1[WPL];               /* new row t-1 */
@@ -236,8 +257,7 @@ struct Skew2 {
     template <int D, int S>
     CA_MDEV void load_row(St &st)
     {
-        LaneVec<WPL>::ld(st.row + D * SK2_RS, st.win[S]);
-        st.win[S][WPL] = dp_ld_cg(st.row + D * SK2_RS + WPL);
+        st.win[S].load(st.row + D * SK2_RS);
     }
 
     /*
@@ -262,19 +282,21 @@ struct Skew2 {
 
         /* ---- this step's rows out of the window; the row three steps ahead shifted to x+1 ---- */
         uint32_t cur[WPL], o1[WPL];
+        {
+            constexpr int SR = MOORE ? S3 : (S + 2) % SLOTS;       /* von Neumann: only (x+1,y) = row t+2 from the right */
+            constexpr int IR = MOORE ? I0 : I2;
+            const uint32_t next = dp_shfl_down(st.win[SR].get(0), 1);  /* lane 31 (the halo lane) gets its own word: unused */
 #pragma unroll
-        for (int j = 0; j < WPL; j++) {
-            cur[j] = st.win[S][j];
-            o1[j] = st.win[S1][j];
-            if (MOORE)
-                st.rsh[I0][j] = dp_funnel_r(st.win[S3][j], st.win[S3][j + 1], 1);
+            for (int j = 0; j < WPL; j++) {
+                cur[j] = st.win[S].get(j);
+                o1[j] = st.win[S1].get(j);
+                st.rsh[IR][j] = dp_funnel_r(st.win[SR].get(j), j + 1 < WPL ? st.win[SR].get(j + 1) : next, 1);
+            }
         }
-        if (!MOORE) {       /* von Neumann: only (x+1,y) = row t+2 from the right */
-            constexpr int S2 = (S + 2) % SLOTS;
-#pragma unroll
-            for (int j = 0; j < WPL; j++) st.rsh[I2][j] = dp_funnel_r(st.win[S2][j], st.win[S2][j + 1], 1);
-        }
-        load_row<S + SLOTS, S>(st);         /* row t + SLOTS takes the slot of row t */
+        /* row t + SLOTS - 1 takes the slot of row t - 1, which the previous step read for the last time: the load has a
+           dead register to land in (into the slot of row t itself it landed in a temporary and was MOVed over right
+           away -- a full L2 latency inside every step, ncu: 1000 cycles per step) */
+        load_row<S + SLOTS - 1, (S + SLOTS - 1) % SLOTS>(st);
 
         /* ---- everything that does not depend on the previous step ---- */
         uint32_t tb[WPL][3];
@@ -340,10 +362,11 @@ struct Skew2 {
             if (!STEADY)
                 nw[j] &= vm[j];
         }
-        LaneVec<WPL>::st(st.row + S * SK2_RS, nw);
+        if (lane < SK2_OWN_LANES)
+            LaneVec<WPL>::st(st.row + S * SK2_RS, nw);
         /* this warp's post of step t: slot t % RING, tag t + 1 */
         const bool posts = STEADY ? st.feeds : (t >= st.out_first && t <= st.out_last);
-        if (lane == 31 && posts)
+        if (lane == SK2_OWN_LANES - 1 && posts)
             dp_st_volatile((int *)st.out_ring + st.rb + S, (int)((nw[WPL - 1] >> 31) + (((uint32_t)t + 1u) << 1)));
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.n1[j] = nw[j];
@@ -363,7 +386,7 @@ struct Skew2 {
     {
         const int lane = dp_lane(), warp = dp_warp_in_block(), nw = (dp_block_threads() >> 5) - 1;
         const int H = p.H, W = p.W;
-        const int X0 = warp * 1024 * WPL, X1 = X0 + 1024 * WPL;
+        const int X0 = warp * sk2_warp_cells(WPL), X1 = X0 + sk2_warp_cells(WPL);
         const int Xe = X1 < W ? X1 : W;                         /* cells X0 <= x < Xe exist */
         const int first = X0 ? 2 * X0 - 1 : 0;                  /* one step before the warp's first cell (X0, 0) */
         const int start = first / SLOTS * SLOTS;
@@ -371,7 +394,7 @@ struct Skew2 {
         int *done = (int *)smem + SK2_SM_DONE + warp;
         St st;
         st.xb = X0 + 32 * WPL * lane;
-        st.row = p.rows + (size_t)start * SK2_RS + (size_t)(warp * 32 + lane) * WPL;
+        st.row = p.rows + (size_t)start * SK2_RS + (size_t)(warp * SK2_OWN_LANES + lane) * WPL;
         st.flagp = (g > 0 && lane == 0) ? p.prog + (g - 1) : nullptr;
         st.have = g > 0 ? 0 : SK2_INF;
         /* posts: the last cell of the warp on the left is (X0-1, y), on diagonals 2 X0 - 2 .. 2 X0 - 2 + H - 1 */
@@ -388,20 +411,24 @@ struct Skew2 {
         st.cons_ok = st.feeds ? st.cons_start + SK2_RING - 2 : SK2_INF;
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
-            st.wmask[j] = bp_valid_mask((st.xb >> 5) + j, W);
+            st.wmask[j] = lane < SK2_OWN_LANES ? bp_valid_mask((st.xb >> 5) + j, W) : 0u;
             st.n1[j] = 0u;
 #pragma unroll
             for (int i = 0; i < 3; i++) st.lsh[i][j] = st.rsh[i][j] = 0u;
         }
         Rule::setup(p, st.tabs);
 
-        /* the window: rows start .. start + SLOTS - 1, and rows start+1, start+2 shifted to x+1 */
+        /* the window: rows start .. start + SLOTS - 2 (the last slot is loaded by the first step), and rows start+1,
+           start+2 shifted to x+1 */
         wait_rows(p, st, start + SLOTS < p.T ? start + SLOTS : p.T);
         fill_window<0>(st);
+        {
+            const uint32_t next1 = dp_shfl_down(st.win[1].get(0), 1), next2 = dp_shfl_down(st.win[2].get(0), 1);
 #pragma unroll
-        for (int j = 0; j < WPL; j++) {
-            st.rsh[1][j] = dp_funnel_r(st.win[1][j], st.win[1][j + 1], 1);
-            st.rsh[2][j] = dp_funnel_r(st.win[2][j], st.win[2][j + 1], 1);
+            for (int j = 0; j < WPL; j++) {
+                st.rsh[1][j] = dp_funnel_r(st.win[1].get(j), j + 1 < WPL ? st.win[1].get(j + 1) : next1, 1);
+                st.rsh[2][j] = dp_funnel_r(st.win[2].get(j), j + 1 < WPL ? st.win[2].get(j + 1) : next2, 1);
+            }
         }
 
         /* groups whose steps all see every cell of the warp inside the grid (and, warps > 0, a post of the left warp) */
@@ -434,7 +461,7 @@ struct Skew2 {
     template <int S>
     CA_MDEV void fill_window(St &st)
     {
-        if constexpr (S < SLOTS) {
+        if constexpr (S < SLOTS - 1) {
             load_row<S, S>(st);
             fill_window<S + 1>(st);
         }
@@ -444,7 +471,7 @@ struct Skew2 {
     CA_MDEV void publish(const Sk2Params &p, int g, const uint32_t *smem)
     {
         const int lane = dp_lane(), nw = (dp_block_threads() >> 5) - 1;
-        const int X0 = lane * 1024 * WPL;
+        const int X0 = lane * sk2_warp_cells(WPL);
         const int first = X0 ? 2 * X0 - 1 : 0;
         const int start = first / SLOTS * SLOTS;        /* rows before a warp's first group are complete as far as it goes */
         int pub = 0;

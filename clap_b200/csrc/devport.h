@@ -21,6 +21,7 @@
 
 #define CA_DEV      __device__ __forceinline__
 #define CA_MDEV     __device__ __forceinline__ static      /* static member function */
+#define CA_MEMBER   __device__ __forceinline__             /* non-static member function */
 #define CA_MCOLD    __device__ __noinline__ static          /* static member function kept out of line (cold paths) */
 #define CA_HOSTDEV  __host__ __device__ __forceinline__
 #define CA_GLOBAL   __global__
@@ -67,6 +68,7 @@ CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return __ldcg(p); }
 CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return __ldcg(p); }
 CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return __ldcg(p); }
 CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return __ldcg(p); }
+CA_DEV unsigned long long dp_ld_cg(const unsigned long long *p) { return __ldcg(p); }
 CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { __stcg(p, v); }
 CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { __stcg(p, v); }
@@ -205,6 +207,7 @@ CA_DEV uint32_t dp_lop3(uint32_t a, uint32_t b, uint32_t c)
 
 #define CA_DEV      static inline
 #define CA_MDEV     static inline
+#define CA_MEMBER   inline
 #define CA_MCOLD    static
 #define CA_HOSTDEV  static inline
 #define CA_GLOBAL   static
@@ -267,6 +270,7 @@ CA_DEV uint32_t dp_ld_cg(const uint32_t *p)       { return dp_ld_cg_any(p); }
 CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return dp_ld_cg_any(p); }
 CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return dp_ld_cg_any(p); }
 CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return dp_ld_cg_any(p); }
+CA_DEV unsigned long long dp_ld_cg(const unsigned long long *p) { return dp_ld_cg_any(p); }
 CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { *p = v; }
 CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { *p = v; }
 CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { *p = v; }

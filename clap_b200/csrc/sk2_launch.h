@@ -30,11 +30,11 @@ SK2_DECLARE_RULE(0) SK2_DECLARE_RULE(1) SK2_DECLARE_RULE(2)
  */
 inline bool sk2_shape_for(long long W, int *WPL, int *warps)
 {
-    if (W < 1 || W > 1024LL * SK2_MAX_WARPS)
+    if (W < 1 || W > 16384)
         return false;
     *WPL = W <= 4096 ? 1 : 2;
     *warps = sk2_warps_for((int)W, *WPL);
-    return true;
+    return *warps * *WPL <= SK2_MAX_WARPS;
 }
 
 } // namespace clapca
