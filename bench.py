@@ -22,7 +22,8 @@ N = 1 workload).  One "step" = one full run of all generations over the volume.
              (tests/golden/cfg4_planes_2048.json) and, at N > 1, all planes against the single-GPU run's
              (tests/golden/plane_hashes_<workload>.json) -- "bit_equal_to_n1".
   secondary  (default N = 1 run only) one compact record per other BASELINE config and next-row kernel:
-             cfg 1 (ca2d 256^2 x 5), cfg 2 (ca3d 128^3 x 10), cfg 3 (ca2d 16384^2 x 100), cfg 5 (terrain 8192^2),
+             cfg 1 (ca2d 256^2 x 5), cfg 2 (ca3d 128^3 x 10), cfg 3 (ca2d 16384^2 x 100; and once more on the diagonal
+             engine, which is not the default), cfg 5 (terrain 8192^2),
              the 256^3 noise bake and the 8192^2 mesh, each with value / roofline / cpu_baseline / e2e / clocks.
 
 Rank 0 prints exactly one JSON line.
@@ -50,6 +51,7 @@ WORKLOADS = {
 CA2D_WORKLOADS = {
     # name: (side, generations, born, surv, nr_states, decay)
     "ca2d_16384": (16384, 100, 0x1E0, 0x1F0, 1, True),     # BASELINE config 3: binary cave smoothing, 1 bit per cell
+    "ca2d_16384_diagonal": (16384, 100, 0x1E0, 0x1F0, 1, True),    # ... on the diagonal engine (ca2d_skew.cuh; not the default)
     "ca2d_4096": (4096, 100, 0x1E0, 0x1F0, 1, True),
     "ca2d_16384_cavetest": (16384, 100, 3 << 2, 3 << 7, 4, True),      # multi-state ca_test rule (terrain.c:391-398)
     "ca2d_256": (256, 5, 3 << 2, 3 << 7, 4, True),         # BASELINE config 1: ca2d_generate(&ca_test, 256, 5)
@@ -63,7 +65,7 @@ FIELD_WORKLOADS = {
     "noise_256": ("noise", 256),            # noise_grad3d_bake_rgba8(256, 4, 2.0, 0.5, 37.0, 0xc14d)
     "noise_64": ("noise", 64),              # the engine's default bake (noise.c:309-317)
 }
-SECONDARY = ["ca2d_256", "ca3d_128", "ca2d_16384", "terrain_8192", "noise_256", "terrain_mesh_8192"]
+SECONDARY = ["ca2d_256", "ca3d_128", "ca2d_16384", "ca2d_16384_diagonal", "terrain_8192", "noise_256", "terrain_mesh_8192"]
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -520,6 +522,7 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
     from clap_b200._lib import NEIGH_M1
     from clap_b200.ca import Rand48
     side, gens, born, surv, nr, decay = CA2D_WORKLOADS[workload]
+    engine = _lib_mod.ENGINE_DIAGONAL if workload.endswith("_diagonal") else _lib_mod.ENGINE_AUTO
     ca = CellAutomaton(workload, born, surv, nr, decay, NEIGH_M1)
     cells = side * side
     updates = cells * gens
@@ -535,7 +538,7 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
 
     def step():
         grid.upload(seed_dev.data_ptr())
-        grid.run2d(ca, gens)
+        grid.run2d(ca, gens, engine=engine)
         return grid.stats()
 
     for _ in range(args.warmup):
@@ -555,7 +558,7 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
     # BASELINE config 3 at full size was run ONCE through the unmodified reference (tests/golden/make_golden_cfg3.py):
     # the population of the final grid must be the reference's
     ref_pop = None
-    if workload == "ca2d_16384":
+    if workload in ("ca2d_16384", "ca2d_16384_diagonal"):
         try:
             with open(os.path.join(GOLDEN, "cfg3_16384.json")) as f:
                 ref_pop = json.load(f)["cave_bin_16384_x100_seed1"]["final_grid"]["population"]
@@ -587,14 +590,14 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
                 t0 = time.perf_counter()
             after = c_uint64(0)
             _lib_mod.check(lib, lib.clapca_ca2d_generate(c_void_p(out.data_ptr()), side, born, surv, nr, int(decay), NEIGH_M1,
-                                                         gens, 0, Rand48(seed48).x, byref(after)))
+                                                         gens, engine, Rand48(seed48).x, byref(after)))
         dt = (time.perf_counter() - t0) / n
         assert int(torch.count_nonzero(out)) == pop, "ca2d_generate result differs from the device-resident run"
         e2e = {"value": updates / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": cells,
                "ms_per_step": dt * 1e3, "steps": n, "call": "clapca_ca2d_generate (device-side seeding + generations + D2H)"}
     cpu = None
     equal_ref = None
-    if not args.no_cpu:
+    if not args.no_cpu and not workload.endswith("_diagonal"):     # the CPU arm of config 3 is on the ca2d_16384 record
         oracle_lib = oracle()
         ref = oracle_lib.ref()
         if workload == "ca2d_256" and ref is not None:

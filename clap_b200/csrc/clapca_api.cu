@@ -1118,15 +1118,15 @@ static int grid_max_value(clapca_grid *g, unsigned *maxv)
 
 /*
  * One-plane grids on the diagonal engine (ca2d_skew.cuh): no in-row chain, no CTA barrier in the sweep.  Measured
- * against the row engine on B200 (profiles/r02_ca2d_skew.txt); CLAPCA_2D_SKEW=0 / 1 forces the row / diagonal engine
- * wherever both apply.
+ * against the row engine on B200 at BASELINE config 3 (profiles/r02_ca2d_diagonal_ab.txt): bit-identical grids, 13.1 ms
+ * against 8.9 ms -- so the row engine stays the default and the diagonal engine runs when it is asked for
+ * (CLAPCA_ENGINE_DIAGONAL, or CLAPCA_2D_SKEW=1 wherever both apply).
  */
-static const long long kSkewMinCells = 1LL << 22;
-static bool sk2_preferred(const clapca_grid *g)
+static bool sk2_preferred(const clapca_grid *)
 {
     if (const char *e = getenv("CLAPCA_2D_SKEW"))
         return atoi(e) != 0;
-    return g->d0 * g->d1 >= kSkewMinCells;
+    return false;
 }
 
 static int run2d_skew(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh, int steps)
@@ -1327,7 +1327,7 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv
     const bool bp_ok = engine != CLAPCA_ENGINE_WAVEFRONT && bp2_supported(g, side, decay, neigh, P);
     const bool sk_ok = engine != CLAPCA_ENGINE_WAVEFRONT && sk2_supported(g, side, decay, neigh, P);
     if (engine == CLAPCA_ENGINE_AUTO)
-        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : (sk_ok ? CLAPCA_ENGINE_DIAGONAL : CLAPCA_ENGINE_WAVEFRONT);
+        engine = bp_ok ? CLAPCA_ENGINE_BITPLANE : CLAPCA_ENGINE_WAVEFRONT;
     if (engine == CLAPCA_ENGINE_DIAGONAL) {
         if (!sk_ok)
             return fail(CLAPCA_ERR_UNSUPPORTED, "2D diagonal engine: needs a full sweep (side >= extent), cell values 0 / 1, at "

@@ -52,8 +52,9 @@ enum {
     CLAPCA_ENGINE_WAVEFRONT = 1,  /* uint8 cells, skewed cell wavefront + grid barrier (any rule/shape) */
     CLAPCA_ENGINE_BITPLANE  = 2,  /* bit-sliced planes, row scan, flag dataflow, all generations fused */
     CLAPCA_ENGINE_DIAGONAL  = 3,  /* 2D, one-plane (binary) grids of at most 16384 columns: bit rows stored along the
-                                     diagonals 2x + y, no in-row chain (ca2d_skew.cuh).  AUTO / BITPLANE pick it for
-                                     large grids and report it in the run stats; asking for it runs it at any size */
+                                     diagonals 2x + y, no in-row chain (ca2d_skew.cuh).  Runs when asked for (or with
+                                     CLAPCA_2D_SKEW=1 under AUTO / BITPLANE) and is named in the run stats; the row
+                                     engine is faster at BASELINE config 3 (8.9 vs 13.1 ms) and stays the default */
 };
 
 /* ---- library lifetime --------------------------------------------------- */
