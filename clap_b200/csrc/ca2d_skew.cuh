@@ -20,16 +20,26 @@
  *   and three LOP3, 2 (W-1) + H steps instead of W row steps of ~150 dependent instructions.
  *
  * Parallelism.  One CTA per generation (claimed by ticket, all generations in flight in one cooperative launch,
- * generation g+1 two step groups behind g, progress counters as in the row engine).  A diagonal is cut by x: warp w /
- * lane l owns WPL consecutive words.  Only x - 1 feeds a cell from the NEW side, so the warps form a chain, not a
- * ring: lanes hand bit 31 to the right by shuffle, a warp hands it to the next warp through a tagged mailbox ring in
- * shared memory (one word = step tag + bit: no fence, no barrier), and the next warp simply runs behind -- no CTA
- * barrier anywhere in the sweep.  A warp only works while the band of valid cells (0 <= t - 2x < H) crosses its words.
+ * generation g+1 two step groups behind g, progress counters as in the row engine).  A diagonal is cut by x: warp w
+ * owns 31 lanes x WPL consecutive words; its lane 31 is a HALO lane that only loads the words right of the span (they
+ * are lane 0's of the next warp) and hands them to lane 30 by shuffle -- one load per lane and step, no special case.
+ * Only x - 1 feeds a cell from the NEW side, so the warps form a chain, not a ring: lanes hand bit 31 to the right by
+ * shuffle, a warp hands it to the next warp through a tagged mailbox ring in shared memory (one word = step tag + bit:
+ * no fence, no barrier), four posts fetched per look so that the steps themselves hold no branch, and the next warp
+ * simply runs a few steps behind -- no CTA barrier anywhere in the sweep.  A warp only works while the band of valid
+ * cells (0 <= t - 2x < H) crosses its words; groups of steps wholly inside the band run without masks.
  *
- * Old rows come from L2 (the previous generation wrote them on another SM) through a register window SLOTS steps
- * deep, the word to the right of the lane's span is loaded next to its own (no shuffle, no special last lane).
- * mbarrier-armed bulk copies were considered for this stream and dropped on the guide's numbers: a try_wait costs
- * 60-90 cycles against a step of ~50.
+ * Old rows come from L2 (the previous generation wrote them on another SM) through a register window SLOTS steps deep.
+ * What ncu taught about that window on B200 (profiles/r02_ncu_full_ca2d_diagonal_first.txt): a load must land in a
+ * register that is DEAD (the slot of the row used one step earlier), a two-word slot must stay ONE 64-bit value until
+ * its first use, and there must be one load per step -- otherwise ptxas parks the result in a shared temporary and
+ * MOVes it out a few instructions later, and every step waits a full L2 latency for a row it needs eleven steps on
+ * (25 ms instead of 13 at BASELINE config 3).  mbarrier-armed bulk copies were considered for this stream and dropped
+ * on the guide's numbers: a try_wait costs 60-90 cycles against a step budget of ~100.
+ *
+ * Measured (profiles/r02_ca2d_diagonal_ab.txt): bit-identical to the row engine at config 3, 13.1 ms against its 8.9 ms
+ * -- a step is bound by ONE warp's dependent instruction stream.  Hence CLAPCA_ENGINE_AUTO measures both engines on the
+ * first large run of a shape class instead of assuming one (clapca_api.cu:run2d_tune).
  */
 #ifndef CLAPCA_CA2D_SKEW_CUH
 #define CLAPCA_CA2D_SKEW_CUH
@@ -76,7 +86,8 @@ CA_HOSTDEV int sk2_rows_alloc(int W, int H)
 /* at most SK2_MAX_WARPS / WPL warps (the kernels' launch bounds): 17856 cells per diagonal either way */
 CA_HOSTDEV int sk2_warps_for(int W, int WPL)        { return (W + sk2_warp_cells(WPL) - 1) / sk2_warp_cells(WPL); }
 
-CA_DEV uint32_t sk2_ones_below(int k)               { return k <= 0 ? 0u : (k >= 32 ? ~0u : ((1u << k) - 1u)); }
+/* bits 0 .. k-1 (none for k <= 0, all for k >= 32): one clamped funnel shift */
+CA_DEV uint32_t sk2_ones_below(int k)               { return dp_funnel_l_clamp(~0u, 0u, (uint32_t)(k > 0 ? k : 0)); }
 
 /*
  * Rules: the new alive bit of a cell with K counted neighbours (K = 0..6, bits k0..k2) plus j = 0..2 more, current
@@ -134,18 +145,19 @@ typedef Sk2RuleConst<0x00Cu, 0x180u> Sk2RuleTest;
 /*
  * A window slot: the lane's words of one old row.  Two words per lane are ONE 64-bit value from the load to the use:
  * as two 32-bit values ptxas gave a few slots unpaired home registers, loaded those rows into a scratch pair and
- * MOVed them out five instructions later -- a full L2 latency inside the step.
+ * MOVed them out five instructions later -- a full L2 latency inside the step.  The halves are taken where the row is
+ * first used (three steps before its diagonal), not where ptxas would like to (next to the load).
  */
 template <int WPL> struct Sk2Win;
 template <> struct Sk2Win<1> {
     uint32_t v;
     CA_MEMBER void load(const uint32_t *p) { v = dp_ld_cg(p); }
-    CA_MEMBER uint32_t get(int) const { return v; }
+    CA_MEMBER void unpack(uint32_t w[1]) const { w[0] = v; }
 };
 template <> struct Sk2Win<2> {
     unsigned long long v;
     CA_MEMBER void load(const uint32_t *p) { v = dp_ld_cg(reinterpret_cast<const unsigned long long *>(p)); }
-    CA_MEMBER uint32_t get(int j) const { return j ? (uint32_t)(v >> 32) : (uint32_t)v; }
+    CA_MEMBER void unpack(uint32_t w[2]) const { dp_unpack64_here(v, w[0], w[1]); }
 };
 
 template <int WPL, bool MOORE, class Rule>
@@ -154,7 +166,8 @@ struct Skew2 {
     static_assert(SLOTS % 3 == 0 && SK2_RING % SLOTS == 0, "the shifted rows rotate with period 3; a group never wraps the ring");
 
     struct St {
-        Sk2Win<WPL> win[SLOTS];         /* old rows t .. t+SLOTS-1, slot = row % SLOTS */
+        Sk2Win<WPL> win[SLOTS];         /* old rows t+4 .. t+SLOTS-1 as loaded, slot = row % SLOTS */
+        uint32_t uw[SLOTS][WPL];        /* old rows t .. t+3 (von Neumann: t+2), unpacked */
         uint32_t rsh[3][WPL];           /* old rows t+1 .. t+3 shifted to x+1, slot = row % 3 */
         uint32_t lsh[3][WPL];           /* new rows t-1 .. t-3 shifted to x-1, slot = row % 3 */
         uint32_t n1[WPL];               /* new row t-1 */
@@ -167,6 +180,7 @@ struct Skew2 {
         uint32_t *out_ring;             /* this warp's posts, steps out_first .. out_last */
         const uint32_t *in_prev;        /* slot of the post of the step before the current group */
         int rb;                         /* ring slot of the current group's first step */
+        uint32_t mailbits;              /* bit k: the left warp's carry into lane 0 at step k of the current block of posts */
         bool has_left, feeds;
         int in_first, in_span, out_first, out_last;
         const int *cons_done;           /* the consumer's step counter */
@@ -228,26 +242,47 @@ struct Skew2 {
     }
 
     /*
-     * the left warp's post of step s (tag s + 1), slow path.  Every decision is taken on ONE lane's load, broadcast:
-     * lanes that polled on their own could disagree and leave the loop apart -- into different warp collectives.
+     * The left warp's posts of the MB steps before steps t .. t+MB-1 (post s: slot s % RING, tag s + 1, bit 0 = bit 31
+     * of its last owned word), fetched TOGETHER so that the steps themselves hold no branch: a warp runs at least MB
+     * steps behind its left neighbour.  Result: bit k of st.mailbits = the carry into lane 0 at step t + k.
+     * S = t % SLOTS.  Every decision is taken on a vote or on one lane's broadcast load: lanes that polled on their own
+     * could disagree and leave the loop apart -- into different warp collectives.
      */
-    CA_MCOLD uint32_t spin_post(const Sk2Params &p, const uint32_t *slot, uint32_t tag)
+    enum { MB = 4 };
+    template <int S, bool STEADY>
+    CA_MDEV void fetch_posts(const Sk2Params &p, St &st, int t)
     {
-        if (dp_any(dp_ld_flag(p.err) != 0))         /* the watchdog has fired somewhere: run on to the end, no more waiting */
-            return 0u;
-        const long long t0 = dp_clock();
-        for (unsigned spins = 1;; spins++) {
-            const uint32_t m = dp_shfl(dp_lane() == 0 ? dp_ld_volatile_u32(slot) : 0u, 0);
-            if ((m >> 1) == tag)
-                return m;
+        static_assert(S % MB == 0 && SLOTS % MB == 0, "blocks of posts are aligned to the step groups");
+        if (STEADY ? !st.has_left : ((unsigned)(t + MB - 2 - st.in_first) > (unsigned)(st.in_span + MB - 1))) {
+            st.mailbits = 0u;           /* no step of the block is inside the left warp's post window */
+            return;
+        }
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            uint32_t bits = 0u;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < MB; k++) {
+                const uint32_t *slot = (S + k) ? st.in_ring + st.rb + (S + k - 1) : st.in_prev;
+                const bool want = STEADY || (unsigned)(t + k - 1 - st.in_first) <= (unsigned)st.in_span;
+                const uint32_t m = dp_ld_volatile_u32(slot);
+                ok = ok && (!want || (m >> 1) == (uint32_t)(t + k));
+                bits |= (want ? (m & 1u) : 0u) << k;
+            }
+            if (dp_all(ok)) {
+                st.mailbits = bits;
+                return;
+            }
             /* right behind the producer: poll fast; a warp waiting for its band to arrive backs off to 2 us */
+            if (spins == 0) t0 = dp_clock();
             dp_nanosleep(spins < 8 ? 20 : (spins < 64 ? 200 : 2000));
-            if ((spins & 255u) == 0u) {
+            if ((spins & 255u) == 255u || spins == 0) {
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
                         dp_atomic_max(p.err, 5);
-                    return 0u;
+                    st.mailbits = 0u;   /* the watchdog has fired: run on to the end, the claim loop exits on err */
+                    return;
                 }
             }
         }
@@ -273,24 +308,18 @@ struct Skew2 {
         constexpr int I0 = S % 3, I1 = (S + 1) % 3, I2 = (S + 2) % 3;      /* t % 3, (t+1) % 3, (t+2) % 3 */
         const int lane = dp_lane();
 
-        /* ---- the left warp's post of step t-1 (slot (t-1) % RING): asked for early, looked at late ---- */
-        uint32_t post = 0u;
-        const uint32_t *slot = S ? st.in_ring + st.rb + (S - 1) : st.in_prev;
-        const bool mail = STEADY ? st.has_left : (unsigned)(t - 1 - st.in_first) <= (unsigned)st.in_span;
-        if (mail)
-            post = dp_ld_volatile_u32(slot);
-
         /* ---- this step's rows out of the window; the row three steps ahead shifted to x+1 ---- */
         uint32_t cur[WPL], o1[WPL];
         {
             constexpr int SR = MOORE ? S3 : (S + 2) % SLOTS;       /* von Neumann: only (x+1,y) = row t+2 from the right */
             constexpr int IR = MOORE ? I0 : I2;
-            const uint32_t next = dp_shfl_down(st.win[SR].get(0), 1);  /* lane 31 (the halo lane) gets its own word: unused */
+            st.win[SR].unpack(st.uw[SR]);
+            const uint32_t next = dp_shfl_down(st.uw[SR][0], 1);   /* lane 31 (the halo lane) gets its own word: unused */
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
-                cur[j] = st.win[S].get(j);
-                o1[j] = st.win[S1].get(j);
-                st.rsh[IR][j] = dp_funnel_r(st.win[SR].get(j), j + 1 < WPL ? st.win[SR].get(j + 1) : next, 1);
+                cur[j] = st.uw[S][j];
+                o1[j] = st.uw[S1][j];
+                st.rsh[IR][j] = dp_funnel_r(st.uw[SR][j], j + 1 < WPL ? st.uw[SR][j + 1] : next, 1);
             }
         }
         /* row t + SLOTS - 1 takes the slot of row t - 1, which the previous step read for the last time: the load has a
@@ -339,13 +368,7 @@ struct Skew2 {
 
         /* ---- behind the previous step: the carry from the left, one shift, three LOP3 ---- */
         uint32_t left = dp_shfl_up(st.n1[WPL - 1], 1);
-        if (mail) {
-            if (dp_any((post >> 1) != (uint32_t)t))        /* a vote: the lanes must agree on the way they take */
-                post = spin_post(p, slot, (uint32_t)t);
-            if (lane == 0) left = post << 31;
-        } else if (lane == 0) {
-            left = 0u;
-        }
+        if (lane == 0) left = st.mailbits << (31 - S % MB);        /* bit 31 = the left warp's carry of step t-1 */
         uint32_t nw[WPL];
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
@@ -376,6 +399,8 @@ struct Skew2 {
     CA_MDEV void steps_from(const Sk2Params &p, St &st, int t)
     {
         if constexpr (S < SLOTS) {
+            if constexpr (S % MB == 0)
+                fetch_posts<S, STEADY>(p, st, t);
             step<S, STEADY>(p, st, t);
             steps_from<S + 1, STEADY>(p, st, t + 1);
         }
@@ -423,11 +448,14 @@ struct Skew2 {
         wait_rows(p, st, start + SLOTS < p.T ? start + SLOTS : p.T);
         fill_window<0>(st);
         {
-            const uint32_t next1 = dp_shfl_down(st.win[1].get(0), 1), next2 = dp_shfl_down(st.win[2].get(0), 1);
+            st.win[0].unpack(st.uw[0]);
+            st.win[1].unpack(st.uw[1]);
+            st.win[2].unpack(st.uw[2]);
+            const uint32_t next1 = dp_shfl_down(st.uw[1][0], 1), next2 = dp_shfl_down(st.uw[2][0], 1);
 #pragma unroll
             for (int j = 0; j < WPL; j++) {
-                st.rsh[1][j] = dp_funnel_r(st.win[1].get(j), j + 1 < WPL ? st.win[1].get(j + 1) : next1, 1);
-                st.rsh[2][j] = dp_funnel_r(st.win[2].get(j), j + 1 < WPL ? st.win[2].get(j + 1) : next2, 1);
+                st.rsh[1][j] = dp_funnel_r(st.uw[1][j], j + 1 < WPL ? st.uw[1][j + 1] : next1, 1);
+                st.rsh[2][j] = dp_funnel_r(st.uw[2][j], j + 1 < WPL ? st.uw[2][j + 1] : next2, 1);
             }
         }
 

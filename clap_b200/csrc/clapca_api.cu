@@ -7,6 +7,8 @@
 #include <cooperative_groups.h>
 
 #include <unordered_set>
+#include <map>
+#include <tuple>
 #include "api_internal.h"
 #include "bp2_launch.h"
 #include "sk2_launch.h"
@@ -1117,16 +1119,28 @@ static int grid_max_value(clapca_grid *g, unsigned *maxv)
 }
 
 /*
- * One-plane grids on the diagonal engine (ca2d_skew.cuh): no in-row chain, no CTA barrier in the sweep.  Measured
+ * One-plane grids on the diagonal engine (ca2d_skew.cuh): no in-row chain, no CTA barrier in the sweep.  First measured
  * against the row engine on B200 at BASELINE config 3 (profiles/r02_ca2d_diagonal_ab.txt): bit-identical grids, 13.1 ms
- * against 8.9 ms -- so the row engine stays the default and the diagonal engine runs when it is asked for
- * (CLAPCA_ENGINE_DIAGONAL, or CLAPCA_2D_SKEW=1 wherever both apply).
+ * against 8.9 ms.  Which engine is faster depends on the shape (and on the kernel version), so nothing is assumed:
+ * CLAPCA_ENGINE_DIAGONAL or CLAPCA_2D_SKEW=1 / 0 force an engine, and otherwise the first large run of a shape class
+ * MEASURES both (run2d_tune below) and later runs of the class take the faster one.
  */
-static bool sk2_preferred(const clapca_grid *)
+enum { SK2_CHOICE_UNKNOWN = 0, SK2_CHOICE_ROW = 1, SK2_CHOICE_DIAGONAL = 2 };
+static const long long kTune2MinCells = 1LL << 22;
+static const int kTune2MinSteps = 16;
+static std::map<std::tuple<int64_t, int64_t, int, uint32_t, uint32_t>, int> g_tune2;
+
+static int sk2_choice(const clapca_grid *g, uint32_t born, uint32_t surv, int neigh, int steps)
 {
     if (const char *e = getenv("CLAPCA_2D_SKEW"))
-        return atoi(e) != 0;
-    return false;
+        return atoi(e) != 0 ? SK2_CHOICE_DIAGONAL : SK2_CHOICE_ROW;
+    if (g->d0 * g->d1 < kTune2MinCells || steps < kTune2MinSteps)
+        return SK2_CHOICE_ROW;
+    if (const char *e = getenv("CLAPCA_2D_TUNE"))
+        if (atoi(e) == 0)
+            return SK2_CHOICE_ROW;
+    auto it = g_tune2.find(std::make_tuple(g->d0, g->d1, neigh, born & 0x1ffu, surv & 0x1ffu));
+    return it == g_tune2.end() ? SK2_CHOICE_UNKNOWN : it->second;
 }
 
 static int run2d_skew(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh, int steps)
@@ -1300,6 +1314,63 @@ static int run2d_bitplane(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t
     return CLAPCA_OK;
 }
 
+/*
+ * First large run of a shape class under AUTO / BITPLANE: measure both engines on this very input, over at most
+ * kTune2Gens generations.  Each engine runs twice from a scratch copy of the input (the second run is the timed one:
+ * the first launch of a kernel pays its module load); then the input comes back and the ROW engine does the caller's
+ * run -- the first call of a class never depends on the outcome.  The diagonal engine is chosen for later runs of
+ * the class only if its grid had the same fingerprint as the row engine's and its run was faster (pack + sweep +
+ * unpack, CUDA events).
+ */
+static const int kTune2Gens = 32;
+static int run2d_tune(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_states, int decay, int neigh, int steps, int P)
+{
+    const auto key = std::make_tuple(g->d0, g->d1, neigh, born & 0x1ffu, surv & 0x1ffu);
+    const int gens = std::min(steps, kTune2Gens);
+    void *copy = nullptr;
+    if (cudaMalloc(&copy, g->n) != cudaSuccess) {
+        (void)cudaGetLastError();               /* no room for the scratch copy: no measurement, the proven engine */
+        g_tune2[key] = SK2_CHOICE_ROW;
+        return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps, P);
+    }
+    int choice = SK2_CHOICE_ROW;
+    float ms_diag = 0.f, ms_row = 0.f;
+    uint64_t h_diag = 0, h_row = 1;
+    bool diag_ok = true, row_ok = true;
+    cudaError_t e = cudaMemcpyAsync(copy, g->cells, g->n, cudaMemcpyDeviceToDevice, g->stream);
+    for (int i = 0; i < 2 && e == cudaSuccess && diag_ok; i++) {
+        if (i) e = cudaMemcpyAsync(g->cells, copy, g->n, cudaMemcpyDeviceToDevice, g->stream);
+        if (e == cudaSuccess)
+            diag_ok = run2d_skew(g, born, surv, nr_states, decay, neigh, gens) == CLAPCA_OK;
+        ms_diag = g->stats.total_ms;
+    }
+    if (e == cudaSuccess && diag_ok)
+        diag_ok = clapca_hash_planes(g->cells, g->n, 1, &h_diag) == CLAPCA_OK;
+    for (int i = 0; i < 2 && e == cudaSuccess && row_ok; i++) {
+        e = cudaMemcpyAsync(g->cells, copy, g->n, cudaMemcpyDeviceToDevice, g->stream);
+        if (e == cudaSuccess)
+            row_ok = run2d_bitplane(g, born, surv, nr_states, decay, neigh, gens, P) == CLAPCA_OK;
+        ms_row = g->stats.total_ms;
+    }
+    if (e == cudaSuccess && row_ok && diag_ok && clapca_hash_planes(g->cells, g->n, 1, &h_row) == CLAPCA_OK &&
+        h_row == h_diag && ms_diag < ms_row)
+        choice = SK2_CHOICE_DIAGONAL;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(g->cells, copy, g->n, cudaMemcpyDeviceToDevice, g->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(g->stream);
+    cudaFree(copy);
+    if (e != cudaSuccess)
+        return fail(CLAPCA_ERR_CUDA, "grid_run2d (engine measurement): %s", cudaGetErrorString(e));
+    g_tune2[key] = choice;
+    if (getenv("CLAPCA_VERBOSE"))
+        fprintf(stderr, "clapca: 2D engines on %lld x %lld, %d generations: diagonal %.3f ms%s, row %.3f ms -> %s\n",
+                (long long)g->d0, (long long)g->d1, gens, ms_diag,
+                diag_ok ? (h_row == h_diag ? "" : " (DIFFERENT GRID)") : " (failed)", ms_row,
+                choice == SK2_CHOICE_DIAGONAL ? "diagonal" : "row");
+    return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps, P);
+}
+
 int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv, uint32_t nr_states, int decay,
                       int neigh, int steps, int engine)
 {
@@ -1338,7 +1409,10 @@ int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born, uint32_t surv
         if (!bp_ok)
             return fail(CLAPCA_ERR_UNSUPPORTED, "2D bit-plane engine: needs a full sweep (side >= extent), rows of at "
                         "most 65536 cells (32768 with values >= 16) and an alive-bit neighbourhood (vnv/mv only without decay)");
-        if (sk_ok && sk2_preferred(g))
+        const int choice = sk_ok ? sk2_choice(g, born, surv, neigh, steps) : SK2_CHOICE_ROW;
+        if (choice == SK2_CHOICE_UNKNOWN)
+            return run2d_tune(g, born, surv, nr_states, decay, neigh, steps, P);
+        if (choice == SK2_CHOICE_DIAGONAL)
             return run2d_skew(g, born, surv, nr_states, decay, neigh, steps);
         return run2d_bitplane(g, born, surv, nr_states, decay, neigh, steps, P);
     }

@@ -69,6 +69,11 @@ CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return __ldcg(p); }
 CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return __ldcg(p); }
 CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return __ldcg(p); }
 CA_DEV unsigned long long dp_ld_cg(const unsigned long long *p) { return __ldcg(p); }
+/* the halves of a 64-bit value, taken HERE (volatile: not hoisted to the load that produced it) */
+CA_DEV void dp_unpack64_here(unsigned long long v, uint32_t &lo, uint32_t &hi)
+{
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
 CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { __stcg(p, v); }
 CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { __stcg(p, v); }
@@ -147,6 +152,8 @@ CA_DEV void dp_set_error(int *p, int v)           { atomicCAS(p, 0, v); }
 CA_DEV int  dp_popc(uint32_t v)                   { return __popc(v); }
 CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s) { return __funnelshift_l(lo, hi, s); }
 CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, s); }
+/* upper word of (hi:lo) << min(s, 32) */
+CA_DEV uint32_t dp_funnel_l_clamp(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_lc(lo, hi, s); }
 
 /*
  * 1-D bulk copies of the TMA engine (cp.async.bulk) and the mbarrier that counts their bytes.  Issued by ONE thread;
@@ -271,6 +278,7 @@ CA_DEV uint2    dp_ld_cg(const uint2 *p)          { return dp_ld_cg_any(p); }
 CA_DEV uint4    dp_ld_cg(const uint4 *p)          { return dp_ld_cg_any(p); }
 CA_DEV uint8_t  dp_ld_cg(const uint8_t *p)        { return dp_ld_cg_any(p); }
 CA_DEV unsigned long long dp_ld_cg(const unsigned long long *p) { return dp_ld_cg_any(p); }
+CA_DEV void dp_unpack64_here(unsigned long long v, uint32_t &lo, uint32_t &hi) { lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
 CA_DEV void     dp_st_cg(uint32_t *p, uint32_t v) { *p = v; }
 CA_DEV void     dp_st_cg(uint2 *p, uint2 v)       { *p = v; }
 CA_DEV void     dp_st_cg(uint4 *p, uint4 v)       { *p = v; }
@@ -334,6 +342,10 @@ CA_DEV uint32_t dp_funnel_l(uint32_t lo, uint32_t hi, int s)
 CA_DEV uint32_t dp_funnel_r(uint32_t lo, uint32_t hi, int s)
 {
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+CA_DEV uint32_t dp_funnel_l_clamp(uint32_t lo, uint32_t hi, uint32_t s)
+{
+    return s >= 32 ? lo : (s ? (hi << s) | (lo >> (32 - s)) : hi);
 }
 
 /*

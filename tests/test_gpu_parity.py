@@ -661,6 +661,21 @@ def test_ca2d_engines_agree_4096(gpu):
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     assert outs[0].any() and not outs[0].all()
 
+def test_ca2d_auto_measures_both_engines_and_stays_exact(gpu, oracle, monkeypatch):
+    """AUTO on a large binary grid measures the row and the diagonal engine on the first run of a shape class
+    (clapca_api.cu:run2d_tune) and takes the faster one afterwards: every run, measuring or not, equals the oracle."""
+    monkeypatch.delenv("CLAPCA_2D_SKEW", raising=False)
+    monkeypatch.delenv("CLAPCA_2D_TUNE", raising=False)
+    rng = np.random.default_rng(62)
+    arr = synth(rng, (2048, 2304), 0.47, 1)         # 4.7 M cells: above the measuring threshold
+    ca = _ca(gpu, 0x1E0, 0x1F0, 1, True, oracle_lib.NEIGH_M1)
+    want = oracle.ca2d_run(arr.copy(), 0x1E0, 0x1F0, 1, 1, oracle_lib.NEIGH_M1, 20, side=2304)
+    for _ in range(3):
+        a = arr.copy()
+        gpu.ca2d_step(ca, a, side=2304, steps=20)
+        assert np.array_equal(a, want)
+
+
 
 @pytest.mark.parametrize("wpl", ["1", "2"])
 def test_ca2d_diagonal_cfg3_full_size_reference_fingerprint(gpu, oracle, monkeypatch, wpl):
