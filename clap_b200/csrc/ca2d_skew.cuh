@@ -276,7 +276,7 @@ struct Skew2 {
             /* right behind the producer: poll fast; a warp waiting for its band to arrive backs off to 2 us */
             if (spins == 0) t0 = dp_clock();
             dp_nanosleep(spins < 8 ? 20 : (spins < 64 ? 200 : 2000));
-            if ((spins & 255u) == 255u || spins == 0) {
+            if ((spins & 255u) == 255u || spins == 8) {    /* spins == 8: a watchdog that fired elsewhere is noticed early */
                 bool bad = dp_ld_flag(p.err) != 0 || (dp_clock() - t0) > p.spin_limit;
                 if (!dp_all(!bad)) {
                     if (dp_lane() == 0)
