@@ -163,6 +163,7 @@ template <> struct Sk2Win<2> {
 template <int WPL, bool MOORE, class Rule>
 struct Skew2 {
     enum { SLOTS = SK2_SLOTS };
+    static constexpr bool kSteadyBuild = false;
     static_assert(SLOTS % 3 == 0 && SK2_RING % SLOTS == 0, "the shifted rows rotate with period 3; a group never wraps the ring");
 
     struct St {
@@ -376,14 +377,18 @@ struct Skew2 {
             if (MOORE) {
                 const uint32_t l1 = dp_funnel_l(j ? st.n1[j - 1] : left, n1, 1);
                 st.lsh[I2][j] = l1;                                    /* row t-1 */
-                const uint32_t A0 = bs_mux(n1, tb[j][1], tb[j][0]), A1 = bs_mux(n1, tb[j][2], tb[j][1]);
+                uint32_t A0 = bs_mux(n1, tb[j][1], tb[j][0]), A1 = bs_mux(n1, tb[j][2], tb[j][1]);
+                if (!STEADY) {      /* the mask on the two candidates: beside the carry's way through the shuffle, not behind it */
+                    A0 &= vm[j];
+                    A1 &= vm[j];
+                }
                 nw[j] = bs_mux(l1, A1, A0);
             } else {
                 st.lsh[I2][j] = dp_funnel_l(j ? st.n1[j - 1] : left, n1, 1);
                 nw[j] = bs_mux(n1, tb[j][1], tb[j][0]);
+                if (!STEADY)
+                    nw[j] &= vm[j];
             }
-            if (!STEADY)
-                nw[j] &= vm[j];
         }
         if (lane < SK2_OWN_LANES)
             LaneVec<WPL>::st(st.row + S * SK2_RS, nw);
@@ -467,8 +472,14 @@ struct Skew2 {
             if (t + SLOTS - 1 >= st.out_first && t <= st.out_last && st.cons_ok < t + SLOTS - 1)
                 wait_ring(p, st, t + SLOTS - 1);
             st.in_prev = st.in_ring + (st.rb ? st.rb - 1 : SK2_RING - 1);
-            if (X1 <= W && t >= full_lo && t + SLOTS - 1 <= full_hi)
-                steps_from<0, true>(p, st, t);
+            /*
+             * The mask-free STEADY build of the steps exists (kSteadyBuild) but is not instantiated: at any moment one
+             * warp of the chain is entering the band and one is leaving it, the chain moves at THEIR pace, and a second
+             * copy of the unrolled group doubles the code the SM's instruction caches have to hold (ncu, first version:
+             * 0.36 cycles per issued instruction without an instruction to issue).
+             */
+            if (kSteadyBuild && X1 <= W && t >= full_lo && t + SLOTS - 1 <= full_hi)
+                steps_from<0, kSteadyBuild>(p, st, t);
             else
                 steps_from<0, false>(p, st, t);
             st.row += SLOTS * SK2_RS;
