@@ -254,10 +254,14 @@ struct Skew2 {
     CA_MDEV void fetch_posts(const Sk2Params &p, St &st, int t)
     {
         static_assert(S % MB == 0 && SLOTS % MB == 0, "blocks of posts are aligned to the step groups");
-        if (STEADY ? !st.has_left : ((unsigned)(t + MB - 2 - st.in_first) > (unsigned)(st.in_span + MB - 1))) {
-            st.mailbits = 0u;           /* no step of the block is inside the left warp's post window */
+        /* the left warp posts at every step from its first to its last (in_first + in_span), which lies behind this
+           warp's first step by construction: only the END of its posts has to be looked at */
+        const int in_last = st.in_first + st.in_span;
+        if (!st.has_left || t - 1 > in_last) {
+            st.mailbits = 0u;
             return;
         }
+        const bool all = STEADY || t + MB - 2 <= in_last;
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
             uint32_t bits = 0u;
@@ -265,7 +269,7 @@ struct Skew2 {
 #pragma unroll
             for (int k = 0; k < MB; k++) {
                 const uint32_t *slot = (S + k) ? st.in_ring + st.rb + (S + k - 1) : st.in_prev;
-                const bool want = STEADY || (unsigned)(t + k - 1 - st.in_first) <= (unsigned)st.in_span;
+                const bool want = all || t + k - 1 <= in_last;
                 const uint32_t m = dp_ld_volatile_u32(slot);
                 ok = ok && (!want || (m >> 1) == (uint32_t)(t + k));
                 bits |= (want ? (m & 1u) : 0u) << k;
@@ -393,8 +397,9 @@ struct Skew2 {
         if (lane < SK2_OWN_LANES)
             LaneVec<WPL>::st(st.row + S * SK2_RS, nw);
         /* this warp's post of step t: slot t % RING, tag t + 1 */
-        const bool posts = STEADY ? st.feeds : (t >= st.out_first && t <= st.out_last);
-        if (lane == SK2_OWN_LANES - 1 && posts)
+        /* posted at EVERY step of a warp that feeds a neighbour: before the first cell of the neighbour's window the bit
+           is 0 and nobody waits for it; the ring's back-pressure (sweep) only covers the steps that are read */
+        if (lane == SK2_OWN_LANES - 1 && st.feeds)
             dp_st_volatile((int *)st.out_ring + st.rb + S, (int)((nw[WPL - 1] >> 31) + (((uint32_t)t + 1u) << 1)));
 #pragma unroll
         for (int j = 0; j < WPL; j++) st.n1[j] = nw[j];
