@@ -1353,7 +1353,7 @@ static int run2d_tune(clapca_grid *g, uint32_t born, uint32_t surv, uint32_t nr_
         ms_row = g->stats.total_ms;
     }
     if (e == cudaSuccess && row_ok && diag_ok && clapca_hash_planes(g->cells, g->n, 1, &h_row) == CLAPCA_OK &&
-        h_row == h_diag && ms_diag < ms_row)
+        h_row == h_diag && ms_diag < 0.98f * ms_row)       /* a clear win, not measurement noise */
         choice = SK2_CHOICE_DIAGONAL;
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(g->cells, copy, g->n, cudaMemcpyDeviceToDevice, g->stream);

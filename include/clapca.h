@@ -208,6 +208,10 @@ void *clapca_grid_stream(clapca_grid *g);
 
 int clapca_grid_run3d(clapca_grid *g, uint32_t surv_mask, uint32_t born_mask, uint32_t nr_states,
                       int steps, int engine, int64_t *population);
+/* CLAPCA_ENGINE_AUTO / _BITPLANE on a binary grid of >= 4 M cells and >= 16 generations: the FIRST run of a (shape,
+ * rule) class also runs the row and the diagonal engine on a scratch copy of the input (at most 32 generations each,
+ * a few tens of milliseconds once per process) and later runs of the class take the one that was faster -- results are
+ * identical either way.  CLAPCA_2D_TUNE=0 skips the measurement (row engine). */
 int clapca_grid_run2d(clapca_grid *g, int64_t side, uint32_t born_mask, uint32_t surv_mask,
                       uint32_t nr_states, int decay, int neigh, int steps, int engine);
 /* xyzarray_count(): core/xyarray.c:68-78 */
