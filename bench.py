@@ -576,7 +576,9 @@ def run_ca2d(args, torch, clap_b200, dev, local, workload):
     else:
         kname = "ca2d_sweep_kernel (all generations fused)"
         note = "dependency-latency bound: the in-place sweep order leaves a chain of side + 2*generations row steps"
-    roof = roofline(workload, kname, kernel_ms, updates, bytes_per_update, note=note)
+    # the committed DRAM byte count belongs to a kernel, not to a workload: under AUTO either engine may have run
+    tkey = workload + "_diagonal" if st["engine"] == "diagonal" and not workload.endswith("_diagonal") else workload
+    roof = roofline(tkey, kname, kernel_ms, updates, bytes_per_update, note=note)
     lib = _lib_mod.lib()
     e2e = None
     if not args.no_e2e:
